@@ -1,0 +1,277 @@
+"""Batched, device-resident entry points of the hot path (torch tensors in, torch tensors out).
+
+The reference API is single-problem (one condition, one eta per call); these are the additive
+batched forms the B200 path is built around — leading ``(B,)`` conditions and ``(B, E)`` eta
+candidates.  The reference-shaped classes in ``donk_b200.traj_opt``,
+``donk_b200.dynamics`` are thin B=1 views over this module.
+
+Everything here calls the CUDA library through ``donk_b200._lib.native()``; there is no CPU path.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from donk_b200 import _lib
+from donk_b200._lib import ILQR_BACKWARD, ILQR_COST, ILQR_FORWARD, ILQR_KL, DonkError
+
+
+def _dev(x, dtype=torch.float64):
+    return _lib.as_device(x, dtype)
+
+
+def spd_factor(A: torch.Tensor, want_inv=True, want_chol=False, want_hld=True):
+    """Cholesky-based inverse / factor / half log-determinant of a batch of SPD matrices.
+
+    ``A (..., d, d)``.  Raises ``numpy.linalg.LinAlgError`` if any matrix is not positive definite
+    (as ``numpy.linalg.cholesky`` does in donk/utils/batched.py:48).
+    """
+    nat = _lib.native()
+    A = _dev(A)
+    d = A.shape[-1]
+    n = A.numel() // (d * d)
+    inv = torch.empty_like(A) if want_inv else None
+    chol = torch.empty_like(A) if want_chol else None
+    hld = torch.empty(A.shape[:-2], dtype=A.dtype, device=A.device) if want_hld else None
+    info = torch.zeros(max(n, 1), dtype=torch.int32, device=A.device)
+    nat.call("spd_factor_f64", n, d, A, inv, chol, hld, info)
+    if int(info.sum().item()) != 0:
+        raise np.linalg.LinAlgError("Matrix is not positive definite")
+    return inv, chol, hld
+
+
+def extended_costs_kl(K: torch.Tensor, k: torch.Tensor, inv_covar: torch.Tensor):
+    """``(..., T, dU, dX), (..., T, dU), (..., T, dU, dU) -> C_kl (..., T, p, p), c_kl (..., T, p)``."""
+    nat = _lib.native()
+    K, k, inv_covar = _dev(K), _dev(k), _dev(inv_covar)
+    dU, dX = K.shape[-2:]
+    p = dX + dU
+    n = K.numel() // (dU * dX)
+    C = torch.empty(K.shape[:-2] + (p, p), dtype=K.dtype, device=K.device)
+    c = torch.empty(K.shape[:-2] + (p,), dtype=K.dtype, device=K.device)
+    nat.call("extended_costs_kl_f64", n, dX, dU, K, k, inv_covar, C, c)
+    return C, c
+
+
+def kl_divergence_action(X, K, k, covar, prev_K, prev_k, prev_covar, prev_inv_covar=None):
+    """Batched ``kl_divergence_action`` for given state means ``X (B,T,dX)`` -> ``kl (B,)``."""
+    nat = _lib.native()
+    X, K, k, covar = _dev(X), _dev(K), _dev(k), _dev(covar)
+    prev_K, prev_k, prev_covar = _dev(prev_K), _dev(prev_k), _dev(prev_covar)
+    B, T, dX = X.shape
+    dU = K.shape[-2]
+    _, _, hld = spd_factor(covar, want_inv=False)
+    if prev_inv_covar is None:
+        prev_inv, _, phld = spd_factor(prev_covar)
+    else:
+        prev_inv = _dev(prev_inv_covar)
+        _, _, phld = spd_factor(prev_covar, want_inv=False)
+    kl = torch.empty(B, dtype=X.dtype, device=X.device)
+    nat.call("kl_divergence_action_f64", B, T, dX, dU, X, K, k, covar, hld, prev_K, prev_k, prev_inv, phld, kl)
+    return kl
+
+
+@dataclass
+class BatchedStepResult:
+    """Result of one batched iLQR step; leading dims ``(B, E)``."""
+
+    eta: torch.Tensor  # (B,E)
+    K: torch.Tensor  # (B,E,T,dU,dX)
+    k: torch.Tensor  # (B,E,T,dU)
+    covar: torch.Tensor  # (B,E,T,dU,dU)
+    inv_covar: torch.Tensor  # (B,E,T,dU,dU)
+    kl_div: torch.Tensor  # (B,E)
+    expected_costs: torch.Tensor  # (B,E)
+    info: torch.Tensor  # (B,E) int32
+    traj_mean: torch.Tensor | None = None  # (B,E,T+1,p)
+    traj_covar: torch.Tensor | None = None  # (B,E,T+1,p,p)
+
+
+def lqr_backward(F, f, C, c, gamma: float = 1.0):
+    """Batched ``backward`` (lqg.py:126-182): ``F (B,T,dX,p) ... -> K, k, covar, inv_covar, info``."""
+    nat = _lib.native()
+    F, f, C, c = _dev(F), _dev(f), _dev(C), _dev(c)
+    B, T, dX, p = F.shape
+    dU = p - dX
+    o = dict(dtype=F.dtype, device=F.device)
+    K = torch.empty(B, 1, T, dU, dX, **o)
+    k = torch.empty(B, 1, T, dU, **o)
+    cov = torch.empty(B, 1, T, dU, dU, **o)
+    inv = torch.empty(B, 1, T, dU, dU, **o)
+    info = torch.zeros(B, 1, dtype=torch.int32, device=F.device)
+    nat.call("ilqr_step_f64", B, 1, T, dX, dU, ILQR_BACKWARD, F, f, None, C, c, None, None, None, None, None, None,
+             None, None, None, None, float(gamma), 0.0, None, K, k, cov, inv, None, None, None, None, info)
+    return K[:, 0], k[:, 0], cov[:, 0], inv[:, 0], info[:, 0]
+
+
+def lqr_forward(F, f, dyn_covar, K, k, pol_covar, x0_mean, x0_covar, regularization: float = 1e-6,
+                C=None, c=None, cc=None):
+    """Batched ``forward`` (lqg.py:185-244) -> ``mean (B,T+1,p), covar (B,T+1,p,p)[, cost (B,)]``.
+
+    With costs ``C, c, cc`` the summed ``expected_costs`` (quadratic_costs.py:106-119) is returned too.
+    """
+    nat = _lib.native()
+    F, f, dyn_covar = _dev(F), _dev(f), _dev(dyn_covar)
+    K, k, pol_covar = _dev(K).unsqueeze(1).contiguous(), _dev(k).unsqueeze(1).contiguous(), _dev(pol_covar).unsqueeze(1).contiguous()
+    x0_mean, x0_covar = _dev(x0_mean), _dev(x0_covar)
+    B, T, dX, p = F.shape
+    dU = p - dX
+    o = dict(dtype=F.dtype, device=F.device)
+    mean = torch.empty(B, 1, T + 1, p, **o)
+    covar = torch.empty(B, 1, T + 1, p, p, **o)
+    info = torch.zeros(B, 1, dtype=torch.int32, device=F.device)
+    flags = ILQR_FORWARD
+    cost = None
+    if C is not None:
+        C, c, cc = _dev(C), _dev(c), _dev(cc)
+        cost = torch.empty(B, 1, **o)
+        flags |= ILQR_COST
+    nat.call("ilqr_step_f64", B, 1, T, dX, dU, flags, F, f, dyn_covar, C, c, cc, None, None, None, None, None, None,
+             x0_mean, x0_covar, None, 1.0, float(regularization), None, K, k, pol_covar, pol_covar, None, cost, mean,
+             covar, info)
+    if cost is not None:
+        return mean[:, 0], covar[:, 0], cost[:, 0]
+    return mean[:, 0], covar[:, 0]
+
+
+class BatchedILQR:
+    """``ILQR(dynamics, prev_pol, costs, initial_state)`` (lqg.py:29-123) for B conditions at once.
+
+    All arguments carry a leading ``B``: dynamics ``F (B,T,dX,p), f (B,T,dX), dyn_covar (B,T,dX,dX)``;
+    previous policy ``prev_K (B,T,dU,dX), prev_k (B,T,dU)`` and ``prev_covar`` and/or ``prev_inv_covar
+    (B,T,dU,dU)``; costs ``C (B,T+1,p,p), c (B,T+1,p), cc (B,T+1)``; ``x0_mean (B,dX), x0_covar (B,dX,dX)``.
+    """
+
+    def __init__(self, F, f, dyn_covar, prev_K, prev_k, C, c, cc, x0_mean, x0_covar, prev_covar=None,
+                 prev_inv_covar=None):
+        self.F, self.f, self.dyn_covar = _dev(F), _dev(f), _dev(dyn_covar)
+        self.prev_K, self.prev_k = _dev(prev_K), _dev(prev_k)
+        self.C, self.c, self.cc = _dev(C), _dev(c), _dev(cc)
+        self.x0_mean, self.x0_covar = _dev(x0_mean), _dev(x0_covar)
+        self.B, self.T, self.dX, p = self.F.shape
+        self.dU = p - self.dX
+        if prev_covar is None and prev_inv_covar is None:
+            raise ValueError("Must provide covar or inv_covar.")
+        # lazy covar / chol_covar / inv_covar of the previous policy (donk/models/tvlg.py:62-99)
+        if prev_covar is not None:
+            self.prev_covar = _dev(prev_covar)
+            inv, _, self.prev_hld = spd_factor(self.prev_covar)
+            self.prev_inv_covar = inv if prev_inv_covar is None else _dev(prev_inv_covar)
+        else:
+            self.prev_inv_covar = _dev(prev_inv_covar)
+            self.prev_covar, _, _ = spd_factor(self.prev_inv_covar, want_hld=False)
+            _, _, self.prev_hld = spd_factor(self.prev_covar, want_inv=False)
+        self.C_kl, self.c_kl = extended_costs_kl(self.prev_K, self.prev_k, self.prev_inv_covar)
+        self._ws = {}
+
+    # -- workspace ---------------------------------------------------------------------------
+    def _buffers(self, E: int, want_traj: bool):
+        key = (E, want_traj)
+        ws = self._ws.get(key)
+        if ws is None:
+            B, T, dX, dU = self.B, self.T, self.dX, self.dU
+            p = dX + dU
+            o = dict(dtype=self.F.dtype, device=self.F.device)
+            ws = dict(
+                K=torch.empty(B, E, T, dU, dX, **o), k=torch.empty(B, E, T, dU, **o),
+                covar=torch.empty(B, E, T, dU, dU, **o), inv_covar=torch.empty(B, E, T, dU, dU, **o),
+                kl=torch.zeros(B, E, **o), cost=torch.zeros(B, E, **o),
+                info=torch.zeros(B, E, dtype=torch.int32, device=self.F.device),
+                tmean=torch.empty(B, E, T + 1, p, **o) if want_traj else None,
+                tcov=torch.empty(B, E, T + 1, p, p, **o) if want_traj else None,
+            )
+            self._ws = {key: ws}  # keep one set only: the policy buffers dominate memory
+        return ws
+
+    def step(self, eta, active: torch.Tensor | None = None, want_traj: bool = False) -> BatchedStepResult:
+        """``ILQR.step`` (lqg.py:55-75) for ``eta (B,E)`` (or ``(B,)``, or a scalar broadcast to all)."""
+        nat = _lib.native()
+        eta = torch.as_tensor(eta, dtype=self.F.dtype).to(self.F.device)
+        if eta.ndim == 0:
+            eta = eta.expand(self.B, 1)
+        elif eta.ndim == 1:
+            eta = eta[:, None]
+        eta = eta.contiguous()
+        E = eta.shape[1]
+        ws = self._buffers(E, want_traj)
+        nat.call("ilqr_step_f64", self.B, E, self.T, self.dX, self.dU,
+                 ILQR_BACKWARD | ILQR_FORWARD | ILQR_KL | ILQR_COST,
+                 self.F, self.f, self.dyn_covar, self.C, self.c, self.cc, self.C_kl, self.c_kl,
+                 self.prev_K, self.prev_k, self.prev_inv_covar, self.prev_hld, self.x0_mean, self.x0_covar,
+                 eta, 1.0, 1e-6, active, ws["K"], ws["k"], ws["covar"], ws["inv_covar"], ws["kl"], ws["cost"],
+                 ws["tmean"], ws["tcov"], ws["info"])
+        return BatchedStepResult(eta, ws["K"], ws["k"], ws["covar"], ws["inv_covar"], ws["kl"], ws["cost"],
+                                 ws["info"], ws["tmean"], ws["tcov"])
+
+    def sample_surface(self, min_eta: float = 1e-6, max_eta: float = 1e16, N: int = 100) -> BatchedStepResult:
+        """``ILQR.sample_surface`` (lqg.py:77-88): N log-spaced eta candidates for every condition."""
+        etas = np.logspace(np.log10(min_eta), np.log10(max_eta), num=N)
+        return self.step(torch.as_tensor(etas).expand(self.B, N))
+
+    def optimize(self, kl_step, min_eta: float = 1e-6, max_eta: float = 1e16, rtol: float = 1e-2,
+                 want_traj: bool = False, raise_on_failure: bool = True):
+        """``ILQR.optimize`` (lqg.py:90-123) for all B conditions in lock-step.
+
+        ``kl_step`` scalar or ``(B,)``.  Returns ``(BatchedStepResult with E=1, status (B,) int32,
+        n_steps)``; status 0 = root found, 1 = constraint inactive at ``min_eta`` (lqg.py:108-109),
+        2 = ``max_eta`` too low (the reference raises ValueError, lqg.py:112-113), 3 = Brent did not
+        converge in 100 iterations (scipy raises RuntimeError).
+        """
+        nat = _lib.native()
+        dev, dt, B = self.F.device, self.F.dtype, self.B
+        kl_step_t = torch.as_tensor(kl_step, dtype=dt).to(dev).expand(B).contiguous()
+        n_steps = 0
+
+        def kl_at(eta_t, active):
+            nonlocal n_steps
+            n_steps += 1
+            r = self.step(eta_t, active=active)
+            bad = (r.info[:, 0] != 0) & (active != 0 if active is not None else True)
+            if bool(bad.any()):
+                raise np.linalg.LinAlgError("Quu is not positive definite")
+            return r.kl_div[:, 0].clone()
+
+        full = lambda v: torch.full((B,), float(v), dtype=dt, device=dev)  # noqa: E731
+        all_active = torch.ones(B, dtype=torch.int32, device=dev)
+        kl_min = kl_at(full(min_eta), all_active)
+        inactive = kl_min <= kl_step_t  # lqg.py:108: constraint already met at maximum deviation
+        active = (~inactive).to(torch.int32).contiguous()
+        status = torch.where(inactive, 1, 0).to(torch.int32)
+        eta_final = full(min_eta)
+        if int(active.sum().item()) > 0:
+            kl_max = kl_at(full(max_eta), active)
+            too_low = (kl_max > kl_step_t) & (active != 0)  # lqg.py:112
+            if bool(too_low.any()):
+                if raise_on_failure:
+                    raise ValueError(f"max_eta eta to low ({max_eta})")
+                status = torch.where(too_low, 2, status).to(torch.int32)
+                active = (active * (~too_low).to(torch.int32)).contiguous()
+            # brentq evaluates f(log min_eta), f(log max_eta) itself (exp(log(x)) may differ from x by an ulp)
+            xa, xb = float(np.log(min_eta)), float(np.log(max_eta))
+            searched = active.clone()
+            # kl_step may differ per condition: fold it into the function values (scalar argument = 0)
+            fa = (kl_at(full(np.exp(xa)), active) - kl_step_t).contiguous()
+            fb = (kl_at(full(np.exp(xb)), active) - kl_step_t).contiguous()
+            state = torch.zeros(B, 12, dtype=dt, device=dev)
+            eta = full(min_eta)
+            bstat = torch.zeros(B, dtype=torch.int32, device=dev)
+            n_active = torch.zeros(1, dtype=torch.int32, device=dev)
+            nat.call("brent_update_f64", B, 0, xa, xb, fa, fb, None, 0.0, 2e-12, float(rtol), 100, state, eta, active,
+                     bstat, n_active)
+            while int(n_active.item()) > 0:
+                fnew = (kl_at(eta, active) - kl_step_t).contiguous()
+                nat.call("brent_update_f64", B, 1, xa, xb, None, None, fnew, 0.0, 2e-12, float(rtol), 100, state,
+                         eta, active, bstat, n_active)
+            bad_sign = (bstat == 2) & (searched != 0)
+            no_conv = (bstat == 3) & (searched != 0)
+            if raise_on_failure and bool(bad_sign.any()):
+                raise ValueError("f(a) and f(b) must have different signs")
+            if raise_on_failure and bool(no_conv.any()):
+                raise RuntimeError("Failed to converge after 100 iterations.")
+            status = torch.where(no_conv | bad_sign, 3, status).to(torch.int32)
+            eta_final = torch.where((searched != 0) & (bstat == 1), eta, eta_final)
+        n_steps += 1
+        result = self.step(eta_final, want_traj=want_traj)
+        return result, status, n_steps

@@ -1,0 +1,124 @@
+// donk_b200 — shared device helpers.
+//
+// Kernels are written as bulk-synchronous CTA phases over shared memory:
+//     TEAM_FOR(i, n_items) { ... }   ctx.sync();
+// No thread-private state is carried across a sync except CTA-uniform values.
+// That discipline lets the very same kernel bodies compile two ways:
+//   * nvcc, sm_100a: TEAM_FOR strides the CTA's threads, sync = __syncthreads();
+//   * g++ with -DDONK_EMU (tests/emu only): one host thread plays the whole CTA,
+//     TEAM_FOR is a sequential loop (optionally reversed, to expose intra-phase
+//     dependencies) and sync is a no-op.
+// The emulation build is test infrastructure for kernel logic on a box without a
+// GPU; it is never loaded by the product path (donk_b200/_lib.py loads the CUDA
+// library only and raises if it is missing).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define DONK_HD __host__ __device__ __forceinline__
+#define DONK_D __device__ __forceinline__
+#else
+#define DONK_HD inline
+#define DONK_D inline
+#endif
+
+namespace donk {
+
+#if defined(DONK_EMU)
+extern int g_emu_reverse;  // tests flip this to run every phase back to front
+struct Ctx {
+  int tid, nt;
+  inline void sync() const {}
+};
+static inline int emu_idx(int it, int n) { return g_emu_reverse ? n - 1 - it : it; }
+#define TEAM_FOR(i, n)                                                               \
+  for (int i##_it = 0, i##_n = (n), i = donk::emu_idx(0, i##_n); i##_it < i##_n;     \
+       ++i##_it, i = donk::emu_idx(i##_it, i##_n))
+#else
+struct Ctx {
+  int tid, nt;
+  DONK_D void sync() const { __syncthreads(); }
+};
+#define TEAM_FOR(i, n) for (int i = ctx.tid; i < (n); i += ctx.nt)
+#endif
+
+DONK_HD int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// Read-only global load (inputs never written by the running kernel).
+template <typename R>
+DONK_HD R ldg(const R* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
+// 4 consecutive values from shared memory; p must be 16-byte aligned for double
+// (two LDS.128) — all tile origins and leading dimensions are multiples of 4.
+DONK_HD void ld4(const double* p, double o[4]) {
+#if defined(__CUDA_ARCH__)
+  const double2 a = *reinterpret_cast<const double2*>(p);
+  const double2 b = *reinterpret_cast<const double2*>(p + 2);
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+#else
+  o[0] = p[0]; o[1] = p[1]; o[2] = p[2]; o[3] = p[3];
+#endif
+}
+DONK_HD void ld4(const float* p, float o[4]) {
+#if defined(__CUDA_ARCH__)
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+#else
+  o[0] = p[0]; o[1] = p[1]; o[2] = p[2]; o[3] = p[3];
+#endif
+}
+
+// 4x4 register tile of a product whose operands are both stored k-major:
+//   acc[r][c] = sum_{k<kdim} A[k*lda + i0 + r] * Bm[k*ldb + j0 + c]
+// 16 FMAs per 4 LDS.128 (double) per k.  i0, j0, lda, ldb multiples of 4.
+template <typename R>
+DONK_HD void tile4x4(const R* __restrict__ A, int lda, int i0, const R* __restrict__ Bm, int ldb, int j0,
+                     int kdim, R acc[4][4]) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = R(0);
+  const R* a = A + i0;
+  const R* b = Bm + j0;
+#pragma unroll 2
+  for (int k = 0; k < kdim; ++k) {
+    R av[4], bv[4];
+    ld4(a, av);
+    ld4(b, bv);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = fma(av[r], bv[c], acc[r][c]);
+    a += lda;
+    b += ldb;
+  }
+}
+
+// Upper-triangular tile enumeration: idx in [0, nt(nt+1)/2) -> (ti <= tj).
+DONK_HD void tri_tile(int idx, int nt, int& ti, int& tj) {
+  int t = 0;
+  while (idx >= nt - t) {
+    idx -= nt - t;
+    ++t;
+  }
+  ti = t;
+  tj = t + idx;
+}
+
+}  // namespace donk
+
+// status codes returned by the C-ABI (same values as include/donk_b200.h)
+#ifndef DONK_OK
+#define DONK_OK 0
+#define DONK_BAD_SHAPE 1
+#define DONK_NOT_PD 2
+#define DONK_CUDA_ERROR 3
+#define DONK_SMEM_LIMIT 4
+#endif

@@ -1,0 +1,185 @@
+/* donk_b200 — C ABI of the B200-native trajectory-optimisation hot path.
+ *
+ * The reference (DiddiZ/donk.ai) is pure Python and has no FFI layer; the boundary it
+ * exposes for this path is its Python API.  Each entry point below replaces the body of
+ * one reference function (cited file:line, relative to the reference root) and is what
+ * a binding of that function would call (see INTEGRATION.md for the ctypes stubs).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to C-contiguous memory owned by the caller;
+ *     the library never allocates or frees caller-visible memory;
+ *   - `_f64` entry points take double, `_f32` float (same layouts);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls
+ *     are asynchronous with respect to the host unless stated;
+ *   - return value: DONK_OK, or an error code; numerical failures that depend on the
+ *     data (a matrix that is not positive definite) are reported per problem through
+ *     the `info` device arrays, not through the return value;
+ *   - no global state; re-entrant; thread-safe per stream.
+ */
+#ifndef DONK_B200_H
+#define DONK_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DONK_OK 0
+#define DONK_BAD_SHAPE 1
+#define DONK_NOT_PD 2
+#define DONK_CUDA_ERROR 3
+#define DONK_SMEM_LIMIT 4
+
+/* flags of donk_ilqr_step_* */
+#define DONK_ILQR_BACKWARD 1
+#define DONK_ILQR_FORWARD 2
+#define DONK_ILQR_KL 4
+#define DONK_ILQR_COST 8
+
+/* Library / build identification: "donk_b200 <version> sm_100a". */
+const char* donk_version(void);
+/* Last CUDA error string seen by this library on the calling thread ("" if none). */
+const char* donk_last_error(void);
+/* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
+unsigned long long donk_launch_count(void);
+
+/* ---- iLQR ------------------------------------------------------------------------------ */
+
+/* ILQR.step batched over B conditions x E eta candidates:  donk/traj_opt/lqg.py:55-75
+ * (backward lqg.py:126-182, forward lqg.py:185-244, kl_divergence_action lqg.py:276-306,
+ * QuadraticCosts.expected_costs donk/costs/quadratic_costs.py:106-119).
+ *
+ *   p = dX+dU.  Inputs per condition b:
+ *     F (B,T,dX,p)  f (B,T,dX)  dyn_covar (B,T,dX,dX)           LinearDynamics
+ *     C (B,T+1,p,p) c (B,T+1,p) cc (B,T+1)                      QuadraticCosts
+ *     C_kl (B,T,p,p) c_kl (B,T,p)     extended costs of prev_pol (may be NULL: plain LQR)
+ *     prevK (B,T,dU,dX) prevk (B,T,dU) prevLam (B,T,dU,dU) = prev_pol.inv_covar,
+ *     prev_hld (B,T) = sum log diag chol(prev_pol.covar)        (needed with DONK_ILQR_KL)
+ *     x0_mean (B,dX) x0_covar (B,dX,dX)                         StateDistribution
+ *     eta (B,E)   Lagrange multipliers (NULL: eta = 1, costs used as given)
+ *     gamma       discount (backward's `gamma`), fwd_reg = forward's `regularization`
+ *     active (B) int32, optional: conditions with 0 are skipped (outputs untouched)
+ *   Outputs per (b,e):
+ *     K (B,E,T,dU,dX) k (B,E,T,dU) pol_covar, pol_inv_covar (B,E,T,dU,dU)   always written
+ *       (with DONK_ILQR_FORWARD but not DONK_ILQR_BACKWARD they are inputs: the policy)
+ *     kl (B,E), cost (B,E)          with DONK_ILQR_KL / DONK_ILQR_COST
+ *     traj_mean (B,E,T+1,p), traj_covar (B,E,T+1,p,p)   optional (NULL to skip)
+ *     info (B,E) int32: 0, or 1+t of the first step whose Quu was not positive definite
+ *       (the reference raises numpy.linalg.LinAlgError there, lqg.py:165)
+ *   DONK_ILQR_KL requires DONK_ILQR_BACKWARD|DONK_ILQR_FORWARD (the log-determinants of the
+ *   new policy come from the backward factorisation).
+ */
+int donk_ilqr_step_f64(int B, int E, int T, int dX, int dU, int flags,
+                       const double* F, const double* f, const double* dyn_covar,
+                       const double* C, const double* c, const double* cc,
+                       const double* C_kl, const double* c_kl,
+                       const double* prevK, const double* prevk, const double* prevLam, const double* prev_hld,
+                       const double* x0_mean, const double* x0_covar,
+                       const double* eta, double gamma, double fwd_reg, const int* active,
+                       double* K, double* k, double* pol_covar, double* pol_inv_covar,
+                       double* kl, double* cost, double* traj_mean, double* traj_covar,
+                       int* info, void* stream);
+int donk_ilqr_step_f32(int B, int E, int T, int dX, int dU, int flags,
+                       const float* F, const float* f, const float* dyn_covar,
+                       const float* C, const float* c, const float* cc,
+                       const float* C_kl, const float* c_kl,
+                       const float* prevK, const float* prevk, const float* prevLam, const float* prev_hld,
+                       const float* x0_mean, const float* x0_covar,
+                       const float* eta, float gamma, float fwd_reg, const int* active,
+                       float* K, float* k, float* pol_covar, float* pol_inv_covar,
+                       float* kl, float* cost, float* traj_mean, float* traj_covar,
+                       int* info, void* stream);
+
+/* extended_costs_kl: donk/traj_opt/lqg.py:247-273.  n = number of (b,t) pairs (B*T).
+ *   K (n,dU,dX) k (n,dU) Lam (n,dU,dU) -> C_kl (n,p,p) c_kl (n,p). */
+int donk_extended_costs_kl_f64(int n, int dX, int dU, const double* K, const double* k, const double* Lam,
+                               double* C_kl, double* c_kl, void* stream);
+
+/* Lazy chol_covar / inv_covar of TimeVaryingLinearGaussian: donk/models/tvlg.py:62-99,
+ * donk/utils/batched.py:6-49.  A (n,d,d) SPD -> Ainv (n,d,d), chol (n,d,d) lower, half_logdet (n) =
+ * sum log diag chol; any output may be NULL.  info (n) int32: 1 where A is not positive definite
+ * (numpy.linalg.cholesky raises LinAlgError there). */
+int donk_spd_factor_f64(int n, int d, const double* A, double* Ainv, double* chol, double* half_logdet,
+                        int* info, void* stream);
+
+/* kl_divergence_action for given states: donk/traj_opt/lqg.py:276-306.
+ *   X (B,T,dX); new policy K,k,covar + hld (B,T); previous policy pK,pk,pLam + phld (B,T) -> kl (B). */
+int donk_kl_divergence_action_f64(int B, int T, int dX, int dU, const double* X,
+                                  const double* K, const double* k, const double* covar, const double* hld,
+                                  const double* pK, const double* pk, const double* pLam, const double* phld,
+                                  double* kl, void* stream);
+
+/* Brent root search of ILQR.optimize, one state machine per condition, advanced in lock-step:
+ * donk/traj_opt/lqg.py:116-123 + scipy.optimize.brentq (xtol=2e-12, maxiter=100 defaults).
+ *   phase 0: fa (B) = kl(step(exp xa)) - kl_step, fb (B) likewise at xb; initialises state.
+ *   phase 1: fnew (B) = kl(step(eta)) of the eta written by the previous call.
+ *   state (B,12) doubles (opaque), eta (B) next multiplier to evaluate (or the root once
+ *   converged), active (B) int32 1 while the search of that condition continues,
+ *   status (B) int32: 0 running, 1 converged, 2 f(a),f(b) same sign, 3 maxiter,
+ *   n_active (1) int32 device counter of still-active conditions.
+ *   kl_step is subtracted from fa/fb/fnew inside. */
+int donk_brent_update_f64(int B, int phase, double xa, double xb, const double* fa, const double* fb,
+                          const double* fnew, double kl_step, double xtol, double rtol, int maxiter,
+                          double* state, double* eta, int* active, int* status, int* n_active, void* stream);
+
+/* ---- dynamics fit ---------------------------------------------------------------------- */
+
+/* fit_lr batched over B conditions: donk/dynamics/linear_dynamics.py:137-189, with the GMM /
+ * normal-inverse-Wishart prior of donk/dynamics/prior/prior_gmm.py:26-41 and prior.py:18-45 fused in.
+ *   X (B,N,T+1,dX), U (B,N,T,dU) -> F (B,T,dX,p), f (B,T,dX), covar (B,T,dX,dX).
+ *   Prior (gmm_K = 0: none): weights (K), means (K,d), covariances (K,d,d), prec_chol (K,d,d)
+ *   with d = 2dX+dU, n_pool = GMMPrior.N, prior_weight as in fit_lr.
+ *   info (B,T) int32: 0 ok, 1 = Sigma[:p,:p] not positive definite after regularisation.
+ *   N <= 1 returns DONK_BAD_SHAPE (the reference raises ValueError, linear_dynamics.py:154). */
+int donk_fit_lr_f64(int B, int N, int T, int dX, int dU, const double* X, const double* U,
+                    int gmm_K, const double* gmm_weights, const double* gmm_means, const double* gmm_covariances,
+                    const double* gmm_prec_chol, double n_pool, double prior_weight, double regularization,
+                    double* F, double* f, double* covar, int* info, void* stream);
+
+/* to_transitions: donk/dynamics/utils.py:4-17.  X (N,T+1,dX), U (N,T,dU) -> XUX (N*T, 2dX+dU). */
+int donk_to_transitions_f64(int N, int T, int dX, int dU, const double* X, const double* U, double* XUX,
+                            void* stream);
+
+/* StateDistribution.fit batched: donk/samples/state_dist.py:27-37 (unbiased covariance).
+ *   X0 (B,N,dX) with row stride `ld` doubles between samples -> mean (B,dX), covar (B,dX,dX). */
+int donk_state_fit_f64(int B, int N, int dX, const double* X0, size_t sample_stride, size_t cond_stride,
+                       double* mean, double* covar, void* stream);
+
+/* ---- GMM prior: EM ----------------------------------------------------------------------- */
+
+/* Number of doubles in the packed sufficient statistics of donk_gmm_em_step_f64:
+ *   [ nk (K) | sum r (x-mu_k) (K,d) | sum r (x-mu_k)(x-mu_k)^T (K,d,d) | sum lse (1) ]. */
+size_t donk_gmm_stats_size(int d, int K);
+/* Workspace bytes donk_gmm_em_step_f64 needs for n_local rows. */
+size_t donk_gmm_workspace_bytes(int n_local, int d, int K);
+
+/* One fused E-step + sufficient-statistics pass over this rank's rows of the transition pool:
+ * sklearn.mixture.GaussianMixture E-step and the sums of the M-step, as called from
+ * GMMPrior.update (donk/dynamics/prior/prior_gmm.py:14-24).  X (n_local,d).
+ * stats receives this rank's partial sums (the caller all-reduces them across ranks). */
+int donk_gmm_em_step_f64(int n_local, int d, int K, const double* X,
+                         const double* weights, const double* means, const double* prec_chol,
+                         double* stats, void* workspace, size_t workspace_bytes, void* stream);
+
+/* M-step finalisation from (all-reduced) statistics of n_total rows: new weights, means,
+ * covariances (+ reg_covar I), precision Cholesky factors, mean log-likelihood.
+ * means is in/out (statistics are centred on the previous means).
+ * info (K) int32: 1 where a covariance is not positive definite (sklearn raises ValueError). */
+int donk_gmm_m_finalize_f64(double n_total, int d, int K, const double* stats, double reg_covar,
+                            double* weights, double* means, double* covariances, double* prec_chol,
+                            double* lower_bound, int* info, void* stream);
+
+/* Responsibilities (predict_proba) of rows X (n,d): resp (n,K).  Used by GMMPrior.eval for callers
+ * that want the NIW object itself (prior_gmm.py:33). */
+int donk_gmm_predict_proba_f64(int n, int d, int K, const double* X, const double* weights, const double* means,
+                               const double* prec_chol, double* resp, void* stream);
+
+/* Precision Cholesky factors from explicit precision matrices (sklearn precisions_init path). */
+int donk_gmm_prec_chol_from_precisions_f64(int d, int K, const double* precisions, double* prec_chol,
+                                           int* info, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DONK_B200_H */

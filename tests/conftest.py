@@ -25,3 +25,20 @@ def golden():
             return {k: z[k] for k in z.files}
 
     return load
+
+
+@pytest.fixture()
+def emu():
+    """Route donk_b200 calls to the host-emulation build of the kernel sources (no GPU needed).
+
+    This checks kernel logic and the Python host layer on CPU; the `-m gpu` tests run the same
+    assertions against the real CUDA library.
+    """
+    from donk_b200 import _lib
+    from emu.build_emu import backend
+
+    nat = backend()
+    _lib.install_test_backend(nat)
+    yield nat
+    nat.lib.donk_emu_set_reverse(0)
+    _lib.install_test_backend(None)

@@ -1,0 +1,129 @@
+"""Kernel logic of the iLQR step (donk_b200/csrc/ilqr.cuh) under host emulation vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from donk_testutil import load_golden, relerr
+from oracle.lqg import ILQRProblem
+
+TOL = 1e-9
+
+
+def _problem(g):
+    return ILQRProblem(g["F"], g["f"], g["dyn_covar"], g["C"], g["c"], g["cc"], g["prev_K"], g["prev_k"],
+                       g["prev_covar"], g["prev_inv_covar"], g["x0_mean"], g["x0_covar"])
+
+
+def _batched(g, reps=1):
+    from donk_b200.batched import BatchedILQR
+
+    r = lambda a: np.broadcast_to(a, (reps,) + a.shape).copy()  # noqa: E731
+    return BatchedILQR(r(g["F"]), r(g["f"]), r(g["dyn_covar"]), r(g["prev_K"]), r(g["prev_k"]), r(g["C"]), r(g["c"]),
+                       r(g["cc"]), r(g["x0_mean"]), r(g["x0_covar"]), prev_covar=r(g["prev_covar"]))
+
+
+@pytest.mark.parametrize("reverse", [0, 1])
+def test_backward_forward_small(emu, reverse):
+    from donk_b200 import batched
+
+    emu.lib.donk_emu_set_reverse(reverse)
+    g = load_golden("lqg_small")
+    K, k, cov, inv, info = batched.lqr_backward(g["bw_F"][None], g["bw_f"][None], g["bw_C"][None], g["bw_c"][None])
+    assert int(info.sum()) == 0
+    assert relerr(K[0], g["bw_K"]) < TOL and relerr(k[0], g["bw_k"]) < TOL
+    assert relerr(cov[0], g["bw_covar"]) < TOL and relerr(inv[0], g["bw_inv_covar"]) < TOL
+    K, k, cov, inv, info = batched.lqr_backward(g["bw_F"][None], g["bw_f"][None], g["bw_C"][None], g["bw_c"][None], gamma=0.9)
+    assert relerr(K[0], g["bwg_K"]) < TOL and relerr(cov[0], g["bwg_covar"]) < TOL
+    mean, covar = batched.lqr_forward(g["fw_F"][None], g["fw_f"][None], g["fw_dyn_covar"][None], g["fw_K"][None],
+                                      g["fw_k"][None], g["fw_pol_covar"][None], g["fw_x0_mean"][None], g["fw_x0_covar"][None])
+    assert relerr(mean[0], g["fw_mean"]) < TOL and relerr(covar[0], g["fw_covar"]) < TOL
+    c = covar[0].numpy()
+    assert np.array_equal(c, np.swapaxes(c, 1, 2))
+
+
+def test_helpers(emu):
+    from donk_b200 import batched
+
+    g = load_golden("lqg_small")
+    C, c = batched.extended_costs_kl(g["ex_K"], g["ex_k"], g["ex_inv_covar"])
+    assert relerr(C, g["ex_C"]) < TOL and relerr(c, g["ex_c"]) < TOL
+    inv, chol, hld = batched.spd_factor(torch.as_tensor(g["ex_covar"]), want_chol=True)
+    assert relerr(inv, g["ex_inv_covar"]) < TOL
+    assert relerr(chol, np.linalg.cholesky(g["ex_covar"])) < TOL
+    assert relerr(hld, np.log(np.diagonal(np.linalg.cholesky(g["ex_covar"]), axis1=1, axis2=2)).sum(-1)) < TOL
+    kl = batched.kl_divergence_action(g["kl_X"][None], g["kl_K"][None], g["kl_k"][None], g["kl_covar"][None],
+                                      g["kl_pK"][None], g["kl_pk"][None], g["kl_pcovar"][None])
+    assert abs(float(kl[0]) - 3.914744335914712) < 1e-12
+    with pytest.raises(np.linalg.LinAlgError):
+        batched.spd_factor(torch.as_tensor(-np.eye(3)[None]))
+
+
+@pytest.mark.parametrize("case,reverse", [("ilqr_c1", 0), ("ilqr_c1", 1), ("ilqr_c2", 0)])
+def test_step_matches_reference(emu, case, reverse):
+    emu.lib.donk_emu_set_reverse(reverse)
+    g = load_golden(case)
+    il = _batched(g, reps=3)
+    assert relerr(il.C_kl[1], g["C_kl"]) < TOL and relerr(il.c_kl[2], g["c_kl"]) < TOL
+    etas = g["etas"]
+    r = il.step(torch.as_tensor(etas).expand(3, len(etas)), want_traj=True)
+    assert int(r.info.sum()) == 0
+    for i in range(len(etas)):
+        for b in (0, 2):
+            assert relerr(r.K[b, i], g[f"s{i}_K"]) < TOL and relerr(r.k[b, i], g[f"s{i}_k"]) < TOL
+            assert relerr(r.covar[b, i], g[f"s{i}_covar"]) < TOL
+            assert relerr(r.inv_covar[b, i], g[f"s{i}_inv_covar"]) < TOL
+            assert relerr(r.traj_mean[b, i], g[f"s{i}_mean"]) < TOL
+            assert abs(float(r.kl_div[b, i]) - g[f"s{i}_kl"]) < 1e-9 * max(1.0, abs(g[f"s{i}_kl"]))
+            assert abs(float(r.expected_costs[b, i]) - g[f"s{i}_cost"]) < 1e-9 * abs(g[f"s{i}_cost"])
+            if f"s{i}_tcovar" in g:
+                assert relerr(r.traj_covar[b, i], g[f"s{i}_tcovar"]) < TOL
+
+
+def test_optimize_follows_reference_brent_path(emu):
+    g = load_golden("ilqr_c1")
+    il = _batched(g, reps=2)
+    for j in (0, 1):
+        res, status, n_steps = il.optimize(float(g[f"o{j}_kl_step"]))
+        assert n_steps == len(g[f"o{j}_visited"])  # same number of ILQR.step evaluations as the reference
+        assert status.tolist() == [0, 0]
+        assert abs(float(res.eta[0, 0]) - g[f"o{j}_eta"]) < 1e-9 * g[f"o{j}_eta"]
+        assert relerr(res.K[1, 0], g[f"o{j}_K"]) < 1e-8 and relerr(res.k[1, 0], g[f"o{j}_k"]) < 1e-8
+        assert abs(float(res.kl_div[0, 0]) - g[f"o{j}_kl"]) < 1e-8
+    # kl_step so large that the constraint is inactive at min_eta (lqg.py:108-109)
+    res, status, n_steps = il.optimize(1e9)
+    assert status.tolist() == [1, 1] and float(res.eta[0, 0]) == 1e-6
+    with pytest.raises(ValueError):
+        il.optimize(1e-30, max_eta=1e-3)
+
+
+def test_multi_condition_packing_and_active_mask(emu):
+    """E=1 packs several conditions per CTA; masked conditions keep their outputs untouched."""
+    from donk_b200 import synthetic
+    from donk_b200.batched import BatchedILQR
+
+    T, dX, dU, N = 12, 5, 3, 12
+    conds = [synthetic.condition(9, i, T, dX, dU, N) for i in range(11)]
+    fits = [oracle.fit_lr(c.X, c.U) for c in conds]
+    x0 = [oracle.state_fit(c.X[:, 0]) for c in conds]
+    st = lambda xs: np.stack(xs)  # noqa: E731
+    il = BatchedILQR(st([f[0] for f in fits]), st([f[1] for f in fits]), st([f[2] for f in fits]),
+                     st([c.prev_K for c in conds]), st([c.prev_k for c in conds]), st([c.C for c in conds]),
+                     st([c.c for c in conds]), st([c.cc for c in conds]), st([m for m, _ in x0]),
+                     st([S for _, S in x0]), prev_covar=st([c.prev_covar for c in conds]))
+    eta = torch.as_tensor(np.logspace(-1, 2, 11))
+    active = torch.ones(11, dtype=torch.int32)
+    active[[3, 7]] = 0
+    r = il.step(eta, active=None)
+    kl_all = r.kl_div[:, 0].clone()
+    r.kl_div.fill_(-1.0)
+    r = il.step(eta, active=active)
+    assert float(r.kl_div[3, 0]) == -1.0 and float(r.kl_div[7, 0]) == -1.0
+    for b, c in enumerate(conds):
+        inv = np.linalg.inv(c.prev_covar)
+        prob = ILQRProblem(*fits[b], c.C, c.c, c.cc, c.prev_K, c.prev_k, c.prev_covar, inv, *x0[b])
+        ref = oracle.ilqr_step(prob, float(eta[b]))
+        assert abs(float(kl_all[b]) - ref.kl_div) < 1e-9 * max(1, abs(ref.kl_div))
+        if b not in (3, 7):
+            assert relerr(r.K[b, 0], ref.K) < TOL
+            assert abs(float(r.expected_costs[b, 0]) - ref.expected_costs) < 1e-9 * abs(ref.expected_costs)
