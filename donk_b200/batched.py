@@ -275,3 +275,224 @@ class BatchedILQR:
         n_steps += 1
         result = self.step(eta_final, want_traj=want_traj)
         return result, status, n_steps
+
+
+# =====================================================================================================
+# Dynamics fit
+# =====================================================================================================
+def to_transitions(X, U) -> torch.Tensor:
+    """``(N,T+1,dX), (N,T,dU) -> (N*T, 2dX+dU)`` rows ``[x_t | u_t | x_{t+1}]`` (donk/dynamics/utils.py:4-17)."""
+    nat = _lib.native()
+    X, U = _dev(X), _dev(U)
+    N, T, dU = U.shape
+    dX = X.shape[-1]
+    out = torch.empty(N * T, 2 * dX + dU, dtype=X.dtype, device=X.device)
+    nat.call("to_transitions_f64", N, T, dX, dU, X, U, out)
+    return out
+
+
+def state_fit(X0):
+    """``StateDistribution.fit`` for ``X0 (B,N,dX)``: mean ``(B,dX)`` and unbiased covariance ``(B,dX,dX)``."""
+    nat = _lib.native()
+    X0 = _dev(X0)
+    B, N, dX = X0.shape
+    mean = torch.empty(B, dX, dtype=X0.dtype, device=X0.device)
+    covar = torch.empty(B, dX, dX, dtype=X0.dtype, device=X0.device)
+    nat.call("state_fit_f64", B, N, dX, X0, dX, N * dX, mean, covar)
+    return mean, covar
+
+
+def state_fit_from_rollouts(X):
+    """Initial-state distribution straight from roll-outs ``X (B,N,T+1,dX)`` (no gather copy)."""
+    nat = _lib.native()
+    X = _dev(X)
+    B, N, T1, dX = X.shape
+    mean = torch.empty(B, dX, dtype=X.dtype, device=X.device)
+    covar = torch.empty(B, dX, dX, dtype=X.dtype, device=X.device)
+    nat.call("state_fit_f64", B, N, dX, X, T1 * dX, N * T1 * dX, mean, covar)
+    return mean, covar
+
+
+def fit_lr(X, U, prior: "DeviceGMM | None" = None, regularization: float = 1e-6, prior_weight: float = 1.0):
+    """Batched ``fit_lr`` (donk/dynamics/linear_dynamics.py:137-189).
+
+    ``X (B,N,T+1,dX), U (B,N,T,dU) -> F (B,T,dX,p), f (B,T,dX), covar (B,T,dX,dX), info (B,T)``.
+    ``prior`` is a fitted :class:`DeviceGMM` (the GMM behind ``GMMPrior``) or ``None``.
+    """
+    nat = _lib.native()
+    X, U = _dev(X), _dev(U)
+    B, N, T1, dX = X.shape
+    _, _, T, dU = U.shape
+    if T1 != T + 1 or U.shape[0] != B or U.shape[1] != N:
+        raise ValueError(f"inconsistent roll-out shapes {tuple(X.shape)} / {tuple(U.shape)}")
+    if N <= 1:
+        raise ValueError(f"Cannot fit dynamics to {N} sample(s)")  # linear_dynamics.py:154-155
+    p = dX + dU
+    o = dict(dtype=X.dtype, device=X.device)
+    F = torch.empty(B, T, dX, p, **o)
+    f = torch.empty(B, T, dX, **o)
+    covar = torch.empty(B, T, dX, dX, **o)
+    info = torch.zeros(B, T, dtype=torch.int32, device=X.device)
+    if prior is None:
+        nat.call("fit_lr_f64", B, N, T, dX, dU, X, U, 0, None, None, None, None, 0.0, 1.0, float(regularization),
+                 F, f, covar, info)
+    else:
+        if prior.d != 2 * dX + dU:
+            raise ValueError(f"prior dimension {prior.d} != {2 * dX + dU}")
+        nat.call("fit_lr_f64", B, N, T, dX, dU, X, U, prior.K, prior.weights, prior.means, prior.covariances,
+                 prior.precisions_cholesky, float(prior.N), float(prior_weight), float(regularization), F, f, covar,
+                 info)
+    return F, f, covar, info
+
+
+# =====================================================================================================
+# GMM EM (GMMPrior.update)
+# =====================================================================================================
+class DeviceGMM:
+    """Full-covariance Gaussian mixture fitted by EM on the device; rows may be sharded over ranks.
+
+    Mirrors what ``GMMPrior`` needs from ``sklearn.mixture.GaussianMixture`` (prior_gmm.py:10-41):
+    ``weights (K)``, ``means (K,d)``, ``covariances (K,d,d)``, ``precisions_cholesky (K,d,d)``,
+    ``lower_bound``, ``n_iter``, ``converged`` and ``N`` (pool size seen by the last ``fit``).
+    Defaults follow sklearn: ``tol=1e-3, reg_covar=1e-6, max_iter=100``.
+    """
+
+    def __init__(self, n_clusters: int, tol: float = 1e-3, reg_covar: float = 1e-6, max_iter: int = 100):
+        self.K = int(n_clusters)
+        self.tol, self.reg_covar, self.max_iter = tol, reg_covar, max_iter
+        self.d = None
+        self.weights = self.means = self.covariances = self.precisions_cholesky = None
+        self.lower_bound = -np.inf
+        self.n_iter = 0
+        self.converged = False
+        self.N = 0
+        self.lower_bounds: list[float] = []
+
+    # -- initialisation ----------------------------------------------------------------------------
+    def set_params(self, weights, means, precisions=None, covariances=None, precisions_cholesky=None):
+        """Explicit start (sklearn ``weights_init / means_init / precisions_init``)."""
+        nat = _lib.native()
+        self.weights, self.means = _dev(weights), _dev(means)
+        self.K, self.d = self.means.shape
+        if precisions_cholesky is not None:
+            self.precisions_cholesky = _dev(precisions_cholesky)
+        elif precisions is not None:
+            prec = _dev(precisions)
+            self.precisions_cholesky = torch.empty_like(prec)
+            info = torch.zeros(self.K, dtype=torch.int32, device=prec.device)
+            nat.call("gmm_prec_chol_from_precisions_f64", self.d, self.K, prec, self.precisions_cholesky, info)
+            if int(info.sum().item()):
+                raise ValueError("'full precision' should be symmetric, positive-definite")
+        self.covariances = _dev(covariances) if covariances is not None else torch.zeros(
+            self.K, self.d, self.d, dtype=torch.float64, device=self.means.device)
+        return self
+
+    def init_from_labels(self, X_local, labels_local, group=None):
+        """Hard-assignment start: one-hot responsibilities followed by an M-step
+        (what sklearn's k-means initialisation feeds ``_initialize``, _base.py:119-128,159).
+
+        Two statistics passes: the first (centred on 0) yields the cluster means, the second is centred
+        on those means so the scatter matrices carry no cancellation error.
+        """
+        nat = _lib.native()
+        X = _dev(X_local)
+        n, d = X.shape
+        self.d = d
+        K = self.K
+        o = dict(dtype=X.dtype, device=X.device)
+        labels = torch.as_tensor(labels_local).to(X.device).long()
+        onehot = torch.zeros(n, K, **o)
+        onehot[torch.arange(n, device=X.device), labels] = 1
+        n_total = torch.tensor([float(n)], **o)
+        self._allreduce(n_total, group)
+        self.weights = torch.full((K,), 1.0 / K, **o)
+        self.means = torch.zeros(K, d, **o)
+        self.covariances = torch.empty(K, d, d, **o)
+        self.precisions_cholesky = torch.empty(K, d, d, **o)
+        ws = torch.empty(nat.size("gmm_workspace_bytes", n, d, K) // 8 + 1, **o)
+        stats = torch.empty(nat.size("gmm_stats_size", d, K), **o)
+        lb = torch.zeros(1, **o)
+        info = torch.zeros(K, dtype=torch.int32, device=X.device)
+        for _ in range(2):
+            nat.call("gmm_em_step_f64", n, d, K, X, None, self.means, None, onehot, stats, ws,
+                     ws.numel() * ws.element_size())
+            self._allreduce(stats, group)
+            nat.call("gmm_m_finalize_f64", float(n_total.item()), d, K, stats, float(self.reg_covar), self.weights,
+                     self.means, self.covariances, self.precisions_cholesky, lb, info)
+        if int(info.sum().item()):
+            raise ValueError("Fitting the mixture model failed because some components have ill-defined "
+                             "empirical covariance")
+        return self
+
+    @staticmethod
+    def _allreduce(t, group):
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+    # -- EM ------------------------------------------------------------------------------------------
+    def em_iteration(self, X, n_total: float, ws, stats, group=None) -> float:
+        """One E+M iteration over this rank's rows; returns the mean log-likelihood (pre-M-step)."""
+        nat = _lib.native()
+        n, d = X.shape
+        nat.call("gmm_em_step_f64", n, d, self.K, X, self.weights, self.means, self.precisions_cholesky, None, stats,
+                 ws, ws.numel() * ws.element_size())
+        self._allreduce(stats, group)  # the one exchange step of the path (NCCL over NVLink)
+        nat.call("gmm_m_finalize_f64", float(n_total), d, self.K, stats, float(self.reg_covar), self.weights,
+                 self.means, self.covariances, self.precisions_cholesky, self._lb, self._info)
+        return self._lb
+
+    def fit(self, X_local, warm_start: bool = False, group=None, check_every: int = 1):
+        """EM until ``|delta lower bound| < tol`` or ``max_iter`` (sklearn/mixture/_base.py:241-305).
+
+        ``X_local (n_local,d)``: this rank's rows of the pool.  Parameters must have been initialised
+        (``set_params`` / ``init_from_labels``) or come from a previous ``fit`` (``warm_start``).
+        """
+        import warnings
+
+        nat = _lib.native()
+        X = _dev(X_local)
+        n, d = X.shape
+        if self.means is None:
+            raise DonkError("DeviceGMM.fit: parameters are not initialised")
+        if d != self.d:
+            raise ValueError(f"X has {d} features, the mixture has {self.d}")
+        o = dict(dtype=X.dtype, device=X.device)
+        n_total_t = torch.tensor([float(n)], **o)
+        self._allreduce(n_total_t, group)
+        n_total = float(n_total_t.item())
+        ws = torch.empty(nat.size("gmm_workspace_bytes", n, d, self.K) // 8 + 1, **o)
+        stats = torch.empty(nat.size("gmm_stats_size", d, self.K), **o)
+        self._lb = torch.zeros(1, **o)
+        self._info = torch.zeros(self.K, dtype=torch.int32, device=X.device)
+        lb = self.lower_bound if warm_start else -np.inf
+        self.converged = False
+        self.lower_bounds = []
+        n_iter = 0
+        for n_iter in range(1, self.max_iter + 1):
+            prev = lb
+            self.em_iteration(X, n_total, ws, stats, group)
+            lb = float(self._lb.item())
+            if int(self._info.sum().item()):
+                raise ValueError("Fitting the mixture model failed because some components have ill-defined "
+                                 "empirical covariance (for instance caused by singleton or collapsed samples).")
+            self.lower_bounds.append(lb)
+            if abs(lb - prev) < self.tol:
+                self.converged = True
+                break
+        self.lower_bound, self.n_iter, self.N = lb, n_iter, int(n_total)
+        if not self.converged and self.max_iter > 0:
+            from donk_b200.dynamics.prior.prior_gmm import ConvergenceWarning
+
+            warnings.warn("Best performing initialization did not converge. Try different init parameters, or "
+                          "increase max_iter, tol, or check for degenerate data.", ConvergenceWarning)
+        return self
+
+    def predict_proba(self, X) -> torch.Tensor:
+        nat = _lib.native()
+        X = _dev(X)
+        n, d = X.shape
+        resp = torch.empty(n, self.K, dtype=X.dtype, device=X.device)
+        nat.call("gmm_predict_proba_f64", n, d, self.K, X, self.weights, self.means, self.precisions_cholesky, resp)
+        return resp

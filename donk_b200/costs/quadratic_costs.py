@@ -1,0 +1,58 @@
+"""Quadratic cost container (donk/costs/quadratic_costs.py:12-139).
+
+Only what the hot path consumes: ``C, c, cc``, ``compute_costs``, ``expected_costs``, ``+``/``*`` and the
+exact L2 constructor used by the synthetic benchmarks.  Symbolic / L1 cost authoring stays host-side in
+the reference and is out of scope.
+"""
+from __future__ import annotations
+
+from typing import Any
+
+import numpy as np
+
+
+class QuadraticCosts:
+    """``cost(x,u) = 1/2 [x u]^T C [x u] + [x u]^T c + cc``."""
+
+    def __init__(self, C, c, cc) -> None:
+        T = c.shape[:-1]
+        dXU = c.shape[-1]
+        assert C.shape == (*T, dXU, dXU), f"{C.shape} != {(*T, dXU, dXU)}"
+        assert c.shape == (*T, dXU), f"{c.shape} != {(*T, dXU)}"
+        assert cc.shape == (*T,), f"{cc.shape} != {(*T, )}"
+        self.C = C
+        self.c = c
+        self.cc = cc
+
+    def __add__(self, other: Any):
+        if isinstance(other, QuadraticCosts):
+            return QuadraticCosts(self.C + other.C, self.c + other.c, self.cc + other.cc)
+        return NotImplemented
+
+    def __mul__(self, other: Any):
+        if np.isscalar(other):
+            return QuadraticCosts(self.C * other, self.c * other, self.cc * other)
+        return NotImplemented
+
+    __rmul__ = __mul__
+
+    def compute_costs(self, X, U):
+        """Costs of trajectories ``X (...,T+1,dX), U (...,T,dU)`` -> ``(...,T+1)`` (quadratic_costs.py:55-92)."""
+        X, U = np.asarray(X), np.asarray(U)
+        pad = np.zeros(U.shape[:-2] + (1, U.shape[-1]))
+        traj = np.concatenate([X, np.concatenate([U, pad], axis=-2)], axis=-1)
+        return np.einsum("...i,...ij,...j->...", traj, self.C, traj) / 2 + np.sum(traj * self.c, axis=-1) + self.cc
+
+    def quadratic_approximation(self, X, U):
+        return self
+
+    def expected_costs(self, traj):
+        """Per-step expected cost under a trajectory distribution (quadratic_costs.py:106-119)."""
+        return self.compute_costs(traj.X_mean, traj.U_mean) + np.einsum("...ij,...ji->...", self.C, traj.covar) / 2
+
+    @staticmethod
+    def quadratic_cost_approximation_l2(t, w):
+        """Exact quadratic form of ``0.5 sum_i w_i (t_i - xu_i)^2`` (quadratic_costs.py:121-139)."""
+        t, w = np.asarray(t, dtype=np.float64), np.asarray(w, dtype=np.float64)
+        n = t.shape[-1]
+        return QuadraticCosts(w[..., :, None] * np.eye(n), -w * t, np.sum(t * w * t, axis=-1) / 2)

@@ -147,6 +147,77 @@ __global__ void brent_kernel(int B, int phase, R xa, R xb, const R* fa, const R*
   if (act) atomicAdd(n_active, 1);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// fit_lr, to_transitions, StateDistribution.fit
+// ---------------------------------------------------------------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(512, 1) fit_lr_kernel(const FitArgs<R> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Ctx ctx{(int)threadIdx.x, (int)blockDim.x};
+  fit_lr_cta<R>(ctx, a, (int)blockIdx.x, reinterpret_cast<R*>(smem_raw));
+}
+
+template <typename R>
+__global__ void to_transitions_kernel(size_t total, int T, int dX, int dU, const R* X, const R* U, R* out) {
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
+    out[idx] = transitions_item<R>(T, dX, dU, X, U, idx);
+}
+
+template <typename R>
+__global__ void state_fit_kernel(size_t total, int N, int dX, const R* X0, size_t ss, size_t cs, R* mean, R* covar) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < total) state_fit_item<R>(N, dX, X0, ss, cs, idx, mean, covar);
+}
+
+// ---------------------------------------------------------------------------------------------
+// GMM EM
+// ---------------------------------------------------------------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(256) gmm_e_kernel(const GmmArgs<R> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Ctx ctx{(int)threadIdx.x, (int)blockDim.x};
+  gmm_e_cta<R>(ctx, a, (int)blockIdx.x, (int)gridDim.x, reinterpret_cast<R*>(smem_raw));
+}
+template <typename R>
+__global__ void __launch_bounds__(384) gmm_m_kernel(const GmmArgs<R> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Ctx ctx{(int)threadIdx.x, (int)blockDim.x};
+  gmm_m_cta<R>(ctx, a, (int)blockIdx.x, reinterpret_cast<R*>(smem_raw));
+}
+template <typename R>
+__global__ void gmm_reduce_kernel(const GmmArgs<R> a, size_t total, R* stats) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < total) gmm_reduce_item<R>(a, idx, stats);
+}
+template <typename R>
+__global__ void __launch_bounds__(256) gmm_finalize_kernel(const GmmFinArgs<R> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Ctx ctx{(int)threadIdx.x, (int)blockDim.x};
+  gmm_finalize_cta<R>(ctx, a, (int)blockIdx.x, reinterpret_cast<R*>(smem_raw));
+}
+template <typename R>
+__global__ void __launch_bounds__(256) gmm_prec_chol_kernel(int d, const R* prec, R* pc, int* info) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Ctx ctx{(int)threadIdx.x, (int)blockDim.x};
+  gmm_prec_chol_cta<R>(ctx, d, prec, pc, info, (int)blockIdx.x, reinterpret_cast<R*>(smem_raw));
+}
+
+int gmm_e_launch(GmmArgs<double>& a, void* stream) {
+  const size_t smem = gmm_e_smem(a.d, a.K) * sizeof(double);
+  if (smem > smem_optin_cap()) return DONK_SMEM_LIMIT;
+  int rc = allow_smem(gmm_e_kernel<double>, smem);
+  if (rc != DONK_OK) return rc;
+  int per_sm = (int)((228 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 8) per_sm = 8;
+  int grid = 148 * per_sm;
+  if (grid > a.nblocks) grid = a.nblocks;
+  gmm_e_kernel<double><<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+  LAUNCHED("gmm_e_kernel");
+  return DONK_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -228,6 +299,144 @@ int donk_brent_update_f64(int B, int phase, double xa, double xb, const double* 
                                                                            xtol, rtol, maxiter, state, eta, active,
                                                                            status, n_active);
   LAUNCHED("brent_kernel");
+  return DONK_OK;
+}
+
+int donk_fit_lr_f64(int B, int N, int T, int dX, int dU, const double* X, const double* U, int gmm_K,
+                    const double* gmm_weights, const double* gmm_means, const double* gmm_covariances,
+                    const double* gmm_prec_chol, double n_pool, double prior_weight, double regularization,
+                    double* F, double* f, double* covar, int* info, void* stream) {
+  if (B < 0 || N <= 1 || T < 1 || dX < 1 || dU < 1 || gmm_K < 0) return DONK_BAD_SHAPE;
+  if (B == 0) return DONK_OK;
+  FitArgs<double> a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.N = N; a.T = T; a.dX = dX; a.dU = dU; a.X = X; a.U = U; a.K = gmm_K;
+  a.gw = gmm_weights; a.gmeans = gmm_means; a.gcov = gmm_covariances; a.gpc = gmm_prec_chol;
+  a.n_pool = n_pool; a.prior_weight = prior_weight; a.reg = regularization;
+  a.F = F; a.f = f; a.covar = covar; a.info = info;
+  size_t bytes = 0;
+  const int force = env_int("DONK_FIT_CHUNK");
+  a.NS = fit_plan(dX, dU, gmm_K, force > 0 ? force : N, sizeof(double), smem_optin_cap(), bytes);
+  if (a.NS == 0) {
+    snprintf(g_err, sizeof(g_err), "fit_lr: dX=%d dU=%d K=%d does not fit shared memory", dX, dU, gmm_K);
+    return DONK_SMEM_LIMIT;
+  }
+  { FitLayout L(dX, dU, gmm_K, N, a.NS); bytes = (size_t)L.total * sizeof(double); }
+  int rc = allow_smem(fit_lr_kernel<double>, bytes);
+  if (rc != DONK_OK) return rc;
+  const int dp = round_up(2 * dX + dU, 4), nt = dp / 4;
+  int threads = round_up(nt * (nt + 1) / 2, 32);
+  if (threads < 128) threads = 128;
+  if (threads > 512) threads = 512;
+  if (env_int("DONK_FIT_THREADS") > 0) threads = env_int("DONK_FIT_THREADS");
+  fit_lr_kernel<double><<<B * T, threads, bytes, (cudaStream_t)stream>>>(a);
+  LAUNCHED("fit_lr_kernel");
+  return DONK_OK;
+}
+
+int donk_to_transitions_f64(int N, int T, int dX, int dU, const double* X, const double* U, double* XUX,
+                            void* stream) {
+  if (N < 0 || T < 1 || dX < 1 || dU < 1) return DONK_BAD_SHAPE;
+  const size_t total = (size_t)N * T * (2 * dX + dU);
+  if (total == 0) return DONK_OK;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  to_transitions_kernel<double><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(total, T, dX, dU, X, U, XUX);
+  LAUNCHED("to_transitions_kernel");
+  return DONK_OK;
+}
+
+int donk_state_fit_f64(int B, int N, int dX, const double* X0, size_t sample_stride, size_t cond_stride,
+                       double* mean, double* covar, void* stream) {
+  if (B < 0 || N < 2 || dX < 1) return DONK_BAD_SHAPE;
+  const size_t total = (size_t)B * dX * dX;
+  if (total == 0) return DONK_OK;
+  state_fit_kernel<double><<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      total, N, dX, X0, sample_stride, cond_stride, mean, covar);
+  LAUNCHED("state_fit_kernel");
+  return DONK_OK;
+}
+
+size_t donk_gmm_stats_size(int d, int K) { return gmm_stats_len(d, K); }
+size_t donk_gmm_workspace_bytes(int n_local, int d, int K) { return gmm_ws_reals(n_local, d, K) * sizeof(double); }
+
+int donk_gmm_em_step_f64(int n_local, int d, int K, const double* X, const double* weights, const double* means,
+                         const double* prec_chol, const double* resp_in, double* stats, void* workspace,
+                         size_t workspace_bytes,
+                         void* stream) {
+  if (n_local < 0 || d < 1 || K < 1) return DONK_BAD_SHAPE;
+  if (workspace_bytes < donk_gmm_workspace_bytes(n_local, d, K)) return DONK_BAD_SHAPE;
+  const size_t total = gmm_stats_len(d, K);
+  if (n_local == 0) {
+    CU(cudaMemsetAsync(stats, 0, total * sizeof(double), (cudaStream_t)stream));
+    return DONK_OK;
+  }
+  GmmArgs<double> a;
+  memset(&a, 0, sizeof(a));
+  a.n = n_local; a.d = d; a.K = K; a.X = X; a.w = weights; a.means = means; a.pc = prec_chol;
+  a.nblocks = (n_local + GMM_TS - 1) / GMM_TS;
+  a.nch = gmm_nch(n_local, d, K);
+  double* ws = static_cast<double*>(workspace);
+  a.resp = ws;
+  a.lse_part = ws + (size_t)n_local * K;
+  a.part = a.lse_part + a.nblocks;
+  int rc = DONK_OK;
+  if (resp_in) {
+    a.resp = const_cast<double*>(resp_in);
+    CU(cudaMemsetAsync(a.lse_part, 0, (size_t)a.nblocks * sizeof(double), (cudaStream_t)stream));
+  } else {
+    rc = gmm_e_launch(a, stream);
+    if (rc != DONK_OK) return rc;
+  }
+  const int threads = gmm_m_threads(d);
+  const size_t smem = gmm_m_smem(d) * sizeof(double);
+  if (threads == 0 || smem > smem_optin_cap()) return DONK_SMEM_LIMIT;
+  rc = allow_smem(gmm_m_kernel<double>, smem);
+  if (rc != DONK_OK) return rc;
+  gmm_m_kernel<double><<<K * a.nch, threads, smem, (cudaStream_t)stream>>>(a);
+  LAUNCHED("gmm_m_kernel");
+  gmm_reduce_kernel<double><<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a, total, stats);
+  LAUNCHED("gmm_reduce_kernel");
+  return DONK_OK;
+}
+
+int donk_gmm_m_finalize_f64(double n_total, int d, int K, const double* stats, double reg_covar, double* weights,
+                            double* means, double* covariances, double* prec_chol, double* lower_bound, int* info,
+                            void* stream) {
+  if (d < 1 || K < 1) return DONK_BAD_SHAPE;
+  GmmFinArgs<double> a;
+  a.d = d; a.K = K; a.n_total = n_total; a.reg_covar = reg_covar; a.stats = stats;
+  a.w = weights; a.means = means; a.cov = covariances; a.pc = prec_chol; a.lower_bound = lower_bound; a.info = info;
+  const size_t smem = gmm_fin_smem(d) * sizeof(double);
+  if (smem > smem_optin_cap()) return DONK_SMEM_LIMIT;
+  int rc = allow_smem(gmm_finalize_kernel<double>, smem);
+  if (rc != DONK_OK) return rc;
+  gmm_finalize_kernel<double><<<K, 256, smem, (cudaStream_t)stream>>>(a);
+  LAUNCHED("gmm_finalize_kernel");
+  return DONK_OK;
+}
+
+int donk_gmm_predict_proba_f64(int n, int d, int K, const double* X, const double* weights, const double* means,
+                               const double* prec_chol, double* resp, void* stream) {
+  if (n < 0 || d < 1 || K < 1) return DONK_BAD_SHAPE;
+  if (n == 0) return DONK_OK;
+  GmmArgs<double> a;
+  memset(&a, 0, sizeof(a));
+  a.n = n; a.d = d; a.K = K; a.X = X; a.w = weights; a.means = means; a.pc = prec_chol;
+  a.nblocks = (n + GMM_TS - 1) / GMM_TS;
+  a.resp = resp;
+  return gmm_e_launch(a, stream);
+}
+
+int donk_gmm_prec_chol_from_precisions_f64(int d, int K, const double* precisions, double* prec_chol, int* info,
+                                           void* stream) {
+  if (d < 1 || K < 1) return DONK_BAD_SHAPE;
+  const size_t smem = gmm_fin_smem(d) * sizeof(double);
+  if (smem > smem_optin_cap()) return DONK_SMEM_LIMIT;
+  int rc = allow_smem(gmm_prec_chol_kernel<double>, smem);
+  if (rc != DONK_OK) return rc;
+  gmm_prec_chol_kernel<double><<<K, 256, smem, (cudaStream_t)stream>>>(d, precisions, prec_chol, info);
+  LAUNCHED("gmm_prec_chol_kernel");
   return DONK_OK;
 }
 

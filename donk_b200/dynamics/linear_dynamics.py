@@ -1,0 +1,52 @@
+"""Time-varying linear-Gaussian dynamics and their least-squares fit
+(donk/dynamics/linear_dynamics.py:16-64,137-189), fitted on the B200."""
+from __future__ import annotations
+
+import numpy as np
+
+from donk_b200.dynamics.dynamics import DynamicsModel
+from donk_b200.models import TimeVaryingLinearGaussian
+
+
+class LinearDynamics(DynamicsModel, TimeVaryingLinearGaussian):
+    """``x' ~ N(F_t [x;u] + f_t, covar_t)``."""
+
+    def __init__(self, F: np.ndarray, f: np.ndarray, covar: np.ndarray):
+        TimeVaryingLinearGaussian.__init__(self, F, f, covar)
+        _, self.dX = f.shape
+        self.dU = F.shape[2] - self.dX
+
+    F = TimeVaryingLinearGaussian.coefficients
+    f = TimeVaryingLinearGaussian.intercept
+
+    def predict(self, x, u, t: int = None, noise=None):
+        return TimeVaryingLinearGaussian.predict(self, np.concatenate([x, u], axis=-1), t, noise)
+
+    def __str__(self) -> str:
+        return f"LinearDynamics[T={self.T}, dX={self.dX}, dU={self.dU}]"
+
+
+def fit_lr(X: np.ndarray, U: np.ndarray, prior=None, regularization: float = 1e-6,
+           prior_weight: float = 1) -> LinearDynamics:
+    """Fit dynamics by per-timestep linear regression under an optional NIW prior.
+
+    Same signature and error behaviour as the reference (linear_dynamics.py:137-189): ``X (N,T+1,dX)``,
+    ``U (N,T,dU)``, ``ValueError`` when ``N <= 1``.  ``prior`` must be a ``donk_b200`` ``GMMPrior`` (its
+    mixture lives on the device and is evaluated inside the fit kernel).
+    """
+    from donk_b200 import batched
+    from donk_b200.dynamics.prior import GMMPrior
+
+    X, U = np.asarray(X, dtype=np.float64), np.asarray(U, dtype=np.float64)
+    N = X.shape[0]
+    if N <= 1:
+        raise ValueError(f"Cannot fit dynamics to {N} sample(s)")
+    gmm = None
+    if prior is not None:
+        if not isinstance(prior, GMMPrior):
+            raise TypeError("fit_lr on the device supports GMMPrior (or None) as prior")
+        gmm = prior._gmm
+    F, f, covar, info = batched.fit_lr(X[None], U[None], gmm, regularization, prior_weight)
+    if int(info.sum()) != 0:
+        raise np.linalg.LinAlgError("Singular matrix")  # numpy.linalg.solve, linear_dynamics.py:184
+    return LinearDynamics(F[0].cpu().numpy(), f[0].cpu().numpy(), covar[0].cpu().numpy())

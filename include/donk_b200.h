@@ -154,12 +154,16 @@ size_t donk_gmm_stats_size(int d, int K);
 /* Workspace bytes donk_gmm_em_step_f64 needs for n_local rows. */
 size_t donk_gmm_workspace_bytes(int n_local, int d, int K);
 
-/* One fused E-step + sufficient-statistics pass over this rank's rows of the transition pool:
+/* One E-step + sufficient-statistics pass over this rank's rows of the transition pool:
  * sklearn.mixture.GaussianMixture E-step and the sums of the M-step, as called from
  * GMMPrior.update (donk/dynamics/prior/prior_gmm.py:14-24).  X (n_local,d).
- * stats receives this rank's partial sums (the caller all-reduces them across ranks). */
+ * stats receives this rank's partial sums (the caller all-reduces them across ranks).
+ * resp_in (n_local,K), optional: use these responsibilities instead of running the E-step (the
+ * one-hot responsibilities of a hard initial labelling, sklearn/mixture/_base.py:119-128); the
+ * lse entry of stats is then 0 and weights / prec_chol are not read. */
 int donk_gmm_em_step_f64(int n_local, int d, int K, const double* X,
                          const double* weights, const double* means, const double* prec_chol,
+                         const double* resp_in,
                          double* stats, void* workspace, size_t workspace_bytes, void* stream);
 
 /* M-step finalisation from (all-reduced) statistics of n_total rows: new weights, means,

@@ -17,7 +17,7 @@ EM iteration (sklearn/mixture/_base.py:263-278, _gaussian_mixture.py:312-313,
      logp_k = -(d log 2pi + |y|^2)/2 + sum log diag P_k + log pi_k,
      lse = logsumexp_k logp_k, log_resp = logp - lse, lower bound = mean(lse).
   M: r = exp(log_resp); nk = sum r + 10 eps; mu_k = r^T X / nk;
-     Sigma_k = (r_k (X-mu_k))^T (X-mu_k) / nk + reg I; pi = nk / n, pi /= sum pi;
+     Sigma_k = (r_k (X-mu_k))^T (X-mu_k) / nk + reg I; pi = nk / sum nk;
      L_k = chol(Sigma_k); P_k = (L_k^-1)^T.
   stop when |lb_i - lb_{i-1}| < tol.
 """
@@ -101,8 +101,7 @@ def gmm_m_step(X, resp, reg_covar: float = 1e-6) -> GMMParams:
         diff = X - means[k]
         cov[k] = (resp[:, k] * diff.T) @ diff / nk[k]
         cov[k].flat[:: d + 1] += reg_covar
-    w = nk / n
-    w = w / w.sum()
+    w = nk / nk.sum()  # sklearn 1.9 _m_step: weights_ = nk, then weights_ /= weights_.sum()
     return GMMParams(w, means, cov, precision_cholesky(cov))
 
 

@@ -27,17 +27,22 @@ def golden():
     return load
 
 
-@pytest.fixture()
-def emu():
-    """Route donk_b200 calls to the host-emulation build of the kernel sources (no GPU needed).
-
-    This checks kernel logic and the Python host layer on CPU; the `-m gpu` tests run the same
-    assertions against the real CUDA library.
+@pytest.fixture(params=["emu", pytest.param("cuda", marks=pytest.mark.gpu)])
+def backend(request):
+    """The kernels under test: ``emu`` = host emulation of the kernel sources (CPU container, checks kernel
+    logic + host layer), ``cuda`` = the real sm_100a library through the C ABI (the parity tests proper,
+    selected with ``-m gpu``).  The same assertions run against both.
     """
     from donk_b200 import _lib
-    from emu.build_emu import backend
 
-    nat = backend()
+    if request.param == "cuda":
+        _lib.install_test_backend(None)
+        nat = _lib.native()  # raises if the CUDA library is missing: no silent fallback
+        yield nat
+        return
+    from emu.build_emu import backend as emu_backend
+
+    nat = emu_backend()
     _lib.install_test_backend(nat)
     yield nat
     nat.lib.donk_emu_set_reverse(0)

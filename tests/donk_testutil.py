@@ -9,8 +9,8 @@ GOLDEN = ROOT / "tests" / "golden"
 
 def relerr(ours, ref):
     """Max-norm relative error per tensor: max|ours-ref| / max|ref|."""
-    ours = np.asarray(ours, dtype=np.float64)
-    ref = np.asarray(ref, dtype=np.float64)
+    ours = np.asarray(to_np(ours), dtype=np.float64)
+    ref = np.asarray(to_np(ref), dtype=np.float64)
     assert ours.shape == ref.shape, f"{ours.shape} != {ref.shape}"
     if ref.size == 0:
         return 0.0
@@ -23,3 +23,18 @@ def relerr(ours, ref):
 def load_golden(name):
     with np.load(GOLDEN / f"{name}.npz") as z:
         return {k: z[k] for k in z.files}
+
+
+def set_reverse(backend, reverse: int):
+    """Emulation only: run every kernel phase back to front (exposes intra-phase dependencies)."""
+    import pytest
+
+    if backend.device_type != "cpu":
+        if reverse:
+            pytest.skip("phase-order reversal exists only under emulation")
+        return
+    backend.lib.donk_emu_set_reverse(reverse)
+
+
+def to_np(t):
+    return t.detach().cpu().numpy() if hasattr(t, "detach") else t

@@ -119,3 +119,130 @@ int donk_emu_brent_update_f64(int B, int phase, double xa, double xb, const doub
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// fit_lr / transitions / state fit / GMM EM under emulation
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int donk_emu_fit_lr_f64(int B, int N, int T, int dX, int dU, const double* X, const double* U, int gmm_K,
+                        const double* gmm_weights, const double* gmm_means, const double* gmm_covariances,
+                        const double* gmm_prec_chol, double n_pool, double prior_weight, double regularization,
+                        double* F, double* f, double* covar, int* info, void*) {
+  if (B < 0 || N <= 1 || T < 1 || dX < 1 || dU < 1 || gmm_K < 0) return DONK_BAD_SHAPE;
+  FitArgs<double> a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.N = N; a.T = T; a.dX = dX; a.dU = dU; a.X = X; a.U = U; a.K = gmm_K;
+  a.gw = gmm_weights; a.gmeans = gmm_means; a.gcov = gmm_covariances; a.gpc = gmm_prec_chol;
+  a.n_pool = n_pool; a.prior_weight = prior_weight; a.reg = regularization;
+  a.F = F; a.f = f; a.covar = covar; a.info = info;
+  size_t bytes = 0;
+  const int force = env_int("DONK_FIT_CHUNK");
+  a.NS = fit_plan(dX, dU, gmm_K, force > 0 ? force : N, sizeof(double), kSmemCap, bytes);
+  if (a.NS == 0) return DONK_SMEM_LIMIT;
+  FitLayout L(dX, dU, gmm_K, N, a.NS);
+  std::vector<double> smem(L.total + 2);
+  Ctx ctx{0, 1};
+  for (int cta = 0; cta < B * T; ++cta) {
+    memset(smem.data(), 0xFF, smem.size() * sizeof(double));
+    fit_lr_cta<double>(ctx, a, cta, smem.data());
+  }
+  return DONK_OK;
+}
+
+int donk_emu_to_transitions_f64(int N, int T, int dX, int dU, const double* X, const double* U, double* XUX, void*) {
+  const size_t total = (size_t)N * T * (2 * dX + dU);
+  for (size_t i = 0; i < total; ++i) XUX[i] = transitions_item<double>(T, dX, dU, X, U, i);
+  return DONK_OK;
+}
+
+int donk_emu_state_fit_f64(int B, int N, int dX, const double* X0, size_t sample_stride, size_t cond_stride,
+                           double* mean, double* covar, void*) {
+  if (B < 0 || N < 2 || dX < 1) return DONK_BAD_SHAPE;
+  for (size_t i = 0; i < (size_t)B * dX * dX; ++i) state_fit_item<double>(N, dX, X0, sample_stride, cond_stride, i, mean, covar);
+  return DONK_OK;
+}
+
+size_t donk_emu_gmm_stats_size(int d, int K) { return gmm_stats_len(d, K); }
+size_t donk_emu_gmm_workspace_bytes(int n_local, int d, int K) { return gmm_ws_reals(n_local, d, K) * sizeof(double); }
+
+static void emu_gmm_e(GmmArgs<double>& a) {
+  std::vector<double> smem(gmm_e_smem(a.d, a.K) + 2);
+  Ctx ctx{0, 1};
+  const int ncta = a.nblocks < 7 ? a.nblocks : 7;  // a few "CTAs", each striding over blocks
+  for (int cta = 0; cta < ncta; ++cta) {
+    memset(smem.data(), 0xFF, smem.size() * sizeof(double));
+    gmm_e_cta<double>(ctx, a, cta, ncta, smem.data());
+  }
+}
+
+int donk_emu_gmm_em_step_f64(int n_local, int d, int K, const double* X, const double* weights, const double* means,
+                             const double* prec_chol, const double* resp_in, double* stats, void* workspace,
+                         size_t workspace_bytes, void*) {
+  if (n_local < 0 || d < 1 || K < 1) return DONK_BAD_SHAPE;
+  if (workspace_bytes < donk_emu_gmm_workspace_bytes(n_local, d, K)) return DONK_BAD_SHAPE;
+  const size_t total = gmm_stats_len(d, K);
+  if (n_local == 0) { memset(stats, 0, total * sizeof(double)); return DONK_OK; }
+  GmmArgs<double> a;
+  memset(&a, 0, sizeof(a));
+  a.n = n_local; a.d = d; a.K = K; a.X = X; a.w = weights; a.means = means; a.pc = prec_chol;
+  a.nblocks = (n_local + GMM_TS - 1) / GMM_TS;
+  a.nch = gmm_nch(n_local, d, K);
+  double* ws = static_cast<double*>(workspace);
+  a.resp = ws; a.lse_part = ws + (size_t)n_local * K; a.part = a.lse_part + a.nblocks;
+  if (resp_in) {
+    a.resp = const_cast<double*>(resp_in);
+    memset(a.lse_part, 0, (size_t)a.nblocks * sizeof(double));
+  } else {
+    emu_gmm_e(a);
+  }
+  if (gmm_m_threads(d) == 0) return DONK_SMEM_LIMIT;
+  std::vector<double> smem(gmm_m_smem(d) + 2);
+  Ctx ctx{0, 1};
+  for (int cta = 0; cta < K * a.nch; ++cta) {
+    memset(smem.data(), 0xFF, smem.size() * sizeof(double));
+    gmm_m_cta<double>(ctx, a, cta, smem.data());
+  }
+  for (size_t i = 0; i < total; ++i) gmm_reduce_item<double>(a, i, stats);
+  return DONK_OK;
+}
+
+int donk_emu_gmm_m_finalize_f64(double n_total, int d, int K, const double* stats, double reg_covar, double* weights,
+                                double* means, double* covariances, double* prec_chol, double* lower_bound, int* info,
+                                void*) {
+  GmmFinArgs<double> a;
+  a.d = d; a.K = K; a.n_total = n_total; a.reg_covar = reg_covar; a.stats = stats;
+  a.w = weights; a.means = means; a.cov = covariances; a.pc = prec_chol; a.lower_bound = lower_bound; a.info = info;
+  std::vector<double> smem(gmm_fin_smem(d) + 2);
+  Ctx ctx{0, 1};
+  for (int k = 0; k < K; ++k) {
+    memset(smem.data(), 0xFF, smem.size() * sizeof(double));
+    gmm_finalize_cta<double>(ctx, a, k, smem.data());
+  }
+  return DONK_OK;
+}
+
+int donk_emu_gmm_predict_proba_f64(int n, int d, int K, const double* X, const double* weights, const double* means,
+                                   const double* prec_chol, double* resp, void*) {
+  if (n == 0) return DONK_OK;
+  GmmArgs<double> a;
+  memset(&a, 0, sizeof(a));
+  a.n = n; a.d = d; a.K = K; a.X = X; a.w = weights; a.means = means; a.pc = prec_chol;
+  a.nblocks = (n + GMM_TS - 1) / GMM_TS;
+  a.resp = resp;
+  emu_gmm_e(a);
+  return DONK_OK;
+}
+
+int donk_emu_gmm_prec_chol_from_precisions_f64(int d, int K, const double* precisions, double* prec_chol, int* info,
+                                               void*) {
+  std::vector<double> smem(gmm_fin_smem(d) + 2);
+  Ctx ctx{0, 1};
+  for (int k = 0; k < K; ++k) {
+    memset(smem.data(), 0xFF, smem.size() * sizeof(double));
+    gmm_prec_chol_cta<double>(ctx, d, precisions, prec_chol, info, k, smem.data());
+  }
+  return DONK_OK;
+}
+
+}  // extern "C"

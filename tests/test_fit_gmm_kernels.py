@@ -1,0 +1,135 @@
+"""fit_lr / GMM EM kernel logic (fitlr.cuh, gmm.cuh) under host emulation vs oracle + reference vectors."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from donk_testutil import load_golden, relerr, set_reverse, to_np
+from oracle.gmm import GMMParams, params_from_precisions
+
+
+def _device_gmm(g, pre="gmm_"):
+    from donk_b200.batched import DeviceGMM
+
+    gm = DeviceGMM(len(g[pre + "weights"]))
+    gm.set_params(g[pre + "weights"], g[pre + "means"], covariances=g[pre + "covariances"],
+                  precisions_cholesky=g[pre + "prec_chol"])
+    gm.N = int(g[pre + "N"])
+    return gm
+
+
+@pytest.mark.parametrize("reverse", [0, 1])
+def test_fit_lr_traj00_rank_deficient(backend, reverse):
+    """tests/dynamics_test.py:21-90: N=15 < p=17, the eigenvalue lift fires at every t."""
+    from donk_b200 import batched
+
+    set_reverse(backend, reverse)
+    g = load_golden("fitlr_traj00")
+    F, f, covar, info = batched.fit_lr(g["X"][None], g["U"][None], None, 1e-6)
+    assert int(info.sum()) == 0
+    assert relerr(F[0], g["F"]) < 1e-8 and relerr(f[0], g["f"]) < 1e-8
+    assert relerr(covar[0], g["covar"]) < 1e-8
+    c = covar[0].cpu().numpy()
+    assert np.array_equal(c, np.swapaxes(c, 1, 2))
+    # literal known answers of the reference test (rows printed with 9 digits; atol for the 1e-23 entries)
+    np.testing.assert_allclose(F[0, 0, -1, :8].cpu().numpy(), [0.0, -9.98390720, -12.9479403, -1.32099334, -1.61173430,
+                                                          -67.0051884, 23.0815914, 0.217293139], rtol=1e-7, atol=1e-9)
+
+
+def test_fit_lr_chunked_samples_match_single_chunk(backend, monkeypatch):
+    from donk_b200 import batched
+
+    g = load_golden("fitlr_traj00")
+    F1, f1, c1, _ = batched.fit_lr(g["X"][None], g["U"][None], None, 1e-6)
+    monkeypatch.setenv("DONK_FIT_CHUNK", "4")
+    F2, f2, c2, _ = batched.fit_lr(g["X"][None], g["U"][None], None, 1e-6)
+    assert relerr(F2, F1.cpu().numpy()) < 1e-9 and relerr(c2, c1.cpu().numpy()) < 1e-9
+
+
+def test_fit_lr_with_gmm_prior(backend):
+    """tests/dynamics_test.py:102-178 (regularization=0, N=3) and a prior_weight / regularised variant."""
+    from donk_b200 import batched
+
+    g = load_golden("fitlr_traj00")
+    gm = _device_gmm(g)
+    F, f, covar, info = batched.fit_lr(g["X"][None, :3], g["U"][None, :3], gm, 0.0)
+    assert int(info.sum()) == 0
+    assert relerr(F[0], g["pF"]) < 1e-8 and relerr(f[0], g["pf"]) < 1e-8 and relerr(covar[0], g["pcovar"]) < 1e-8
+    np.testing.assert_allclose(F[0, -1, 0].cpu().numpy()[:4], [0.058843, 0.017633, -0.049648, -0.016292], atol=1e-6)
+    F, f, covar, info = batched.fit_lr(g["X"][None, :6], g["U"][None, :6], gm, 1e-6, prior_weight=0.5)
+    assert relerr(F[0], g["wF"]) < 1e-8 and relerr(f[0], g["wf"]) < 1e-8 and relerr(covar[0], g["wcovar"]) < 1e-8
+
+
+def test_fit_lr_synthetic_config2_with_prior(backend):
+    from donk_b200 import batched
+
+    g = load_golden("ilqr_c2")
+    gm = _device_gmm(g)
+    X, U = g["X"][None, :, :13], g["U"][None, :, :12]  # first 12 steps keep the emulated run short
+    F, f, covar, info = batched.fit_lr(np.ascontiguousarray(X), np.ascontiguousarray(U), gm)
+    assert relerr(F[0], g["F"][:12]) < 1e-8 and relerr(f[0], g["f"][:12]) < 1e-8
+    assert relerr(covar[0], g["dyn_covar"][:12]) < 1e-8
+    m, S = batched.state_fit_from_rollouts(g["X"][None])
+    assert relerr(m[0], g["x0_mean"]) < 1e-12 and relerr(S[0], g["x0_covar"]) < 1e-12
+
+
+def test_fit_lr_batch_and_errors(backend):
+    from donk_b200 import batched, synthetic
+
+    conds = [synthetic.condition(5, i, 6, 4, 2, 9) for i in range(3)]
+    X = np.stack([c.X for c in conds])
+    U = np.stack([c.U for c in conds])
+    F, f, covar, info = batched.fit_lr(X, U)
+    for b, c in enumerate(conds):
+        Fo, fo, co = oracle.fit_lr(c.X, c.U)
+        assert relerr(F[b], Fo) < 1e-9 and relerr(f[b], fo) < 1e-9 and relerr(covar[b], co) < 1e-9
+    with pytest.raises(ValueError):
+        batched.fit_lr(X[:, :1], U[:, :1])
+    T = batched.to_transitions(conds[0].X, conds[0].U)
+    assert np.array_equal(T.cpu().numpy(), oracle.to_transitions(conds[0].X, conds[0].U))
+
+
+def test_gmm_em_iterations_match_sklearn(backend):
+    from donk_b200.batched import DeviceGMM
+
+    g = load_golden("gmm_em")
+    X = g["X"]
+    for it in (1, 3, 5):
+        gm = DeviceGMM(3, tol=0.0, max_iter=it).set_params(g["w0"], g["m0"], precisions=g["p0"])
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            gm.fit(X)
+        assert relerr(gm.weights, g[f"it{it}_weights"]) < 1e-9
+        assert relerr(gm.means, g[f"it{it}_means"]) < 1e-9
+        assert relerr(gm.covariances, g[f"it{it}_covariances"]) < 1e-9
+        assert relerr(gm.precisions_cholesky, g[f"it{it}_prec_chol"]) < 1e-9
+        assert abs(gm.lower_bound - g[f"it{it}_lower_bound"]) < 1e-10 * abs(g[f"it{it}_lower_bound"])
+    gm = DeviceGMM(3).set_params(g["w0"], g["m0"], precisions=g["p0"]).fit(X)  # default stop rule
+    assert gm.n_iter == int(g["d_n_iter"]) and gm.converged == bool(g["d_converged"])
+    assert relerr(gm.covariances, g["d_covariances"]) < 1e-9
+    gm.fit(g["X2"], warm_start=True)  # second update warm-starts (prior_gmm.py:24)
+    assert gm.n_iter == int(g["w_n_iter"])
+    assert relerr(gm.means, g["w_means"]) < 1e-9 and relerr(gm.covariances, g["w_covariances"]) < 1e-9
+    assert relerr(gm.predict_proba(g["pp_rows"]), g["pp"]) < 1e-9
+
+
+def test_gmm_label_init_and_prior_api(backend):
+    """GMMPrior(8, random_state=0).update(...) reproduces the sklearn fit of tests/dynamics_test.py:115-116."""
+    from donk_b200.dynamics.linear_dynamics import fit_lr
+    from donk_b200.dynamics.prior import GMMPrior
+
+    g = load_golden("fitlr_traj00")
+    XUX = oracle.to_transitions(g["X"], g["U"])
+    prior = GMMPrior(8, random_state=0)
+    prior.update(XUX)
+    assert prior.N == int(g["gmm_N"]) and prior.gmm.n_iter_ == int(g["gmm_n_iter"])
+    assert relerr(prior.gmm.means_, g["gmm_means"]) < 1e-8
+    assert relerr(prior.gmm.covariances_, g["gmm_covariances"]) < 1e-8
+    assert relerr(prior.gmm.weights_, g["gmm_weights"]) < 1e-8
+    niw = prior.eval(g["ev_xux"])
+    assert relerr(niw.mu0, g["ev_mu0"]) < 1e-8 and relerr(niw.Phi, g["ev_Phi"]) < 1e-8
+    dyn = fit_lr(g["X"][:3], g["U"][:3], prior, regularization=0)
+    assert relerr(dyn.F, g["pF"]) < 1e-7 and relerr(dyn.covar, g["pcovar"]) < 1e-7
+    assert str(dyn) == "LinearDynamics[T=44, dX=15, dU=2]"

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 import oracle
-from donk_testutil import load_golden, relerr
+from donk_testutil import load_golden, relerr, set_reverse, to_np
 from oracle.lqg import ILQRProblem
 
 TOL = 1e-9
@@ -24,10 +24,10 @@ def _batched(g, reps=1):
 
 
 @pytest.mark.parametrize("reverse", [0, 1])
-def test_backward_forward_small(emu, reverse):
+def test_backward_forward_small(backend, reverse):
     from donk_b200 import batched
 
-    emu.lib.donk_emu_set_reverse(reverse)
+    set_reverse(backend, reverse)
     g = load_golden("lqg_small")
     K, k, cov, inv, info = batched.lqr_backward(g["bw_F"][None], g["bw_f"][None], g["bw_C"][None], g["bw_c"][None])
     assert int(info.sum()) == 0
@@ -38,11 +38,11 @@ def test_backward_forward_small(emu, reverse):
     mean, covar = batched.lqr_forward(g["fw_F"][None], g["fw_f"][None], g["fw_dyn_covar"][None], g["fw_K"][None],
                                       g["fw_k"][None], g["fw_pol_covar"][None], g["fw_x0_mean"][None], g["fw_x0_covar"][None])
     assert relerr(mean[0], g["fw_mean"]) < TOL and relerr(covar[0], g["fw_covar"]) < TOL
-    c = covar[0].numpy()
+    c = covar[0].cpu().numpy()
     assert np.array_equal(c, np.swapaxes(c, 1, 2))
 
 
-def test_helpers(emu):
+def test_helpers(backend):
     from donk_b200 import batched
 
     g = load_golden("lqg_small")
@@ -60,8 +60,8 @@ def test_helpers(emu):
 
 
 @pytest.mark.parametrize("case,reverse", [("ilqr_c1", 0), ("ilqr_c1", 1), ("ilqr_c2", 0)])
-def test_step_matches_reference(emu, case, reverse):
-    emu.lib.donk_emu_set_reverse(reverse)
+def test_step_matches_reference(backend, case, reverse):
+    set_reverse(backend, reverse)
     g = load_golden(case)
     il = _batched(g, reps=3)
     assert relerr(il.C_kl[1], g["C_kl"]) < TOL and relerr(il.c_kl[2], g["c_kl"]) < TOL
@@ -80,7 +80,7 @@ def test_step_matches_reference(emu, case, reverse):
                 assert relerr(r.traj_covar[b, i], g[f"s{i}_tcovar"]) < TOL
 
 
-def test_optimize_follows_reference_brent_path(emu):
+def test_optimize_follows_reference_brent_path(backend):
     g = load_golden("ilqr_c1")
     il = _batched(g, reps=2)
     for j in (0, 1):
@@ -97,7 +97,7 @@ def test_optimize_follows_reference_brent_path(emu):
         il.optimize(1e-30, max_eta=1e-3)
 
 
-def test_multi_condition_packing_and_active_mask(emu):
+def test_multi_condition_packing_and_active_mask(backend):
     """E=1 packs several conditions per CTA; masked conditions keep their outputs untouched."""
     from donk_b200 import synthetic
     from donk_b200.batched import BatchedILQR
@@ -114,6 +114,7 @@ def test_multi_condition_packing_and_active_mask(emu):
     eta = torch.as_tensor(np.logspace(-1, 2, 11))
     active = torch.ones(11, dtype=torch.int32)
     active[[3, 7]] = 0
+    active = active.to(backend.device)
     r = il.step(eta, active=None)
     kl_all = r.kl_div[:, 0].clone()
     r.kl_div.fill_(-1.0)

@@ -1,0 +1,162 @@
+"""The drop-in Python API (same names / signatures / errors as the reference) on top of the kernels.
+
+Mirrors the reference's own tests: tests/traj_opt_test.py, tests/dynamics_test.py, tests/samples_test.py,
+tests/utils_test.py, tests/costs_test.py:258-301.
+"""
+import pickle
+
+import numpy as np
+import pytest
+
+from donk_testutil import load_golden, relerr
+
+
+def test_lqg_module_functions(backend):
+    from donk_b200.dynamics import LinearDynamics
+    from donk_b200.policy import LinearGaussianPolicy
+    from donk_b200.samples import StateDistribution
+    from donk_b200.traj_opt import lqg
+
+    g = load_golden("lqg_small")
+    dyn = LinearDynamics(g["fw_F"], g["fw_f"], g["fw_dyn_covar"])
+    pol = LinearGaussianPolicy(g["fw_K"], g["fw_k"], g["fw_pol_covar"])
+    traj = lqg.forward(dyn, pol, StateDistribution(g["fw_x0_mean"], g["fw_x0_covar"]))
+    assert traj.mean.shape == (6, 5) and traj.covar.shape == (6, 5, 5)
+    assert relerr(traj.mean, g["fw_mean"]) < 1e-9 and relerr(traj.covar, g["fw_covar"]) < 1e-9
+    assert np.array_equal(traj.covar, np.swapaxes(traj.covar, 1, 2))  # tests/traj_opt_test.py:63
+    assert np.array_equal(traj.X_mean, traj.mean[:, :3]) and np.array_equal(traj.U_covar, traj.covar[:-1, 3:, 3:])
+    pol = lqg.backward(LinearDynamics(g["bw_F"], g["bw_f"], g["fw_dyn_covar"]), g["bw_C"], g["bw_c"])
+    assert relerr(pol.K, g["bw_K"]) < 1e-9 and relerr(pol.inv_covar, g["bw_inv_covar"]) < 1e-9
+    prev = LinearGaussianPolicy(g["ex_K"], g["ex_k"], g["ex_covar"])
+    C, c = lqg.extended_costs_kl(prev)  # lazy inv_covar from covar (tvlg.py:88-99)
+    assert relerr(C, g["ex_C"]) < 1e-9 and relerr(c, g["ex_c"]) < 1e-9
+    kl = lqg.kl_divergence_action(g["kl_X"], LinearGaussianPolicy(g["kl_K"], g["kl_k"], g["kl_covar"]),
+                                  LinearGaussianPolicy(g["kl_pK"], g["kl_pk"], g["kl_pcovar"]))
+    assert abs(kl - 3.914744335914712) < 1e-12
+    with pytest.raises(np.linalg.LinAlgError):  # Quu not positive definite (lqg.py:165)
+        lqg.backward(LinearDynamics(g["bw_F"], g["bw_f"], g["fw_dyn_covar"]), -g["bw_C"], g["bw_c"])
+
+
+def test_ilqr_class(backend):
+    from donk_b200.costs import QuadraticCosts
+    from donk_b200.dynamics import LinearDynamics
+    from donk_b200.policy import LinearGaussianPolicy
+    from donk_b200.samples import StateDistribution
+    from donk_b200.traj_opt import ILQR
+    from donk_b200.traj_opt import lqg
+
+    g = load_golden("ilqr_c1")
+    dyn = LinearDynamics(g["F"], g["f"], g["dyn_covar"])
+    prev = LinearGaussianPolicy(g["prev_K"], g["prev_k"], g["prev_covar"])
+    costs = QuadraticCosts(g["C"], g["c"], g["cc"])
+    x0 = StateDistribution(g["x0_mean"], g["x0_covar"])
+    ilqr = ILQR(dyn, prev, costs, x0)
+    assert relerr(ilqr.C_kl, g["C_kl"]) < 1e-9
+    r = ilqr.step(float(g["etas"][2]))
+    assert relerr(r.policy.K, g["s2_K"]) < 1e-9 and abs(r.kl_div - g["s2_kl"]) < 1e-9
+    assert relerr(r.trajectory.covar, g["s2_tcovar"]) < 1e-9
+    assert abs(r.expected_costs - g["s2_cost"]) < 1e-9 * abs(g["s2_cost"])
+    assert relerr(r.policy.chol_covar, np.linalg.cholesky(g["s2_covar"])) < 1e-9
+    r = ilqr.optimize(1.0)
+    assert abs(r.eta - g["o0_eta"]) < 1e-9 * g["o0_eta"] and relerr(r.policy.K, g["o0_K"]) < 1e-8
+    surf = ilqr.sample_surface(1e-3, 1e4, N=8)
+    assert len(surf) == 8 and surf[0].eta == pytest.approx(1e-3)
+    assert abs(surf[0].kl_div - g["s1_kl"]) < 1e-9 * abs(g["s1_kl"])
+    with pytest.raises(ValueError, match="max_eta eta to low"):
+        ilqr.optimize(1e-30, max_eta=1e-3)
+    pickle.dumps(r)  # results stay plain numpy holders (datalogging / shelve compatibility)
+    # step_adjust (lqg.py:309-350)
+    dyn2 = LinearDynamics(g["sa_F2"], g["sa_f2"], g["sa_cov2"])
+    new_pol = LinearGaussianPolicy(g["o0_K"], g["o0_k"], g["o0_covar"])
+    mult = lqg.step_adjust(1.0, dyn2, new_pol, x0, costs, dyn, prev, x0, costs)
+    assert abs(mult - float(g["sa_mult"])) < 1e-9
+
+
+def test_fit_lr_api(backend):
+    from donk_b200.dynamics import LinearDynamics
+    from donk_b200.dynamics.linear_dynamics import fit_lr
+
+    g = load_golden("fitlr_traj00")
+    dyn = fit_lr(g["X"], g["U"], regularization=1e-6)
+    assert dyn.F.shape == (44, 15, 17) and dyn.f.shape == (44, 15) and dyn.covar.shape == (44, 15, 15)
+    assert (dyn.T, dyn.dX, dyn.dU) == (44, 15, 2)
+    assert relerr(dyn.F, g["F"]) < 1e-8
+    assert np.array_equal(dyn.covar, np.swapaxes(dyn.covar, 1, 2))  # tests/dynamics_test.py:84
+    for t in range(44):
+        assert np.all(np.linalg.eigvalsh(dyn.covar[t]) >= -1e-12)
+    with pytest.raises(ValueError):  # tests/dynamics_test.py:92-100
+        fit_lr(np.empty((1, 5, 3)), np.empty((1, 4, 2)), regularization=1e-6)
+    d = LinearDynamics(F=np.array([[[1, 0, 1], [0, 1, 1]]]), f=np.array([[0, 1]]),
+                       covar=np.array([[[0.1, 0.1], [0.1, 0.1]]]))
+    assert np.array_equal(d.predict(x=[1, 1], u=[1], t=0, noise=None), [2, 3])  # tests/dynamics_test.py:10-19
+    assert str(LinearDynamics(np.empty((4, 3, 5)), np.empty((4, 3)), np.empty((4, 3, 3)))) == \
+        "LinearDynamics[T=4, dX=3, dU=2]"
+
+
+def test_value_types_and_helpers(backend):
+    from donk_b200.costs import QuadraticCosts
+    from donk_b200.dynamics.prior import NormalInverseWishart
+    from donk_b200.samples import StateDistribution, TrajectoryDistribution, TransitionPool
+    from donk_b200.utils import regularize, symmetrize, trace_of_product
+    from donk_b200.utils.batched import batched_cholesky, batched_inv_spd
+
+    rng = np.random.default_rng(0)
+    X, U = rng.standard_normal((3, 11, 5)), rng.standard_normal((3, 10, 3))
+    pool = TransitionPool()
+    pool.add(X, U)  # tests/samples_test.py:9-31
+    assert np.array_equal(pool.get_transitions(),
+                          np.c_[X[:, :-1].reshape(-1, 5), U.reshape(-1, 3), X[:, 1:].reshape(-1, 5)])
+    assert np.array_equal(pool.get_transitions(N=5),
+                          np.c_[X[2, -6:-1].reshape(-1, 5), U[2, -5:].reshape(-1, 3), X[2, -5:].reshape(-1, 5)])
+    assert not pool.get_transitions().flags.writeable
+    capped = TransitionPool(capacity=7)
+    capped.add(X, U)
+    assert capped.get_transitions().shape == (7, 13)
+    A = rng.uniform(size=(4, 3, 3))
+    B = A.copy()
+    assert symmetrize(B) is B and np.array_equal(B, np.swapaxes(B, 1, 2))  # tests/utils_test.py:30-47
+    assert regularize(B, 0.5) is B
+    assert np.allclose(trace_of_product(A, B), np.trace(A @ B, axis1=1, axis2=2))
+    spd = B + 3 * np.eye(3)
+    assert relerr(batched_cholesky(spd), np.linalg.cholesky(spd)) < 1e-12
+    assert relerr(batched_inv_spd(np.linalg.cholesky(spd)), np.linalg.inv(spd)) < 1e-10
+    m = load_golden("misc")
+    sd = StateDistribution.fit(m["X0"])
+    assert relerr(sd.mean, m["sd_mean"]) < 1e-12 and relerr(sd.covar, m["sd_covar"]) < 1e-12
+    ec = QuadraticCosts(m["C"], m["c"], m["cc"]).expected_costs(TrajectoryDistribution(m["mean"], m["covar"], 4, 2))
+    assert relerr(ec, m["expected"]) < 1e-12
+    prior = NormalInverseWishart.non_informative_prior(1).posterior(np.array([1]), np.array([[0.5]]), 1)
+    assert np.allclose(prior.map_mean(), [1]) and np.allclose(prior.map_covar(), [[0.5]])  # dynamics_test.py:222-232
+
+
+def test_traj_opt_algorithm_two_iterations(backend):
+    """TrajOptAlgorithm.iteration (traj_opt.py:35-96) vs the same sequence through the oracle."""
+    import oracle
+    from donk_b200 import synthetic
+    from donk_b200.costs import QuadraticCosts
+    from donk_b200.policy import LinearGaussianPolicy
+    from donk_b200.traj_opt import TrajOptAlgorithm
+    from oracle.lqg import ILQRProblem
+
+    T, dX, dU, N = 10, 4, 2, 10
+    c0, c1 = synthetic.condition(8, 0, T, dX, dU, N), synthetic.condition(8, 1, T, dX, dU, N)
+    costs = QuadraticCosts(c0.C, c0.c, c0.cc)
+    algo = TrajOptAlgorithm(kl_step=1.0)
+    algo.iteration(c0.X, c0.U, costs, prev_pol=LinearGaussianPolicy(c0.prev_K, c0.prev_k, c0.prev_covar))
+    pol1 = algo.pol
+    algo.iteration(c1.X, c1.U, costs)
+    # oracle, same order of operations
+    F0, f0, S0 = oracle.fit_lr(c0.X, c0.U)
+    x00 = oracle.state_fit(c0.X[:, 0])
+    p0 = ILQRProblem(F0, f0, S0, c0.C, c0.c, c0.cc, c0.prev_K, c0.prev_k, c0.prev_covar,
+                     np.linalg.inv(c0.prev_covar), *x00)
+    r0, _ = oracle.ilqr_optimize(p0, 1.0)
+    assert relerr(pol1.K, r0.K) < 1e-8
+    F1, f1, S1 = oracle.fit_lr(c1.X, c1.U)
+    x01 = oracle.state_fit(c1.X[:, 0])
+    p1 = ILQRProblem(F1, f1, S1, c0.C, c0.c, c0.cc, r0.K, r0.k, r0.covar, r0.inv_covar, *x01)
+    r1, _ = oracle.ilqr_optimize(p1, 1.0)
+    assert relerr(algo.pol.K, r1.K) < 1e-7
+    mult, *_ = oracle.step_adjust(1.0, (F1, f1, S1), (r1.K, r1.k, r1.covar), x01, (c0.C, c0.c, c0.cc),
+                                  (F0, f0, S0), (r0.K, r0.k, r0.covar), x00, (c0.C, c0.c, c0.cc))
+    assert abs(algo.kl_step_mult - mult) < 1e-6
