@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""Benchmark of the donk.ai trajectory-optimisation hot path on B200 (one JSON line on stdout).
+
+Headline workload (BASELINE.json configs[2], the largest single-GPU configuration of the metric
+"iLQR backward-pass solves/sec"): batched ILQR.step over 4096 conditions x 16 eta candidates per GPU,
+T=100, dX=20, dU=6, fp64.  One *solve* = one (condition, eta) problem: backward Riccati recursion +
+forward Gaussian pass + KL + expected cost (donk/traj_opt/lqg.py:55-75).  One *step* = one launch of
+the fused kernel over all 65 536 solves of a rank.  The dynamics are produced on the device by the
+fit_lr kernel from synthetic roll-outs; fit_lr and GMM-EM throughput are
+reported next to it under "extra".
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N>1: launched by torchrun, one rank per GPU, conditions sharded (weak scaling, no data-path
+collective for ILQR; the EM extra all-reduces its statistics over NCCL).
+--impl reference: the CPU restatement of the reference (oracle/, numpy/scipy — the reference itself is
+Python and cannot travel to the GPU box) on all host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOAD = dict(T=100, dX=20, dU=6, N=64, B=4096, E=16)
+ETA_GRID = np.logspace(-2, 2, 16)  # the sample_surface form of SURVEY.md 8(d) config 3
+
+
+def ilqr_flops_per_solve(T, dX, dU):
+    """Algorithmic flops of one ILQR.step (SURVEY.md section 8(a) "Sizes"), mul+add = 2."""
+    p = dX + dU
+    back = 2 * dX * dX * p + 2 * dX * p * p + 2 * dX * dX + 2 * dX * p + (7 / 3) * dU ** 3 + 2 * dU * dU * dX + 2 * dX * dX * dU
+    fwd = 2 * dU * dX * dX + 2 * dU * dU * dX + 2 * dX * p * p + 2 * dX * dX * p
+    klc = 2 * dU * dX + 4 * dU * dU + dU ** 3 / 3 + 4 * p * p
+    return T * (back + fwd + klc)
+
+
+def ilqr_bytes_per_launch(B, E, T, dX, dU):
+    """Algorithmic HBM bytes of one launch: every input once per condition, policy scratch written by the
+    backward pass and read back by the forward pass, results."""
+    p = dX + dU
+    per_cond = T * (dX * p + dX + dX * dX) + (T + 1) * (p * p + p + 1) + T * (p * p + p) \
+        + T * (dU * dX + dU + dU * dU + 1) + dX + dX * dX
+    pol = T * (dU * dX + dU + 2 * dU * dU)
+    return 8 * (B * per_cond + B * E * (2 * pol - T * dU * dU + 3))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference on all host cores (bounded sample)
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    seed, T, dX, dU, N, etas = args
+    import oracle
+    from donk_b200 import synthetic
+    from oracle.lqg import ILQRProblem
+
+    c = synthetic.condition(3, seed, T, dX, dU, N)
+    F, f, S = oracle.fit_lr(c.X, c.U)
+    m, S0 = oracle.state_fit(c.X[:, 0])
+    prob = ILQRProblem(F, f, S, c.C, c.c, c.cc, c.prev_K, c.prev_k, c.prev_covar, np.linalg.inv(c.prev_covar), m, S0)
+    t0 = time.perf_counter()
+    for eta in etas:
+        oracle.ilqr_step(prob, float(eta))
+    return time.perf_counter() - t0
+
+
+def cpu_ilqr_sample(pool, cores, conds_per_core, etas):
+    """One bounded sample: cores*conds_per_core conditions x len(etas) ILQR.step calls over all host cores.
+    Returns (solves, wall seconds of the timed part)."""
+    w = WORKLOAD
+    jobs = [(i, w["T"], w["dX"], w["dU"], w["N"], etas) for i in range(cores * conds_per_core)]
+    per = pool.map(_cpu_worker, jobs, chunksize=conds_per_core)
+    # workers run concurrently, one per core; problem set-up (synthetic roll-outs, fit_lr) is outside the
+    # metric, so the timed region is the slowest worker's time inside ILQR.step
+    return len(jobs) * len(etas), max(per) * conds_per_core
+
+
+def run_reference(args):
+    import multiprocessing as mp
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for _ in range(args.warmup):
+            cpu_ilqr_sample(pool, cores, 1, ETA_GRID[:4])
+        solves = 0
+        secs = 0.0
+        for _ in range(args.steps):
+            s, t = cpu_ilqr_sample(pool, cores, 1, ETA_GRID)
+            solves += s
+            secs += t
+    value = solves / secs
+    w = WORKLOAD
+    line = {
+        "impl": "reference", "metric": "ilqr_solves_per_sec", "value": value, "unit": "solves/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(1),
+        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port",
+                         "sample": f"{cores} conditions x 16 eta per step (T={w['T']},dX={w['dX']},dU={w['dU']}), "
+                                   f"oracle ILQR.step, one process per core"},
+        "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    w = WORKLOAD
+    return {
+        "workload": f"batched ILQR.step: {w['B']} conditions x {w['E']} eta per GPU, T={w['T']}, dX={w['dX']}, "
+                    f"dU={w['dU']} (BASELINE.json configs[2]); dynamics from fit_lr on N={w['N']} synthetic roll-outs",
+        "conditions_per_gpu": w["B"], "eta_candidates": w["E"], "T": w["T"], "dX": w["dX"], "dU": w["dU"],
+        "solve": "one (condition, eta): backward + forward + KL + expected cost",
+        "parallelism": f"conditions sharded over {n_gpus} GPU(s), no collective",
+        "l2": f"inputs per launch ({ilqr_bytes_per_launch(w['B'], w['E'], w['T'], w['dX'], w['dU']) / 1e9:.1f} GB "
+              f"algorithmic traffic) exceed the 126 MB L2; no flush between steps",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the GPU work of this script runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 6]
+        os.unlink(self.f.name)
+        sm, pw, mx, reasons = [], [], None, set()
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                pw.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": mx, "reasons": ["no samples"]}
+        load = [s for s, w_ in zip(sm, pw) if w_ >= 0.6 * max(pw)]  # samples taken under load
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "samples_under_load": len(load), "power_w_max": max(pw)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from donk_b200 import _lib, batched, synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dry = args.dry_run_emu  # tests only: tiny sizes on the host emulation of the kernels, to check this script
+    if dry:
+        sys.path.insert(0, str(ROOT / "tests"))
+        from emu.build_emu import backend as emu_backend
+
+        _lib.install_test_backend(emu_backend())
+        WORKLOAD.update(T=6, dX=4, dU=2, N=8, B=5, E=16)
+        dev = torch.device("cpu")
+        if world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("gloo")
+    else:
+        assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+        torch.cuda.set_device(local)
+        dev = torch.device("cuda", local)
+        if world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=dev)
+    nat = _lib.native()
+    w = WORKLOAD
+    B, E, T, dX, dU, N = w["B"], w["E"], w["T"], w["dX"], w["dU"], w["N"]
+    p = dX + dU
+
+    def sync():
+        if not dry:
+            torch.cuda.synchronize()
+
+    def barrier():
+        sync()
+        if world > 1:
+            dist.barrier()
+        sync()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        if dry:
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                fn()
+            return max_over_ranks(1e3 * (time.perf_counter() - t0))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()  # torch's current stream == the stream the library launches on
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    clocks = ClockSampler(local)
+    # ---- synthetic inputs on the device (untimed) ------------------------------------------------
+    ro = synthetic.rollout_batch_torch(B, T, dX, dU, N, seed=3000 + rank, device=dev)
+    C, c, cc = synthetic.l2_costs(T, dX, dU)
+    Cb = torch.as_tensor(C, device=dev).expand(B, T + 1, p, p).contiguous()
+    cb = torch.as_tensor(c, device=dev).expand(B, T + 1, p).contiguous()
+    ccb = torch.as_tensor(cc, device=dev).expand(B, T + 1).contiguous()
+    eta = torch.as_tensor(ETA_GRID, device=dev).expand(B, E).contiguous()
+
+    # ---- extra: fit_lr (also produces the dynamics the headline consumes) ----------------------------
+    holder = {}
+
+    def fit_once():
+        holder["fit"] = batched.fit_lr(ro["X"], ro["U"])
+
+    fit_ms = timed(fit_once, max(2, args.steps // 2), 2) / max(2, args.steps // 2)
+    F, f, dyn_covar, info = holder["fit"]
+    assert int(info.sum().item()) == 0, "fit_lr: matrix not positive definite"
+    x0m, x0S = batched.state_fit_from_rollouts(ro["X"])
+    il = batched.BatchedILQR(F, f, dyn_covar, ro["prev_K"], ro["prev_k"], Cb, cb, ccb, x0m, x0S,
+                             prev_covar=ro["prev_covar"])
+    del ro["X"], ro["U"]
+    if not dry:
+        torch.cuda.empty_cache()
+
+    # ---- headline: device-resident ILQR.step -----------------------------------------------------------
+    def step_once():
+        holder["res"] = il.step(eta)
+
+    step_once()
+    sync()
+    assert int(holder["res"].info.sum().item()) == 0, "ILQR.step: Quu not positive definite"
+    timed(step_once, 0, args.warmup)
+    l0 = nat.launch_count()
+    ms = timed(step_once, args.steps, 0)
+    launches = nat.launch_count() - l0
+    ms_per_step = ms / args.steps
+    solves_per_step = B * E * world
+    value = solves_per_step / (ms_per_step * 1e-3)
+
+    # ---- parity spot check against the oracle (2 conditions x 16 eta) -----------------------------------
+    parity = None
+    if rank == 0:
+        import oracle
+        from oracle.lqg import ILQRProblem
+
+        res = holder["res"]
+        worst = 0.0
+        for b in (0, B - 1):
+            g = lambda t: t[b].cpu().numpy()  # noqa: E731
+            prob = ILQRProblem(g(F), g(f), g(dyn_covar), C, c, cc, g(il.prev_K), g(il.prev_k), g(il.prev_covar),
+                               g(il.prev_inv_covar), g(x0m), g(x0S))
+            for e in (0, 7, 15):
+                ref = oracle.ilqr_step(prob, float(ETA_GRID[e]))
+                worst = max(worst, np.max(np.abs(res.K[b, e].cpu().numpy() - ref.K)) / np.max(np.abs(ref.K)),
+                            abs(float(res.kl_div[b, e]) - ref.kl_div) / max(1.0, abs(ref.kl_div)),
+                            abs(float(res.expected_costs[b, e]) - ref.expected_costs) / abs(ref.expected_costs))
+        parity = worst
+
+    # ---- e2e: host buffers in, results out, through the public batched API ------------------------------
+    pin = (lambda t: t) if dry else (lambda t: t.pin_memory())
+    host = {k: pin(v.cpu()) for k, v in dict(F=F, f=f, S=dyn_covar, pK=il.prev_K, pk=il.prev_k,
+                                                      pS=il.prev_covar, C=Cb, c=cb, cc=ccb, m=x0m, S0=x0S,
+                                                      eta=eta).items()}
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    out_host = pin(torch.empty(2, B, E, dtype=torch.float64))
+    d2h = out_host.numel() * 8
+
+    def e2e_once():
+        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        il2 = batched.BatchedILQR(d["F"], d["f"], d["S"], d["pK"], d["pk"], d["C"], d["c"], d["cc"], d["m"], d["S0"],
+                                  prev_covar=d["pS"])
+        il2._ws = il._ws  # reuse the policy scratch buffers (allocation is not part of the path)
+        r = il2.step(d["eta"])
+        out_host[0].copy_(r.kl_div, non_blocking=True)
+        out_host[1].copy_(r.expected_costs, non_blocking=True)
+        sync()
+
+    e2e_steps = max(1, min(args.steps, 5))
+    e2e_ms = timed(e2e_once, e2e_steps, 1) / e2e_steps
+    e2e_value = solves_per_step / (e2e_ms * 1e-3)
+    clk = clocks.stop()
+    del host, il
+    if not dry:
+        torch.cuda.empty_cache()
+
+    # ---- FP64 pipe probe: the roofline denominator of the FP64-bound step kernel ---------------------------
+    import ctypes
+
+    scratch = torch.zeros(8, dtype=torch.float64, device=dev)
+    peaks = {}
+    for mode, name in ((0, "dfma"), (1, "dmma")):
+        flops = ctypes.c_double(0)
+        best = 0.0
+        for it in range(0 if dry else 4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            nat.call("fp64_probe", mode, 148 * 8, 20000, scratch, ctypes.byref(flops))
+            e1.record()
+            torch.cuda.synchronize()
+            if it:
+                best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        peaks[name] = best
+    fp64_peak = max(peaks.values()) or None
+    flops_per_launch = ilqr_flops_per_solve(T, dX, dU) * B * E
+    achieved_tf = flops_per_launch / (ms_per_step * 1e-3) / 1e12 / world * world  # per-GPU kernel time == step time
+    hbm_peak = json.load(open(ROOT / "MEASURED_PEAKS.json"))["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
+    bytes_per_launch = ilqr_bytes_per_launch(B, E, T, dX, dU)
+
+    # ---- extra: GMM EM iteration on a sharded transition pool (BASELINE.json configs[3]) --------------------
+    extra = {"fit_lr": {"timestep_fits_per_sec": B * T * world / (fit_ms * 1e-3), "ms_per_launch": fit_ms,
+                        "config": f"B={B} conditions/GPU, T={T}, dX={dX}, dU={dU}, N={N}, no prior"}}
+    try:
+        n_rows, d, K = (600 if dry else args.em_rows) // world, (10 if dry else 72), (3 if dry else 16)
+        Xp, w0, m0, p0 = synthetic.gmm_pool_torch(n_rows, d, K, seed=4000 + rank, device=dev)
+        gm = batched.DeviceGMM(K, tol=0.0, max_iter=1).set_params(w0, m0, precisions=p0)
+        o = dict(dtype=torch.float64, device=dev)
+        ws = torch.empty(nat.size("gmm_workspace_bytes", n_rows, d, K) // 8 + 1, **o)
+        stats = torch.empty(nat.size("gmm_stats_size", d, K), **o)
+        gm._lb = torch.zeros(1, **o)
+        gm._info = torch.zeros(K, dtype=torch.int32, device=dev)
+        em_ms = timed(lambda: gm.em_iteration(Xp, float(n_rows * world), ws, stats), 5, 2) / 5
+        em_flops = n_rows * K * (2 * d * (d + 1) + 4 * d)
+        extra["gmm_em"] = {"transitions_per_sec_per_iteration": n_rows * world / (em_ms * 1e-3), "ms_per_iteration": em_ms,
+                           "config": f"{n_rows * world} rows total ({n_rows}/GPU), d={d}, K={K}, one E+M iteration "
+                                     f"incl. all-reduce and M finalise",
+                           "achieved_tflops_per_gpu": em_flops / (em_ms * 1e-3) / 1e12,
+                           "achieved_hbm_gbs_per_gpu": n_rows * d * 8 / (em_ms * 1e-3) / 1e9}
+        del Xp, ws
+    except Exception as ex:  # the extra must not take the headline down
+        extra["gmm_em"] = {"error": repr(ex)[:200]}
+
+    # ---- CPU baseline (rank 0, N=1 only): oracle port on all host cores, bounded sample --------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu and not dry:
+        import multiprocessing as mp
+
+        cores = os.cpu_count() or 1
+        with mp.get_context("fork").Pool(cores) as pool:
+            cpu_ilqr_sample(pool, cores, 1, ETA_GRID[:2])
+            s, t = cpu_ilqr_sample(pool, cores, 1, ETA_GRID)
+        cpu = {"value": s / t, "unit": "solves/s", "cores": cores, "kind": "port",
+               "sample": f"{cores} conditions x 16 eta (T={T},dX={dX},dU={dU}) through oracle.ilqr_step, one process "
+                         f"per core, {t:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": "ilqr_solves_per_sec", "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world),
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": None,
+                         "kernel": "ilqr_step_kernel<double>",
+                         "peak_source": f"in-run FP64 probe on this GPU (dfma {peaks['dfma']:.1f}, dmma {peaks['dmma']:.1f} "
+                                        f"TFLOP/s); MEASURED_PEAKS.json holds no FP64 figure",
+                         "algorithmic_flops_per_launch": flops_per_launch,
+                         "hbm": {"achieved": bytes_per_launch / (ms_per_step * 1e-3) / 1e9, "peak": hbm_peak,
+                                 "unit": "GB/s", "algorithmic_bytes_per_launch": bytes_per_launch,
+                                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)"}},
+            "cpu_baseline": cpu,
+            "parity_max_rel_err_vs_oracle": parity,
+            "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--em-rows", type=int, default=10_000_000, help="rows of the GMM-EM extra (total over GPUs)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--dry-run-emu", action="store_true", help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

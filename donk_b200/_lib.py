@@ -39,6 +39,7 @@ SIGNATURES = {
     "gmm_m_finalize_f64": [c_double, c_int, c_int, P, c_double, P, P, P, P, P, P, P],
     "gmm_predict_proba_f64": [c_int] * 3 + [P] * 5 + [P],
     "gmm_prec_chol_from_precisions_f64": [c_int] * 2 + [P] * 3 + [P],
+    "fp64_probe": [c_int, c_int, c_int, P, ctypes.POINTER(c_double), P],
 }
 _SIZE_FUNCS = {
     "gmm_stats_size": [c_int, c_int],

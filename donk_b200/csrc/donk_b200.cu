@@ -218,6 +218,44 @@ int gmm_e_launch(GmmArgs<double>& a, void* stream) {
   return DONK_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// FP64 pipe probes (roofline denominators for the FP64-bound kernels; MEASURED_PEAKS.json only holds
+// HBM and bf16 tensor peaks).  mode 0: dependent-chain-free DFMA on CUDA cores; mode 1: DMMA
+// (mma.sync.m8n8k4.f64) to see whether the tensor path offers more FP64 throughput on sm_100a.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp64_probe_kernel(int mode, int iters, double* out) {
+  const double s = 1.0 + 1e-9 * threadIdx.x;
+  if (mode == 0) {
+    double a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = 0.5 + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a[i] = fma(a[i], s, 1e-3);
+    }
+    double acc = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc += a[i];
+    if (acc == 123.456) out[0] = acc;
+  } else {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i][0] = 0.0; c[i][1] = 0.0; }
+    const double av = s, bv = 1.0 - 1e-9 * threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(av), "d"(bv));
+    }
+    double acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc += c[i][0] + c[i][1];
+    if (acc == 123.456) out[0] = acc;
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -437,6 +475,17 @@ int donk_gmm_prec_chol_from_precisions_f64(int d, int K, const double* precision
   if (rc != DONK_OK) return rc;
   gmm_prec_chol_kernel<double><<<K, 256, smem, (cudaStream_t)stream>>>(d, precisions, prec_chol, info);
   LAUNCHED("gmm_prec_chol_kernel");
+  return DONK_OK;
+}
+
+/* FP64 throughput probe: launches blocks x 256 threads, each doing `iters` rounds of 16 independent DFMA
+ * (mode 0: 32 flop/thread/round) or 8 DMMA m8n8k4 (mode 1: 8*512 flop/warp/round).  Returns via *flops the
+ * number of floating-point operations the launch performs; time it with events on `stream`. */
+int donk_fp64_probe(int mode, int blocks, int iters, double* scratch, double* flops, void* stream) {
+  if (blocks < 1 || iters < 1 || mode < 0 || mode > 1) return DONK_BAD_SHAPE;
+  fp64_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(mode, iters, scratch);
+  LAUNCHED("fp64_probe_kernel");
+  if (flops) *flops = mode == 0 ? (double)blocks * 256 * iters * 32.0 : (double)blocks * 8 * iters * 8 * 512.0;
   return DONK_OK;
 }
 

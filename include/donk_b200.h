@@ -183,6 +183,13 @@ int donk_gmm_predict_proba_f64(int n, int d, int K, const double* X, const doubl
 int donk_gmm_prec_chol_from_precisions_f64(int d, int K, const double* precisions, double* prec_chol,
                                            int* info, void* stream);
 
+/* ---- diagnostics ------------------------------------------------------------------------ */
+
+/* FP64 pipe throughput probe (roofline denominator of the FP64-bound kernels): mode 0 = DFMA on the
+ * CUDA cores, mode 1 = DMMA m8n8k4.  `flops` (host pointer) receives the operation count of the launch;
+ * the caller times it with events on `stream`.  scratch: >= 1 double of device memory. */
+int donk_fp64_probe(int mode, int blocks, int iters, double* scratch, double* flops, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
