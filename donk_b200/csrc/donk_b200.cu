@@ -54,6 +54,8 @@ size_t smem_optin_cap() {
 template <typename KernelT>
 int allow_smem(KernelT kernel, size_t bytes) {
   if (bytes > 48 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  // ask for the full shared-memory carve-out so that several CTAs fit one SM
+  CU(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   return DONK_OK;
 }
 
@@ -62,6 +64,13 @@ int allow_smem(KernelT kernel, size_t bytes) {
 // ---------------------------------------------------------------------------------------------
 template <typename R>
 __global__ void __launch_bounds__(512, 1) ilqr_step_kernel(const IlqrArgs<R> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Ctx ctx{(int)threadIdx.x, (int)blockDim.x};
+  ilqr_cta<R>(ctx, a, (int)blockIdx.x, reinterpret_cast<R*>(smem_raw));
+}
+// Same body compiled for <= 320 threads with a register budget that lets several CTAs share an SM.
+template <typename R>
+__global__ void __launch_bounds__(320, 2) ilqr_step_kernel_occ2(const IlqrArgs<R> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Ctx ctx{(int)threadIdx.x, (int)blockDim.x};
   ilqr_cta<R>(ctx, a, (int)blockIdx.x, reinterpret_cast<R*>(smem_raw));
@@ -83,9 +92,15 @@ int ilqr_step_launch(IlqrArgs<R> a, void* stream) {
   }
   a.S = pl.S;
   a.ES = pl.ES;
-  rc = allow_smem(ilqr_step_kernel<R>, pl.smem);
-  if (rc != DONK_OK) return rc;
-  ilqr_step_kernel<R><<<pl.grid, pl.threads, pl.smem, (cudaStream_t)stream>>>(a);
+  if (pl.threads <= 320 && !env_int("DONK_ILQR_OCC1")) {
+    rc = allow_smem(ilqr_step_kernel_occ2<R>, pl.smem);
+    if (rc != DONK_OK) return rc;
+    ilqr_step_kernel_occ2<R><<<pl.grid, pl.threads, pl.smem, (cudaStream_t)stream>>>(a);
+  } else {
+    rc = allow_smem(ilqr_step_kernel<R>, pl.smem);
+    if (rc != DONK_OK) return rc;
+    ilqr_step_kernel<R><<<pl.grid, pl.threads, pl.smem, (cudaStream_t)stream>>>(a);
+  }
   LAUNCHED("ilqr_step_kernel");
   return DONK_OK;
 }

@@ -35,6 +35,17 @@ if what in ("ilqr", "fit"):
         for _ in range(2):
             r = il.step(eta)
         torch.cuda.synchronize()
+        if len(sys.argv) > 3:  # timing mode: ms per step over n launches
+            n = int(sys.argv[3])
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                r = il.step(eta)
+            e1.record()
+            torch.cuda.synchronize()
+            import os
+            print("cfg", {k: v for k, v in os.environ.items() if k.startswith("DONK_")}, "B", B,
+                  "ms_per_step", e0.elapsed_time(e1) / n, "solves_per_s", B * E / (e0.elapsed_time(e1) / n * 1e-3))
         print("kl", float(r.kl_div[0, 0]), "info", int(r.info.sum()))
 else:
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 2_000_000
