@@ -76,6 +76,38 @@ __global__ void __launch_bounds__(320, 2) ilqr_step_kernel_occ2(const IlqrArgs<R
   ilqr_cta<R>(ctx, a, (int)blockIdx.x, reinterpret_cast<R*>(smem_raw));
 }
 
+// One team of L threads per (condition, eta) problem; see ilqr_plan_team.
+template <typename R>
+__device__ __forceinline__ void ilqr_team_body(const IlqrArgs<R>& a, int L, int G, size_t team_bytes,
+                                               long long n_teams) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int team = (int)threadIdx.x / L, lane = (int)threadIdx.x % L;
+  const long long g = (long long)blockIdx.x * G + team;
+  if (team >= G || g >= n_teams) return;  // whole teams leave together; no CTA-wide barrier is used
+  Ctx ctx;
+  ctx.tid = lane;
+  ctx.nt = L;
+  if (L > 32) {
+    ctx.bar = 1 + team;
+    ctx.mask = 0;
+  } else {
+    ctx.bar = -1;
+    const int w = (int)threadIdx.x & 31;
+    ctx.mask = L == 32 ? 0xffffffffu : (((1u << L) - 1u) << (w - (w % L)));
+  }
+  ilqr_cta<R>(ctx, a, (int)g, reinterpret_cast<R*>(smem_raw + (size_t)team * team_bytes));
+}
+template <typename R>
+__global__ void __launch_bounds__(256, 2) ilqr_team_kernel(const IlqrArgs<R> a, int L, int G, size_t team_bytes,
+                                                            long long n_teams) {
+  ilqr_team_body<R>(a, L, G, team_bytes, n_teams);
+}
+template <typename R>
+__global__ void __launch_bounds__(512, 1) ilqr_team_kernel_big(const IlqrArgs<R> a, int L, int G, size_t team_bytes,
+                                                                long long n_teams) {
+  ilqr_team_body<R>(a, L, G, team_bytes, n_teams);
+}
+
 template <typename R>
 int ilqr_step_launch(IlqrArgs<R> a, void* stream) {
   if (a.B < 0 || a.E < 1 || a.T < 1 || a.dX < 1 || a.dU < 1) return DONK_BAD_SHAPE;
@@ -83,8 +115,31 @@ int ilqr_step_launch(IlqrArgs<R> a, void* stream) {
     return DONK_BAD_SHAPE;
   if (a.B == 0) return DONK_OK;
   IlqrPlan pl;
-  int rc = ilqr_plan(a.B, a.E, a.dX, a.dU, sizeof(R), smem_optin_cap(), env_int("DONK_ILQR_SLOTS"),
-                     env_int("DONK_ILQR_THREADS"), pl);
+  int rc;
+  if (!env_int("DONK_ILQR_CTA_MODE")) {
+    rc = ilqr_plan_team(a.B, a.E, a.dX, a.dU, sizeof(R), smem_optin_cap(), env_int("DONK_ILQR_LANES"),
+                        env_int("DONK_ILQR_TEAMS"), pl);
+    if (rc == DONK_OK) {
+      a.S = 1;
+      a.ES = 1;
+      const IlqrLayout lay(a.dX, a.dU);
+      if (pl.threads <= 256) {
+        rc = allow_smem(ilqr_team_kernel<R>, pl.smem);
+        if (rc != DONK_OK) return rc;
+        ilqr_team_kernel<R><<<pl.grid, pl.threads, pl.smem, (cudaStream_t)stream>>>(
+            a, pl.L, pl.G, lay.bytes(1, 1, sizeof(R)), (long long)a.B * a.E);
+      } else {
+        rc = allow_smem(ilqr_team_kernel_big<R>, pl.smem);
+        if (rc != DONK_OK) return rc;
+        ilqr_team_kernel_big<R><<<pl.grid, pl.threads, pl.smem, (cudaStream_t)stream>>>(
+            a, pl.L, pl.G, lay.bytes(1, 1, sizeof(R)), (long long)a.B * a.E);
+      }
+      LAUNCHED("ilqr_team_kernel");
+      return DONK_OK;
+    }
+  }
+  rc = ilqr_plan(a.B, a.E, a.dX, a.dU, sizeof(R), smem_optin_cap(), env_int("DONK_ILQR_SLOTS"),
+                 env_int("DONK_ILQR_THREADS"), pl);
   if (rc != DONK_OK) {
     snprintf(g_err, sizeof(g_err), "ilqr_step: dX=%d dU=%d does not fit %zu bytes of shared memory", a.dX, a.dU,
              smem_optin_cap());

@@ -50,8 +50,16 @@ int donk_emu_ilqr_step_f64(int B, int E, int T, int dX, int dU, int flags, const
     return DONK_BAD_SHAPE;
   if (B == 0) return DONK_OK;
   IlqrPlan pl;
-  int rc = ilqr_plan(B, E, dX, dU, sizeof(double), kSmemCap, env_int("DONK_ILQR_SLOTS"), 0, pl);
-  if (rc != DONK_OK) return rc;
+  int rc;
+  if (!env_int("DONK_ILQR_CTA_MODE")) {  // team launch: one slot per team, "cta" index = problem index
+    rc = ilqr_plan_team(B, E, dX, dU, sizeof(double), kSmemCap, 0, 0, pl);
+    if (rc != DONK_OK) return rc;
+    pl.smem = IlqrLayout(dX, dU).bytes(1, 1, sizeof(double));
+    pl.grid = B * E;
+  } else {
+    rc = ilqr_plan(B, E, dX, dU, sizeof(double), kSmemCap, env_int("DONK_ILQR_SLOTS"), 0, pl);
+    if (rc != DONK_OK) return rc;
+  }
   a.S = pl.S;
   a.ES = pl.ES;
   std::vector<double> smem(pl.smem / sizeof(double) + 2);
