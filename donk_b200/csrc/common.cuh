@@ -51,7 +51,47 @@ struct Ctx {
 #define TEAM_FOR(i, n) for (int i = ctx.tid; i < (n); i += ctx.nt)
 #endif
 
+// Warp-team kernels (ilqr_warp.cuh): a CTA of G warps, one problem per warp; CTA-wide steps only hand over
+// the staged per-condition inputs.  Under emulation one host thread plays all warps of the CTA in turn.
+#if defined(DONK_EMU)
+struct WCtx {
+  int tid, nthreads, team, lane, G;
+  inline void cta_sync() const {}
+  inline void team_sync() const {}
+};
+#define CTA_FOR(i, n)                                                               \
+  for (int i##_it = 0, i##_n = (n), i = donk::emu_idx(0, i##_n); i##_it < i##_n;     \
+       ++i##_it, i = donk::emu_idx(i##_it, i##_n))
+#define LANE_FOR(i, n) CTA_FOR(i, n)
+#define TEAMS_DO(tm) for (int tm = 0; tm < w.G; ++tm)
+#else
+struct WCtx {
+  int tid, nthreads, team, lane, G;
+  DONK_D void cta_sync() const { __syncthreads(); }
+  DONK_D void team_sync() const { __syncwarp(); }
+};
+#define CTA_FOR(i, n) for (int i = w.tid; i < (n); i += w.nthreads)
+#define LANE_FOR(i, n) for (int i = w.lane; i < (n); i += 32)
+#define TEAMS_DO(tm) for (int tm = w.team, tm##_once = 0; tm##_once == 0; tm##_once = 1)
+#endif
+
 DONK_HD int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// 1/sqrt(x): device intrinsic (MUFU.RSQ64H + Newton steps); plain expression under emulation
+DONK_HD double rsqrt_r(double x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+DONK_HD float rsqrt_r(float x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrtf(x);
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
 
 // Read-only global load (inputs never written by the running kernel).
 template <typename R>
@@ -107,6 +147,54 @@ DONK_HD void tile4x4(const R* __restrict__ A, int lda, int i0, const R* __restri
     a += lda;
     b += ldb;
   }
+}
+
+// TM x TN register tile of a product whose operands are both stored k-major (generalises tile4x4):
+//   acc[r][c] = sum_{k<kdim} A[k*lda + r] * Bm[k*ldb + c]      (A, Bm already offset to the tile origin)
+// VA / VB: the operand origin and leading dimension are 16-byte aligned and TM / TN even -> LDS.128.
+template <typename R, int TM, int TN, bool VA, bool VB>
+DONK_HD void tile_km(const R* __restrict__ A, int lda, const R* __restrict__ Bm, int ldb, int kdim, R (&acc)[TM][TN]) {
+#pragma unroll
+  for (int r = 0; r < TM; ++r)
+#pragma unroll
+    for (int c = 0; c < TN; ++c) acc[r][c] = R(0);
+#pragma unroll 4
+  for (int k = 0; k < kdim; ++k) {
+    R av[TM], bv[TN];
+    if (VA && TM == 4) ld4(A, av);
+    else {
+#pragma unroll
+      for (int r = 0; r < TM; ++r) av[r] = A[r];
+    }
+    if (VB && TN == 4) ld4(Bm, bv);
+    else {
+#pragma unroll
+      for (int c = 0; c < TN; ++c) bv[c] = Bm[c];
+    }
+#pragma unroll
+    for (int r = 0; r < TM; ++r)
+#pragma unroll
+      for (int c = 0; c < TN; ++c) acc[r][c] = fma(av[r], bv[c], acc[r][c]);
+    A += lda;
+    Bm += ldb;
+  }
+}
+
+// 8-byte (or 4-byte for float) asynchronous global -> shared copy (LDGSTS); plain copy under emulation.
+template <typename R>
+DONK_D void cp_async(R* dst, const R* src) {
+#if defined(__CUDA_ARCH__)
+  const unsigned s = (unsigned)__cvta_generic_to_shared(dst);
+  if (sizeof(R) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(src) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(src) : "memory");
+#else
+  *dst = *src;
+#endif
+}
+DONK_D void cp_async_wait_all() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+#endif
 }
 
 // Upper-triangular tile enumeration: idx in [0, nt(nt+1)/2) -> (ti <= tj).

@@ -11,6 +11,7 @@
 #include "fitlr.cuh"
 #include "gmm.cuh"
 #include "ilqr.cuh"
+#include "ilqr_warp.cuh"
 
 using namespace donk;
 
@@ -108,6 +109,30 @@ __global__ void __launch_bounds__(512, 1) ilqr_team_kernel_big(const IlqrArgs<R>
   ilqr_team_body<R>(a, L, G, team_bytes, n_teams);
 }
 
+// Warp-per-problem fast path with compile-time dimensions (ilqr_warp.cuh).
+template <typename R, int DX, int DU>
+__global__ void __launch_bounds__(512, 1) ilqr_warp_kernel(const IlqrArgs<R> a, int ES) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WCtx w{(int)threadIdx.x, (int)blockDim.x, (int)threadIdx.x >> 5, (int)threadIdx.x & 31, (int)blockDim.x >> 5};
+  ilqr_warp_cta<R, DX, DU>(w, a, (int)blockIdx.x, ES, reinterpret_cast<R*>(smem_raw));
+}
+
+template <typename R, int DX, int DU>
+int ilqr_warp_launch(const IlqrArgs<R>& a, void* stream) {
+  int G, ES, grid;
+  size_t bytes;
+  int rc = ilqr_warp_plan<R, DX, DU>(a.B, a.E, smem_optin_cap(), env_int("DONK_ILQR_WARPS"), G, ES, grid, bytes);
+  if (rc != DONK_OK) return rc;
+  rc = allow_smem(ilqr_warp_kernel<R, DX, DU>, bytes);
+  if (rc != DONK_OK) return rc;
+  ilqr_warp_kernel<R, DX, DU><<<grid, 32 * G, bytes, (cudaStream_t)stream>>>(a, ES);
+  LAUNCHED("ilqr_warp_kernel");
+  return DONK_OK;
+}
+
+// (dX, dU) pairs with a warp-kernel instantiation: the BASELINE.json configurations that fit one warp.
+#define DONK_WARP_DIMS(X) X(20, 6) X(14, 7) X(6, 2)
+
 template <typename R>
 int ilqr_step_launch(IlqrArgs<R> a, void* stream) {
   if (a.B < 0 || a.E < 1 || a.T < 1 || a.dX < 1 || a.dU < 1) return DONK_BAD_SHAPE;
@@ -116,7 +141,13 @@ int ilqr_step_launch(IlqrArgs<R> a, void* stream) {
   if (a.B == 0) return DONK_OK;
   IlqrPlan pl;
   int rc;
-  if (!env_int("DONK_ILQR_CTA_MODE")) {
+  if (!env_int("DONK_ILQR_GENERIC")) {
+#define DONK_TRY_WARP(DXV, DUV) \
+  if (a.dX == DXV && a.dU == DUV) return ilqr_warp_launch<R, DXV, DUV>(a, stream);
+    DONK_WARP_DIMS(DONK_TRY_WARP)
+#undef DONK_TRY_WARP
+  }
+  if (env_int("DONK_ILQR_TEAM_MODE")) {
     rc = ilqr_plan_team(a.B, a.E, a.dX, a.dU, sizeof(R), smem_optin_cap(), env_int("DONK_ILQR_LANES"),
                         env_int("DONK_ILQR_TEAMS"), pl);
     if (rc == DONK_OK) {

@@ -13,6 +13,7 @@
 #include "../../donk_b200/csrc/fitlr.cuh"
 #include "../../donk_b200/csrc/gmm.cuh"
 #include "../../donk_b200/csrc/ilqr.cuh"
+#include "../../donk_b200/csrc/ilqr_warp.cuh"
 
 namespace donk {
 int g_emu_reverse = 0;
@@ -24,6 +25,21 @@ static const size_t kSmemCap = 227 * 1024;
 static int env_int(const char* name) {
   const char* v = getenv(name);
   return v ? atoi(v) : 0;
+}
+
+template <int DX, int DU>
+static int emu_ilqr_warp(const IlqrArgs<double>& a) {
+  int G, ES, grid;
+  size_t bytes;
+  int rc = ilqr_warp_plan<double, DX, DU>(a.B, a.E, kSmemCap, env_int("DONK_ILQR_WARPS"), G, ES, grid, bytes);
+  if (rc != DONK_OK) return rc;
+  std::vector<double> smem(bytes / sizeof(double) + 2);
+  WCtx w{0, 1, 0, 0, G};
+  for (int cta = 0; cta < grid; ++cta) {
+    memset(smem.data(), 0xFF, smem.size() * sizeof(double));
+    ilqr_warp_cta<double, DX, DU>(w, a, cta, ES, smem.data());
+  }
+  return DONK_OK;
 }
 
 extern "C" {
@@ -51,7 +67,12 @@ int donk_emu_ilqr_step_f64(int B, int E, int T, int dX, int dU, int flags, const
   if (B == 0) return DONK_OK;
   IlqrPlan pl;
   int rc;
-  if (!env_int("DONK_ILQR_CTA_MODE")) {  // team launch: one slot per team, "cta" index = problem index
+  if (!env_int("DONK_ILQR_GENERIC")) {
+    if (dX == 20 && dU == 6) return emu_ilqr_warp<20, 6>(a);
+    if (dX == 14 && dU == 7) return emu_ilqr_warp<14, 7>(a);
+    if (dX == 6 && dU == 2) return emu_ilqr_warp<6, 2>(a);
+  }
+  if (env_int("DONK_ILQR_TEAM_MODE")) {  // team launch: one slot per team, "cta" index = problem index
     rc = ilqr_plan_team(B, E, dX, dU, sizeof(double), kSmemCap, 0, 0, pl);
     if (rc != DONK_OK) return rc;
     pl.smem = IlqrLayout(dX, dU).bytes(1, 1, sizeof(double));

@@ -128,3 +128,46 @@ def test_multi_condition_packing_and_active_mask(backend):
         if b not in (3, 7):
             assert relerr(r.K[b, 0], ref.K) < TOL
             assert abs(float(r.expected_costs[b, 0]) - ref.expected_costs) < 1e-9 * abs(ref.expected_costs)
+
+
+@pytest.mark.parametrize("dims,reverse", [((20, 6), 0), ((20, 6), 1), ((6, 2), 0), ((14, 7), 1)])
+def test_warp_kernel_dims_vs_oracle(backend, dims, reverse):
+    """The compile-time-dimension warp kernel (ilqr_warp.cuh): several eta per condition, several conditions,
+    a masked condition, and E=1 packing (several conditions per CTA)."""
+    from donk_b200 import synthetic
+    from donk_b200.batched import BatchedILQR
+
+    set_reverse(backend, reverse)
+    dX, dU = dims
+    T, N, B = 7, dX + dU + 6, 5
+    conds = [synthetic.condition(12, i, T, dX, dU, N) for i in range(B)]
+    fits = [oracle.fit_lr(c.X, c.U) for c in conds]
+    x0 = [oracle.state_fit(c.X[:, 0]) for c in conds]
+    st = lambda xs: np.stack(xs)  # noqa: E731
+    il = BatchedILQR(st([f[0] for f in fits]), st([f[1] for f in fits]), st([f[2] for f in fits]),
+                     st([c.prev_K for c in conds]), st([c.prev_k for c in conds]), st([c.C for c in conds]),
+                     st([c.c for c in conds]), st([c.cc for c in conds]), st([m for m, _ in x0]),
+                     st([S for _, S in x0]), prev_covar=st([c.prev_covar for c in conds]))
+    etas = np.array([1e-3, 0.3, 2.0, 50.0, 1e5])
+    r = il.step(torch.as_tensor(etas).expand(B, len(etas)), want_traj=True)
+    assert int(r.info.sum()) == 0
+    probs = []
+    for b, c in enumerate(conds):
+        probs.append(ILQRProblem(*fits[b], c.C, c.c, c.cc, c.prev_K, c.prev_k, c.prev_covar,
+                                 np.linalg.inv(c.prev_covar), *x0[b]))
+    for b in (0, B - 1):
+        for e, eta in enumerate(etas):
+            ref = oracle.ilqr_step(probs[b], float(eta))
+            assert relerr(r.K[b, e], ref.K) < TOL and relerr(r.k[b, e], ref.k) < TOL
+            assert relerr(r.covar[b, e], ref.covar) < TOL and relerr(r.inv_covar[b, e], ref.inv_covar) < TOL
+            assert relerr(r.traj_mean[b, e], ref.mean) < TOL and relerr(r.traj_covar[b, e], ref.traj_covar) < TOL
+            assert abs(float(r.kl_div[b, e]) - ref.kl_div) < 1e-9 * max(1.0, abs(ref.kl_div))
+            assert abs(float(r.expected_costs[b, e]) - ref.expected_costs) < 1e-9 * abs(ref.expected_costs)
+    # E = 1: conditions packed per CTA, one masked out
+    active = torch.ones(B, dtype=torch.int32)
+    active[2] = 0
+    r1 = il.step(torch.as_tensor(etas), active=active.to(backend.device))
+    for b in (0, 1, 3, 4):
+        ref = oracle.ilqr_step(probs[b], float(etas[b]))
+        assert relerr(r1.K[b, 0], ref.K) < TOL
+        assert abs(float(r1.kl_div[b, 0]) - ref.kl_div) < 1e-9 * max(1.0, abs(ref.kl_div))
