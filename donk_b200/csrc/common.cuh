@@ -180,6 +180,86 @@ DONK_HD void tile_km(const R* __restrict__ A, int lda, const R* __restrict__ Bm,
   }
 }
 
+// Warp-collective block product on the FP64 tensor path (mma.sync.m8n8k4.f64, "DMMA"):
+//   C[i][j] = sum_{k < 4*K4} A[k*lda + i] * Bm[k*ldb + j],   i < 8*RA, j < 8*RB   (both operands k-major)
+// A and Bm point at the block origin.  Every lane ends up with two adjacent columns of one row per 8x8
+// fragment and hands them to epi(i, j, v0, v1) (j even; values of columns j and j+1).  One LDS.64 per
+// fragment and k4-step feeds 8 DFMA-equivalents per lane, which is what makes the step kernel FP64-bound
+// instead of shared-memory-bound (profiles/r01/README.md).  Leading dimensions with lda % 16 in {4, 12}
+// make the fragment loads bank-conflict free.  Rows/columns beyond the valid range may be over-read
+// (their outputs are discarded by the epilogue); the k range must be zero-padded in one operand and
+// finite in the other.  float has no such instruction: each lane computes its two outputs with FFMA.
+template <typename R, int RA, int RB, class Epi>
+DONK_D void warp_mma(const WCtx& w, const R* __restrict__ A, int lda, const R* __restrict__ Bm, int ldb, int K4,
+                     Epi&& epi) {
+#if defined(__CUDA_ARCH__)
+  const int g = w.lane >> 2, tq = w.lane & 3;
+  R c[RA][RB][2];
+#pragma unroll
+  for (int ra = 0; ra < RA; ++ra)
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb) { c[ra][rb][0] = R(0); c[ra][rb][1] = R(0); }
+  if (sizeof(R) == 8) {
+    const R* ap = A + tq * lda + g;
+    const R* bp = Bm + tq * ldb + g;
+#pragma unroll 2
+    for (int k4 = 0; k4 < K4; ++k4) {
+      R af[RA], bf[RB];
+#pragma unroll
+      for (int ra = 0; ra < RA; ++ra) af[ra] = ap[8 * ra];
+#pragma unroll
+      for (int rb = 0; rb < RB; ++rb) bf[rb] = bp[8 * rb];
+#pragma unroll
+      for (int ra = 0; ra < RA; ++ra)
+#pragma unroll
+        for (int rb = 0; rb < RB; ++rb) {
+          double d0 = (double)c[ra][rb][0], d1 = (double)c[ra][rb][1];
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(d0), "+d"(d1)
+                       : "d"((double)af[ra]), "d"((double)bf[rb]));
+          c[ra][rb][0] = (R)d0;
+          c[ra][rb][1] = (R)d1;
+        }
+      ap += 4 * lda;
+      bp += 4 * ldb;
+    }
+  } else {
+    for (int k = 0; k < 4 * K4; ++k) {
+#pragma unroll
+      for (int ra = 0; ra < RA; ++ra) {
+        const R av = A[k * lda + 8 * ra + g];
+#pragma unroll
+        for (int rb = 0; rb < RB; ++rb) {
+          c[ra][rb][0] = fma(av, Bm[k * ldb + 8 * rb + 2 * tq], c[ra][rb][0]);
+          c[ra][rb][1] = fma(av, Bm[k * ldb + 8 * rb + 2 * tq + 1], c[ra][rb][1]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int ra = 0; ra < RA; ++ra)
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb) epi(8 * ra + g, 8 * rb + 2 * tq, c[ra][rb][0], c[ra][rb][1]);
+#else
+  (void)w;
+  for (int i = 0; i < 8 * RA; ++i)
+    for (int j = 0; j < 8 * RB; j += 2) {
+      R v0 = R(0), v1 = R(0);
+      for (int k = 0; k < 4 * K4; ++k) {
+        v0 = fma(A[k * lda + i], Bm[k * ldb + j], v0);
+        v1 = fma(A[k * lda + i], Bm[k * ldb + j + 1], v1);
+      }
+      epi(i, j, v0, v1);
+    }
+#endif
+}
+
+// smallest leading dimension >= n that is a multiple of 4 and makes DMMA fragment loads conflict free
+constexpr int ld_pad(int n) {
+  int m = (n + 3) / 4 * 4;
+  return m % 8 == 0 ? m + 4 : m;
+}
+
 // 8-byte (or 4-byte for float) asynchronous global -> shared copy (LDGSTS); plain copy under emulation.
 template <typename R>
 DONK_D void cp_async(R* dst, const R* src) {

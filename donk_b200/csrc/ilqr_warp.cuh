@@ -1,20 +1,27 @@
-// donk_b200 — iLQR step, warp-per-problem variant with compile-time state/action dimensions.
+// donk_b200 — iLQR step, warp-per-problem variant with compile-time state/action dimensions (fast path).
 //
 // Same math and reference lines as ilqr.cuh (ILQR.step, donk/traj_opt/lqg.py:55-75; backward :126-182;
-// forward :185-244; kl_divergence_action :276-306; expected_costs quadratic_costs.py:106-119); this is the
-// fast path for small/medium dimensions (a problem fits one warp), selected by the launcher when an
-// instantiation for (dX, dU) exists.  What changed against the generic kernel, and why (ncu, profiles/r01):
-// only 14 % of the generic kernel's instructions were tile DFMAs, the rest runtime index arithmetic,
-// scalar dot-product loops and global loads inside the phases.  Here
-//   * a CTA is G warps = the eta candidates of one condition (or G conditions when E = 1); each warp owns one
-//     (condition, eta) problem and synchronises with __syncwarp only;
-//   * dimensions are template parameters: tiles are lane-static, all offsets are immediates, no div/mod;
-//   * the vectors ride in the padding column P of the matrices: F_ext = [F | f], M[:,P] = q / v / mu, so
-//     w = V f + v, q = c + F^T w, mu_u = K mu_x + k and F mu come out of the matrix tiles for free;
-//   * the per-condition inputs of step t (F_t, f_t, C_t, C_kl_t, ... ) are staged once per CTA with cp.async,
-//     overlapped with the phases that do not read them (Cholesky / gains / value update);
-//   * Quu (dU x dU) is factored redundantly in every lane's registers (no shared-memory round trips, no
-//     syncs); divisions are replaced by rsqrt / reciprocal multiplies, C/eta by C * (1/eta) (<= 1 ulp).
+// forward :185-244; kl_divergence_action :276-306; expected_costs quadratic_costs.py:106-119); selected by
+// the launcher when an instantiation for (dX, dU) exists.  How it got here (ncu evidence, profiles/r01):
+//   v1 generic CTA kernel: 14 % of the instructions were tile DFMAs, the rest runtime index arithmetic,
+//      scalar loops, global loads inside phases                                  ->  7 % of FP64 peak
+//   v3 warp per problem, compile-time dims, DFMA register tiles: shared-memory wavefronts at 78 % of peak;
+//      a warp-wide LDS.64 costs 2 wavefronts whether or not lanes share addresses, so only >= 8x8
+//      register tiles would be FP64-bound                                        -> 18 %
+//   v4 (this file): the six products of a step run on the FP64 tensor path (mma.sync.m8n8k4.f64, same
+//      37 TFLOP/s as DFMA on B200): one LDS.64 per fragment feeds 8 DFMA-equivalents per lane.
+// Structure:
+//   * a CTA is G warps = the eta candidates of one condition (or G conditions when E = 1); each warp owns
+//     one (condition, eta) problem in its own shared-memory area and synchronises with __syncwarp only;
+//   * dimensions are template parameters; every buffer has a leading dimension with ld % 16 in {4, 12}
+//     (conflict-free fragment loads), K ranges are zero-padded to multiples of 4;
+//   * vectors ride in column P of the matrices: F_ext = [F | f], M[:,P] = q / v / mu, K_ext = [K | k], so
+//     w = V f + v, q = c + F^T w, v = q_x + Qxu k, mu_u = K mu_x + k, F mu and K_prev mu_x come out of the
+//     matrix products for free;
+//   * per-condition inputs of step t are staged once per CTA with cp.async (backward: overlapped with the
+//     factorisation / gains / value update, which only touch team-private data);
+//   * Quu (dU x dU) is factored redundantly in every lane's registers (no shared-memory round trips);
+//     divisions become rsqrt / reciprocal multiplies, C/eta becomes C * (1/eta) (<= 1 ulp).
 #pragma once
 #include "common.cuh"
 #include "ilqr.cuh"
@@ -23,60 +30,40 @@ namespace donk {
 
 template <int DX, int DU>
 struct WarpDims {
+  static_assert(DU <= 8 && DX + 1 <= 32, "warp kernel: dU <= 8, dX <= 31");
   static constexpr int P = DX + DU, PE = P + 1;
-  static constexpr int PP = (PE + 3) / 4 * 4;    // leading dimension of M, W, F_ext (even, 16-byte rows)
-  static constexpr int DXP = (DX + 3) / 4 * 4;   // leading dimension of Rt, F^T
-  static constexpr int DUP = (DU + 3) / 4 * 4;
-  static constexpr int KLD = (DX + 1 + 3) / 4 * 4;  // Kb rows: [K_a | k_a | 0]
-  // B1: W_ext (DX x PP) in TM1 x 4 tiles, one per lane if possible
-  static constexpr int NTJ1 = PP / 4;
-  static constexpr int CAP1 = 32 / NTJ1 > 0 ? 32 / NTJ1 : 1;
-  static constexpr int TM1 = (DX + CAP1 - 1) / CAP1;
-  static constexpr int NTI1 = (DX + TM1 - 1) / TM1;
-  // B2: Q_ext upper triangle in 4 x 4 tiles
-  static constexpr int NTP = PP / 4, NTRI2 = NTP * (NTP + 1) / 2;
-  // F3: Rt_ext (PE x DX) in 4 x TN3 tiles
-  static constexpr int TN3 = TM1, NTI3 = NTI1;
-  // B5 / F4: DX x DX upper triangle in 2 x 4 tiles
-  static constexpr int NR5 = (DX + 1) / 2, NC5 = DXP / 4;
+  static constexpr int DX4 = (DX + 3) / 4 * 4, P4 = (P + 3) / 4 * 4, DU4 = (DU + 3) / 4 * 4;
+  static constexpr int PP = ld_pad(PE);       // leading dimension of M, W_ext, F_ext
+  static constexpr int DXP = ld_pad(DX);      // leading dimension of Rt_ext, F^T
+  static constexpr int KLD = ld_pad(DX + 1);  // backward: Kb[a][j] = [K | k]
+  static constexpr int KTL = ld_pad(DU);      // forward: Kt[k][a] = K^T, and K_prev^T in the stage area
+  static constexpr int NBP = (PE + 7) / 8;    // 8-column blocks covering columns 0..P
+  static constexpr int NBX = (DX + 7) / 8;    // ... covering the state block
+  static constexpr int NBX1 = (DX + 8) / 8;   // ... covering columns 0..DX (state block + the k column)
+  static constexpr int BP = P / 8;            // the block that holds column P
   // team area (reals)
-  static constexpr int RSZ = DX * PP > PE * DXP ? DX * PP : PE * DXP;
-  static constexpr int KSZ = DU * KLD > DX * DUP ? DU * KLD : DX * DUP;
-  static constexpr int oM = 0, oR = oM + PE * PP, oK = oR + (RSZ + 3) / 4 * 4, oKv = oK + (KSZ + 3) / 4 * 4;
-  static constexpr int oPc = oKv + DUP, oLds = oPc + (DU * DU + 3) / 4 * 4, oDel = oLds + DUP, oRow = oDel + DUP;
-  static constexpr int oScal = oRow + PP, TEAM = oScal + 8;  // scal: 0 inv_eta 1 kl 2 cost 3 logdet 4 notpd 5 eta
+  static constexpr int MSZ = P * PP;
+  static constexpr int RSZ = (DX4 * PP > P4 * DXP ? DX4 * PP : P4 * DXP) + 8;
+  static constexpr int KSZ = (DU4 * KLD > DX4 * KTL ? DU4 * KLD : DX4 * KTL) + 8;
+  static constexpr int oM = 0, oR = oM + MSZ, oK = oR + RSZ, oKv = oK + KSZ;
+  static constexpr int oPc = oKv + 8, oLds = oPc + (DU * DU + 3) / 4 * 4, oDel = oLds + 8, oRow = oDel + 8;
+  static constexpr int oScal = oRow + 32, TEAM = oScal + 8;  // scal: 0 1/eta 1 kl 2 cost 3 logdet 4 notpd
   // stage area per condition (reals): backward and forward views share the storage
-  static constexpr int oFx = 0;                                   // bwd: F_ext (DX x PP); fwd: F^T (P x DXP)
-  static constexpr int FXS = DX * PP > P * DXP ? DX * PP : P * DXP;
-  static constexpr int oCs = oFx + (FXS + 3) / 4 * 4;             // C_t (P*P)
-  static constexpr int oCk = oCs + (P * P + 3) / 4 * 4;           // bwd: C_kl_t (P*P); fwd: dyn_covar_t (DX*DX) | prevK | prevLam
-  static constexpr int CKS = P * P > DX * DX + DU * DX + DU * DU ? P * P : DX * DX + DU * DX + DU * DU;
-  static constexpr int oVec = oCk + (CKS + 3) / 4 * 4;            // cs (P) | ck (P) / fwd: cs (P) | fv (DX) | pk (DU) | cc, phld
-  static constexpr int STAGE = oVec + 2 * PP + DXP + DUP + 4;
+  static constexpr int oFx = 0;  // bwd: F_ext (DX4 x PP); fwd: F^T (P4 x DXP)
+  static constexpr int FXS = (DX4 * PP > P4 * DXP ? DX4 * PP : P4 * DXP) + 8;
+  static constexpr int oCs = oFx + FXS;                    // C_t (P*P)
+  static constexpr int oCk = oCs + (P * P + 3) / 4 * 4;    // bwd: C_kl_t; fwd: dyn_covar_t | K_prev^T (DX4 x KTL) | Lam_prev
+  static constexpr int FWD2 = DX * DX + DX4 * KTL + 8 + DU * DU;
+  static constexpr int CKS = (P * P > FWD2 ? P * P : FWD2);
+  static constexpr int oVec = oCk + (CKS + 3) / 4 * 4;     // cs (PP) | ck (PP) / fwd: cs (PP) | fv (DXP) | pk (8) | cc, phld
+  static constexpr int STAGE = oVec + 2 * PP + DXP + 8 + 4;
 };
-
-template <int TM, int NR, int NC>
-DONK_HD bool tri2_tile(int idx, int& ti, int& tj) {
-  // enumerate (ti, tj) tiles of TM x 4 blocks that touch the upper triangle (4 tj + 3 >= TM ti)
-  for (int r = 0; r < NR; ++r) {
-    const int first = (TM * r) / 4;  // first column tile with 4 tj + 3 >= TM r
-    const int cnt = NC - first;
-    if (idx < cnt) { ti = r; tj = first + idx; return true; }
-    idx -= cnt;
-  }
-  return false;
-}
-template <int TM, int NR, int NC>
-DONK_HD constexpr int tri2_count() {
-  int n = 0;
-  for (int r = 0; r < NR; ++r) n += NC - (TM * r) / 4;
-  return n;
-}
 
 template <typename R, int DX, int DU>
 DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, R* smem) {
   using D = WarpDims<DX, DU>;
-  constexpr int P = D::P, PE = D::PE, PP = D::PP, DXP = D::DXP, DUP = D::DUP, KLD = D::KLD;
+  constexpr int P = D::P, PE = D::PE, PP = D::PP, DXP = D::DXP, KLD = D::KLD, KTL = D::KTL;
+  constexpr int DX4 = D::DX4, P4 = D::P4, DU4 = D::DU4;
   const int G = w.G, T = a.T, E = a.E;
   const int NC = G / ES, n_ech = (E + ES - 1) / ES;
   const int cg = cta / n_ech, ec = cta % n_ech;
@@ -85,7 +72,6 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
   const R gamma = a.gamma;
   constexpr size_t szF = (size_t)DX * P, szC = (size_t)P * P, szK = (size_t)DU * DX, szS = (size_t)DU * DU;
 
-  // team -> problem (uniform arithmetic, no shared state needed)
   auto team_b = [&](int tm) { return cg * NC + tm / ES; };
   auto team_e = [&](int tm) { return ec * ES + tm % ES; };
   auto team_valid = [&](int tm) {
@@ -105,41 +91,38 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
 #define STAGEP(tm) (stages + (size_t)((tm) / ES) * D::STAGE)
 #define PIDX(tm) ((size_t)team_b(tm) * E + team_e(tm))
 
+  // zero everything once: K paddings must be exact zeros, over-read rows/columns must be finite
+  CTA_FOR(idx, G * D::TEAM + NC * D::STAGE) smem[idx] = R(0);
+  w.cta_sync();
   TEAMS_DO(tm) {
     if (!team_valid(tm)) continue;
     R* tp = TEAMP(tm);
-    LANE_FOR(i, 8) {
-      const R eta = a.eta ? a.eta[PIDX(tm)] : R(1);
-      tp[D::oScal + i] = i == 0 ? R(1) / eta : (i == 5 ? eta : R(0));
-    }
+    LANE_FOR(one, 1) tp[D::oScal + 0] = a.eta ? R(1) / a.eta[PIDX(tm)] : R(1);
   }
 
   // =========================================================================================
   // Backward pass
   // =========================================================================================
   if (a.flags & ILQR_BACKWARD) {
-    // ---- async staging of step t: F_ext = [F_t | f_t | 0], C_t, C_kl_t, c_t, c_kl_t ------------------
+    // async staging of step t: F_ext = [F_t | f_t | 0] (rows DX..DX4-1 stay zero), C_t, C_kl_t, c_t, c_kl_t
     auto stage_bwd = [&](int t) {
       for (int ci = 0; ci < NC; ++ci) {
         const int b = cond_b(ci);
         if (b < 0) continue;
         R* st = stages + (size_t)ci * D::STAGE;
         const size_t bt = (size_t)b * T + t, bt1 = (size_t)b * (T + 1) + t;
-        CTA_FOR(idx, DX * PP) {
-          const int k = idx / PP, j = idx % PP;  // compile-time divisors
-          if (j < P) cp_async(st + D::oFx + idx, a.F + bt * szF + (size_t)k * P + j);
-          else if (j == P) cp_async(st + D::oFx + idx, a.f + bt * DX + k);
-          else st[D::oFx + idx] = R(0);
+        CTA_FOR(idx, DX * PE) {
+          const int k = idx / PE, j = idx % PE;  // compile-time divisors
+          if (j < P) cp_async(st + D::oFx + k * PP + j, a.F + bt * szF + (size_t)k * P + j);
+          else cp_async(st + D::oFx + k * PP + P, a.f + bt * DX + k);
         }
         CTA_FOR(idx, P * P) {
           cp_async(st + D::oCs + idx, a.C + bt1 * szC + idx);
           if (a.C_kl) cp_async(st + D::oCk + idx, a.C_kl + bt * szC + idx);
-          else st[D::oCk + idx] = R(0);
         }
         CTA_FOR(i, P) {
           cp_async(st + D::oVec + i, a.c + bt1 * P + i);
           if (a.c_kl) cp_async(st + D::oVec + PP + i, a.c_kl + bt * P + i);
-          else st[D::oVec + PP + i] = R(0);
         }
       }
     };
@@ -164,59 +147,49 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
         if (!team_valid(tm)) continue;
         R* tp = TEAMP(tm);
         const R* st = STAGEP(tm);
-        // ---- B1: W_ext = V [F | f] (+ v in column P) ------------------------------------------------
-        LANE_FOR(it, D::NTI1 * D::NTJ1) {
-          const int ti = it / D::NTJ1, tj = it % D::NTJ1;
-          R acc[D::TM1][4];
-          tile_km<R, D::TM1, 4, D::TM1 == 4, true>(tp + D::oM + D::TM1 * ti, PP, st + D::oFx + 4 * tj, PP, DX, acc);
-#pragma unroll
-          for (int r = 0; r < D::TM1; ++r) {
-            const int i = D::TM1 * ti + r;
-            if (i < DX) {
-              if (4 * tj <= P && P < 4 * tj + 4) acc[r][P - 4 * tj] += tp[D::oM + i * PP + P];  // w = V f + v
-#pragma unroll
-              for (int c = 0; c < 4; ++c) tp[D::oR + i * PP + 4 * tj + c] = acc[r][c];
-            }
+        // ---- B1: W_ext = V [F | f] (+ v in column P) ----------------------------------------------------
+        warp_mma<R, D::NBX, D::NBP>(w, tp + D::oM, PP, st + D::oFx, PP, DX4 / 4, [&](int i, int j, R v0, R v1) {
+          if (i < DX && j < PP) {
+            if (j == P) v0 += tp[D::oM + i * PP + P];
+            if (j + 1 == P) v1 += tp[D::oM + i * PP + P];
+            tp[D::oR + i * PP + j] = v0;
+            tp[D::oR + i * PP + j + 1] = v1;
           }
-        }
+        });
         w.team_sync();
-        // ---- B2: Q_ext = C_ext + gamma [F|f]^T W_ext, upper tiles, mirrored; column P is q ---------------
+        // ---- B2: Q_ext = C_ext + gamma [F|f]^T W_ext, upper blocks, mirrored; column P is q ---------------
         {
           const R ie = tp[D::oScal + 0];
-          LANE_FOR(it, D::NTRI2) {
-            int ti, tj;
-            tri_tile(it, D::NTP, ti, tj);
-            R acc[4][4];
-            tile_km<R, 4, 4, true, true>(st + D::oFx + 4 * ti, PP, tp + D::oR + 4 * tj, PP, DX, acc);
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const int i = 4 * ti + r, j = 4 * tj + c;
-                if (i <= j && i < P) {
-                  if (j < P) {
-                    const R val = fma(st[D::oCs + i * P + j], ie, st[D::oCk + i * P + j]) + gamma * acc[r][c];
-                    tp[D::oM + i * PP + j] = val;
-                    tp[D::oM + j * PP + i] = val;
-                  } else if (j == P) {
-                    tp[D::oM + i * PP + P] = fma(st[D::oVec + i], ie, st[D::oVec + PP + i]) + gamma * acc[r][c];
-                  }
-                }
+          auto epi = [&](int i, int jj, R acc) {
+            if (i < P && i <= jj) {
+              if (jj < P) {
+                const R val = fma(st[D::oCs + i * P + jj], ie, st[D::oCk + i * P + jj]) + gamma * acc;
+                tp[D::oM + i * PP + jj] = val;
+                tp[D::oM + jj * PP + i] = val;
+              } else if (jj == P) {
+                tp[D::oM + i * PP + P] = fma(st[D::oVec + i], ie, st[D::oVec + PP + i]) + gamma * acc;
               }
             }
-          }
+          };
+#define DONK_B2_ROW(RB_ROW)                                                                                      \
+  if (RB_ROW < D::NBP)                                                                                           \
+    warp_mma<R, 1, (D::NBP - RB_ROW > 0 ? D::NBP - RB_ROW : 1)>(                                                  \
+        w, st + D::oFx + 8 * RB_ROW, PP, tp + D::oR + 8 * RB_ROW, PP, DX4 / 4,                                    \
+        [&](int i, int j, R v0, R v1) { epi(8 * RB_ROW + i, 8 * RB_ROW + j, v0); epi(8 * RB_ROW + i, 8 * RB_ROW + j + 1, v1); });
+          DONK_B2_ROW(0) DONK_B2_ROW(1) DONK_B2_ROW(2) DONK_B2_ROW(3) DONK_B2_ROW(4)
+#undef DONK_B2_ROW
         }
         w.team_sync();
       }
-      // all teams are done with the staged inputs of step t: start fetching step t-1 while the
-      // factorisation, gains and value update (which only touch team-private data) run
+      // all teams are done with the staged inputs of step t: fetch step t-1 while the factorisation, gains and
+      // value update (team-private data only) run
       w.cta_sync();
       if (t > 0) stage_bwd(t - 1);
       TEAMS_DO(tm) {
         if (!team_valid(tm)) continue;
         R* tp = TEAMP(tm);
         const size_t pt = PIDX(tm) * T + t;
-        // ---- B34: Quu = L L^T in registers (every lane, redundantly); K = -Quu^-1 Qux; k = -Quu^-1 q_u ----
+        // ---- B34: Quu = L L^T in registers (every lane, redundantly); [K | k] = -Quu^-1 [Qux | q_u] --------
         LANE_FOR(ln, 32) {
           R Lm[DU][DU];  // lower triangle used
 #pragma unroll
@@ -232,8 +205,8 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
             for (int k = 0; k < j; ++k) sj = fma(-Lm[j][k], Lm[j][k], sj);
             bad = bad || !(sj > R(0));
             const R rs = rsqrt_r(sj);
-            idg[j] = rs;           // 1 / L_jj
-            Lm[j][j] = sj * rs;    // L_jj
+            idg[j] = rs;         // 1 / L_jj
+            Lm[j][j] = sj * rs;  // L_jj
 #pragma unroll
             for (int i = j + 1; i < DU; ++i) {
               R si = Lm[i][j];
@@ -249,9 +222,8 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
             tp[D::oLds + ln] = log(dsel);
           }
           if (ln == 31 && bad && tp[D::oScal + 4] == R(0)) tp[D::oScal + 4] = R(t + 1);
-          // in-place inverse of the lower factor: Li = L^-1
 #pragma unroll
-          for (int c = 0; c < DU; ++c) {
+          for (int c = 0; c < DU; ++c) {  // in-place inverse of the lower factor: Li = L^-1
             Lm[c][c] = idg[c];
 #pragma unroll
             for (int i = c + 1; i < DU; ++i) {
@@ -261,8 +233,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
               Lm[i][c] = -acc * idg[i];
             }
           }
-          // pol_covar = Quu^-1 = Li^T Li (symmetric by construction, lqg.py:165-166); lane e stores entry e
-          {
+          {  // pol_covar = Quu^-1 = Li^T Li (symmetric by construction, lqg.py:165-166); lane e stores entry e
             int e = 0;
 #pragma unroll
             for (int i = 0; i < DU; ++i)
@@ -280,21 +251,20 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
                 }
               }
           }
-          // column ln of K (ln < DX), or k (ln == DX): z = -Li^T (Li x), x = Qux[:, ln] / q_u
-          if (ln <= DX) {
+          if (ln <= DX) {  // column ln of K (ln < DX) or k (ln == DX): z = -Li^T (Li x), x = Qux[:, ln] / q_u
             const int col = ln < DX ? ln : P;
             R x[DU];
 #pragma unroll
             for (int b2 = 0; b2 < DU; ++b2) x[b2] = tp[D::oM + (DX + b2) * PP + col];
 #pragma unroll
-            for (int i = DU - 1; i >= 0; --i) {  // y = Li x (in place, bottom up)
+            for (int i = DU - 1; i >= 0; --i) {
               R acc = R(0);
 #pragma unroll
               for (int k = 0; k <= i; ++k) acc = fma(Lm[i][k], x[k], acc);
               x[i] = acc;
             }
 #pragma unroll
-            for (int i = 0; i < DU; ++i) {  // z = Li^T y (in place, top down)
+            for (int i = 0; i < DU; ++i) {
               R acc = R(0);
 #pragma unroll
               for (int k = i; k < DU; ++k) acc = fma(Lm[k][i], x[k], acc);
@@ -309,29 +279,28 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
           }
         }
         w.team_sync();
-        // ---- B5: V = Qxx + Qxu K (upper, mirrored); v = q_x + Qxu k (lqg.py:178-180) ---------------------
-        LANE_FOR(it, (tri2_count<2, D::NR5, D::NC5>())) {
-          int ti, tj;
-          tri2_tile<2, D::NR5, D::NC5>(it, ti, tj);
-          R acc[2][4];
-          tile_km<R, 2, 4, false, true>(tp + D::oM + DX * PP + 2 * ti, PP, tp + D::oK + 4 * tj, KLD, DU, acc);
-#pragma unroll
-          for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const int i = 2 * ti + r, j = 4 * tj + c;
-              if (i <= j && j < DX) {
-                const R val = tp[D::oM + i * PP + j] + acc[r][c];
-                tp[D::oM + i * PP + j] = val;
-                tp[D::oM + j * PP + i] = val;
+        // ---- B5: [V | v] = [Qxx | q_x] + Qxu [K | k] (upper blocks, mirrored) (lqg.py:178-180) ---------------
+        {
+          auto epi = [&](int i, int jj, R acc) {
+            if (i < DX) {
+              if (jj < DX) {
+                if (i <= jj) {
+                  const R val = tp[D::oM + i * PP + jj] + acc;
+                  tp[D::oM + i * PP + jj] = val;
+                  tp[D::oM + jj * PP + i] = val;
+                }
+              } else if (jj == DX) {
+                tp[D::oM + i * PP + P] += acc;
               }
             }
-        }
-        LANE_FOR(i, DX) {
-          R acc = tp[D::oM + i * PP + P];
-#pragma unroll
-          for (int a2 = 0; a2 < DU; ++a2) acc = fma(tp[D::oM + (DX + a2) * PP + i], tp[D::oK + a2 * KLD + DX], acc);
-          tp[D::oM + i * PP + P] = acc;
+          };
+#define DONK_B5_ROW(RB_ROW)                                                                                        \
+  if (RB_ROW < D::NBX)                                                                                             \
+    warp_mma<R, 1, (D::NBX1 - RB_ROW > 0 ? D::NBX1 - RB_ROW : 1)>(                                                  \
+        w, tp + D::oM + DX * PP + 8 * RB_ROW, PP, tp + D::oK + 8 * RB_ROW, KLD, DU4 / 4,                            \
+        [&](int i, int j, R v0, R v1) { epi(8 * RB_ROW + i, 8 * RB_ROW + j, v0); epi(8 * RB_ROW + i, 8 * RB_ROW + j + 1, v1); });
+          DONK_B5_ROW(0) DONK_B5_ROW(1) DONK_B5_ROW(2) DONK_B5_ROW(3)
+#undef DONK_B5_ROW
         }
         LANE_FOR(one, 1) {
           R ld = R(0);
@@ -352,15 +321,22 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
   if (a.flags & ILQR_FORWARD) {
     const R reg = a.fwd_reg;
     const bool do_kl = (a.flags & ILQR_KL) != 0, do_cost = (a.flags & ILQR_COST) != 0;
-    constexpr int oD = D::oCk, oPK = D::oCk + DX * DX, oPL = oPK + DU * DX;      // inside the stage area
-    constexpr int oCsV = D::oVec, oFv = D::oVec + PP, oPk = oFv + DXP, oCc = oPk + DUP;
+    constexpr int oD = D::oCk, oPK = D::oCk + DX * DX, oPL = oPK + DX4 * KTL + 8;  // inside the stage area
+    constexpr int oCsV = D::oVec, oFv = D::oVec + PP, oPk = oFv + DXP, oCc = oPk + 8;
+    // the stage and K areas change layout: clear the paddings the forward products rely on
+    CTA_FOR(idx, NC * D::STAGE) stages[idx] = R(0);
+    TEAMS_DO(tm) {
+      R* tp = TEAMP(tm);
+      LANE_FOR(idx, D::KSZ) tp[D::oK + idx] = R(0);
+    }
+    w.cta_sync();
     auto stage_fwd = [&](int t) {
       for (int ci = 0; ci < NC; ++ci) {
         const int b = cond_b(ci);
         if (b < 0) continue;
         R* st = stages + (size_t)ci * D::STAGE;
         const size_t bt = (size_t)b * T + t, bt1 = (size_t)b * (T + 1) + t;
-        CTA_FOR(idx, DX * P) {  // F^T: element (k, i) <- F[i][k]
+        CTA_FOR(idx, DX * P) {  // F^T: element (k, i) <- F[i][k]; rows P..P4-1 stay zero
           const int i = idx / P, k = idx % P;
           cp_async(st + D::oFx + k * DXP + i, a.F + bt * szF + idx);
         }
@@ -372,7 +348,10 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
           CTA_FOR(one, 1) cp_async(st + oCc, a.cc + bt1);
         }
         if (do_kl) {
-          CTA_FOR(idx, DU * DX) cp_async(st + oPK + idx, a.prevK + bt * szK + idx);
+          CTA_FOR(idx, DU * DX) {  // K_prev^T: element (k, a) <- K_prev[a][k]
+            const int a2 = idx / DX, k = idx % DX;
+            cp_async(st + oPK + k * KTL + a2, a.prevK + bt * szK + idx);
+          }
           CTA_FOR(idx, DU * DU) cp_async(st + oPL + idx, a.prevLam + bt * szS + idx);
           CTA_FOR(i, DU) cp_async(st + oPk + i, a.prevk + bt * DU + i);
           CTA_FOR(one, 1) cp_async(st + oCc + 1, a.prev_hld + bt);
@@ -384,7 +363,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
       const size_t pt = PIDX(tm) * T + t;
       LANE_FOR(idx, DU * DX) {
         const int a2 = idx / DX, k = idx % DX;
-        tp[D::oK + k * DUP + a2] = a.K[pt * szK + idx];
+        tp[D::oK + k * KTL + a2] = a.K[pt * szK + idx];
       }
       LANE_FOR(i, DU) tp[D::oKv + i] = a.k[pt * DU + i];
       LANE_FOR(idx, DU * DU) tp[D::oPc + idx] = a.pcov[pt * szS + idx];
@@ -394,6 +373,8 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
       if (!team_valid(tm)) continue;
       R* tp = TEAMP(tm);
       const int b = team_b(tm);
+      LANE_FOR(idx, D::MSZ) tp[D::oM + idx] = R(0);
+      w.team_sync();
       LANE_FOR(idx, DX * DX) tp[D::oM + (idx / DX) * PP + idx % DX] = ldg(a.x0S + (size_t)b * DX * DX + idx);
       LANE_FOR(i, DX) tp[D::oM + i * PP + P] = ldg(a.x0m + (size_t)b * DX + i);
       stage_policy(tm, 0);
@@ -406,77 +387,67 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
         if (!team_valid(tm)) continue;
         R* tp = TEAMP(tm);
         const R* st = STAGEP(tm);
-        // ---- F1: [Sigma_ux | mu_u] = K [Sigma_xx | mu_x] (+ k) (lqg.py:227-230) ----------------------------
-        {
-          constexpr int NA = (DU + 1) / 2;
-          constexpr int NJX = (DX + 3) / 4;             // column tiles covering the state block
-          constexpr int JP = P / 4;                     // the tile that holds column P (mu)
-          constexpr int NJ = NJX + (JP >= NJX ? 1 : 0);
-          LANE_FOR(it, NA * NJ) {
-            const int ta = it / NJ, q = it % NJ, tj = q < NJX ? q : JP;
-            R acc[2][4];
-            tile_km<R, 2, 4, false, true>(tp + D::oK + 2 * ta, DUP, tp + D::oM + 4 * tj, PP, DX, acc);
+        // ---- F1: [Sigma_ux | mu_u] = K [Sigma_xx | mu_x] (+ k); K_prev mu_x (lqg.py:227-230, 294) --------------
+        warp_mma<R, 1, D::NBP>(w, tp + D::oK, KTL, tp + D::oM, PP, DX4 / 4, [&](int a2, int j, R v0, R v1) {
+          if (a2 < DU) {
 #pragma unroll
-            for (int r = 0; r < 2; ++r)
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const int a2 = 2 * ta + r, j = 4 * tj + c;
-                if (a2 < DU) {
-                  if (j < DX) {
-                    tp[D::oM + (DX + a2) * PP + j] = acc[r][c];
-                    tp[D::oM + j * PP + DX + a2] = acc[r][c];
-                  } else if (j == P) {
-                    tp[D::oM + (DX + a2) * PP + P] = acc[r][c] + tp[D::oKv + a2];
-                  }
-                }
+            for (int h = 0; h < 2; ++h) {
+              const int jj = j + h;
+              const R acc = h ? v1 : v0;
+              if (jj < DX) {
+                tp[D::oM + (DX + a2) * PP + jj] = acc;
+                tp[D::oM + jj * PP + DX + a2] = acc;
+              } else if (jj == P) {
+                tp[D::oM + (DX + a2) * PP + P] = acc + tp[D::oKv + a2];
               }
-          }
-        }
-        w.team_sync();
-        // ---- F2: Sigma_uu = Sigma_ux K^T + pol_covar (lqg.py:231) --------------------------------------------
-        LANE_FOR(it, DU * (DU + 1) / 2) {
-          int ai = 0, rem = it;
-          while (rem > ai) { rem -= ai + 1; ++ai; }
-          const int bi = rem;  // bi <= ai
-          R acc = tp[D::oPc + ai * DU + bi];
-#pragma unroll 4
-          for (int k = 0; k < DX; ++k) acc = fma(tp[D::oM + k * PP + DX + ai], tp[D::oK + k * DUP + bi], acc);
-          tp[D::oM + (DX + ai) * PP + DX + bi] = acc;
-          tp[D::oM + (DX + bi) * PP + DX + ai] = acc;
-        }
-        w.team_sync();
-        // ---- F3: Rt_ext = ([F] [Sigma | mu])^T (PE x DX); cost rows; KL delta; optional outputs ----------------
-        LANE_FOR(it, D::NTP * D::NTI3) {
-          const int tj = it / D::NTI3, ti = it % D::NTI3;
-          R acc[4][D::TN3];
-          tile_km<R, 4, D::TN3, true, D::TN3 == 4>(tp + D::oM + 4 * tj, PP, st + D::oFx + D::TN3 * ti, DXP, P, acc);
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            const int j = 4 * tj + r;
-            if (j < PE) {
-#pragma unroll
-              for (int c = 0; c < D::TN3; ++c)
-                if (D::TN3 * ti + c < DX) tp[D::oR + j * DXP + D::TN3 * ti + c] = acc[r][c];
             }
           }
-        }
-        if (do_cost) {
-          LANE_FOR(i, P) {  // row i of 1/2 [mu^T C mu + tr(C (Sigma + reg I))] + mu^T c
-            const R mi = tp[D::oM + i * PP + P];
-            R acc = R(0);
-#pragma unroll 2
-            for (int j = 0; j < P; ++j)
-              acc = fma(st[D::oCs + i * P + j], fma(mi, tp[D::oM + j * PP + P], tp[D::oM + j * PP + i]), acc);
-            acc = fma(st[D::oCs + i * P + i], reg, acc);
-            tp[D::oRow + i] = acc * R(0.5) + mi * st[oCsV + i];
-          }
-        }
+        });
         if (do_kl) {
-          LANE_FOR(ai, DU) {  // delta_u = (K_prev - K) mu_x + k_prev - k (lqg.py:294)
-            R acc = st[oPk + ai] - tp[D::oKv + ai];
-#pragma unroll 4
-            for (int k = 0; k < DX; ++k) acc = fma(st[oPK + ai * DX + k] - tp[D::oK + k * DUP + ai], tp[D::oM + k * PP + P], acc);
-            tp[D::oDel + ai] = acc;
+          warp_mma<R, 1, 1>(w, st + oPK, KTL, tp + D::oM + 8 * D::BP, PP, DX4 / 4, [&](int a2, int j, R v0, R v1) {
+            if (a2 < DU) {
+              if (8 * D::BP + j == P) tp[D::oDel + a2] = v0 + st[oPk + a2];
+              if (8 * D::BP + j + 1 == P) tp[D::oDel + a2] = v1 + st[oPk + a2];
+            }
+          });
+        }
+        w.team_sync();
+        // ---- F2: Sigma_uu = Sigma_ux K^T + pol_covar (upper, mirrored) (lqg.py:231); delta_u ---------------------
+        warp_mma<R, 1, 1>(w, tp + D::oM + DX, PP, tp + D::oK, KTL, DX4 / 4, [&](int a2, int j, R v0, R v1) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int bb = j + h;
+            if (a2 <= bb && bb < DU) {
+              const R val = (h ? v1 : v0) + tp[D::oPc + a2 * DU + bb];
+              tp[D::oM + (DX + a2) * PP + DX + bb] = val;
+              tp[D::oM + (DX + bb) * PP + DX + a2] = val;
+            }
+          }
+        });
+        if (do_kl) {
+          LANE_FOR(a2, DU) tp[D::oDel + a2] -= tp[D::oM + (DX + a2) * PP + P];  // (K_prev mu_x + k_prev) - mu_u
+        }
+        w.team_sync();
+        // ---- F3: Rt_ext = ([F] [Sigma | mu])^T (PE x DX); cost partials; optional outputs --------------------------
+        warp_mma<R, D::NBP, D::NBX>(w, tp + D::oM, PP, st + D::oFx, DXP, P4 / 4, [&](int j, int i, R v0, R v1) {
+          if (j < PE) {
+            if (i < DX) tp[D::oR + j * DXP + i] = v0;
+            if (i + 1 < DX) tp[D::oR + j * DXP + i + 1] = v1;
+          }
+        });
+        if (do_cost) {
+          // 1/2 sum_ij C_ij (Sigma_ij + mu_i mu_j) + 1/2 reg tr C + mu^T c: upper triangle, weight 2 off the diagonal
+          LANE_FOR(ln, 32) {
+            R acc = R(0);
+            for (int i = ln; i < P; i += 32) {
+              const R mi = tp[D::oM + i * PP + P];
+              R row = R(0);
+              for (int j = i + 1; j < P; ++j)
+                row = fma(st[D::oCs + i * P + j], fma(mi, tp[D::oM + j * PP + P], tp[D::oM + i * PP + j]), row);
+              const R cii = st[D::oCs + i * P + i];
+              acc += row + R(0.5) * cii * fma(mi, mi, tp[D::oM + i * PP + i] + reg) + mi * st[oCsV + i];
+            }
+            tp[D::oRow + ln] = acc;
           }
         }
         if (a.tcov) {
@@ -489,49 +460,52 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
           LANE_FOR(i, P) a.tmean[(PIDX(tm) * (T + 1) + t) * P + i] = tp[D::oM + i * PP + P];
         }
         w.team_sync();
-        // ---- F4: Sigma'_xx = (F Sigma) F^T + dyn_covar (upper, mirrored); mu' = F mu + f; scalars ----------------
-        LANE_FOR(it, (tri2_count<2, D::NR5, D::NC5>())) {
-          int ti, tj;
-          tri2_tile<2, D::NR5, D::NC5>(it, ti, tj);
-          R acc[2][4];
-          tile_km<R, 2, 4, false, true>(tp + D::oR + 2 * ti, DXP, st + D::oFx + 4 * tj, DXP, P, acc);
-#pragma unroll
-          for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const int i = 2 * ti + r, j = 4 * tj + c;
-              if (i <= j && j < DX) {
-                const R val = acc[r][c] + st[oD + i * DX + j];
-                tp[D::oM + i * PP + j] = val;
-                tp[D::oM + j * PP + i] = val;
-              }
+        // ---- F4: Sigma'_xx = (F Sigma) F^T + dyn_covar (upper blocks, mirrored); mu' = F mu + f; scalars -------------
+        {
+          auto epi = [&](int i, int jj, R acc) {
+            if (i <= jj && jj < DX) {
+              const R val = acc + st[oD + i * DX + jj];
+              tp[D::oM + i * PP + jj] = val;
+              tp[D::oM + jj * PP + i] = val;
             }
+          };
+#define DONK_F4_ROW(RB_ROW)                                                                                        \
+  if (RB_ROW < D::NBX)                                                                                             \
+    warp_mma<R, 1, (D::NBX - RB_ROW > 0 ? D::NBX - RB_ROW : 1)>(                                                    \
+        w, tp + D::oR + 8 * RB_ROW, DXP, st + D::oFx + 8 * RB_ROW, DXP, P4 / 4,                                     \
+        [&](int i, int j, R v0, R v1) { epi(8 * RB_ROW + i, 8 * RB_ROW + j, v0); epi(8 * RB_ROW + i, 8 * RB_ROW + j + 1, v1); });
+          DONK_F4_ROW(0) DONK_F4_ROW(1) DONK_F4_ROW(2) DONK_F4_ROW(3)
+#undef DONK_F4_ROW
         }
         LANE_FOR(i, DX) tp[D::oM + i * PP + P] = tp[D::oR + P * DXP + i] + st[oFv + i];
-        LANE_FOR(one, 1) {
-          if (do_cost) {
-            R acc = R(0);
-#pragma unroll
-            for (int i = 0; i < P; ++i) acc += tp[D::oRow + i];
-            tp[D::oScal + 2] += acc + st[oCc];
-          }
-          if (do_kl) {
-            R tr = R(0), quad = R(0);
-#pragma unroll
-            for (int i = 0; i < DU; ++i) {
-              R row = R(0);
+        LANE_FOR(ln, DU + 1) {
+          if (ln < DU) {
+            if (do_kl) {  // row ln of  tr(Lam_prev Sigma_new) + delta^T Lam_prev delta  (lqg.py:295-304)
+              R tr = R(0), row = R(0);
 #pragma unroll
               for (int j = 0; j < DU; ++j) {
-                const R lij = st[oPL + i * DU + j];
-                tr = fma(lij, tp[D::oPc + j * DU + i], tr);
+                const R lij = st[oPL + ln * DU + j];
+                tr = fma(lij, tp[D::oPc + j * DU + ln], tr);
                 row = fma(lij, tp[D::oDel + j], row);
               }
-              quad = fma(tp[D::oDel + i], row, quad);
+              tp[D::oLds + ln] = fma(tp[D::oDel + ln], row, tr);
             }
-            tp[D::oScal + 1] += (tr + quad - R(DU)) * R(0.5) + st[oCc + 1];
+          } else if (do_cost) {
+            R acc = R(0);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc += tp[D::oRow + i];
+            tp[D::oScal + 2] += acc + st[oCc];
           }
         }
         w.team_sync();
+        if (do_kl) {
+          LANE_FOR(one, 1) {
+            R s = R(0);
+#pragma unroll
+            for (int j = 0; j < DU; ++j) s += tp[D::oLds + j];
+            tp[D::oScal + 1] += (s - R(DU)) * R(0.5) + st[oCc + 1];
+          }
+        }
         if (t + 1 < T) stage_policy(tm, t + 1);
       }
       w.cta_sync();  // everyone is done with the staged inputs of step t
@@ -548,12 +522,16 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
       R* tp = TEAMP(tm);
       const size_t bT = (size_t)team_b(tm) * (T + 1) + T;
       if (do_cost) {
-        LANE_FOR(i, DX) {
-          const R mi = tp[D::oM + i * PP + P];
+        LANE_FOR(ln, 32) {
           R acc = R(0);
-          for (int j = 0; j < DX; ++j)
-            acc = fma(ldg(a.C + bT * szC + (size_t)i * P + j), fma(mi, tp[D::oM + j * PP + P], tp[D::oM + j * PP + i]), acc);
-          tp[D::oRow + i] = acc * R(0.5) + mi * ldg(a.c + bT * P + i);
+          for (int i = ln; i < DX; i += 32) {
+            const R mi = tp[D::oM + i * PP + P];
+            R row = R(0);
+            for (int j = 0; j < DX; ++j)
+              row = fma(ldg(a.C + bT * szC + (size_t)i * P + j), fma(mi, tp[D::oM + j * PP + P], tp[D::oM + j * PP + i]), row);
+            acc += row * R(0.5) + mi * ldg(a.c + bT * P + i);
+          }
+          tp[D::oRow + ln] = acc;
         }
       }
       if (a.tcov) {
@@ -577,7 +555,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
       const size_t pi = PIDX(tm);
       if ((a.flags & ILQR_FORWARD) && (a.flags & ILQR_COST) && a.cost) {
         R acc = R(0);
-        for (int i = 0; i < DX; ++i) acc += tp[D::oRow + i];
+        for (int i = 0; i < 32; ++i) acc += tp[D::oRow + i];
         a.cost[pi] = tp[D::oScal + 2] + acc + ldg(a.cc + (size_t)team_b(tm) * (T + 1) + T);
       }
       if ((a.flags & ILQR_FORWARD) && (a.flags & ILQR_KL) && a.kl) a.kl[pi] = (tp[D::oScal + 1] + tp[D::oScal + 3]) / R(T);
