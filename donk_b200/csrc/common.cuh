@@ -189,16 +189,22 @@ DONK_HD void tile_km(const R* __restrict__ A, int lda, const R* __restrict__ Bm,
 // make the fragment loads bank-conflict free.  Rows/columns beyond the valid range may be over-read
 // (their outputs are discarded by the epilogue); the k range must be zero-padded in one operand and
 // finite in the other.  float has no such instruction: each lane computes its two outputs with FFMA.
-template <typename R, int RA, int RB, class Epi>
-DONK_D void warp_mma(const WCtx& w, const R* __restrict__ A, int lda, const R* __restrict__ Bm, int ldb, int K4,
-                     Epi&& epi) {
+struct NoPre {};
+
+template <typename R, int RA, int RB, class Pre, class Epi>
+DONK_D void warp_mma_pre(const WCtx& w, const R* __restrict__ A, int lda, const R* __restrict__ Bm, int ldb, int K4,
+                         Pre&& pre, Epi&& epi) {
 #if defined(__CUDA_ARCH__)
   const int g = w.lane >> 2, tq = w.lane & 3;
-  R c[RA][RB][2];
+  R c[RA][RB][2], pv[RA][RB][2];
 #pragma unroll
   for (int ra = 0; ra < RA; ++ra)
 #pragma unroll
-    for (int rb = 0; rb < RB; ++rb) { c[ra][rb][0] = R(0); c[ra][rb][1] = R(0); }
+    for (int rb = 0; rb < RB; ++rb) {
+      c[ra][rb][0] = R(0); c[ra][rb][1] = R(0);
+      pv[ra][rb][0] = R(0); pv[ra][rb][1] = R(0);
+      pre(8 * ra + g, 8 * rb + 2 * tq, pv[ra][rb][0], pv[ra][rb][1]);  // issued before the product: latency hidden
+    }
   if (sizeof(R) == 8) {
     const R* ap = A + tq * lda + g;
     const R* bp = Bm + tq * ldb + g;
@@ -239,19 +245,80 @@ DONK_D void warp_mma(const WCtx& w, const R* __restrict__ A, int lda, const R* _
 #pragma unroll
   for (int ra = 0; ra < RA; ++ra)
 #pragma unroll
-    for (int rb = 0; rb < RB; ++rb) epi(8 * ra + g, 8 * rb + 2 * tq, c[ra][rb][0], c[ra][rb][1]);
+    for (int rb = 0; rb < RB; ++rb)
+      epi(8 * ra + g, 8 * rb + 2 * tq, c[ra][rb][0], c[ra][rb][1], pv[ra][rb][0], pv[ra][rb][1]);
 #else
   (void)w;
   for (int i = 0; i < 8 * RA; ++i)
     for (int j = 0; j < 8 * RB; j += 2) {
+      R p0 = R(0), p1 = R(0);
+      pre(i, j, p0, p1);
       R v0 = R(0), v1 = R(0);
       for (int k = 0; k < 4 * K4; ++k) {
         v0 = fma(A[k * lda + i], Bm[k * ldb + j], v0);
         v1 = fma(A[k * lda + i], Bm[k * ldb + j + 1], v1);
       }
-      epi(i, j, v0, v1);
+      epi(i, j, v0, v1, p0, p1);
     }
 #endif
+}
+
+template <typename R, int RA, int RB, class Epi>
+DONK_D void warp_mma(const WCtx& w, const R* __restrict__ A, int lda, const R* __restrict__ Bm, int ldb, int K4,
+                     Epi&& epi) {
+  warp_mma_pre<R, RA, RB>(w, A, lda, Bm, ldb, K4, [](int, int, R&, R&) {},
+                          [&](int i, int j, R v0, R v1, R, R) { epi(i, j, v0, v1); });
+}
+
+// Sum of x over the lanes of the warp, added to *slot (shared memory) by lane 0.  Under emulation the lanes of
+// a LANE_FOR run one after the other, so each simply adds its value.
+template <typename R>
+DONK_D void team_accumulate(const WCtx& w, R* slot, R x) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  if (w.lane == 0) *slot += x;
+#else
+  (void)w;
+  *slot += x;
+#endif
+}
+
+// two adjacent shared-memory values at a 16-byte aligned address: one STS.128 / LDS.128
+template <typename R>
+DONK_HD void st2(R* p, R v0, R v1) {
+#if defined(__CUDA_ARCH__)
+  if (sizeof(R) == 8) {
+    *reinterpret_cast<double2*>(p) = make_double2((double)v0, (double)v1);
+    return;
+  }
+#endif
+  p[0] = v0; p[1] = v1;
+}
+template <typename R>
+DONK_HD void ld2(const R* p, R& v0, R& v1) {
+#if defined(__CUDA_ARCH__)
+  if (sizeof(R) == 8) {
+    const double2 t = *reinterpret_cast<const double2*>(p);
+    v0 = (R)t.x; v1 = (R)t.y;
+    return;
+  }
+#endif
+  v0 = p[0]; v1 = p[1];
+}
+
+// two adjacent read-only values; one 16-byte load when the address is known to be 16-byte aligned
+template <typename R>
+DONK_HD void ldg2(const R* p, bool aligned16, R& v0, R& v1) {
+#if defined(__CUDA_ARCH__)
+  if (sizeof(R) == 8 && aligned16) {
+    const double2 t = __ldg(reinterpret_cast<const double2*>(p));
+    v0 = (R)t.x; v1 = (R)t.y;
+    return;
+  }
+#endif
+  (void)aligned16;
+  v0 = ldg(p); v1 = ldg(p + 1);
 }
 
 // smallest leading dimension >= n that is a multiple of 4 and makes DMMA fragment loads conflict free

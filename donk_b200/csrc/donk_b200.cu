@@ -111,7 +111,13 @@ __global__ void __launch_bounds__(512, 1) ilqr_team_kernel_big(const IlqrArgs<R>
 
 // Warp-per-problem fast path with compile-time dimensions (ilqr_warp.cuh).
 template <typename R, int DX, int DU>
-__global__ void __launch_bounds__(512, 1) ilqr_warp_kernel(const IlqrArgs<R> a, int ES) {
+__global__ void __launch_bounds__(512, 1) ilqr_warp_kernel_big(const IlqrArgs<R> a, int ES) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WCtx w{(int)threadIdx.x, (int)blockDim.x, (int)threadIdx.x >> 5, (int)threadIdx.x & 31, (int)blockDim.x >> 5};
+  ilqr_warp_cta<R, DX, DU>(w, a, (int)blockIdx.x, ES, reinterpret_cast<R*>(smem_raw));
+}
+template <typename R, int DX, int DU>
+__global__ void __launch_bounds__(256, 2) ilqr_warp_kernel(const IlqrArgs<R> a, int ES) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WCtx w{(int)threadIdx.x, (int)blockDim.x, (int)threadIdx.x >> 5, (int)threadIdx.x & 31, (int)blockDim.x >> 5};
   ilqr_warp_cta<R, DX, DU>(w, a, (int)blockIdx.x, ES, reinterpret_cast<R*>(smem_raw));
@@ -123,9 +129,15 @@ int ilqr_warp_launch(const IlqrArgs<R>& a, void* stream) {
   size_t bytes;
   int rc = ilqr_warp_plan<R, DX, DU>(a.B, a.E, smem_optin_cap(), env_int("DONK_ILQR_WARPS"), G, ES, grid, bytes);
   if (rc != DONK_OK) return rc;
-  rc = allow_smem(ilqr_warp_kernel<R, DX, DU>, bytes);
-  if (rc != DONK_OK) return rc;
-  ilqr_warp_kernel<R, DX, DU><<<grid, 32 * G, bytes, (cudaStream_t)stream>>>(a, ES);
+  if (G <= 8) {
+    rc = allow_smem(ilqr_warp_kernel<R, DX, DU>, bytes);
+    if (rc != DONK_OK) return rc;
+    ilqr_warp_kernel<R, DX, DU><<<grid, 32 * G, bytes, (cudaStream_t)stream>>>(a, ES);
+  } else {
+    rc = allow_smem(ilqr_warp_kernel_big<R, DX, DU>, bytes);
+    if (rc != DONK_OK) return rc;
+    ilqr_warp_kernel_big<R, DX, DU><<<grid, 32 * G, bytes, (cudaStream_t)stream>>>(a, ES);
+  }
   LAUNCHED("ilqr_warp_kernel");
   return DONK_OK;
 }

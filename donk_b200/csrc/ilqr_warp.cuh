@@ -48,15 +48,15 @@ struct WarpDims {
   static constexpr int oM = 0, oR = oM + MSZ, oK = oR + RSZ, oKv = oK + KSZ;
   static constexpr int oPc = oKv + 8, oLds = oPc + (DU * DU + 3) / 4 * 4, oDel = oLds + 8, oRow = oDel + 8;
   static constexpr int oScal = oRow + 32, TEAM = oScal + 8;  // scal: 0 1/eta 1 kl 2 cost 3 logdet 4 notpd
-  // stage area per condition (reals): backward and forward views share the storage
+  // stage area per condition (reals): backward and forward views share the storage.  Only what the products
+  // read many times is staged (F_t, K_prev_t); C_t, C_kl_t, dyn_covar_t are read once per problem and step and
+  // come straight from global memory, prefetched into registers ahead of the product they are added to.
   static constexpr int oFx = 0;  // bwd: F_ext (DX4 x PP); fwd: F^T (P4 x DXP)
   static constexpr int FXS = (DX4 * PP > P4 * DXP ? DX4 * PP : P4 * DXP) + 8;
-  static constexpr int oCs = oFx + FXS;                    // C_t (P*P)
-  static constexpr int oCk = oCs + (P * P + 3) / 4 * 4;    // bwd: C_kl_t; fwd: dyn_covar_t | K_prev^T (DX4 x KTL) | Lam_prev
-  static constexpr int FWD2 = DX * DX + DX4 * KTL + 8 + DU * DU;
-  static constexpr int CKS = (P * P > FWD2 ? P * P : FWD2);
-  static constexpr int oVec = oCk + (CKS + 3) / 4 * 4;     // cs (PP) | ck (PP) / fwd: cs (PP) | fv (DXP) | pk (8) | cc, phld
-  static constexpr int STAGE = oVec + 2 * PP + DXP + 8 + 4;
+  static constexpr int oPK = oFx + FXS;                    // fwd: K_prev^T (DX4 x KTL)
+  static constexpr int oPL = oPK + DX4 * KTL + 8;          // fwd: Lam_prev (DU x DU)
+  static constexpr int oVec = oPL + (DU * DU + 3) / 4 * 4; // fwd: f (DXP) | k_prev (8) | cc, phld (4)
+  static constexpr int STAGE = oVec + DXP + 8 + 4;
 };
 
 template <typename R, int DX, int DU>
@@ -110,19 +110,11 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
         const int b = cond_b(ci);
         if (b < 0) continue;
         R* st = stages + (size_t)ci * D::STAGE;
-        const size_t bt = (size_t)b * T + t, bt1 = (size_t)b * (T + 1) + t;
+        const size_t bt = (size_t)b * T + t;
         CTA_FOR(idx, DX * PE) {
           const int k = idx / PE, j = idx % PE;  // compile-time divisors
           if (j < P) cp_async(st + D::oFx + k * PP + j, a.F + bt * szF + (size_t)k * P + j);
           else cp_async(st + D::oFx + k * PP + P, a.f + bt * DX + k);
-        }
-        CTA_FOR(idx, P * P) {
-          cp_async(st + D::oCs + idx, a.C + bt1 * szC + idx);
-          if (a.C_kl) cp_async(st + D::oCk + idx, a.C_kl + bt * szC + idx);
-        }
-        CTA_FOR(i, P) {
-          cp_async(st + D::oVec + i, a.c + bt1 * P + i);
-          if (a.c_kl) cp_async(st + D::oVec + PP + i, a.c_kl + bt * P + i);
         }
       }
     };
@@ -152,30 +144,55 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
           if (i < DX && j < PP) {
             if (j == P) v0 += tp[D::oM + i * PP + P];
             if (j + 1 == P) v1 += tp[D::oM + i * PP + P];
-            tp[D::oR + i * PP + j] = v0;
-            tp[D::oR + i * PP + j + 1] = v1;
+            st2(tp + D::oR + i * PP + j, v0, v1);  // j even, PP even: 16-byte aligned
           }
         });
         w.team_sync();
-        // ---- B2: Q_ext = C_ext + gamma [F|f]^T W_ext, upper blocks, mirrored; column P is q ---------------
+        // ---- B2: Q_ext = C_ext + gamma [F|f]^T W_ext, upper blocks; column P is q.  Only the xu block is mirrored
+        //      (Qux feeds the gains and the value update); Qxx / Quu are consumed from their upper triangles. ----------
         {
           const R ie = tp[D::oScal + 0];
-          auto epi = [&](int i, int jj, R acc) {
-            if (i < P && i <= jj) {
-              if (jj < P) {
-                const R val = fma(st[D::oCs + i * P + jj], ie, st[D::oCk + i * P + jj]) + gamma * acc;
-                tp[D::oM + i * PP + jj] = val;
-                tp[D::oM + jj * PP + i] = val;
-              } else if (jj == P) {
-                tp[D::oM + i * PP + P] = fma(st[D::oVec + i], ie, st[D::oVec + PP + i]) + gamma * acc;
-              }
+          const int b = team_b(tm);
+          const R* Cg = a.C + ((size_t)b * (T + 1) + t) * szC;
+          const R* Kg = a.C_kl ? a.C_kl + ((size_t)b * T + t) * szC : nullptr;
+          const R* cg = a.c + ((size_t)b * (T + 1) + t) * P;
+          const R* kg = a.c_kl ? a.c_kl + ((size_t)b * T + t) * P : nullptr;
+          // C_ext entries (i, j), (i, j+1) of the fragment, read from global memory before the product starts
+          auto pre = [&](int i, int j, R& p0, R& p1) {
+            if (i >= P || i > j + 1) return;
+            if (j + 1 < P) {
+              R c0, c1, k0 = R(0), k1 = R(0);
+              ldg2(Cg + i * P + j, P % 2 == 0, c0, c1);
+              if (Kg) ldg2(Kg + i * P + j, P % 2 == 0, k0, k1);
+              p0 = fma(c0, ie, k0);
+              p1 = fma(c1, ie, k1);
+            } else {
+              if (j < P) p0 = fma(ldg(Cg + i * P + j), ie, Kg ? ldg(Kg + i * P + j) : R(0));
+              const R cv = fma(ldg(cg + i), ie, kg ? ldg(kg + i) : R(0));
+              if (j == P) p0 = cv;
+              if (j + 1 == P) p1 = cv;
+            }
+          };
+          auto epi = [&](int i, int j, R v0, R v1, R p0, R p1) {
+            if (i >= P || i > j + 1 || j > P) return;
+            const R q0 = fma(gamma, v0, p0), q1 = fma(gamma, v1, p1);
+            if (i <= j && j + 1 <= P) {
+              st2(tp + D::oM + i * PP + j, q0, q1);
+            } else {
+              if (i <= j) tp[D::oM + i * PP + j] = q0;
+              if (j + 1 <= P) tp[D::oM + i * PP + j + 1] = q1;
+            }
+            if (i < DX) {  // mirror Qxu -> Qux
+              if (j >= DX && j < P) tp[D::oM + j * PP + i] = q0;
+              if (j + 1 >= DX && j + 1 < P) tp[D::oM + (j + 1) * PP + i] = q1;
             }
           };
 #define DONK_B2_ROW(RB_ROW)                                                                                      \
   if (RB_ROW < D::NBP)                                                                                           \
-    warp_mma<R, 1, (D::NBP - RB_ROW > 0 ? D::NBP - RB_ROW : 1)>(                                                  \
+    warp_mma_pre<R, 1, (D::NBP - RB_ROW > 0 ? D::NBP - RB_ROW : 1)>(                                              \
         w, st + D::oFx + 8 * RB_ROW, PP, tp + D::oR + 8 * RB_ROW, PP, DX4 / 4,                                    \
-        [&](int i, int j, R v0, R v1) { epi(8 * RB_ROW + i, 8 * RB_ROW + j, v0); epi(8 * RB_ROW + i, 8 * RB_ROW + j + 1, v1); });
+        [&](int i, int j, R& p0, R& p1) { pre(8 * RB_ROW + i, 8 * RB_ROW + j, p0, p1); },                         \
+        [&](int i, int j, R v0, R v1, R p0, R p1) { epi(8 * RB_ROW + i, 8 * RB_ROW + j, v0, v1, p0, p1); });
           DONK_B2_ROW(0) DONK_B2_ROW(1) DONK_B2_ROW(2) DONK_B2_ROW(3) DONK_B2_ROW(4)
 #undef DONK_B2_ROW
         }
@@ -195,7 +212,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
 #pragma unroll
           for (int i = 0; i < DU; ++i)
 #pragma unroll
-            for (int j = 0; j <= i; ++j) Lm[i][j] = tp[D::oM + (DX + i) * PP + DX + j];
+            for (int j = 0; j <= i; ++j) Lm[i][j] = tp[D::oM + (DX + j) * PP + DX + i];  // upper triangle of Quu
           R idg[DU];
           bool bad = false;
 #pragma unroll
@@ -245,7 +262,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
                 if (ln == (e & 31)) {
                   a.pcov[pt * szS + i * DU + j] = acc;
                   a.pcov[pt * szS + j * DU + i] = acc;
-                  const R quu = tp[D::oM + (DX + i) * PP + DX + j];
+                  const R quu = tp[D::oM + (DX + j) * PP + DX + i];
                   a.pinv[pt * szS + i * DU + j] = quu;
                   a.pinv[pt * szS + j * DU + i] = quu;
                 }
@@ -281,16 +298,29 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
         w.team_sync();
         // ---- B5: [V | v] = [Qxx | q_x] + Qxu [K | k] (upper blocks, mirrored) (lqg.py:178-180) ---------------
         {
-          auto epi = [&](int i, int jj, R acc) {
-            if (i < DX) {
-              if (jj < DX) {
-                if (i <= jj) {
-                  const R val = tp[D::oM + i * PP + jj] + acc;
-                  tp[D::oM + i * PP + jj] = val;
-                  tp[D::oM + jj * PP + i] = val;
+          auto epi = [&](int i, int j, R v0, R v1) {
+            if (i >= DX || i > j + 1 || j > DX) return;
+            if (i <= j && j + 1 < DX) {
+              R m0, m1;
+              ld2(tp + D::oM + i * PP + j, m0, m1);
+              m0 += v0; m1 += v1;
+              st2(tp + D::oM + i * PP + j, m0, m1);
+              tp[D::oM + j * PP + i] = m0;
+              tp[D::oM + (j + 1) * PP + i] = m1;
+            } else {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int jj = j + h;
+                const R acc = h ? v1 : v0;
+                if (jj < DX) {
+                  if (i <= jj) {
+                    const R val = tp[D::oM + i * PP + jj] + acc;
+                    tp[D::oM + i * PP + jj] = val;
+                    tp[D::oM + jj * PP + i] = val;
+                  }
+                } else if (jj == DX) {
+                  tp[D::oM + i * PP + P] += acc;
                 }
-              } else if (jj == DX) {
-                tp[D::oM + i * PP + P] += acc;
               }
             }
           };
@@ -298,7 +328,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
   if (RB_ROW < D::NBX)                                                                                             \
     warp_mma<R, 1, (D::NBX1 - RB_ROW > 0 ? D::NBX1 - RB_ROW : 1)>(                                                  \
         w, tp + D::oM + DX * PP + 8 * RB_ROW, PP, tp + D::oK + 8 * RB_ROW, KLD, DU4 / 4,                            \
-        [&](int i, int j, R v0, R v1) { epi(8 * RB_ROW + i, 8 * RB_ROW + j, v0); epi(8 * RB_ROW + i, 8 * RB_ROW + j + 1, v1); });
+        [&](int i, int j, R v0, R v1) { epi(8 * RB_ROW + i, 8 * RB_ROW + j, v0, v1); });
           DONK_B5_ROW(0) DONK_B5_ROW(1) DONK_B5_ROW(2) DONK_B5_ROW(3)
 #undef DONK_B5_ROW
         }
@@ -321,8 +351,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
   if (a.flags & ILQR_FORWARD) {
     const R reg = a.fwd_reg;
     const bool do_kl = (a.flags & ILQR_KL) != 0, do_cost = (a.flags & ILQR_COST) != 0;
-    constexpr int oD = D::oCk, oPK = D::oCk + DX * DX, oPL = oPK + DX4 * KTL + 8;  // inside the stage area
-    constexpr int oCsV = D::oVec, oFv = D::oVec + PP, oPk = oFv + DXP, oCc = oPk + 8;
+    constexpr int oPK = D::oPK, oPL = D::oPL, oFv = D::oVec, oPk = oFv + DXP, oCc = oPk + 8;  // inside the stage area
     // the stage and K areas change layout: clear the paddings the forward products rely on
     CTA_FOR(idx, NC * D::STAGE) stages[idx] = R(0);
     TEAMS_DO(tm) {
@@ -340,11 +369,8 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
           const int i = idx / P, k = idx % P;
           cp_async(st + D::oFx + k * DXP + i, a.F + bt * szF + idx);
         }
-        CTA_FOR(idx, DX * DX) cp_async(st + oD + idx, a.dyn_covar + bt * DX * DX + idx);
         CTA_FOR(i, DX) cp_async(st + oFv + i, a.f + bt * DX + i);
         if (do_cost) {
-          CTA_FOR(idx, P * P) cp_async(st + D::oCs + idx, a.C + bt1 * szC + idx);
-          CTA_FOR(i, P) cp_async(st + oCsV + i, a.c + bt1 * P + i);
           CTA_FOR(one, 1) cp_async(st + oCc, a.cc + bt1);
         }
         if (do_kl) {
@@ -358,15 +384,15 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
         }
       }
     };
-    auto stage_policy = [&](int tm, int t) {  // K_t^T, k_t, pol_covar_t of this team's problem (plain loads)
+    auto stage_policy = [&](int tm, int t) {  // K_t^T, k_t, pol_covar_t of this team's problem (async)
       R* tp = TEAMP(tm);
       const size_t pt = PIDX(tm) * T + t;
       LANE_FOR(idx, DU * DX) {
         const int a2 = idx / DX, k = idx % DX;
-        tp[D::oK + k * KTL + a2] = a.K[pt * szK + idx];
+        cp_async(tp + D::oK + k * KTL + a2, a.K + pt * szK + idx);
       }
-      LANE_FOR(i, DU) tp[D::oKv + i] = a.k[pt * DU + i];
-      LANE_FOR(idx, DU * DU) tp[D::oPc + idx] = a.pcov[pt * szS + idx];
+      LANE_FOR(i, DU) cp_async(tp + D::oKv + i, a.k + pt * DU + i);
+      LANE_FOR(idx, DU * DU) cp_async(tp + D::oPc + idx, a.pcov + pt * szS + idx);
     };
     stage_fwd(0);
     TEAMS_DO(tm) {
@@ -387,18 +413,25 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
         if (!team_valid(tm)) continue;
         R* tp = TEAMP(tm);
         const R* st = STAGEP(tm);
+        const int b = team_b(tm);
         // ---- F1: [Sigma_ux | mu_u] = K [Sigma_xx | mu_x] (+ k); K_prev mu_x (lqg.py:227-230, 294) --------------
         warp_mma<R, 1, D::NBP>(w, tp + D::oK, KTL, tp + D::oM, PP, DX4 / 4, [&](int a2, int j, R v0, R v1) {
           if (a2 < DU) {
+            if (j + 1 < DX) {
+              st2(tp + D::oM + (DX + a2) * PP + j, v0, v1);
+              tp[D::oM + j * PP + DX + a2] = v0;
+              tp[D::oM + (j + 1) * PP + DX + a2] = v1;
+            } else {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int jj = j + h;
-              const R acc = h ? v1 : v0;
-              if (jj < DX) {
-                tp[D::oM + (DX + a2) * PP + jj] = acc;
-                tp[D::oM + jj * PP + DX + a2] = acc;
-              } else if (jj == P) {
-                tp[D::oM + (DX + a2) * PP + P] = acc + tp[D::oKv + a2];
+              for (int h = 0; h < 2; ++h) {
+                const int jj = j + h;
+                const R acc = h ? v1 : v0;
+                if (jj < DX) {
+                  tp[D::oM + (DX + a2) * PP + jj] = acc;
+                  tp[D::oM + jj * PP + DX + a2] = acc;
+                } else if (jj == P) {
+                  tp[D::oM + (DX + a2) * PP + P] = acc + tp[D::oKv + a2];
+                }
               }
             }
           }
@@ -428,27 +461,110 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
           LANE_FOR(a2, DU) tp[D::oDel + a2] -= tp[D::oM + (DX + a2) * PP + P];  // (K_prev mu_x + k_prev) - mu_u
         }
         w.team_sync();
-        // ---- F3: Rt_ext = ([F] [Sigma | mu])^T (PE x DX); cost partials; optional outputs --------------------------
-        warp_mma<R, D::NBP, D::NBX>(w, tp + D::oM, PP, st + D::oFx, DXP, P4 / 4, [&](int j, int i, R v0, R v1) {
-          if (j < PE) {
-            if (i < DX) tp[D::oR + j * DXP + i] = v0;
-            if (i + 1 < DX) tp[D::oR + j * DXP + i + 1] = v1;
+        // ---- F3: Rt_ext = ([F] [Sigma | mu])^T (PE x DX).  The expected cost of step t rides on the A fragments:
+        //      every lane sees 1/32 of [Sigma | mu] anyway and adds C_kj (Sigma_kj + mu_k mu_j [+ reg]) for it --------
+        {
+          const R* Cg = a.C + ((size_t)b * (T + 1) + t) * szC;
+          const R* cg = a.c + ((size_t)b * (T + 1) + t) * P;
+#if defined(__CUDA_ARCH__)
+          const int g = w.lane >> 2, tq = w.lane & 3;
+          R c[D::NBP][D::NBX][2];
+#pragma unroll
+          for (int ra = 0; ra < D::NBP; ++ra)
+#pragma unroll
+            for (int rb = 0; rb < D::NBX; ++rb) { c[ra][rb][0] = R(0); c[ra][rb][1] = R(0); }
+          R muj[D::NBP], cn[D::NBP];
+          auto loadC = [&](int k, int ra) {
+            const int j = 8 * ra + g;
+            return (do_cost && k < P && j < P) ? ldg(Cg + k * P + j) : R(0);
+          };
+#pragma unroll
+          for (int ra = 0; ra < D::NBP; ++ra) {
+            muj[ra] = 8 * ra + g < P ? tp[D::oM + (8 * ra + g) * PP + P] : R(0);
+            cn[ra] = loadC(tq, ra);
           }
-        });
-        if (do_cost) {
-          // 1/2 sum_ij C_ij (Sigma_ij + mu_i mu_j) + 1/2 reg tr C + mu^T c: upper triangle, weight 2 off the diagonal
-          LANE_FOR(ln, 32) {
-            R acc = R(0);
-            for (int i = ln; i < P; i += 32) {
-              const R mi = tp[D::oM + i * PP + P];
-              R row = R(0);
-              for (int j = i + 1; j < P; ++j)
-                row = fma(st[D::oCs + i * P + j], fma(mi, tp[D::oM + j * PP + P], tp[D::oM + i * PP + j]), row);
-              const R cii = st[D::oCs + i * P + i];
-              acc += row + R(0.5) * cii * fma(mi, mi, tp[D::oM + i * PP + i] + reg) + mi * st[oCsV + i];
+          R cost = R(0);
+          const R* ap = tp + D::oM + tq * PP + g;
+          const R* bp = st + D::oFx + tq * DXP + g;
+          for (int k4 = 0; k4 < P4 / 4; ++k4) {
+            const int k = 4 * k4 + tq;
+            R cc_[D::NBP], af[D::NBP], bf[D::NBX];
+#pragma unroll
+            for (int ra = 0; ra < D::NBP; ++ra) { cc_[ra] = cn[ra]; cn[ra] = loadC(k + 4, ra); af[ra] = ap[8 * ra]; }
+#pragma unroll
+            for (int rb = 0; rb < D::NBX; ++rb) bf[rb] = bp[8 * rb];
+            if (do_cost) {
+              const R muk = k < P ? tp[D::oM + k * PP + P] : R(0);
+#pragma unroll
+              for (int ra = 0; ra < D::NBP; ++ra) {
+                R sv = fma(muk, muj[ra], af[ra]);
+                if (k == 8 * ra + g) sv += reg;
+                cost = fma(cc_[ra], sv, cost);
+              }
             }
-            tp[D::oRow + ln] = acc;
+#pragma unroll
+            for (int ra = 0; ra < D::NBP; ++ra)
+#pragma unroll
+              for (int rb = 0; rb < D::NBX; ++rb) {
+                if (sizeof(R) == 8) {
+                  double d0 = (double)c[ra][rb][0], d1 = (double)c[ra][rb][1];
+                  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                               : "+d"(d0), "+d"(d1)
+                               : "d"((double)af[ra]), "d"((double)bf[rb]));
+                  c[ra][rb][0] = (R)d0;
+                  c[ra][rb][1] = (R)d1;
+                }
+              }
+            ap += 4 * PP;
+            bp += 4 * DXP;
           }
+          if (sizeof(R) != 8) {  // float: no tensor path, each lane computes its two outputs per fragment
+            for (int k = 0; k < P4; ++k)
+#pragma unroll
+              for (int ra = 0; ra < D::NBP; ++ra) {
+                const R av = tp[D::oM + k * PP + 8 * ra + g];
+#pragma unroll
+                for (int rb = 0; rb < D::NBX; ++rb) {
+                  c[ra][rb][0] = fma(av, st[D::oFx + k * DXP + 8 * rb + 2 * tq], c[ra][rb][0]);
+                  c[ra][rb][1] = fma(av, st[D::oFx + k * DXP + 8 * rb + 2 * tq + 1], c[ra][rb][1]);
+                }
+              }
+          }
+#pragma unroll
+          for (int ra = 0; ra < D::NBP; ++ra)
+#pragma unroll
+            for (int rb = 0; rb < D::NBX; ++rb) {
+              const int j = 8 * ra + g, i = 8 * rb + 2 * tq;
+              if (j < PE) {
+                if (i + 1 < DX) st2(tp + D::oR + j * DXP + i, c[ra][rb][0], c[ra][rb][1]);
+                else if (i < DX) tp[D::oR + j * DXP + i] = c[ra][rb][0];
+              }
+            }
+          if (do_cost) {
+            cost *= R(0.5);
+            if (w.lane < P) cost = fma(tp[D::oM + w.lane * PP + P], ldg(cg + w.lane), cost);
+            team_accumulate(w, tp + D::oScal + 2, cost);
+          }
+#else
+          for (int j = 0; j < PE; ++j)
+            for (int i = 0; i < DX; ++i) {
+              R acc = R(0);
+              for (int k = 0; k < P4; ++k) acc = fma(tp[D::oM + k * PP + j], st[D::oFx + k * DXP + i], acc);
+              tp[D::oR + j * DXP + i] = acc;
+            }
+          if (do_cost) {
+            R cost = R(0);
+            for (int k = 0; k < P; ++k)
+              for (int j = 0; j < P; ++j) {
+                R sv = fma(tp[D::oM + k * PP + P], tp[D::oM + j * PP + P], tp[D::oM + k * PP + j]);
+                if (k == j) sv += reg;
+                cost = fma(Cg[k * P + j], sv, cost);
+              }
+            cost *= R(0.5);
+            for (int i = 0; i < P; ++i) cost = fma(tp[D::oM + i * PP + P], cg[i], cost);
+            tp[D::oScal + 2] += cost;
+          }
+#endif
         }
         if (a.tcov) {
           LANE_FOR(idx, P * P) {
@@ -462,49 +578,55 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
         w.team_sync();
         // ---- F4: Sigma'_xx = (F Sigma) F^T + dyn_covar (upper blocks, mirrored); mu' = F mu + f; scalars -------------
         {
-          auto epi = [&](int i, int jj, R acc) {
-            if (i <= jj && jj < DX) {
-              const R val = acc + st[oD + i * DX + jj];
-              tp[D::oM + i * PP + jj] = val;
-              tp[D::oM + jj * PP + i] = val;
+          const R* Dg = a.dyn_covar + ((size_t)b * T + t) * DX * DX;
+          auto pre = [&](int i, int j, R& p0, R& p1) {
+            if (i >= DX || i > j + 1 || j >= DX) return;
+            if (j + 1 < DX) ldg2(Dg + i * DX + j, DX % 2 == 0, p0, p1);
+            else p0 = ldg(Dg + i * DX + j);
+          };
+          auto epi = [&](int i, int j, R v0, R v1, R p0, R p1) {
+            if (i >= DX || i > j + 1 || j >= DX) return;
+            const R s0 = v0 + p0, s1 = v1 + p1;
+            if (i <= j && j + 1 < DX) {
+              st2(tp + D::oM + i * PP + j, s0, s1);
+              tp[D::oM + j * PP + i] = s0;
+              tp[D::oM + (j + 1) * PP + i] = s1;
+            } else {
+              if (i <= j) { tp[D::oM + i * PP + j] = s0; tp[D::oM + j * PP + i] = s0; }
+              if (j + 1 < DX) { tp[D::oM + i * PP + j + 1] = s1; tp[D::oM + (j + 1) * PP + i] = s1; }
             }
           };
 #define DONK_F4_ROW(RB_ROW)                                                                                        \
   if (RB_ROW < D::NBX)                                                                                             \
-    warp_mma<R, 1, (D::NBX - RB_ROW > 0 ? D::NBX - RB_ROW : 1)>(                                                    \
+    warp_mma_pre<R, 1, (D::NBX - RB_ROW > 0 ? D::NBX - RB_ROW : 1)>(                                                \
         w, tp + D::oR + 8 * RB_ROW, DXP, st + D::oFx + 8 * RB_ROW, DXP, P4 / 4,                                     \
-        [&](int i, int j, R v0, R v1) { epi(8 * RB_ROW + i, 8 * RB_ROW + j, v0); epi(8 * RB_ROW + i, 8 * RB_ROW + j + 1, v1); });
+        [&](int i, int j, R& p0, R& p1) { pre(8 * RB_ROW + i, 8 * RB_ROW + j, p0, p1); },                           \
+        [&](int i, int j, R v0, R v1, R p0, R p1) { epi(8 * RB_ROW + i, 8 * RB_ROW + j, v0, v1, p0, p1); });
           DONK_F4_ROW(0) DONK_F4_ROW(1) DONK_F4_ROW(2) DONK_F4_ROW(3)
 #undef DONK_F4_ROW
         }
         LANE_FOR(i, DX) tp[D::oM + i * PP + P] = tp[D::oR + P * DXP + i] + st[oFv + i];
-        LANE_FOR(ln, DU + 1) {
-          if (ln < DU) {
-            if (do_kl) {  // row ln of  tr(Lam_prev Sigma_new) + delta^T Lam_prev delta  (lqg.py:295-304)
-              R tr = R(0), row = R(0);
+        if (do_kl) {
+          LANE_FOR(ln, DU) {  // row ln of  tr(Lam_prev Sigma_new) + delta^T Lam_prev delta  (lqg.py:295-304)
+            R tr = R(0), row = R(0);
 #pragma unroll
-              for (int j = 0; j < DU; ++j) {
-                const R lij = st[oPL + ln * DU + j];
-                tr = fma(lij, tp[D::oPc + j * DU + ln], tr);
-                row = fma(lij, tp[D::oDel + j], row);
-              }
-              tp[D::oLds + ln] = fma(tp[D::oDel + ln], row, tr);
+            for (int j = 0; j < DU; ++j) {
+              const R lij = st[oPL + ln * DU + j];
+              tr = fma(lij, tp[D::oPc + j * DU + ln], tr);
+              row = fma(lij, tp[D::oDel + j], row);
             }
-          } else if (do_cost) {
-            R acc = R(0);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) acc += tp[D::oRow + i];
-            tp[D::oScal + 2] += acc + st[oCc];
+            tp[D::oLds + ln] = fma(tp[D::oDel + ln], row, tr);
           }
         }
         w.team_sync();
-        if (do_kl) {
-          LANE_FOR(one, 1) {
+        LANE_FOR(one, 1) {
+          if (do_kl) {
             R s = R(0);
 #pragma unroll
             for (int j = 0; j < DU; ++j) s += tp[D::oLds + j];
             tp[D::oScal + 1] += (s - R(DU)) * R(0.5) + st[oCc + 1];
           }
+          if (do_cost) tp[D::oScal + 2] += st[oCc];
         }
         if (t + 1 < T) stage_policy(tm, t + 1);
       }
@@ -577,7 +699,9 @@ inline size_t ilqr_warp_bytes(int G, int NC) {
 // teams per CTA: as many eta candidates of one condition as fit (<= 16 warps), else several conditions
 template <typename R, int DX, int DU>
 inline int ilqr_warp_plan(int B, int E, size_t smem_cap, int force_G, int& G, int& ES, int& grid, size_t& bytes) {
-  int g = force_G > 0 ? force_G : 16;
+  // 8 warps per CTA by default: two CTAs share an SM and drift apart, so the tensor-heavy products of one overlap
+  // the factorisation / epilogue / staging phases of the other (one 16-warp CTA runs its warps in lock-step)
+  int g = force_G > 0 ? force_G : 8;
   for (; g >= 1; --g) {
     ES = E < g ? E : g;
     G = (g / ES) * ES;
