@@ -191,19 +191,21 @@ DONK_HD void tile_km(const R* __restrict__ A, int lda, const R* __restrict__ Bm,
 // finite in the other.  float has no such instruction: each lane computes its two outputs with FFMA.
 struct NoPre {};
 
-template <typename R, int RA, int RB, class Pre, class Epi>
+template <typename R, int RA, int RB, int NP, class Pre, class Epi>
 DONK_D void warp_mma_pre(const WCtx& w, const R* __restrict__ A, int lda, const R* __restrict__ Bm, int ldb, int K4,
                          Pre&& pre, Epi&& epi) {
 #if defined(__CUDA_ARCH__)
   const int g = w.lane >> 2, tq = w.lane & 3;
-  R c[RA][RB][2], pv[RA][RB][2];
+  R c[RA][RB][2], pv[RA][RB][NP];
 #pragma unroll
   for (int ra = 0; ra < RA; ++ra)
 #pragma unroll
     for (int rb = 0; rb < RB; ++rb) {
       c[ra][rb][0] = R(0); c[ra][rb][1] = R(0);
-      pv[ra][rb][0] = R(0); pv[ra][rb][1] = R(0);
-      pre(8 * ra + g, 8 * rb + 2 * tq, pv[ra][rb][0], pv[ra][rb][1]);  // issued before the product: latency hidden
+#pragma unroll
+      for (int q = 0; q < NP; ++q) pv[ra][rb][q] = R(0);
+      // raw loads only (no arithmetic on the loaded values): they stay in flight while the product runs
+      pre(8 * ra + g, 8 * rb + 2 * tq, pv[ra][rb]);
     }
   if (sizeof(R) == 8) {
     const R* ap = A + tq * lda + g;
@@ -246,19 +248,20 @@ DONK_D void warp_mma_pre(const WCtx& w, const R* __restrict__ A, int lda, const 
   for (int ra = 0; ra < RA; ++ra)
 #pragma unroll
     for (int rb = 0; rb < RB; ++rb)
-      epi(8 * ra + g, 8 * rb + 2 * tq, c[ra][rb][0], c[ra][rb][1], pv[ra][rb][0], pv[ra][rb][1]);
+      epi(8 * ra + g, 8 * rb + 2 * tq, c[ra][rb][0], c[ra][rb][1], pv[ra][rb]);
 #else
   (void)w;
   for (int i = 0; i < 8 * RA; ++i)
     for (int j = 0; j < 8 * RB; j += 2) {
-      R p0 = R(0), p1 = R(0);
-      pre(i, j, p0, p1);
+      R pv[NP];
+      for (int q = 0; q < NP; ++q) pv[q] = R(0);
+      pre(i, j, pv);
       R v0 = R(0), v1 = R(0);
       for (int k = 0; k < 4 * K4; ++k) {
         v0 = fma(A[k * lda + i], Bm[k * ldb + j], v0);
         v1 = fma(A[k * lda + i], Bm[k * ldb + j + 1], v1);
       }
-      epi(i, j, v0, v1, p0, p1);
+      epi(i, j, v0, v1, pv);
     }
 #endif
 }
@@ -266,8 +269,8 @@ DONK_D void warp_mma_pre(const WCtx& w, const R* __restrict__ A, int lda, const 
 template <typename R, int RA, int RB, class Epi>
 DONK_D void warp_mma(const WCtx& w, const R* __restrict__ A, int lda, const R* __restrict__ Bm, int ldb, int K4,
                      Epi&& epi) {
-  warp_mma_pre<R, RA, RB>(w, A, lda, Bm, ldb, K4, [](int, int, R&, R&) {},
-                          [&](int i, int j, R v0, R v1, R, R) { epi(i, j, v0, v1); });
+  warp_mma_pre<R, RA, RB, 1>(w, A, lda, Bm, ldb, K4, [](int, int, R*) {},
+                             [&](int i, int j, R v0, R v1, const R*) { epi(i, j, v0, v1); });
 }
 
 // Sum of x over the lanes of the warp, added to *slot (shared memory) by lane 0.  Under emulation the lanes of
@@ -281,6 +284,15 @@ DONK_D void team_accumulate(const WCtx& w, R* slot, R x) {
 #else
   (void)w;
   *slot += x;
+#endif
+}
+
+// hint: bring the 128-byte line at p into L2 (no-op under emulation)
+DONK_D void prefetch_l2(const void* p) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
 #endif
 }
 

@@ -139,6 +139,14 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
         if (!team_valid(tm)) continue;
         R* tp = TEAMP(tm);
         const R* st = STAGEP(tm);
+        if (t > 0) {  // pull next step's C / C_kl rows into L2 while this step computes (one 128-byte line per lane)
+          const int b = team_b(tm);
+          constexpr int LINES = (P * P * (int)sizeof(R) + 127) / 128;
+          LANE_FOR(ln, LINES) {
+            if ((tm % ES) * 2 < ES) prefetch_l2(a.C + ((size_t)b * (T + 1) + t - 1) * szC + (size_t)ln * (128 / sizeof(R)));
+            else if (a.C_kl) prefetch_l2(a.C_kl + ((size_t)b * T + t - 1) * szC + (size_t)ln * (128 / sizeof(R)));
+          }
+        }
         // ---- B1: W_ext = V [F | f] (+ v in column P) ----------------------------------------------------
         warp_mma<R, D::NBX, D::NBP>(w, tp + D::oM, PP, st + D::oFx, PP, DX4 / 4, [&](int i, int j, R v0, R v1) {
           if (i < DX && j < PP) {
@@ -157,25 +165,21 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
           const R* Kg = a.C_kl ? a.C_kl + ((size_t)b * T + t) * szC : nullptr;
           const R* cg = a.c + ((size_t)b * (T + 1) + t) * P;
           const R* kg = a.c_kl ? a.c_kl + ((size_t)b * T + t) * P : nullptr;
-          // C_ext entries (i, j), (i, j+1) of the fragment, read from global memory before the product starts
-          auto pre = [&](int i, int j, R& p0, R& p1) {
+          // C and C_kl entries (i, j), (i, j+1) of the fragment: raw loads issued before the product starts
+          auto pre = [&](int i, int j, R* pv) {
             if (i >= P || i > j + 1) return;
             if (j + 1 < P) {
-              R c0, c1, k0 = R(0), k1 = R(0);
-              ldg2(Cg + i * P + j, P % 2 == 0, c0, c1);
-              if (Kg) ldg2(Kg + i * P + j, P % 2 == 0, k0, k1);
-              p0 = fma(c0, ie, k0);
-              p1 = fma(c1, ie, k1);
+              ldg2(Cg + i * P + j, P % 2 == 0, pv[0], pv[1]);
+              if (Kg) ldg2(Kg + i * P + j, P % 2 == 0, pv[2], pv[3]);
             } else {
-              if (j < P) p0 = fma(ldg(Cg + i * P + j), ie, Kg ? ldg(Kg + i * P + j) : R(0));
-              const R cv = fma(ldg(cg + i), ie, kg ? ldg(kg + i) : R(0));
-              if (j == P) p0 = cv;
-              if (j + 1 == P) p1 = cv;
+              if (j < P) { pv[0] = ldg(Cg + i * P + j); if (Kg) pv[2] = ldg(Kg + i * P + j); }
+              const int h = j == P ? 0 : 1;  // which of the two columns is the vector column P
+              if (j == P || j + 1 == P) { pv[h] = ldg(cg + i); if (kg) pv[2 + h] = ldg(kg + i); }
             }
           };
-          auto epi = [&](int i, int j, R v0, R v1, R p0, R p1) {
+          auto epi = [&](int i, int j, R v0, R v1, const R* pv) {
             if (i >= P || i > j + 1 || j > P) return;
-            const R q0 = fma(gamma, v0, p0), q1 = fma(gamma, v1, p1);
+            const R q0 = fma(gamma, v0, fma(pv[0], ie, pv[2])), q1 = fma(gamma, v1, fma(pv[1], ie, pv[3]));
             if (i <= j && j + 1 <= P) {
               st2(tp + D::oM + i * PP + j, q0, q1);
             } else {
@@ -189,10 +193,10 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
           };
 #define DONK_B2_ROW(RB_ROW)                                                                                      \
   if (RB_ROW < D::NBP)                                                                                           \
-    warp_mma_pre<R, 1, (D::NBP - RB_ROW > 0 ? D::NBP - RB_ROW : 1)>(                                              \
+    warp_mma_pre<R, 1, (D::NBP - RB_ROW > 0 ? D::NBP - RB_ROW : 1), 4>(                                           \
         w, st + D::oFx + 8 * RB_ROW, PP, tp + D::oR + 8 * RB_ROW, PP, DX4 / 4,                                    \
-        [&](int i, int j, R& p0, R& p1) { pre(8 * RB_ROW + i, 8 * RB_ROW + j, p0, p1); },                         \
-        [&](int i, int j, R v0, R v1, R p0, R p1) { epi(8 * RB_ROW + i, 8 * RB_ROW + j, v0, v1, p0, p1); });
+        [&](int i, int j, R* pv) { pre(8 * RB_ROW + i, 8 * RB_ROW + j, pv); },                                    \
+        [&](int i, int j, R v0, R v1, const R* pv) { epi(8 * RB_ROW + i, 8 * RB_ROW + j, v0, v1, pv); });
           DONK_B2_ROW(0) DONK_B2_ROW(1) DONK_B2_ROW(2) DONK_B2_ROW(3) DONK_B2_ROW(4)
 #undef DONK_B2_ROW
         }
@@ -414,6 +418,13 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
         R* tp = TEAMP(tm);
         const R* st = STAGEP(tm);
         const int b = team_b(tm);
+        if (t + 1 < T) {  // pull next step's C / dyn_covar rows into L2
+          constexpr int LINES = (P * P * (int)sizeof(R) + 127) / 128, LINESD = (DX * DX * (int)sizeof(R) + 127) / 128;
+          LANE_FOR(ln, LINES + LINESD) {
+            if (ln < LINES) { if (do_cost) prefetch_l2(a.C + ((size_t)b * (T + 1) + t + 1) * szC + (size_t)ln * (128 / sizeof(R))); }
+            else prefetch_l2(a.dyn_covar + ((size_t)b * T + t + 1) * DX * DX + (size_t)(ln - LINES) * (128 / sizeof(R)));
+          }
+        }
         // ---- F1: [Sigma_ux | mu_u] = K [Sigma_xx | mu_x] (+ k); K_prev mu_x (lqg.py:227-230, 294) --------------
         warp_mma<R, 1, D::NBP>(w, tp + D::oK, KTL, tp + D::oM, PP, DX4 / 4, [&](int a2, int j, R v0, R v1) {
           if (a2 < DU) {
@@ -473,7 +484,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
           for (int ra = 0; ra < D::NBP; ++ra)
 #pragma unroll
             for (int rb = 0; rb < D::NBX; ++rb) { c[ra][rb][0] = R(0); c[ra][rb][1] = R(0); }
-          R muj[D::NBP], cn[D::NBP];
+          R muj[D::NBP], cn[D::NBP], cn2[D::NBP];
           auto loadC = [&](int k, int ra) {
             const int j = 8 * ra + g;
             return (do_cost && k < P && j < P) ? ldg(Cg + k * P + j) : R(0);
@@ -482,6 +493,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
           for (int ra = 0; ra < D::NBP; ++ra) {
             muj[ra] = 8 * ra + g < P ? tp[D::oM + (8 * ra + g) * PP + P] : R(0);
             cn[ra] = loadC(tq, ra);
+            cn2[ra] = loadC(tq + 4, ra);
           }
           R cost = R(0);
           const R* ap = tp + D::oM + tq * PP + g;
@@ -490,7 +502,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
             const int k = 4 * k4 + tq;
             R cc_[D::NBP], af[D::NBP], bf[D::NBX];
 #pragma unroll
-            for (int ra = 0; ra < D::NBP; ++ra) { cc_[ra] = cn[ra]; cn[ra] = loadC(k + 4, ra); af[ra] = ap[8 * ra]; }
+            for (int ra = 0; ra < D::NBP; ++ra) { cc_[ra] = cn[ra]; cn[ra] = cn2[ra]; cn2[ra] = loadC(k + 8, ra); af[ra] = ap[8 * ra]; }
 #pragma unroll
             for (int rb = 0; rb < D::NBX; ++rb) bf[rb] = bp[8 * rb];
             if (do_cost) {
@@ -579,14 +591,14 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
         // ---- F4: Sigma'_xx = (F Sigma) F^T + dyn_covar (upper blocks, mirrored); mu' = F mu + f; scalars -------------
         {
           const R* Dg = a.dyn_covar + ((size_t)b * T + t) * DX * DX;
-          auto pre = [&](int i, int j, R& p0, R& p1) {
+          auto pre = [&](int i, int j, R* pv) {
             if (i >= DX || i > j + 1 || j >= DX) return;
-            if (j + 1 < DX) ldg2(Dg + i * DX + j, DX % 2 == 0, p0, p1);
-            else p0 = ldg(Dg + i * DX + j);
+            if (j + 1 < DX) ldg2(Dg + i * DX + j, DX % 2 == 0, pv[0], pv[1]);
+            else pv[0] = ldg(Dg + i * DX + j);
           };
-          auto epi = [&](int i, int j, R v0, R v1, R p0, R p1) {
+          auto epi = [&](int i, int j, R v0, R v1, const R* pv) {
             if (i >= DX || i > j + 1 || j >= DX) return;
-            const R s0 = v0 + p0, s1 = v1 + p1;
+            const R s0 = v0 + pv[0], s1 = v1 + pv[1];
             if (i <= j && j + 1 < DX) {
               st2(tp + D::oM + i * PP + j, s0, s1);
               tp[D::oM + j * PP + i] = s0;
@@ -598,10 +610,10 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
           };
 #define DONK_F4_ROW(RB_ROW)                                                                                        \
   if (RB_ROW < D::NBX)                                                                                             \
-    warp_mma_pre<R, 1, (D::NBX - RB_ROW > 0 ? D::NBX - RB_ROW : 1)>(                                                \
+    warp_mma_pre<R, 1, (D::NBX - RB_ROW > 0 ? D::NBX - RB_ROW : 1), 2>(                                             \
         w, tp + D::oR + 8 * RB_ROW, DXP, st + D::oFx + 8 * RB_ROW, DXP, P4 / 4,                                     \
-        [&](int i, int j, R& p0, R& p1) { pre(8 * RB_ROW + i, 8 * RB_ROW + j, p0, p1); },                           \
-        [&](int i, int j, R v0, R v1, R p0, R p1) { epi(8 * RB_ROW + i, 8 * RB_ROW + j, v0, v1, p0, p1); });
+        [&](int i, int j, R* pv) { pre(8 * RB_ROW + i, 8 * RB_ROW + j, pv); },                                      \
+        [&](int i, int j, R v0, R v1, const R* pv) { epi(8 * RB_ROW + i, 8 * RB_ROW + j, v0, v1, pv); });
           DONK_F4_ROW(0) DONK_F4_ROW(1) DONK_F4_ROW(2) DONK_F4_ROW(3)
 #undef DONK_F4_ROW
         }
