@@ -100,7 +100,7 @@ def run_reference(args):
         solves = 0
         secs = 0.0
         for _ in range(args.steps):
-            s, t = cpu_ilqr_sample(pool, cores, 1, ETA_GRID)
+            s, t = cpu_ilqr_sample(pool, cores, 4, ETA_GRID)
             solves += s
             secs += t
     value = solves / secs
@@ -111,7 +111,7 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(1),
         "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port",
-                         "sample": f"{cores} conditions x 16 eta per step (T={w['T']},dX={w['dX']},dU={w['dU']}), "
+                         "sample": f"{4 * cores} conditions x 16 eta per step (T={w['T']},dX={w['dX']},dU={w['dU']}), "
                                    f"oracle ILQR.step, one process per core"},
         "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -304,29 +304,30 @@ def run_ours(args):
         parity = worst
 
     # ---- e2e: host buffers in, results out, through the public batched API ------------------------------
+    # (chunked double-buffered pipeline: the H2D copy of chunk c+1 overlaps the solve of chunk c)
     pin = (lambda t: t) if dry else (lambda t: t.pin_memory())
-    host = {k: pin(v.cpu()) for k, v in dict(F=F, f=f, S=dyn_covar, pK=il.prev_K, pk=il.prev_k,
-                                                      pS=il.prev_covar, C=Cb, c=cb, cc=ccb, m=x0m, S0=x0S,
-                                                      eta=eta).items()}
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
-    out_host = pin(torch.empty(2, B, E, dtype=torch.float64))
-    d2h = out_host.numel() * 8
+    host = {k: pin(v.cpu()) for k, v in dict(F=F, f=f, dyn_covar=dyn_covar, prev_K=il.prev_K, prev_k=il.prev_k,
+                                             prev_covar=il.prev_covar, C=Cb, c=cb, cc=ccb, x0_mean=x0m,
+                                             x0_covar=x0S).items()}
+    eta_host = pin(eta.cpu())
+    dev_res = (holder["res"].kl_div.cpu(), holder["res"].expected_costs.cpu())
+    del il, holder["res"]
+    if not dry:
+        torch.cuda.empty_cache()
+    pipe = batched.HostPipelinedILQR(host, E, chunks=args.e2e_chunks)
+    h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
 
     def e2e_once():
-        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        il2 = batched.BatchedILQR(d["F"], d["f"], d["S"], d["pK"], d["pk"], d["C"], d["c"], d["cc"], d["m"], d["S0"],
-                                  prev_covar=d["pS"])
-        il2._ws = il._ws  # reuse the policy scratch buffers (allocation is not part of the path)
-        r = il2.step(d["eta"])
-        out_host[0].copy_(r.kl_div, non_blocking=True)
-        out_host[1].copy_(r.expected_costs, non_blocking=True)
-        sync()
+        holder["e2e"] = pipe.step(eta_host)
 
     e2e_steps = max(1, min(args.steps, 5))
     e2e_ms = timed(e2e_once, e2e_steps, 1) / e2e_steps
     e2e_value = solves_per_step / (e2e_ms * 1e-3)
+    kl_h, cost_h, info_h = holder["e2e"]
+    assert int(info_h.sum()) == 0
+    assert torch.allclose(kl_h, dev_res[0], rtol=1e-12, atol=1e-12) and torch.allclose(cost_h, dev_res[1], rtol=1e-12)
     clk = clocks.stop()
-    del host, il
+    del host, pipe
     if not dry:
         torch.cuda.empty_cache()
 
@@ -384,10 +385,10 @@ def run_ours(args):
         cores = os.cpu_count() or 1
         with mp.get_context("fork").Pool(cores) as pool:
             cpu_ilqr_sample(pool, cores, 1, ETA_GRID[:2])
-            s, t = cpu_ilqr_sample(pool, cores, 1, ETA_GRID)
+            s, t = cpu_ilqr_sample(pool, cores, 8, ETA_GRID)
         cpu = {"value": s / t, "unit": "solves/s", "cores": cores, "kind": "port",
-               "sample": f"{cores} conditions x 16 eta (T={T},dX={dX},dU={dU}) through oracle.ilqr_step, one process "
-                         f"per core, {t:.1f} s"}
+               "sample": f"{8 * cores} conditions x 16 eta (T={T},dX={dX},dU={dU}) through oracle.ilqr_step, one process "
+                         f"per core, {t:.1f} s wall ({t * cores:.0f} core-seconds)"}
 
     if rank == 0:
         line = {
@@ -424,6 +425,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--em-rows", type=int, default=10_000_000, help="rows of the GMM-EM extra (total over GPUs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="condition chunks of the host-buffer pipeline")
     ap.add_argument("--dry-run-emu", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -496,3 +496,77 @@ class DeviceGMM:
         resp = torch.empty(n, self.K, dtype=X.dtype, device=X.device)
         nat.call("gmm_predict_proba_f64", n, d, self.K, X, self.weights, self.means, self.precisions_cholesky, resp)
         return resp
+
+
+# =====================================================================================================
+# Host-resident inputs: chunked, double-buffered H2D -> step -> D2H pipeline
+# =====================================================================================================
+class HostPipelinedILQR:
+    """``ILQR.step`` for conditions whose inputs live in (pinned) host memory.
+
+    The conditions are cut into chunks; chunk c+1 is copied to the device on one stream while chunk c is
+    being solved on the other, so a step costs about max(PCIe time, kernel time) instead of their sum.
+    ``host`` maps the ``BatchedILQR`` argument names (F, f, dyn_covar, prev_K, prev_k, prev_covar, C, c, cc,
+    x0_mean, x0_covar) to CPU tensors with leading dimension B (pinned for asynchronous copies).
+    """
+
+    KEYS = ("F", "f", "dyn_covar", "prev_K", "prev_k", "prev_covar", "C", "c", "cc", "x0_mean", "x0_covar")
+
+    def __init__(self, host: dict, E: int, chunks: int = 8):
+        nat = _lib.native()
+        self.host = {k: host[k] for k in self.KEYS}
+        self.B = self.host["F"].shape[0]
+        self.E = E
+        self.chunks = max(1, min(chunks, self.B))
+        self.bc = (self.B + self.chunks - 1) // self.chunks
+        self.dev = nat.device
+        self.cuda = self.dev.type == "cuda"
+        n_slots = 2 if self.cuda else 1
+        self.streams = [torch.cuda.Stream(self.dev) for _ in range(n_slots)] if self.cuda else [None]
+        # per-slot device staging buffers and policy scratch (allocated once)
+        self.slots = []
+        for _ in range(n_slots):
+            bufs = {k: torch.empty((self.bc,) + tuple(v.shape[1:]), dtype=v.dtype, device=self.dev)
+                    for k, v in self.host.items()}
+            bufs["eta"] = torch.empty(self.bc, E, dtype=torch.float64, device=self.dev)
+            self.slots.append(dict(bufs=bufs, ws=None))
+        pin = (lambda t: t.pin_memory()) if self.cuda else (lambda t: t)
+        self.kl = pin(torch.empty(self.B, E, dtype=torch.float64))
+        self.cost = pin(torch.empty(self.B, E, dtype=torch.float64))
+        self.info = pin(torch.zeros(self.B, E, dtype=torch.int32))
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.host.values()) + self.B * E * 8
+        self.d2h_bytes = self.kl.numel() * 8 * 2 + self.info.numel() * 4
+
+    def step(self, eta_host: torch.Tensor):
+        """Solve all conditions for ``eta_host (B,E)`` (CPU tensor); returns pinned ``kl, cost, info``."""
+        import contextlib
+
+        for c in range(self.chunks):
+            lo, hi = c * self.bc, min((c + 1) * self.bc, self.B)
+            if lo >= hi:
+                break
+            n = hi - lo
+            slot = self.slots[c % len(self.slots)]
+            stream = self.streams[c % len(self.streams)]
+            ctx = torch.cuda.stream(stream) if self.cuda else contextlib.nullcontext()
+            with ctx:
+                d = {}
+                for k, v in self.host.items():
+                    d[k] = slot["bufs"][k][:n]
+                    d[k].copy_(v[lo:hi], non_blocking=True)
+                eta = slot["bufs"]["eta"][:n]
+                eta.copy_(eta_host[lo:hi], non_blocking=True)
+                il = BatchedILQR(d["F"], d["f"], d["dyn_covar"], d["prev_K"], d["prev_k"], d["C"], d["c"], d["cc"],
+                                 d["x0_mean"], d["x0_covar"], prev_covar=d["prev_covar"])
+                if slot["ws"] is not None and n == self.bc:
+                    il._ws = slot["ws"]
+                r = il.step(eta)
+                if n == self.bc:
+                    slot["ws"] = il._ws
+                self.kl[lo:hi].copy_(r.kl_div, non_blocking=True)
+                self.cost[lo:hi].copy_(r.expected_costs, non_blocking=True)
+                self.info[lo:hi].copy_(r.info, non_blocking=True)
+        if self.cuda:
+            for s in self.streams:
+                s.synchronize()
+        return self.kl, self.cost, self.info
