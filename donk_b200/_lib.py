@@ -35,8 +35,8 @@ SIGNATURES = {
     "fit_lr_f64": [c_int] * 5 + [P, P, c_int, P, P, P, P, c_double, c_double, c_double, P, P, P, P, P],
     "to_transitions_f64": [c_int] * 4 + [P, P, P, P],
     "state_fit_f64": [c_int] * 3 + [P, c_size_t, c_size_t, P, P, P],
-    "gmm_em_step_f64": [c_int] * 3 + [P] * 6 + [P, c_size_t, P],
-    "gmm_m_finalize_f64": [c_double, c_int, c_int, P, c_double, P, P, P, P, P, P, P],
+    "gmm_em_step_f64": [c_int] * 3 + [P] * 7 + [P, c_size_t, P],
+    "gmm_m_finalize_f64": [c_double, c_int, c_int, P, P, c_double, P, P, P, P, P, P, P],
     "gmm_predict_proba_f64": [c_int] * 3 + [P] * 5 + [P],
     "gmm_prec_chol_from_precisions_f64": [c_int] * 2 + [P] * 3 + [P],
     "fp64_probe": [c_int, c_int, c_int, P, ctypes.POINTER(c_double), P],

@@ -413,12 +413,13 @@ class DeviceGMM:
         stats = torch.empty(nat.size("gmm_stats_size", d, K), **o)
         lb = torch.zeros(1, **o)
         info = torch.zeros(K, dtype=torch.int32, device=X.device)
+        shift = torch.empty(K, d, **o)
         for _ in range(2):
-            nat.call("gmm_em_step_f64", n, d, K, X, None, self.means, None, onehot, stats, ws,
+            nat.call("gmm_em_step_f64", n, d, K, X, None, self.means, None, onehot, stats, shift, ws,
                      ws.numel() * ws.element_size())
             self._allreduce(stats, group)
-            nat.call("gmm_m_finalize_f64", float(n_total.item()), d, K, stats, float(self.reg_covar), self.weights,
-                     self.means, self.covariances, self.precisions_cholesky, lb, info)
+            nat.call("gmm_m_finalize_f64", float(n_total.item()), d, K, stats, shift, float(self.reg_covar),
+                     self.weights, self.means, self.covariances, self.precisions_cholesky, lb, info)
         if int(info.sum().item()):
             raise ValueError("Fitting the mixture model failed because some components have ill-defined "
                              "empirical covariance")
@@ -436,11 +437,13 @@ class DeviceGMM:
         """One E+M iteration over this rank's rows; returns the mean log-likelihood (pre-M-step)."""
         nat = _lib.native()
         n, d = X.shape
+        if getattr(self, "_shift", None) is None or self._shift.shape != self.means.shape:
+            self._shift = torch.empty_like(self.means)
         nat.call("gmm_em_step_f64", n, d, self.K, X, self.weights, self.means, self.precisions_cholesky, None, stats,
-                 ws, ws.numel() * ws.element_size())
+                 self._shift, ws, ws.numel() * ws.element_size())
         self._allreduce(stats, group)  # the one exchange step of the path (NCCL over NVLink)
-        nat.call("gmm_m_finalize_f64", float(n_total), d, self.K, stats, float(self.reg_covar), self.weights,
-                 self.means, self.covariances, self.precisions_cholesky, self._lb, self._info)
+        nat.call("gmm_m_finalize_f64", float(n_total), d, self.K, stats, self._shift, float(self.reg_covar),
+                 self.weights, self.means, self.covariances, self.precisions_cholesky, self._lb, self._info)
         return self._lb
 
     def fit(self, X_local, warm_start: bool = False, group=None, check_every: int = 1):

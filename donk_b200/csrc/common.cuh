@@ -334,7 +334,7 @@ DONK_HD void ldg2(const R* p, bool aligned16, R& v0, R& v1) {
 }
 
 // smallest leading dimension >= n that is a multiple of 4 and makes DMMA fragment loads conflict free
-constexpr int ld_pad(int n) {
+DONK_HD constexpr int ld_pad(int n) {
   int m = (n + 3) / 4 * 4;
   return m % 8 == 0 ? m + 4 : m;
 }

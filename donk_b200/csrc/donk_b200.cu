@@ -10,6 +10,7 @@
 #include "../../include/donk_b200.h"
 #include "fitlr.cuh"
 #include "gmm.cuh"
+#include "gmm_mma.cuh"
 #include "ilqr.cuh"
 #include "ilqr_warp.cuh"
 
@@ -316,6 +317,62 @@ __global__ void __launch_bounds__(256) gmm_prec_chol_kernel(int d, const R* prec
   gmm_prec_chol_cta<R>(ctx, d, prec, pc, info, (int)blockIdx.x, reinterpret_cast<R*>(smem_raw));
 }
 
+template <int NB, int RA>
+__global__ void __launch_bounds__(256, 1) gmm_e_mma_kernel(const GmmArgs<double> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WCtx w{(int)threadIdx.x, (int)blockDim.x, (int)threadIdx.x >> 5, (int)threadIdx.x & 31, (int)blockDim.x >> 5};
+  gmm_e_mma_cta<double, NB, RA>(w, a, (int)blockIdx.x, (int)gridDim.x, reinterpret_cast<double*>(smem_raw));
+}
+template <int NBW, int KC>
+__global__ void __launch_bounds__(NBW <= 6 ? 256 : 512, NBW <= 6 ? 2 : 1) gmm_m_mma_kernel(const GmmArgs<double> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WCtx w{(int)threadIdx.x, (int)blockDim.x, (int)threadIdx.x >> 5, (int)threadIdx.x & 31, (int)blockDim.x >> 5};
+  gmm_m_mma_cta<double, NBW, KC>(w, a, (int)blockIdx.x, reinterpret_cast<double*>(smem_raw));
+}
+
+template <int NB, int RA>
+int gmm_e_mma_launch(GmmArgs<double>& a, const GmmMmaPlan& pl, void* stream) {
+  const int TS = 8 * RA * pl.Ge;
+  a.nblocks = (a.n + TS - 1) / TS;
+  const size_t smem = gmm_e_mma_smem<NB, RA>(a.K, pl.Ge) * sizeof(double);
+  if (smem > smem_optin_cap()) return DONK_SMEM_LIMIT;
+  int rc = allow_smem(gmm_e_mma_kernel<NB, RA>, smem);
+  if (rc != DONK_OK) return rc;
+  int grid = 148;  // one CTA per SM: the rest of the SM's memory is L1 for the P_k all warps walk together
+  if (grid > a.nblocks) grid = a.nblocks;
+  gmm_e_mma_kernel<NB, RA><<<grid, 32 * pl.Ge, smem, (cudaStream_t)stream>>>(a);
+  LAUNCHED("gmm_e_mma_kernel");
+  return DONK_OK;
+}
+
+int gmm_e_mma_dispatch(GmmArgs<double>& a, const GmmMmaPlan& pl, void* stream) {
+  switch (pl.NB) {
+    case 2: return gmm_e_mma_launch<2, 2>(a, pl, stream);
+    case 5: return gmm_e_mma_launch<5, 2>(a, pl, stream);
+    case 6: return gmm_e_mma_launch<6, 2>(a, pl, stream);
+    case 9: return gmm_e_mma_launch<9, 2>(a, pl, stream);
+    default: return gmm_e_mma_launch<18, 1>(a, pl, stream);
+  }
+}
+
+int gmm_m_mma_dispatch(GmmArgs<double>& a, const GmmMmaPlan& pl, void* stream) {
+  const size_t smem = gmm_m_mma_smem(a.d, pl.KC) * sizeof(double);
+  if (smem > smem_optin_cap()) return DONK_SMEM_LIMIT;
+  const int grid = ((a.K + pl.KC - 1) / pl.KC) * a.nch;
+  int rc;
+  if (pl.NBW <= 6) {
+    rc = allow_smem(gmm_m_mma_kernel<6, 2>, smem);
+    if (rc != DONK_OK) return rc;
+    gmm_m_mma_kernel<6, 2><<<grid, 32 * pl.Gm, smem, (cudaStream_t)stream>>>(a);
+  } else {
+    rc = allow_smem(gmm_m_mma_kernel<11, 2>, smem);
+    if (rc != DONK_OK) return rc;
+    gmm_m_mma_kernel<11, 2><<<grid, 32 * pl.Gm, smem, (cudaStream_t)stream>>>(a);
+  }
+  LAUNCHED("gmm_m_mma_kernel");
+  return DONK_OK;
+}
+
 int gmm_e_launch(GmmArgs<double>& a, void* stream) {
   const size_t smem = gmm_e_smem(a.d, a.K) * sizeof(double);
   if (smem > smem_optin_cap()) return DONK_SMEM_LIMIT;
@@ -512,9 +569,8 @@ size_t donk_gmm_stats_size(int d, int K) { return gmm_stats_len(d, K); }
 size_t donk_gmm_workspace_bytes(int n_local, int d, int K) { return gmm_ws_reals(n_local, d, K) * sizeof(double); }
 
 int donk_gmm_em_step_f64(int n_local, int d, int K, const double* X, const double* weights, const double* means,
-                         const double* prec_chol, const double* resp_in, double* stats, void* workspace,
-                         size_t workspace_bytes,
-                         void* stream) {
+                         const double* prec_chol, const double* resp_in, double* stats, double* shift,
+                         void* workspace, size_t workspace_bytes, void* stream) {
   if (n_local < 0 || d < 1 || K < 1) return DONK_BAD_SHAPE;
   if (workspace_bytes < donk_gmm_workspace_bytes(n_local, d, K)) return DONK_BAD_SHAPE;
   const size_t total = gmm_stats_len(d, K);
@@ -532,13 +588,25 @@ int donk_gmm_em_step_f64(int n_local, int d, int K, const double* X, const doubl
   a.lse_part = ws + (size_t)n_local * K;
   a.part = a.lse_part + a.nblocks;
   int rc = DONK_OK;
+  const GmmMmaPlan pl = gmm_mma_plan(n_local, d, K);
+  const bool mma = pl.ok && !env_int("DONK_GMM_GENERIC") && weights != nullptr;
   if (resp_in) {
     a.resp = const_cast<double*>(resp_in);
     CU(cudaMemsetAsync(a.lse_part, 0, (size_t)a.nblocks * sizeof(double), (cudaStream_t)stream));
   } else {
-    rc = gmm_e_launch(a, stream);
+    rc = mma ? gmm_e_mma_dispatch(a, pl, stream) : gmm_e_launch(a, stream);
     if (rc != DONK_OK) return rc;
   }
+  if (mma) {
+    a.nch = pl.nch;
+    a.shift_out = shift;
+    rc = gmm_m_mma_dispatch(a, pl, stream);
+    if (rc != DONK_OK) return rc;
+    gmm_reduce_kernel<double><<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a, total, stats);
+    LAUNCHED("gmm_reduce_kernel");
+    return DONK_OK;
+  }
+  if (shift) CU(cudaMemcpyAsync(shift, means, (size_t)K * d * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   const int threads = gmm_m_threads(d);
   const size_t smem = gmm_m_smem(d) * sizeof(double);
   if (threads == 0 || smem > smem_optin_cap()) return DONK_SMEM_LIMIT;
@@ -551,12 +619,12 @@ int donk_gmm_em_step_f64(int n_local, int d, int K, const double* X, const doubl
   return DONK_OK;
 }
 
-int donk_gmm_m_finalize_f64(double n_total, int d, int K, const double* stats, double reg_covar, double* weights,
-                            double* means, double* covariances, double* prec_chol, double* lower_bound, int* info,
-                            void* stream) {
+int donk_gmm_m_finalize_f64(double n_total, int d, int K, const double* stats, const double* shift, double reg_covar,
+                            double* weights, double* means, double* covariances, double* prec_chol,
+                            double* lower_bound, int* info, void* stream) {
   if (d < 1 || K < 1) return DONK_BAD_SHAPE;
   GmmFinArgs<double> a;
-  a.d = d; a.K = K; a.n_total = n_total; a.reg_covar = reg_covar; a.stats = stats;
+  a.d = d; a.K = K; a.n_total = n_total; a.reg_covar = reg_covar; a.stats = stats; a.shift = shift;
   a.w = weights; a.means = means; a.cov = covariances; a.pc = prec_chol; a.lower_bound = lower_bound; a.info = info;
   const size_t smem = gmm_fin_smem(d) * sizeof(double);
   if (smem > smem_optin_cap()) return DONK_SMEM_LIMIT;

@@ -42,6 +42,7 @@ struct GmmArgs {
   // M pass
   int nch;                           // row ranges per cluster
   R* part;                           // (K,nch,1+d+d*d)
+  R* shift_out;                      // (K,d) centring point of the statistics (written by the M pass), or null
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -328,6 +329,7 @@ struct GmmFinArgs {
   int d, K;
   R n_total, reg_covar;
   const R* stats;
+  const R* shift;  // (K,d) centring point the statistics were accumulated around (null: the current means)
   R *w, *means, *cov, *pc, *lower_bound;
   int* info;
 };
@@ -345,16 +347,16 @@ DONK_D void gmm_finalize_cta(const Ctx& ctx, const GmmFinArgs<R>& a, int k, R* s
   const R nk = nk_raw + eps10;  // _gaussian_mixture.py:312
   const R* s = a.stats + K + (size_t)k * d;
   const R* S = a.stats + (size_t)K * (1 + d) + (size_t)k * d * d;
-  // delta = new mean - old mean;  new mean = (sum r x) / nk with sum r x = s + nk_raw mu_old
+  // delta = new mean - centre;  new mean = (sum r x) / nk with sum r x = s + nk_raw centre
   TEAM_FOR(j, d) {
-    const R mo = a.means[(size_t)k * d + j];
+    const R mo = a.shift ? a.shift[(size_t)k * d + j] : a.means[(size_t)k * d + j];
     const R mn = (s[j] + nk_raw * mo) / nk;
     dl[j] = mn - mo;
     dg[j] = mn;
   }
   ctx.sync();
   TEAM_FOR(j, d) a.means[(size_t)k * d + j] = dg[j];
-  // Sigma = sum r (x - mu_new)(x - mu_new)^T / nk + reg I, expanded around the old mean
+  // Sigma = sum r (x - mu_new)(x - mu_new)^T / nk + reg I, expanded around the centring point
   TEAM_FOR(idx, d * d) {
     const int i = idx / d, j = idx % d;
     if (i > j) continue;
@@ -436,7 +438,9 @@ inline int gmm_m_threads(int d) {
 // workspace layout in reals: resp (n,K) | lse_part (nblocks) | part (K,nch,1+d+d*d)
 inline size_t gmm_ws_reals(int n, int d, int K) {
   const size_t nblocks = ((size_t)n + GMM_TS - 1) / GMM_TS;
-  return (size_t)n * K + nblocks + (size_t)K * gmm_nch(n, d, K) * gmm_part_len(d);
+  int nch = gmm_nch(n, d, K);
+  if (nch < 160) nch = 160;  // the tensor-path M pass (gmm_mma.cuh) uses up to 148*4/ceil(K/2) ranges
+  return (size_t)n * K + nblocks + (size_t)K * nch * gmm_part_len(d);
 }
 
 }  // namespace donk

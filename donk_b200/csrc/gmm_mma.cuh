@@ -1,0 +1,365 @@
+// donk_b200 — GMM EM, E and M passes on the FP64 tensor path (mma.sync.m8n8k4.f64).
+//
+// Same iteration as gmm.cuh (sklearn.mixture.GaussianMixture as called from GMMPrior.update,
+// donk/dynamics/prior/prior_gmm.py:14-24); these are the fast kernels, the scalar-FMA ones in gmm.cuh stay
+// as the generic fallback (d > 144) and as the emulation reference.
+//
+//   gmm_e_mma_cta  E pass.  CTA = G warps, tile of 8*RA*G rows staged feature-major (k-major A operand);
+//                  per cluster y = x P_k + sP_k as DMMA fragments against the upper-triangular P_k read
+//                  through L1 (all warps of the CTA walk the same P_k), only blocks on or above the
+//                  diagonal are multiplied; row sums of y^2 by a 4-lane shuffle; then softmax, resp, lse.
+//   gmm_m_mma_cta  M pass.  CTA = (group of KC clusters, row range).  Rows are staged once, shifted by the
+//                  mixture mean x_bar (cluster independent, keeps cancellation at the cluster-separation
+//                  level); the scatter sum_n r_nk (x-x_bar)(x-x_bar)^T is accumulated as DMMA fragments that stay in
+//                  registers for the whole range: the sample index is the k dimension, the A fragment is
+//                  scaled by r_nk in registers, the B fragment is shared by the KC clusters.
+//                  sum r (x - x_bar) and sum r come from a small FMA side loop.
+#pragma once
+#include "common.cuh"
+#include "gmm.cuh"
+
+namespace donk {
+
+// ------------------------------------------------------------------------------------------------------
+// E pass
+// ------------------------------------------------------------------------------------------------------
+template <int NB, int RA>
+DONK_HD size_t gmm_e_mma_smem(int K, int G) {
+  const int TS = 8 * RA * G, ldt = ld_pad(TS);
+  return (size_t)8 * NB * ldt + (size_t)K * 8 * NB + round_up(K, 4) + (size_t)TS * K + 8;
+}
+
+template <typename R, int NB, int RA>
+DONK_D void gmm_e_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, int ncta, R* sm) {
+  const int d = a.d, K = a.K, G = w.G;
+  const int TS = 8 * RA * G, ldt = ld_pad(TS), D8 = 8 * NB;
+  R* Xt = sm;                       // [D8][ldt]   feature-major rows of the tile
+  R* sP = Xt + (size_t)D8 * ldt;    // [K][D8]     -(mu_k P_k)
+  R* ldet = sP + (size_t)K * D8;    // [K]         sum log diag P_k + log pi_k
+  R* logp = ldet + round_up(K, 4);  // [TS][K]
+  const size_t dd = (size_t)d * d;
+  CTA_FOR(idx, D8 * ldt) Xt[idx] = R(0);
+  CTA_FOR(idx, K * D8) {
+    const int k = idx / D8, j = idx % D8;
+    R acc = R(0);
+    if (j < d) {
+      const R* P = a.pc + (size_t)k * dd;
+      for (int i = 0; i <= j; ++i) acc = fma(ldg(a.means + (size_t)k * d + i), ldg(P + (size_t)i * d + j), acc);
+    }
+    sP[idx] = -acc;
+  }
+  CTA_FOR(k, K) {
+    const R* P = a.pc + (size_t)k * dd;
+    R acc = R(0);
+    for (int i = 0; i < d; ++i) acc += log(ldg(P + (size_t)i * d + i));
+    ldet[k] = acc + log(ldg(a.w + k));
+  }
+  w.cta_sync();
+  const R cst = R(d) * R(1.8378770664093453);  // d log(2 pi)
+  for (int blk = cta; blk < a.nblocks; blk += ncta) {
+    const size_t n0 = (size_t)blk * TS;
+    CTA_FOR(idx, TS * d) {
+      const int r = idx / d, j = idx % d;
+      Xt[j * ldt + r] = n0 + r < (size_t)a.n ? ldg(a.X + (n0 + r) * d + j) : R(0);
+    }
+    w.cta_sync();
+    for (int k = 0; k < K; ++k) {
+      const R* P = a.pc + (size_t)k * dd;
+      TEAMS_DO(tm) {
+        const int i0 = 8 * RA * tm;
+#if !defined(DONK_EMU)
+        const int g = w.lane >> 2, tq = w.lane & 3;
+        R c[RA][NB][2];
+#pragma unroll
+        for (int ra = 0; ra < RA; ++ra)
+#pragma unroll
+          for (int jb = 0; jb < NB; ++jb) { c[ra][jb][0] = R(0); c[ra][jb][1] = R(0); }
+#pragma unroll
+        for (int fb = 0; fb < NB; ++fb) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int f = 8 * fb + 4 * h + tq;  // feature index = k dimension of the product
+            R af[RA];
+#pragma unroll
+            for (int ra = 0; ra < RA; ++ra) af[ra] = Xt[f * ldt + i0 + 8 * ra + g];
+#pragma unroll
+            for (int jb = fb; jb < NB; ++jb) {  // P_k is upper triangular: blocks below the diagonal are zero
+              const int j = 8 * jb + g;
+              const R bf = (f < d && j < d) ? ldg(P + (size_t)f * d + j) : R(0);
+#pragma unroll
+              for (int ra = 0; ra < RA; ++ra) {
+                double d0 = (double)c[ra][jb][0], d1 = (double)c[ra][jb][1];
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(d0), "+d"(d1)
+                             : "d"((double)af[ra]), "d"((double)bf));
+                c[ra][jb][0] = (R)d0;
+                c[ra][jb][1] = (R)d1;
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int ra = 0; ra < RA; ++ra) {
+          R ss = R(0);
+#pragma unroll
+          for (int jb = 0; jb < NB; ++jb) {
+            const int j = 8 * jb + 2 * tq;
+            const R y0 = c[ra][jb][0] + sP[k * D8 + j], y1 = c[ra][jb][1] + sP[k * D8 + j + 1];
+            ss = fma(y0, y0, ss);  // padded columns: c = 0 and sP = 0
+            ss = fma(y1, y1, ss);
+          }
+          ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+          ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+          if (tq == 0) logp[(i0 + 8 * ra + g) * K + k] = -(cst + ss) / 2 + ldet[k];
+        }
+#else
+        for (int r = 0; r < 8 * RA; ++r) {
+          R ss = R(0);
+          for (int j = 0; j < d; ++j) {
+            R y = sP[k * D8 + j];
+            for (int f = 0; f <= j; ++f) y = fma(Xt[f * ldt + i0 + r], P[(size_t)f * d + j], y);
+            ss = fma(y, y, ss);
+          }
+          logp[(i0 + r) * K + k] = -(cst + ss) / 2 + ldet[k];
+        }
+#endif
+      }
+    }
+    w.cta_sync();
+    CTA_FOR(r, TS) {
+      if (n0 + r >= (size_t)a.n) { logp[r * K] = R(0); continue; }
+      R* lp = logp + r * K;
+      R m = lp[0];
+      for (int k = 1; k < K; ++k) m = lp[k] > m ? lp[k] : m;
+      R s = R(0);
+      for (int k = 0; k < K; ++k) s += exp(lp[k] - m);
+      const R lse = m + log(s);
+      for (int k = 0; k < K; ++k) a.resp[(n0 + r) * K + k] = exp(lp[k] - lse);
+      lp[0] = lse;
+    }
+    w.cta_sync();
+    if (a.lse_part) {
+      CTA_FOR(one, 1) {
+        R acc = R(0);
+        for (int r = 0; r < TS; ++r) acc += logp[r * K];
+        a.lse_part[blk] = acc;
+      }
+    }
+    w.cta_sync();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// M pass
+// ------------------------------------------------------------------------------------------------------
+enum { GMM_MTS = 64 };  // rows per staged tile of the M pass
+
+DONK_HD size_t gmm_m_mma_smem(int d, int KC) {
+  const int D8 = round_up(d, 8), ld = ld_pad(D8);
+  return (size_t)2 * GMM_MTS * ld + (size_t)2 * GMM_MTS * KC + D8 + 8;
+}
+
+// block q of the row-major enumeration of the upper triangle of an nb x nb block grid
+DONK_HD void tri_block(int q, int nb, int& ib, int& jb) {
+  int r = 0;
+  while (q >= nb - r) { q -= nb - r; ++r; }
+  ib = r; jb = r + q;
+}
+
+template <typename R, int NBW, int KC>
+DONK_D void gmm_m_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, R* sm) {
+  const int d = a.d, K = a.K, G = w.G, TS = GMM_MTS;
+  const int nb = (d + 7) / 8, D8 = 8 * nb, ld = ld_pad(D8), nblk = nb * (nb + 1) / 2;
+  const int ngroups = (K + KC - 1) / KC;
+  const int kg = cta / a.nch, ch = cta % a.nch;
+  (void)ngroups;
+  R* Xs = sm;                                   // [2][TS][ld]  rows minus x_bar (double buffered)
+  R* rr = Xs + (size_t)2 * TS * ld;             // [2][TS][KC]  responsibilities of the KC clusters
+  R* xbar = rr + (size_t)2 * TS * KC;           // [D8]
+  const size_t rows_per = ((size_t)a.n + a.nch - 1) / a.nch;
+  const size_t row0 = (size_t)ch * rows_per;
+  const size_t row1 = row0 + rows_per < (size_t)a.n ? row0 + rows_per : (size_t)a.n;
+  const size_t pl = gmm_part_len(d);
+
+  CTA_FOR(j, D8) {  // x_bar = sum_k pi_k mu_k: the common centring point of this iteration
+    R acc = R(0);
+    if (j < d)
+      for (int k = 0; k < K; ++k) acc = fma(ldg(a.w + k), ldg(a.means + (size_t)k * d + j), acc);
+    xbar[j] = acc;
+  }
+  CTA_FOR(idx, 2 * TS * ld) Xs[idx] = R(0);
+  w.cta_sync();
+  if (cta == 0 && a.shift_out) {
+    CTA_FOR(idx, K * d) a.shift_out[idx] = xbar[idx % d];
+  }
+
+  // block range of every warp (contiguous in row-major order: consecutive blocks share their A fragment)
+  const int per = (nblk + G - 1) / G;
+
+#if !defined(DONK_EMU)
+  const int g = w.lane >> 2, tq = w.lane & 3;
+  const int q0 = w.team * per;
+  int ib[NBW], jb[NBW];
+  bool ok[NBW];
+  R acc[NBW][KC][2];
+#pragma unroll
+  for (int i = 0; i < NBW; ++i) {
+    ok[i] = i < per && q0 + i < nblk;
+    ib[i] = 0; jb[i] = 0;
+    if (ok[i]) tri_block(q0 + i, nb, ib[i], jb[i]);
+#pragma unroll
+    for (int c = 0; c < KC; ++c) { acc[i][c][0] = R(0); acc[i][c][1] = R(0); }
+  }
+  R side[KC];  // thread tid < d: sum_n r_nc (x - x_bar)[tid]; thread tid == d: sum_n r_nc
+#pragma unroll
+  for (int c = 0; c < KC; ++c) side[c] = R(0);
+#else
+  std::vector<R> accS((size_t)KC * d * d, R(0)), accs((size_t)KC * d, R(0)), accn(KC, R(0));
+#endif
+
+  auto stage = [&](size_t n0, int buf) {
+    R* xs = Xs + (size_t)buf * TS * ld;
+    R* rk = rr + (size_t)buf * TS * KC;
+    CTA_FOR(idx, TS * d) {
+      const int r = idx / d, j = idx % d;
+      if (n0 + r < row1) cp_async(xs + r * ld + j, a.X + (n0 + r) * d + j);
+      else xs[r * ld + j] = R(0);
+    }
+    CTA_FOR(idx, TS * KC) {
+      const int r = idx / KC, c = idx % KC;
+      const int k = kg * KC + c;
+      if (n0 + r < row1 && k < K) cp_async(rk + idx, a.resp + (n0 + r) * K + k);
+      else rk[idx] = R(0);
+    }
+  };
+
+  int buf = 0;
+  if (row0 < row1) stage(row0, 0);
+  for (size_t n0 = row0; n0 < row1; n0 += TS) {
+    cp_async_wait_all();
+    w.cta_sync();
+    if (n0 + TS < row1) stage(n0 + TS, buf ^ 1);  // next tile lands while this one is multiplied
+    R* xs = Xs + (size_t)buf * TS * ld;
+    const R* rk = rr + (size_t)buf * TS * KC;
+    // centre the freshly landed tile on x_bar (in place; rows beyond the range stay zero)
+    CTA_FOR(idx, TS * d) {
+      const int r = idx / d, j = idx % d;
+      if (n0 + r < row1) xs[r * ld + j] -= xbar[j];
+    }
+    w.cta_sync();
+#if !defined(DONK_EMU)
+    for (int k4 = 0; k4 < TS / 4; ++k4) {
+      const int n = 4 * k4 + tq;
+      R rv[KC];
+#pragma unroll
+      for (int c = 0; c < KC; ++c) rv[c] = rk[n * KC + c];
+      R av = R(0), bv;
+#pragma unroll
+      for (int i = 0; i < NBW; ++i) {
+        if (!ok[i]) continue;
+        if (i == 0 || ib[i] != ib[i - 1]) av = xs[n * ld + 8 * ib[i] + g];
+        bv = xs[n * ld + 8 * jb[i] + g];
+#pragma unroll
+        for (int c = 0; c < KC; ++c) {
+          double d0 = (double)acc[i][c][0], d1 = (double)acc[i][c][1];
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(d0), "+d"(d1)
+                       : "d"((double)(av * rv[c])), "d"((double)bv));
+          acc[i][c][0] = (R)d0;
+          acc[i][c][1] = (R)d1;
+        }
+      }
+    }
+    if (w.tid <= d) {
+      for (int r = 0; r < TS; ++r) {
+        const R xv = w.tid < d ? xs[r * ld + w.tid] : R(1);
+#pragma unroll
+        for (int c = 0; c < KC; ++c) side[c] = fma(rk[r * KC + c], xv, side[c]);
+      }
+    }
+#else
+    for (int c = 0; c < KC; ++c)
+      for (int r = 0; r < TS; ++r) {
+        const R rv = rk[r * KC + c];
+        accn[c] += rv;
+        for (int i = 0; i < d; ++i) {
+          const R wi = rv * xs[r * ld + i];
+          accs[(size_t)c * d + i] += wi;
+          for (int j = i; j < d; ++j) accS[((size_t)c * d + i) * d + j] = fma(wi, xs[r * ld + j], accS[((size_t)c * d + i) * d + j]);
+        }
+      }
+#endif
+    buf ^= 1;
+    w.cta_sync();
+  }
+  cp_async_wait_all();
+
+  // partial of (cluster, range): [nk | s (d) | S (d,d) both halves]
+#if !defined(DONK_EMU)
+#pragma unroll
+  for (int c = 0; c < KC; ++c) {
+    const int k = kg * KC + c;
+    if (k >= K) continue;
+    R* out = a.part + ((size_t)k * a.nch + ch) * pl;
+    if (w.tid < d) out[1 + w.tid] = side[c];
+    else if (w.tid == d) out[0] = side[c];
+#pragma unroll
+    for (int i = 0; i < NBW; ++i) {
+      if (!ok[i]) continue;
+      const int gi = 8 * ib[i] + g, gj = 8 * jb[i] + 2 * tq;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (gi <= gj + h && gj + h < d) {
+          out[1 + d + (size_t)gi * d + gj + h] = acc[i][c][h];
+          out[1 + d + (size_t)(gj + h) * d + gi] = acc[i][c][h];
+        }
+      }
+    }
+  }
+#else
+  for (int c = 0; c < KC; ++c) {
+    const int k = kg * KC + c;
+    if (k >= K) continue;
+    R* out = a.part + ((size_t)k * a.nch + ch) * pl;
+    out[0] = accn[c];
+    for (int i = 0; i < d; ++i) out[1 + i] = accs[(size_t)c * d + i];
+    for (int i = 0; i < d; ++i)
+      for (int j = i; j < d; ++j) {
+        out[1 + d + (size_t)i * d + j] = accS[((size_t)c * d + i) * d + j];
+        out[1 + d + (size_t)j * d + i] = accS[((size_t)c * d + i) * d + j];
+      }
+  }
+#endif
+}
+
+// ---- launch planning shared by the CUDA library and the emulation ---------------------------------------------
+struct GmmMmaPlan {
+  int NB, RA, Ge;      // E pass: 8-column blocks, 8-row fragments per warp, warps per CTA
+  int NBW, KC, Gm;     // M pass: blocks per warp, clusters per CTA, warps per CTA
+  int nch;             // row ranges per cluster group
+  int ok;
+};
+inline GmmMmaPlan gmm_mma_plan(int n, int d, int K) {
+  GmmMmaPlan p{};
+  const int nb = (d + 7) / 8;
+  p.ok = nb <= 18;
+  p.NB = nb <= 2 ? 2 : nb <= 5 ? 5 : nb <= 6 ? 6 : nb <= 9 ? 9 : 18;
+  p.RA = p.NB <= 9 ? 2 : 1;
+  p.Ge = 8;
+  p.KC = 2;
+  p.Gm = nb <= 9 ? 8 : 16;
+  p.NBW = nb <= 9 ? 6 : 11;
+  const size_t smem = gmm_m_mma_smem(d, p.KC) * sizeof(double) + 1024;
+  int per_sm = (int)((228 * 1024) / smem);
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  const int groups = (K + p.KC - 1) / p.KC;
+  int nch = (148 * per_sm) / groups;
+  const int max_ch = (n + GMM_MTS - 1) / GMM_MTS;
+  if (nch > max_ch) nch = max_ch;
+  if (nch < 1) nch = 1;
+  p.nch = nch;
+  return p;
+}
+
+}  // namespace donk

@@ -160,19 +160,22 @@ size_t donk_gmm_workspace_bytes(int n_local, int d, int K);
  * stats receives this rank's partial sums (the caller all-reduces them across ranks).
  * resp_in (n_local,K), optional: use these responsibilities instead of running the E-step (the
  * one-hot responsibilities of a hard initial labelling, sklearn/mixture/_base.py:119-128); the
- * lse entry of stats is then 0 and weights / prec_chol are not read. */
+ * lse entry of stats is then 0 and weights / prec_chol are not read.
+ * shift (K,d), output: the point every cluster's statistics are centred on (first- and second-order sums are
+ * taken of x - shift_k to avoid cancellation); pass it on to donk_gmm_m_finalize_f64. */
 int donk_gmm_em_step_f64(int n_local, int d, int K, const double* X,
                          const double* weights, const double* means, const double* prec_chol,
                          const double* resp_in,
-                         double* stats, void* workspace, size_t workspace_bytes, void* stream);
+                         double* stats, double* shift, void* workspace, size_t workspace_bytes, void* stream);
 
 /* M-step finalisation from (all-reduced) statistics of n_total rows: new weights, means,
  * covariances (+ reg_covar I), precision Cholesky factors, mean log-likelihood.
- * means is in/out (statistics are centred on the previous means).
+ * shift (K,d): the centring point written by donk_gmm_em_step_f64 (NULL: the current means); means is output
+ * (and the centring point when shift is NULL).
  * info (K) int32: 1 where a covariance is not positive definite (sklearn raises ValueError). */
-int donk_gmm_m_finalize_f64(double n_total, int d, int K, const double* stats, double reg_covar,
-                            double* weights, double* means, double* covariances, double* prec_chol,
-                            double* lower_bound, int* info, void* stream);
+int donk_gmm_m_finalize_f64(double n_total, int d, int K, const double* stats, const double* shift,
+                            double reg_covar, double* weights, double* means, double* covariances,
+                            double* prec_chol, double* lower_bound, int* info, void* stream);
 
 /* Responsibilities (predict_proba) of rows X (n,d): resp (n,K).  Used by GMMPrior.eval for callers
  * that want the NIW object itself (prior_gmm.py:33). */

@@ -59,3 +59,19 @@ else:
         gm.fit(X)
     torch.cuda.synchronize()
     print("lb", gm.lower_bound)
+    if len(sys.argv) > 3:
+        import os
+        nat = _lib.native()
+        o = dict(dtype=torch.float64, device=dev)
+        ws = torch.empty(nat.size("gmm_workspace_bytes", n, d, K) // 8 + 1, **o)
+        stats = torch.empty(nat.size("gmm_stats_size", d, K), **o)
+        gm._lb = torch.zeros(1, **o); gm._info = torch.zeros(K, dtype=torch.int32, device=dev)
+        it = int(sys.argv[3])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(it):
+            gm.em_iteration(X, float(n), ws, stats)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / it
+        print("cfg", {k: v for k, v in os.environ.items() if k.startswith("DONK_")}, "n", n, "ms_per_iter", ms,
+              "rows_per_s", n / (ms * 1e-3), "lb", float(gm._lb))

@@ -12,6 +12,7 @@
 
 #include "../../donk_b200/csrc/fitlr.cuh"
 #include "../../donk_b200/csrc/gmm.cuh"
+#include "../../donk_b200/csrc/gmm_mma.cuh"
 #include "../../donk_b200/csrc/ilqr.cuh"
 #include "../../donk_b200/csrc/ilqr_warp.cuh"
 
@@ -205,9 +206,26 @@ static void emu_gmm_e(GmmArgs<double>& a) {
   }
 }
 
+}  // extern "C"
+
+template <int NB, int RA>
+static void emu_gmm_e_mma(GmmArgs<double>& a, const GmmMmaPlan& pl) {
+  const int TS = 8 * RA * pl.Ge;
+  a.nblocks = (a.n + TS - 1) / TS;
+  std::vector<double> smem(gmm_e_mma_smem<NB, RA>(a.K, pl.Ge) + 2);
+  WCtx w{0, 1, 0, 0, pl.Ge};
+  const int ncta = a.nblocks < 5 ? a.nblocks : 5;
+  for (int cta = 0; cta < ncta; ++cta) {
+    memset(smem.data(), 0xFF, smem.size() * sizeof(double));
+    gmm_e_mma_cta<double, NB, RA>(w, a, cta, ncta, smem.data());
+  }
+}
+
+extern "C" {
+
 int donk_emu_gmm_em_step_f64(int n_local, int d, int K, const double* X, const double* weights, const double* means,
-                             const double* prec_chol, const double* resp_in, double* stats, void* workspace,
-                         size_t workspace_bytes, void*) {
+                             const double* prec_chol, const double* resp_in, double* stats, double* shift,
+                             void* workspace, size_t workspace_bytes, void*) {
   if (n_local < 0 || d < 1 || K < 1) return DONK_BAD_SHAPE;
   if (workspace_bytes < donk_emu_gmm_workspace_bytes(n_local, d, K)) return DONK_BAD_SHAPE;
   const size_t total = gmm_stats_len(d, K);
@@ -219,12 +237,37 @@ int donk_emu_gmm_em_step_f64(int n_local, int d, int K, const double* X, const d
   a.nch = gmm_nch(n_local, d, K);
   double* ws = static_cast<double*>(workspace);
   a.resp = ws; a.lse_part = ws + (size_t)n_local * K; a.part = a.lse_part + a.nblocks;
+  const GmmMmaPlan pl = gmm_mma_plan(n_local, d, K);
+  const bool mma = pl.ok && !env_int("DONK_GMM_GENERIC") && weights != nullptr;
   if (resp_in) {
     a.resp = const_cast<double*>(resp_in);
     memset(a.lse_part, 0, (size_t)a.nblocks * sizeof(double));
+  } else if (mma) {
+    switch (pl.NB) {
+      case 2: emu_gmm_e_mma<2, 2>(a, pl); break;
+      case 5: emu_gmm_e_mma<5, 2>(a, pl); break;
+      case 6: emu_gmm_e_mma<6, 2>(a, pl); break;
+      case 9: emu_gmm_e_mma<9, 2>(a, pl); break;
+      default: emu_gmm_e_mma<18, 1>(a, pl); break;
+    }
   } else {
     emu_gmm_e(a);
   }
+  if (mma) {
+    a.nch = pl.nch;
+    a.shift_out = shift;
+    std::vector<double> smem(gmm_m_mma_smem(d, pl.KC) + 2);
+    WCtx w{0, 1, 0, 0, pl.Gm};
+    const int grid = ((K + pl.KC - 1) / pl.KC) * a.nch;
+    for (int cta = 0; cta < grid; ++cta) {
+      memset(smem.data(), 0xFF, smem.size() * sizeof(double));
+      if (pl.NBW <= 6) gmm_m_mma_cta<double, 6, 2>(w, a, cta, smem.data());
+      else gmm_m_mma_cta<double, 11, 2>(w, a, cta, smem.data());
+    }
+    for (size_t i = 0; i < total; ++i) gmm_reduce_item<double>(a, i, stats);
+    return DONK_OK;
+  }
+  if (shift) memcpy(shift, means, (size_t)K * d * sizeof(double));
   if (gmm_m_threads(d) == 0) return DONK_SMEM_LIMIT;
   std::vector<double> smem(gmm_m_smem(d) + 2);
   Ctx ctx{0, 1};
@@ -236,11 +279,11 @@ int donk_emu_gmm_em_step_f64(int n_local, int d, int K, const double* X, const d
   return DONK_OK;
 }
 
-int donk_emu_gmm_m_finalize_f64(double n_total, int d, int K, const double* stats, double reg_covar, double* weights,
-                                double* means, double* covariances, double* prec_chol, double* lower_bound, int* info,
-                                void*) {
+int donk_emu_gmm_m_finalize_f64(double n_total, int d, int K, const double* stats, const double* shift,
+                                double reg_covar, double* weights, double* means, double* covariances,
+                                double* prec_chol, double* lower_bound, int* info, void*) {
   GmmFinArgs<double> a;
-  a.d = d; a.K = K; a.n_total = n_total; a.reg_covar = reg_covar; a.stats = stats;
+  a.d = d; a.K = K; a.n_total = n_total; a.reg_covar = reg_covar; a.stats = stats; a.shift = shift;
   a.w = weights; a.means = means; a.cov = covariances; a.pc = prec_chol; a.lower_bound = lower_bound; a.info = info;
   std::vector<double> smem(gmm_fin_smem(d) + 2);
   Ctx ctx{0, 1};
