@@ -319,6 +319,21 @@ DONK_HD void ld2(const R* p, R& v0, R& v1) {
   v0 = p[0]; v1 = p[1];
 }
 
+// *slot += sum_{r < n} f(r), n <= 32: one item per lane on the device (every lane joins the shuffle), a plain loop
+// under emulation.  The caller synchronises the team before reading *slot.
+template <typename R, class F>
+DONK_D void team_reduce_add(const WCtx& w, R* slot, int n, F&& f) {
+#if !defined(DONK_EMU)
+  R x = (int)w.lane < n ? f((int)w.lane) : R(0);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  if (w.lane == 0) *slot += x;
+#else
+  (void)w;
+  for (int r = 0; r < n; ++r) *slot += f(r);
+#endif
+}
+
 // two adjacent read-only values; one 16-byte load when the address is known to be 16-byte aligned
 template <typename R>
 DONK_HD void ldg2(const R* p, bool aligned16, R& v0, R& v1) {

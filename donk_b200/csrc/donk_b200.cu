@@ -9,12 +9,17 @@
 
 #include "../../include/donk_b200.h"
 #include "fitlr.cuh"
+#include "fitlr_warp.cuh"
 #include "gmm.cuh"
 #include "gmm_mma.cuh"
 #include "ilqr.cuh"
 #include "ilqr_warp.cuh"
 
 using namespace donk;
+
+// (dX, dU) pairs with warp-kernel instantiations (ILQR step, fit_lr): the BASELINE.json configurations that
+// fit one warp per problem; other dimensions run the generic CTA kernels.
+#define DONK_WARP_DIMS(X) X(20, 6) X(14, 7) X(6, 2)
 
 namespace {
 
@@ -143,8 +148,6 @@ int ilqr_warp_launch(const IlqrArgs<R>& a, void* stream) {
   return DONK_OK;
 }
 
-// (dX, dU) pairs with a warp-kernel instantiation: the BASELINE.json configurations that fit one warp.
-#define DONK_WARP_DIMS(X) X(20, 6) X(14, 7) X(6, 2)
 
 template <typename R>
 int ilqr_step_launch(IlqrArgs<R> a, void* stream) {
@@ -270,6 +273,27 @@ __global__ void __launch_bounds__(512, 1) fit_lr_kernel(const FitArgs<R> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Ctx ctx{(int)threadIdx.x, (int)blockDim.x};
   fit_lr_cta<R>(ctx, a, (int)blockIdx.x, reinterpret_cast<R*>(smem_raw));
+}
+
+template <typename R, int DX, int DU>
+__global__ void __launch_bounds__(256, 1) fit_warp_kernel(const FitArgs<R> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WCtx w{(int)threadIdx.x, (int)blockDim.x, (int)threadIdx.x >> 5, (int)threadIdx.x & 31, (int)blockDim.x >> 5};
+  fit_warp_cta<R, DX, DU>(w, a, (int)blockIdx.x, reinterpret_cast<R*>(smem_raw));
+}
+template <typename R, int DX, int DU>
+int fit_warp_launch(const FitArgs<R>& a, void* stream) {
+  int G;
+  size_t bytes;
+  int rc = fit_warp_plan<R, DX, DU>(smem_optin_cap() / 2 - 1024, env_int("DONK_FIT_WARPS"), G, bytes);
+  if (rc != DONK_OK) rc = fit_warp_plan<R, DX, DU>(smem_optin_cap(), env_int("DONK_FIT_WARPS"), G, bytes);
+  if (rc != DONK_OK) return rc;
+  rc = allow_smem(fit_warp_kernel<R, DX, DU>, bytes);
+  if (rc != DONK_OK) return rc;
+  const long long nfits = (long long)a.B * a.T;
+  fit_warp_kernel<R, DX, DU><<<(unsigned)((nfits + G - 1) / G), 32 * G, bytes, (cudaStream_t)stream>>>(a);
+  LAUNCHED("fit_warp_kernel");
+  return DONK_OK;
 }
 
 template <typename R>
@@ -522,6 +546,12 @@ int donk_fit_lr_f64(int B, int N, int T, int dX, int dU, const double* X, const 
   a.gw = gmm_weights; a.gmeans = gmm_means; a.gcov = gmm_covariances; a.gpc = gmm_prec_chol;
   a.n_pool = n_pool; a.prior_weight = prior_weight; a.reg = regularization;
   a.F = F; a.f = f; a.covar = covar; a.info = info;
+  if (gmm_K == 0 && !env_int("DONK_FIT_GENERIC")) {  // warp-per-fit fast path for the instantiated dimensions
+#define DONK_TRY_FITW(DXV, DUV) \
+  if (dX == DXV && dU == DUV) return fit_warp_launch<double, DXV, DUV>(a, stream);
+    DONK_WARP_DIMS(DONK_TRY_FITW)
+#undef DONK_TRY_FITW
+  }
   size_t bytes = 0;
   const int force = env_int("DONK_FIT_CHUNK");
   a.NS = fit_plan(dX, dU, gmm_K, force > 0 ? force : N, sizeof(double), smem_optin_cap(), bytes);

@@ -22,6 +22,17 @@ if what in ("ilqr", "fit"):
     for _ in range(2):
         F, f, S, info = batched.fit_lr(ro["X"], ro["U"])
     torch.cuda.synchronize()
+    if what == "fit" and len(sys.argv) > 3:
+        import os
+        n = int(sys.argv[3])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            F, f, S, info = batched.fit_lr(ro["X"], ro["U"])
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        print("cfg", {k: v for k, v in os.environ.items() if k.startswith("DONK_")}, "B", B, "ms_per_launch", ms,
+              "fits_per_s", B * T / (ms * 1e-3), "info", int(info.sum()))
     if what == "ilqr":
         p = dX + dU
         C, c, cc = synthetic.l2_costs(T, dX, dU)

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../donk_b200/csrc/fitlr.cuh"
+#include "../../donk_b200/csrc/fitlr_warp.cuh"
 #include "../../donk_b200/csrc/gmm.cuh"
 #include "../../donk_b200/csrc/gmm_mma.cuh"
 #include "../../donk_b200/csrc/ilqr.cuh"
@@ -39,6 +40,22 @@ static int emu_ilqr_warp(const IlqrArgs<double>& a) {
   for (int cta = 0; cta < grid; ++cta) {
     memset(smem.data(), 0xFF, smem.size() * sizeof(double));
     ilqr_warp_cta<double, DX, DU>(w, a, cta, ES, smem.data());
+  }
+  return DONK_OK;
+}
+
+template <int DX, int DU>
+static int emu_fit_warp(const FitArgs<double>& a) {
+  int G;
+  size_t bytes;
+  int rc = fit_warp_plan<double, DX, DU>(kSmemCap, 0, G, bytes);
+  if (rc != DONK_OK) return rc;
+  std::vector<double> smem(bytes / sizeof(double) + 2);
+  WCtx w{0, 1, 0, 0, G};
+  const long long nfits = (long long)a.B * a.T;
+  for (long long cta = 0; cta < (nfits + G - 1) / G; ++cta) {
+    memset(smem.data(), 0xFF, smem.size() * sizeof(double));
+    fit_warp_cta<double, DX, DU>(w, a, (int)cta, smem.data());
   }
   return DONK_OK;
 }
@@ -166,6 +183,11 @@ int donk_emu_fit_lr_f64(int B, int N, int T, int dX, int dU, const double* X, co
   a.gw = gmm_weights; a.gmeans = gmm_means; a.gcov = gmm_covariances; a.gpc = gmm_prec_chol;
   a.n_pool = n_pool; a.prior_weight = prior_weight; a.reg = regularization;
   a.F = F; a.f = f; a.covar = covar; a.info = info;
+  if (gmm_K == 0 && !env_int("DONK_FIT_GENERIC")) {
+    if (dX == 20 && dU == 6) return emu_fit_warp<20, 6>(a);
+    if (dX == 14 && dU == 7) return emu_fit_warp<14, 7>(a);
+    if (dX == 6 && dU == 2) return emu_fit_warp<6, 2>(a);
+  }
   size_t bytes = 0;
   const int force = env_int("DONK_FIT_CHUNK");
   a.NS = fit_plan(dX, dU, gmm_K, force > 0 ? force : N, sizeof(double), kSmemCap, bytes);

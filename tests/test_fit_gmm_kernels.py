@@ -133,3 +133,23 @@ def test_gmm_label_init_and_prior_api(backend):
     dyn = fit_lr(g["X"][:3], g["U"][:3], prior, regularization=0)
     assert relerr(dyn.F, g["pF"]) < 1e-7 and relerr(dyn.covar, g["pcovar"]) < 1e-7
     assert str(dyn) == "LinearDynamics[T=44, dX=15, dU=2]"
+
+
+@pytest.mark.parametrize("dims,N,reverse", [((20, 6), 64, 0), ((20, 6), 19, 1), ((14, 7), 50, 0), ((6, 2), 20, 0),
+                                            ((6, 2), 5, 1)])
+def test_fit_lr_warp_kernel_dims(backend, dims, N, reverse):
+    """Warp-per-fit kernel (fitlr_warp.cuh): well-conditioned fits (fast path) and N <= p (eigenvalue lift)."""
+    from donk_b200 import batched, synthetic
+
+    set_reverse(backend, reverse)
+    dX, dU = dims
+    T, B = 5, 3
+    conds = [synthetic.condition(21, i, T, dX, dU, N) for i in range(B)]
+    X, U = np.stack([c.X for c in conds]), np.stack([c.U for c in conds])
+    F, f, covar, info = batched.fit_lr(X, U)
+    assert int(info.sum()) == 0
+    for b, c in enumerate(conds):
+        Fo, fo, co = oracle.fit_lr(c.X, c.U)
+        assert relerr(F[b], Fo) < 1e-8 and relerr(f[b], fo) < 1e-8 and relerr(covar[b], co) < 1e-8
+    cv = covar.cpu().numpy()
+    assert np.array_equal(cv, np.swapaxes(cv, -1, -2))
