@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(512, 1) fit_lr_kernel(const FitArgs<R> a) {
 }
 
 template <typename R, int DX, int DU>
-__global__ void __launch_bounds__(256, 1) fit_warp_kernel(const FitArgs<R> a) {
+__global__ void __launch_bounds__(128, 3) fit_warp_kernel(const FitArgs<R> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WCtx w{(int)threadIdx.x, (int)blockDim.x, (int)threadIdx.x >> 5, (int)threadIdx.x & 31, (int)blockDim.x >> 5};
   fit_warp_cta<R, DX, DU>(w, a, (int)blockIdx.x, reinterpret_cast<R*>(smem_raw));
@@ -285,9 +285,10 @@ template <typename R, int DX, int DU>
 int fit_warp_launch(const FitArgs<R>& a, void* stream) {
   int G;
   size_t bytes;
-  int rc = fit_warp_plan<R, DX, DU>(smem_optin_cap() / 2 - 1024, env_int("DONK_FIT_WARPS"), G, bytes);
+  int rc = fit_warp_plan<R, DX, DU>(smem_optin_cap() / 3 - 1024, env_int("DONK_FIT_WARPS"), G, bytes);
   if (rc != DONK_OK) rc = fit_warp_plan<R, DX, DU>(smem_optin_cap(), env_int("DONK_FIT_WARPS"), G, bytes);
   if (rc != DONK_OK) return rc;
+  if (G > 4) G = 4, bytes = (size_t)4 * FitWarpDims<DX, DU>::TEAM * sizeof(R);  // kernel is compiled for <= 128 threads
   rc = allow_smem(fit_warp_kernel<R, DX, DU>, bytes);
   if (rc != DONK_OK) return rc;
   const long long nfits = (long long)a.B * a.T;

@@ -1,16 +1,19 @@
 // donk_b200 — fit_lr, warp-per-fit variant with compile-time dimensions (fast path, no prior).
 //
 // Same math and reference lines as fitlr.cuh (fit_lr, donk/dynamics/linear_dynamics.py:137-189).  The generic
-// kernel spends a CTA and ~200 __syncthreads on every (condition, t); here one warp owns a fit:
-//   1. moments in one pass on the FP64 tensor path: samples are staged in chunks (cp.async, double buffered),
-//      shifted by the first sample (keeps the one-pass covariance free of cancellation) and multiplied as DMMA
-//      fragments S += Xs^T Xs with the sample index as k dimension; A and B fragments are the same registers;
-//   2. the eigenvalue test of linear_dynamics.py:178-181 is decided by a Cholesky attempt on Sigma_pp - reg I:
-//      it succeeds iff lambda_min > reg, i.e. iff the reference would not regularise.  Only if it fails the
-//      smallest eigenvalue is computed (Householder tridiagonalisation + Sturm multisection, warp level) and
-//      the diagonal lifted by reg - lambda_min;
-//   3. Cholesky of Sigma_pp, triangular solves for F^T (one right-hand side per lane), Sigma_pp F^T and the Schur
-//      complement as DMMA block products.
+// kernel spends a CTA and ~200 __syncthreads on every (condition, t); here one warp owns a fit and needs only
+// ~16 KB of shared memory, so ~14 fits are in flight per SM (ncu: the first warp version, 42 KB per fit, ran 4
+// warps per SM and was bound by dependent-FMA latency):
+//   1. moments in one pass on the FP64 tensor path: every lane loads its DMMA fragment elements of
+//      [x_t | u_t | x_{t+1}] straight from global memory (one sample row = k index), shifted by the first sample
+//      (keeps the one-pass covariance free of cancellation); S += Xs^T Xs with A and B fragments being the same
+//      registers; column sums ride along;
+//   2. the eigenvalue test of linear_dynamics.py:178-181 is decided by a Cholesky attempt on Sigma_pp - reg I
+//      (succeeds iff lambda_min > reg, i.e. iff the reference would not regularise); only if it fails the smallest
+//      eigenvalue is computed (Householder tridiagonalisation + Sturm multisection) and the diagonal lifted.
+//      All factorisations work in the lower triangle of Sigma_pp; the upper triangle keeps the original;
+//   3. Cholesky, forward solve Y = L^-1 Sigma_px (one right-hand side per lane), Schur complement
+//      Sigma_x'x' - Y^T Y as DMMA blocks (symmetric and PSD by construction), backward solve F^T = L^-T Y.
 #pragma once
 #include "common.cuh"
 #include "fitlr.cuh"
@@ -23,24 +26,19 @@ namespace donk {
 template <int DX, int DU>
 struct FitWarpDims {
   static constexpr int P = DX + DU, D = P + DX;
-  static constexpr int D8 = (D + 7) / 8 * 8, NBD = D8 / 8, LDX = ld_pad(D8);
+  static constexpr int D8 = (D + 7) / 8 * 8, NBD = D8 / 8;
   static constexpr int P4 = (P + 3) / 4 * 4, PA = ld_pad(P), DXP = ld_pad(DX);
-  static constexpr int NBP = (P + 7) / 8, NBX = (DX + 7) / 8;
-  static constexpr int NS = 16;  // samples per staged chunk (4 k4-steps)
+  static constexpr int NBX = (DX + 7) / 8;
   static constexpr int oSpp = 0, oSpx = oSpp + P4 * PA + 8, oSxx = oSpx + P4 * DXP + 8;
-  static constexpr int oW1 = oSxx + DX * DXP + 8, oW2 = oW1 + P4 * PA + 8;
-  static constexpr int CH = 2 * NS * LDX > 2 * (P4 * DXP + 8) ? 2 * NS * LDX : 2 * (P4 * DXP + 8);
-  static constexpr int oCh = oW2 + P4 * PA + 8;       // sample chunks (2 buffers); later Z | Gt
-  static constexpr int oMu = oCh + CH + 8;            // shifted mean (D8) | shift x0 (D8)
-  static constexpr int oTd = oMu + 2 * D8, oTe = oTd + PA, oV = oTe + PA, oWw = oV + PA;
-  static constexpr int oScal = oWw + PA, TEAM = oScal + 8;
+  static constexpr int oMu = oSxx + DX * DXP + 8;  // mean (D8)
+  static constexpr int oTd = oMu + D8, oTe = oTd + PA + 4, oV = oTe + PA + 4, oWw = oV + PA + 4;
+  static constexpr int oScal = oWw + PA + 4, TEAM = oScal + 8;
 };
 
 template <typename R, int DX, int DU>
 DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
   using D = FitWarpDims<DX, DU>;
-  constexpr int P = D::P, d = D::D, D8 = D::D8, NBD = D::NBD, LDX = D::LDX, P4 = D::P4, PA = D::PA, DXP = D::DXP;
-  constexpr int NS = D::NS;
+  constexpr int P = D::P, d = D::D, P4 = D::P4, PA = D::PA, DXP = D::DXP;
   const int N = a.N, T = a.T;
   const long long nfits = (long long)a.B * T;
   const R eps = sizeof(R) == 8 ? R(2.220446049250313e-16) : R(1.1920929e-7);
@@ -50,83 +48,79 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
     if (fit >= nfits) continue;
     const int b = (int)(fit / T), t = (int)(fit % T);
     R* tp = smem + (size_t)tm * D::TEAM;
-    R* Spp = tp + D::oSpp;
-    R* Spx = tp + D::oSpx;
+    R* Spp = tp + D::oSpp;  // upper triangle + diagonal: Sigma_pp; strict lower triangle: work space for factors
+    R* Spx = tp + D::oSpx;  // Sigma_px, then Y = L^-1 Sigma_px, then Z = F^T
     R* Sxx = tp + D::oSxx;
-    R* W1 = tp + D::oW1;
-    R* W2 = tp + D::oW2;
     R* mu = tp + D::oMu;
-    R* x0 = mu + D8;
+    R* td = tp + D::oTd;
+    R* te = tp + D::oTe;
+    R* vv = tp + D::oV;
+    R* ww = tp + D::oWw;
+    R* scal = tp + D::oScal;
     LANE_FOR(idx, D::TEAM) tp[idx] = R(0);
     w.team_sync();
-    LANE_FOR(j, d) x0[j] = xux_load(a, b, 0, t, j);  // shift: the first sample of this (condition, t)
-    auto stage = [&](int ch, int buf) {
-      R* xs = tp + D::oCh + buf * NS * LDX;
-      LANE_FOR(idx, NS * d) {
-        const int r = idx / d, j = idx % d, n = ch * NS + r;
-        if (n < N) {
-          const R* src = j < DX ? a.X + (((size_t)b * N + n) * (T + 1) + t) * DX + j
-                       : j < P ? a.U + (((size_t)b * N + n) * T + t) * DU + (j - DX)
-                               : a.X + (((size_t)b * N + n) * (T + 1) + t + 1) * DX + (j - P);
-          cp_async(xs + r * LDX + j, src);
-        } else {
-          xs[r * LDX + j] = x0[j];  // shifted value 0: contributes nothing
-        }
-      }
-    };
-    const int nchunk = (N + NS - 1) / NS;
-    w.team_sync();
-    stage(0, 0);
 
-    // ---- 1. S = sum_n (x_n - x0)(x_n - x0)^T (upper blocks), column sums ---------------------------------------
+    // ---- 1. S = sum_n (x_n - x_0)(x_n - x_0)^T (upper blocks) and column sums, fragments straight from global ----
+    auto store_sigma = [&](int i, int j, R val) {  // element (i <= j) of the joint covariance, blocked storage
+      if (j < P) { Spp[i * PA + j] = val; Spp[j * PA + i] = val; }
+      else if (i < P) Spx[i * DXP + (j - P)] = val;
+      else { Sxx[(i - P) * DXP + (j - P)] = val; Sxx[(j - P) * DXP + (i - P)] = val; }
+    };
 #if !defined(DONK_EMU)
     {
+      constexpr int NBD = D::NBD, NTRI = NBD * (NBD + 1) / 2;
       const int g = w.lane >> 2, tq = w.lane & 3;
-      constexpr int NTRI = NBD * (NBD + 1) / 2;
-      R acc[NTRI][2];
-      R csum[NBD], sh[NBD];
+      const R* ptr[NBD];   // address of column 8 ib + g of sample 0
+      size_t stride[NBD];  // distance between consecutive samples
+      bool ok[NBD];
+      R acc[NTRI][2], csum[NBD], sh[NBD], cur[NBD], nxt[NBD];
+#pragma unroll
+      for (int ib = 0; ib < NBD; ++ib) {
+        const int j = 8 * ib + g;
+        ok[ib] = j < d;
+        if (j < DX) { ptr[ib] = a.X + (((size_t)b * N) * (T + 1) + t) * DX + j; stride[ib] = (size_t)(T + 1) * DX; }
+        else if (j < P) { ptr[ib] = a.U + (((size_t)b * N) * T + t) * DU + (j - DX); stride[ib] = (size_t)T * DU; }
+        else if (j < d) { ptr[ib] = a.X + (((size_t)b * N) * (T + 1) + t + 1) * DX + (j - P); stride[ib] = (size_t)(T + 1) * DX; }
+        else { ptr[ib] = a.X; stride[ib] = 0; }
+        sh[ib] = ok[ib] ? ldg(ptr[ib]) : R(0);  // shift: the first sample
+        csum[ib] = R(0);
+      }
 #pragma unroll
       for (int q = 0; q < NTRI; ++q) { acc[q][0] = R(0); acc[q][1] = R(0); }
+      auto load = [&](int n, R* dst) {
 #pragma unroll
-      for (int ib = 0; ib < NBD; ++ib) { csum[ib] = R(0); sh[ib] = x0[8 * ib + g]; }
-      for (int ch = 0; ch < nchunk; ++ch) {
-        cp_async_wait_all();
-        w.team_sync();
-        if (ch + 1 < nchunk) stage(ch + 1, (ch + 1) & 1);
-        const R* xs = tp + D::oCh + (ch & 1) * NS * LDX;
+        for (int ib = 0; ib < NBD; ++ib) dst[ib] = (ok[ib] && n < N) ? ldg(ptr[ib] + (size_t)n * stride[ib]) : sh[ib];
+      };
+      load(tq, nxt);
+      for (int k4 = 0; k4 < (N + 3) / 4; ++k4) {
 #pragma unroll
-        for (int k4 = 0; k4 < NS / 4; ++k4) {
-          R fr[NBD];
+        for (int ib = 0; ib < NBD; ++ib) cur[ib] = nxt[ib];
+        load(4 * (k4 + 1) + tq, nxt);  // the next sample row is in flight while this one is multiplied
 #pragma unroll
-          for (int ib = 0; ib < NBD; ++ib) {
-            fr[ib] = xs[(4 * k4 + tq) * LDX + 8 * ib + g] - sh[ib];
-            csum[ib] += fr[ib];
+        for (int ib = 0; ib < NBD; ++ib) { cur[ib] -= sh[ib]; csum[ib] += cur[ib]; }
+        int q = 0;
+#pragma unroll
+        for (int ib = 0; ib < NBD; ++ib)
+#pragma unroll
+          for (int jb = ib; jb < NBD; ++jb, ++q) {
+            double d0 = (double)acc[q][0], d1 = (double)acc[q][1];
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(d0), "+d"(d1)
+                         : "d"((double)cur[ib]), "d"((double)cur[jb]));
+            acc[q][0] = (R)d0;
+            acc[q][1] = (R)d1;
           }
-          int q = 0;
-#pragma unroll
-          for (int ib = 0; ib < NBD; ++ib)
-#pragma unroll
-            for (int jb = ib; jb < NBD; ++jb, ++q) {
-              double d0 = (double)acc[q][0], d1 = (double)acc[q][1];
-              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                           : "+d"(d0), "+d"(d1)
-                           : "d"((double)fr[ib]), "d"((double)fr[jb]));
-              acc[q][0] = (R)d0;
-              acc[q][1] = (R)d1;
-            }
-        }
-        w.team_sync();
       }
-      // mean of the shifted samples
 #pragma unroll
       for (int ib = 0; ib < NBD; ++ib) {
         R s = csum[ib];
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (tq == 0) mu[8 * ib + g] = s / R(N);
+        csum[ib] = s / R(N);  // every lane of the quad now holds the shifted mean of column 8 ib + g
+        if (tq == 0 && ok[ib]) mu[8 * ib + g] = sh[ib] + csum[ib];
       }
-      w.team_sync();
-      // Sigma = S / N - m m^T, biased (linear_dynamics.py:165), into the blocked storage (both halves)
+      // Sigma = S / N - m m^T, biased (linear_dynamics.py:165): the lane holds row 8 ib + g, columns 8 jb + 2 tq + h;
+      // the shifted mean of column j lives in the quad g' = j % 8 and is fetched by shuffle
       int q = 0;
 #pragma unroll
       for (int ib = 0; ib < NBD; ++ib)
@@ -134,83 +128,72 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
         for (int jb = ib; jb < NBD; ++jb, ++q) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
+            const R mj = __shfl_sync(0xffffffffu, csum[jb], 4 * (2 * tq + h));
             const int i = 8 * ib + g, j = 8 * jb + 2 * tq + h;
-            if (i <= j && j < d) {
-              const R val = acc[q][h] / R(N) - mu[i] * mu[j];
-              if (j < P) { Spp[i * PA + j] = val; Spp[j * PA + i] = val; }
-              else if (i < P) Spx[i * DXP + (j - P)] = val;
-              else { Sxx[(i - P) * DXP + (j - P)] = val; Sxx[(j - P) * DXP + (i - P)] = val; }
-            }
+            if (i <= j && j < d) store_sigma(i, j, acc[q][h] / R(N) - csum[ib] * mj);
           }
         }
     }
 #else
     {
-      std::vector<R> S((size_t)d * d, R(0)), cs(d, R(0));
-      for (int ch = 0; ch < nchunk; ++ch) {
-        if (ch + 1 < nchunk) stage(ch + 1, (ch + 1) & 1);
-        const R* xs = tp + D::oCh + (ch & 1) * NS * LDX;
-        for (int r = 0; r < NS; ++r)
-          for (int i = 0; i < d; ++i) {
-            const R xi = xs[r * LDX + i] - x0[i];
-            cs[i] += xi;
-            for (int j = i; j < d; ++j) S[(size_t)i * d + j] = fma(xi, xs[r * LDX + j] - x0[j], S[(size_t)i * d + j]);
-          }
-      }
-      for (int i = 0; i < d; ++i) mu[i] = cs[i] / R(N);
-      for (int i = 0; i < d; ++i)
-        for (int j = i; j < d; ++j) {
-          const R val = S[(size_t)i * d + j] / R(N) - mu[i] * mu[j];
-          if (j < P) { Spp[i * PA + j] = val; Spp[j * PA + i] = val; }
-          else if (i < P) Spx[i * DXP + (j - P)] = val;
-          else { Sxx[(i - P) * DXP + (j - P)] = val; Sxx[(j - P) * DXP + (i - P)] = val; }
+      std::vector<R> S((size_t)d * d, R(0)), cs(d, R(0)), x0(d), xr(d);
+      for (int j = 0; j < d; ++j) x0[j] = xux_load(a, b, 0, t, j);
+      for (int n = 0; n < N; ++n) {
+        for (int j = 0; j < d; ++j) xr[j] = xux_load(a, b, n, t, j) - x0[j];
+        for (int i = 0; i < d; ++i) {
+          cs[i] += xr[i];
+          for (int j = i; j < d; ++j) S[(size_t)i * d + j] = fma(xr[i], xr[j], S[(size_t)i * d + j]);
         }
+      }
+      for (int i = 0; i < d; ++i) { cs[i] /= R(N); mu[i] = x0[i] + cs[i]; }
+      for (int i = 0; i < d; ++i)
+        for (int j = i; j < d; ++j) store_sigma(i, j, S[(size_t)i * d + j] / R(N) - cs[i] * cs[j]);
     }
 #endif
     w.team_sync();
 
-    // warp-level Cholesky of A - shift*I (A symmetric P x P, ld PA) into L (strict lower) and dg (diagonal);
-    // returns through `flag` (shared) whether a pivot was not positive
-    auto chol = [&](const R* A, R shift, R* L, R* dg, R* flag) {
+    // In-place Cholesky of (A - shift I): A is read from the upper triangle + diagonal of Spp, the factor goes to
+    // the strict lower triangle, its diagonal to dg.  *flag (shared) becomes 1 if a pivot is not positive.
+    auto chol = [&](R shift, R* dg, R* flag) {
       LANE_FOR(one, 1) *flag = R(0);
       w.team_sync();
       for (int j = 0; j < P; ++j) {
         LANE_FOR(r, P - j) {
           const int i = j + r;
-          R sj = A[j * PA + j] - shift, si = A[i * PA + j];
+          R sj = Spp[j * PA + j] - shift, si = Spp[j * PA + i];  // A[i][j] from the upper triangle
           for (int k = 0; k < j; ++k) {
-            const R ljk = L[j * PA + k];
+            const R ljk = Spp[j * PA + k];
             sj = fma(-ljk, ljk, sj);
-            si = fma(-L[i * PA + k], ljk, si);
+            si = fma(-Spp[i * PA + k], ljk, si);
           }
           if (i == j) {
             dg[j] = sqrt(sj);
             if (!(sj > R(0))) *flag = R(1);
           } else {
-            L[i * PA + j] = si * rsqrt_r(sj);
+            Spp[i * PA + j] = si * rsqrt_r(sj);
           }
         }
         w.team_sync();
       }
     };
-    R* td = tp + D::oTd;
-    R* te = tp + D::oTe;
-    R* vv = tp + D::oV;
-    R* ww = tp + D::oWw;
-    R* scal = tp + D::oScal;
 
     // ---- 2. does the reference regularise?  lambda_min(Sigma_pp) < reg  <=>  Sigma_pp - reg I is not PD ------------
-    chol(Spp, a.reg, W1, td, scal + 0);
-    if (scal[0] != R(0)) {  // warp-uniform: slow path, smallest eigenvalue of Sigma_pp (linear_dynamics.py:178)
-      R* A = W2;
-      LANE_FOR(idx, P * PA) A[idx] = Spp[idx];
+    chol(a.reg, ww, scal + 0);
+    if (scal[0] != R(0)) {  // warp-uniform slow path: smallest eigenvalue of Sigma_pp (linear_dynamics.py:178)
+      // Householder tridiagonalisation in the strict lower triangle; td is the working (finally the tridiagonal)
+      // diagonal, te the sub-diagonal, vv the Householder vector, ww = tau A v
+      LANE_FOR(idx, P * P) {
+        const int i = idx / P, j = idx % P;
+        if (j < i) Spp[i * PA + j] = Spp[j * PA + i];
+      }
+      LANE_FOR(i, P) td[i] = Spp[i * PA + i];
       w.team_sync();
       for (int k = 0; k + 2 < P; ++k) {
         LANE_FOR(one, 1) { scal[1] = R(0); scal[2] = R(0); }
         w.team_sync();
-        team_reduce_add(w, scal + 1, P - k - 2, [&](int r) { return A[(k + 2 + r) * PA + k] * A[(k + 2 + r) * PA + k]; });
+        team_reduce_add(w, scal + 1, P - k - 2, [&](int r) { const R x = Spp[(k + 2 + r) * PA + k]; return x * x; });
         w.team_sync();
-        const R xnorm2 = scal[1], alpha = A[(k + 1) * PA + k];
+        const R xnorm2 = scal[1], alpha = Spp[(k + 1) * PA + k];
         R tau = R(0), beta = alpha, scale = R(0);
         if (xnorm2 > R(0)) {
           const R nrm = sqrt(alpha * alpha + xnorm2);
@@ -218,30 +201,33 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
           tau = (beta - alpha) / beta;
           scale = R(1) / (alpha - beta);
         }
-        LANE_FOR(i, P - k - 1) vv[k + 1 + i] = i == 0 ? R(1) : A[(k + 1 + i) * PA + k] * scale;
+        LANE_FOR(i, P - k - 1) vv[k + 1 + i] = i == 0 ? R(1) : Spp[(k + 1 + i) * PA + k] * scale;
+        LANE_FOR(one, 1) te[k] = beta;
         w.team_sync();
         if (tau != R(0)) {
           team_reduce_add(w, scal + 2, P - k - 1, [&](int i) {
-            const R* row = A + (k + 1 + i) * PA;
+            const int ri = k + 1 + i;
             R acc = R(0);
-            for (int j = k + 1; j < P; ++j) acc = fma(row[j], vv[j], acc);
-            ww[k + 1 + i] = tau * acc;
-            return tau * acc * vv[k + 1 + i];
+            for (int j = k + 1; j < P; ++j) {
+              const R aij = j == ri ? td[ri] : (j < ri ? Spp[ri * PA + j] : Spp[j * PA + ri]);
+              acc = fma(aij, vv[j], acc);
+            }
+            ww[ri] = tau * acc;
+            return tau * acc * vv[ri];
           });
           w.team_sync();
           const R al2 = -tau * scal[2] / 2;
           LANE_FOR(i, P - k - 1) {
             const int ri = k + 1 + i;
             const R vi = vv[ri], wi = fma(al2, vi, ww[ri]);
-            for (int j = k + 1; j < P; ++j) A[ri * PA + j] -= vi * fma(al2, vv[j], ww[j]) + wi * vv[j];
+            for (int j = k + 1; j < ri; ++j) Spp[ri * PA + j] -= vi * fma(al2, vv[j], ww[j]) + wi * vv[j];
+            td[ri] -= R(2) * vi * wi;
           }
+          w.team_sync();
         }
-        LANE_FOR(one, 1) { td[k] = A[k * PA + k]; te[k] = beta; }
-        w.team_sync();
       }
       LANE_FOR(one, 1) {
-        if (P >= 2) { td[P - 2] = A[(P - 2) * PA + P - 2]; te[P - 2] = A[(P - 1) * PA + P - 2]; }
-        td[P - 1] = A[(P - 1) * PA + P - 1];
+        if (P >= 2) te[P - 2] = Spp[(P - 1) * PA + P - 2];
       }
       w.team_sync();
       R lo = td[0], hi = td[0], emax = R(0);
@@ -256,7 +242,7 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
       const R pivmin = (sizeof(R) == 8 ? R(2.3e-308) : R(1.2e-38)) * (emax * emax > R(1) ? emax * emax : R(1));
       lo -= R(2) * eps * tnorm * R(P) + R(2) * pivmin;
       hi += R(2) * eps * tnorm * R(P) + R(2) * pivmin;
-      R* cnt = vv;  // counts as reals (P <= 32 sections fit)
+      R* cnt = vv;  // eigenvalue counts of the 32 section points
       for (int round = 0; round < 16; ++round) {
         const R width = hi - lo;
         LANE_FOR(q, 32) {
@@ -289,48 +275,19 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
       w.team_sync();
     }
 
-    // ---- 3. Cholesky of Sigma_pp and the two triangular solves for Z = Sigma_pp^-1 Sigma_px = F^T (one right-hand
-    //         side per lane).  Substitution keeps the residual Sigma_pp Z - Sigma_px at rounding level, which the Schur
-    //         complement below needs when the fit is (nearly) exact; an explicit inverse does not. --------------------
-    chol(Spp, R(0), W1, td, scal + 3);
-    R* Z = tp + D::oCh;
-    R* Gt = Z + P4 * DXP + 8;
-    LANE_FOR(idx, 2 * (P4 * DXP + 8)) Z[idx] = R(0);
-    w.team_sync();
-    LANE_FOR(c, DX) {
+    // ---- 3. Cholesky of Sigma_pp; Y = L^-1 Sigma_px; covar = Sigma_x'x' - Y^T Y; Z = L^-T Y = F^T ----------------------
+    chol(R(0), td, scal + 3);
+    LANE_FOR(c, DX) {  // forward substitution, one right-hand side per lane
       for (int i = 0; i < P; ++i) {
         R acc = Spx[i * DXP + c];
-        for (int k = 0; k < i; ++k) acc = fma(-W1[i * PA + k], Z[k * DXP + c], acc);
-        Z[i * DXP + c] = acc / td[i];
-      }
-      for (int i = P - 1; i >= 0; --i) {
-        R acc = Z[i * DXP + c];
-        for (int k = i + 1; k < P; ++k) acc = fma(-W1[k * PA + i], Z[k * DXP + c], acc);
-        Z[i * DXP + c] = acc / td[i];
+        for (int k = 0; k < i; ++k) acc = fma(-Spp[i * PA + k], Spx[k * DXP + c], acc);
+        Spx[i * DXP + c] = acc / td[i];
       }
     }
     w.team_sync();
-    // Gt = Sigma_pp Z
-    warp_mma<R, D::NBP, D::NBX>(w, Spp, PA, Z, DXP, P4 / 4, [&](int i, int c, R v0, R v1) {
-      if (i < P) {
-        if (c < DX) Gt[i * DXP + c] = v0;
-        if (c + 1 < DX) Gt[i * DXP + c + 1] = v1;
-      }
-    });
-    // outputs F[i][j] = Z[j][i], f = mu_x' - F mu_p (mu = x0 + shifted mean)   (linear_dynamics.py:184-185)
     const size_t bt = (size_t)b * T + t;
-    LANE_FOR(idx, DX * P) {
-      const int i = idx / P, j = idx % P;
-      a.F[bt * DX * P + idx] = Z[j * DXP + i];
-    }
-    LANE_FOR(i, DX) {
-      R acc = R(0);
-      for (int j = 0; j < P; ++j) acc = fma(Z[j * DXP + i], x0[j] + mu[j], acc);
-      a.f[bt * DX + i] = (x0[P + i] + mu[P + i]) - acc;
-    }
-    w.team_sync();
-    // covar = Sigma_x'x' - Z^T Gt (upper blocks, mirrored)   (linear_dynamics.py:186-188)
     {
+      // Sigma_xp Sigma_pp^-1 Sigma_px = Y^T Y: symmetric and PSD by construction (linear_dynamics.py:186-188)
       auto epi = [&](int i, int j, R v0, R v1) {
         if (i < DX && i <= j + 1) {
           if (i <= j && j < DX) {
@@ -348,10 +305,29 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
 #define DONK_FIT_ROW(RB_ROW)                                                                              \
   if (RB_ROW < D::NBX)                                                                                    \
     warp_mma<R, 1, (D::NBX - RB_ROW > 0 ? D::NBX - RB_ROW : 1)>(                                           \
-        w, Gt + 8 * RB_ROW, DXP, Z + 8 * RB_ROW, DXP, P4 / 4,                                              \
+        w, Spx + 8 * RB_ROW, DXP, Spx + 8 * RB_ROW, DXP, P4 / 4,                                           \
         [&](int i, int j, R v0, R v1) { epi(8 * RB_ROW + i, 8 * RB_ROW + j, v0, v1); });
       DONK_FIT_ROW(0) DONK_FIT_ROW(1) DONK_FIT_ROW(2) DONK_FIT_ROW(3)
 #undef DONK_FIT_ROW
+    }
+    w.team_sync();
+    LANE_FOR(c, DX) {  // backward substitution
+      for (int i = P - 1; i >= 0; --i) {
+        R acc = Spx[i * DXP + c];
+        for (int k = i + 1; k < P; ++k) acc = fma(-Spp[k * PA + i], Spx[k * DXP + c], acc);
+        Spx[i * DXP + c] = acc / td[i];
+      }
+    }
+    w.team_sync();
+    // outputs F[i][j] = Z[j][i], f = mu_x' - F mu_p   (linear_dynamics.py:184-185)
+    LANE_FOR(idx, DX * P) {
+      const int i = idx / P, j = idx % P;
+      a.F[bt * DX * P + idx] = Spx[j * DXP + i];
+    }
+    LANE_FOR(i, DX) {
+      R acc = R(0);
+      for (int j = 0; j < P; ++j) acc = fma(Spx[j * DXP + i], mu[j], acc);
+      a.f[bt * DX + i] = mu[P + i] - acc;
     }
     LANE_FOR(one, 1) {
       if (a.info) a.info[bt] = scal[3] != R(0);
