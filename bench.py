@@ -353,6 +353,10 @@ def run_ours(args):
     achieved_tf = flops_per_launch / (ms_per_step * 1e-3) / 1e12 / world * world  # per-GPU kernel time == step time
     hbm_peak = json.load(open(ROOT / "MEASURED_PEAKS.json"))["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
     bytes_per_launch = ilqr_bytes_per_launch(B, E, T, dX, dU)
+    traffic = None  # DRAM bytes per launch from the committed ncu --set full capture (scaled by solves per launch)
+    tp = ROOT / "profiles" / "ilqr_traffic.json"
+    if tp.exists() and (dX, dU, T) == (20, 6, 100):
+        traffic = json.load(open(tp))["dram_bytes_per_solve"] * B * E
 
     # ---- extra: GMM EM iteration on a sharded transition pool (BASELINE.json configs[3]) --------------------
     extra = {"fit_lr": {"timestep_fits_per_sec": B * T * world / (fit_ms * 1e-3), "ms_per_launch": fit_ms,
@@ -400,8 +404,8 @@ def run_ours(args):
                     "ms_per_step": e2e_ms},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": None,
-                         "kernel": "ilqr_step_kernel<double>",
+                         "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": traffic,
+                         "kernel": "ilqr_warp_kernel<double,20,6> (products on mma.sync.m8n8k4.f64)",
                          "peak_source": f"in-run FP64 probe on this GPU (dfma {peaks['dfma']:.1f}, dmma {peaks['dmma']:.1f} "
                                         f"TFLOP/s); MEASURED_PEAKS.json holds no FP64 figure",
                          "algorithmic_flops_per_launch": flops_per_launch,

@@ -208,11 +208,11 @@ int ilqr_step_launch(IlqrArgs<R> a, void* stream) {
 }
 
 template <typename R>
-__global__ void extended_costs_kernel(int n, int dX, int dU, const R* K, const R* k, const R* Lam, R* C, R* c) {
-  const int p = dX + dU;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)n * p) return;
-  extended_costs_item<R>(idx / p, (int)(idx % p), dX, dU, K, k, Lam, C, c);
+__global__ void __launch_bounds__(256) extended_costs_kernel(int n, int npairs, int dX, int dU, const R* K, const R* k,
+                                                             const R* Lam, R* C, R* c) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Ctx ctx{(int)threadIdx.x, (int)blockDim.x};
+  extended_costs_cta<R>(ctx, n, npairs, (int)blockIdx.x, dX, dU, K, k, Lam, C, c, reinterpret_cast<R*>(smem_raw));
 }
 
 template <typename R>
@@ -483,9 +483,13 @@ int donk_extended_costs_kl_f64(int n, int dX, int dU, const double* K, const dou
                                double* C_kl, double* c_kl, void* stream) {
   if (n < 0 || dX < 1 || dU < 1) return DONK_BAD_SHAPE;
   if (n == 0) return DONK_OK;
-  const size_t items = (size_t)n * (dX + dU);
-  extended_costs_kernel<double><<<(unsigned)((items + 127) / 128), 128, 0, (cudaStream_t)stream>>>(n, dX, dU, K, k,
-                                                                                                    Lam, C_kl, c_kl);
+  const int npairs = 4;
+  const size_t smem = extended_costs_smem(dX, dU) * npairs * sizeof(double);
+  if (smem > smem_optin_cap()) return DONK_SMEM_LIMIT;
+  int rc = allow_smem(extended_costs_kernel<double>, smem);
+  if (rc != DONK_OK) return rc;
+  extended_costs_kernel<double><<<(unsigned)((n + npairs - 1) / npairs), 256, smem, (cudaStream_t)stream>>>(
+      n, npairs, dX, dU, K, k, Lam, C_kl, c_kl);
   LAUNCHED("extended_costs_kernel");
   return DONK_OK;
 }

@@ -660,6 +660,76 @@ DONK_HD void extended_costs_item(size_t bt, int i, int dX, int dU, const R* K, c
   }
 }
 
+// extended_costs_kl for a group of (b,t) pairs per CTA: inputs staged in shared memory, outputs written with
+// consecutive threads on consecutive addresses (the one-thread-per-row version above wrote with stride p and took as
+// long as the whole iLQR step at config 3).  shared per pair: K (dU*dX) | k (dU) | Lam (dU*dU) | G = Lam K (dU*dX) | g = Lam k (dU)
+DONK_HD size_t extended_costs_smem(int dX, int dU) { return (size_t)2 * dU * dX + 2 * dU + (size_t)dU * dU; }
+template <typename R>
+DONK_D void extended_costs_cta(const Ctx& ctx, int n, int npairs, int cta, int dX, int dU, const R* K, const R* k,
+                               const R* Lam, R* C, R* c, R* sm) {
+  const int p = dX + dU, per = (int)extended_costs_smem(dX, dU);
+  const size_t first = (size_t)cta * npairs;
+  TEAM_FOR(idx, npairs * per) {
+    const int q = idx / per, r = idx % per;
+    const size_t bt = first + q;
+    if (bt >= (size_t)n) continue;
+    R v = R(0);
+    if (r < dU * dX) v = ldg(K + bt * dU * dX + r);
+    else if (r < dU * dX + dU) v = ldg(k + bt * dU + (r - dU * dX));
+    else if (r < dU * dX + dU + dU * dU) v = ldg(Lam + bt * dU * dU + (r - dU * dX - dU));
+    sm[idx] = v;
+  }
+  ctx.sync();
+  TEAM_FOR(idx, npairs * dU * (dX + 1)) {  // G = Lam K, g = Lam k
+    const int q = idx / (dU * (dX + 1)), r = idx % (dU * (dX + 1)), a2 = r / (dX + 1), j = r % (dX + 1);
+    if (first + q >= (size_t)n) continue;
+    R* s = sm + (size_t)q * per;
+    const R* Ks = s;
+    const R* ks = s + dU * dX;
+    const R* Ls = ks + dU;
+    R acc = R(0);
+    for (int b2 = 0; b2 < dU; ++b2) acc = fma(Ls[a2 * dU + b2], j < dX ? Ks[b2 * dX + j] : ks[b2], acc);
+    if (j < dX) s[dU * dX + dU + dU * dU + a2 * dX + j] = acc;
+    else s[2 * dU * dX + dU + dU * dU + a2] = acc;
+  }
+  ctx.sync();
+  TEAM_FOR(idx, npairs * (p * p + p)) {
+    const int q = idx / (p * p + p), r = idx % (p * p + p);
+    const size_t bt = first + q;
+    if (bt >= (size_t)n) continue;
+    const R* s = sm + (size_t)q * per;
+    const R* Ks = s;
+    const R* Ls = s + dU * dX + dU;
+    const R* Gs = Ls + dU * dU;
+    const R* gs = Gs + dU * dX;
+    if (r < p * p) {
+      const int i = r / p, j = r % p;
+      R v;
+      if (i < dX && j < dX) {  // K^T Lam K
+        v = R(0);
+        for (int a2 = 0; a2 < dU; ++a2) v = fma(Ks[a2 * dX + i], Gs[a2 * dX + j], v);
+      } else if (i < dX) {  // -K^T Lam = -(Lam K)^T
+        v = -Gs[(j - dX) * dX + i];
+      } else if (j < dX) {  // -Lam K
+        v = -Gs[(i - dX) * dX + j];
+      } else {
+        v = Ls[(i - dX) * dU + (j - dX)];
+      }
+      C[bt * p * p + r] = v;
+    } else {
+      const int i = r - p * p;
+      R v;
+      if (i < dX) {  // K^T Lam k
+        v = R(0);
+        for (int a2 = 0; a2 < dU; ++a2) v = fma(Ks[a2 * dX + i], gs[a2], v);
+      } else {
+        v = -gs[i - dX];
+      }
+      c[bt * p + i] = v;
+    }
+  }
+}
+
 // Cholesky-based inverse and half log-determinant of one small SPD matrix held in global memory
 // (TimeVaryingLinearGaussian lazy chol_covar / inv_covar, donk/models/tvlg.py:62-99,
 // donk/utils/batched.py:6-49).  ws: 2*d*d scratch.  Returns 0 or 1 (not PD).

@@ -113,8 +113,13 @@ int donk_emu_ilqr_step_f64(int B, int E, int T, int dX, int dU, int flags, const
 
 int donk_emu_extended_costs_kl_f64(int n, int dX, int dU, const double* K, const double* k, const double* Lam,
                                    double* C_kl, double* c_kl, void*) {
-  const int p = dX + dU;
-  for (size_t idx = 0; idx < (size_t)n * p; ++idx) extended_costs_item<double>(idx / p, (int)(idx % p), dX, dU, K, k, Lam, C_kl, c_kl);
+  const int npairs = 4;
+  std::vector<double> smem(extended_costs_smem(dX, dU) * npairs + 2);
+  Ctx ctx{0, 1};
+  for (int cta = 0; cta < (n + npairs - 1) / npairs; ++cta) {
+    memset(smem.data(), 0xFF, smem.size() * sizeof(double));
+    extended_costs_cta<double>(ctx, n, npairs, cta, dX, dU, K, k, Lam, C_kl, c_kl, smem.data());
+  }
   return DONK_OK;
 }
 
