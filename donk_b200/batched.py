@@ -573,3 +573,62 @@ class HostPipelinedILQR:
             for s in self.streams:
                 s.synchronize()
         return self.kl, self.cost, self.info
+
+
+# =====================================================================================================
+# Full GPS inner iteration for B conditions at once (TrajOptAlgorithm.iteration, traj_opt.py:35-96)
+# =====================================================================================================
+class BatchedTrajOpt:
+    """``TrajOptAlgorithm`` (donk/traj_opt/traj_opt.py:12-96) over a batch of conditions, device resident.
+
+    Per condition: fit the initial-state distribution, fit the dynamics (optionally under a shared GMM prior),
+    run KL-constrained iLQR with ``kl_step * kl_step_mult`` and adapt ``kl_step_mult`` from predicted vs. actual
+    improvement (``step_adjust``, lqg.py:309-350).  ``kl_step_mult`` is a ``(B,)`` tensor.
+    """
+
+    def __init__(self, kl_step: float, max_step_mult: float = 10, min_step_mult: float = 0.1,
+                 dynamics_regularization: float = 1e-6):
+        self.kl_step = kl_step
+        self.max_step_mult, self.min_step_mult = max_step_mult, min_step_mult
+        self.dynamics_regularization = dynamics_regularization
+        self.kl_step_mult = None
+        self.dyn = self.pol = self.x0 = self.costs = None
+        self.last = None
+
+    def _total_cost(self, dyn, pol, x0, costs):
+        _, _, cost = lqr_forward(dyn[0], dyn[1], dyn[2], pol[0], pol[1], pol[2], x0[0], x0[1], 1e-6, *costs)
+        return cost
+
+    def iteration(self, X, U, C, c, cc, prev_K=None, prev_k=None, prev_covar=None, prior: "DeviceGMM | None" = None):
+        """One iteration on roll-outs ``X (B,N,T+1,dX), U (B,N,T,dU)`` with quadratic costs ``C, c, cc``.
+
+        The policy to stay close to is ``(prev_K, prev_k, prev_covar)`` or, if omitted, the policy of the previous
+        iteration.  Returns the ``BatchedStepResult`` of the optimisation (E = 1).
+        """
+        X, U = _dev(X), _dev(U)
+        B = X.shape[0]
+        prev_dyn, prev_x0, prev_costs = self.dyn, self.x0, self.costs
+        if prev_K is None:
+            prev_K, prev_k, prev_covar = self.pol
+        prev_pol = (_dev(prev_K), _dev(prev_k), _dev(prev_covar))
+        if self.kl_step_mult is None:
+            self.kl_step_mult = torch.ones(B, dtype=torch.float64, device=X.device)
+        self.x0 = state_fit_from_rollouts(X)
+        F, f, S, info = fit_lr(X, U, prior, self.dynamics_regularization)
+        if int(info.sum().item()):
+            raise np.linalg.LinAlgError("Singular matrix")
+        self.dyn = (F, f, S)
+        self.costs = (_dev(C), _dev(c), _dev(cc))
+        ilqr = BatchedILQR(F, f, S, prev_pol[0], prev_pol[1], *self.costs, self.x0[0], self.x0[1],
+                           prev_covar=prev_pol[2])
+        res, status, n_steps = ilqr.optimize(self.kl_step * self.kl_step_mult)
+        self.pol = (res.K[:, 0].clone(), res.k[:, 0].clone(), res.covar[:, 0].clone())
+        self.last = dict(status=status, n_steps=n_steps, eta=res.eta[:, 0].clone(), kl=res.kl_div[:, 0].clone())
+        if prev_dyn is not None:  # step_adjust (lqg.py:309-350)
+            previous = self._total_cost(prev_dyn, prev_pol, prev_x0, prev_costs)
+            predicted = self._total_cost(prev_dyn, self.pol, prev_x0, prev_costs)
+            actual = self._total_cost(self.dyn, self.pol, self.x0, self.costs)
+            mult = self.kl_step_mult * 0.5 * (predicted - previous) / (predicted - actual)
+            self.kl_step_mult = torch.clamp(mult, self.min_step_mult, self.max_step_mult)
+            self.last.update(previous_costs=previous, predicted_new_costs=predicted, actual_new_costs=actual)
+        return res

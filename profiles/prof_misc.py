@@ -1,0 +1,60 @@
+"""Timings of the secondary paths on the GPU: ILQR.optimize (config 3), generic kernels at config-5 / config-2 dims."""
+import sys, time
+from pathlib import Path
+import numpy as np, torch
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from donk_b200 import _lib, batched, synthetic  # noqa: E402
+
+dev = torch.device("cuda", 0)
+def timed(fn, n=3):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): out = fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n, out
+
+def build(B, T, dX, dU, N, prior=None):
+    ro = synthetic.rollout_batch_torch(B, T, dX, dU, N, seed=7, device=dev)
+    p = dX + dU
+    ms, (F, f, S, info) = timed(lambda: batched.fit_lr(ro["X"], ro["U"], prior))
+    assert int(info.sum()) == 0
+    C, c, cc = synthetic.l2_costs(T, dX, dU)
+    x0m, x0S = batched.state_fit_from_rollouts(ro["X"])
+    il = batched.BatchedILQR(F, f, S, ro["prev_K"], ro["prev_k"],
+                             torch.as_tensor(C, device=dev).expand(B, T + 1, p, p).contiguous(),
+                             torch.as_tensor(c, device=dev).expand(B, T + 1, p).contiguous(),
+                             torch.as_tensor(cc, device=dev).expand(B, T + 1).contiguous(), x0m, x0S, prev_covar=ro["prev_covar"])
+    return ro, il, ms
+
+what = sys.argv[1]
+if what == "optimize":
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+    ro, il, fit_ms = build(B, 100, 20, 6, 64)
+    ms, (res, status, n_steps) = timed(lambda: il.optimize(1.0, raise_on_failure=False), 2)
+    print(f"optimize config3 B={B}: {ms:.1f} ms, {n_steps} batched steps, {B / (ms * 1e-3):.0f} optimize/s, status counts",
+          torch.bincount(status, minlength=4).tolist(), "fit_ms", fit_ms)
+elif what == "config5":
+    B, T = int(sys.argv[2]), int(sys.argv[3])
+    ro, il, fit_ms = build(B, T, 64, 16, 128)
+    print(f"fit_lr (64,16) N=128 B={B} T={T}: {fit_ms:.1f} ms = {B * T / (fit_ms * 1e-3):.0f} fits/s")
+    eta = torch.ones(B, 1, dtype=torch.float64, device=dev)
+    ms, r = timed(lambda: il.step(eta), 2)
+    print(f"ILQR.step (64,16) B={B} T={T} E=1: {ms:.1f} ms = {B / (ms * 1e-3):.1f} solves/s, info {int(r.info.sum())}")
+    ms, (res, status, n_steps) = timed(lambda: il.optimize(1.0, raise_on_failure=False), 1)
+    print(f"ILQR.optimize (64,16) B={B}: {ms:.1f} ms, {n_steps} steps, status", torch.bincount(status, minlength=4).tolist())
+elif what == "config2":
+    B = int(sys.argv[2])
+    T, dX, dU, N, K = 100, 14, 7, 50, 4
+    ro = synthetic.rollout_batch_torch(B, T, dX, dU, N, seed=7, device=dev)
+    pool = batched.to_transitions(ro["X"][:8].reshape(-1, T + 1, dX), ro["U"][:8].reshape(-1, T, dU))
+    d = 2 * dX + dU
+    rng = np.random.default_rng(0)
+    idx = rng.choice(pool.shape[0], K, replace=False)
+    gm = batched.DeviceGMM(K).set_params(np.full(K, 1 / K), pool[idx].cpu().numpy(), precisions=np.broadcast_to(np.eye(d), (K, d, d)).copy())
+    t0 = time.perf_counter(); gm.fit(pool); torch.cuda.synchronize()
+    print(f"GMM fit on {pool.shape[0]} rows d={d} K={K}: {gm.n_iter} iterations, {1e3 * (time.perf_counter() - t0):.1f} ms, converged {gm.converged}")
+    ms, (F, f, S, info) = timed(lambda: batched.fit_lr(ro["X"], ro["U"], gm))
+    print(f"fit_lr + GMM prior (14,7) N=50 K=4, B={B}: {ms:.1f} ms = {B * T / (ms * 1e-3):.0f} fits/s, info {int(info.sum())}")
+    ms, _ = timed(lambda: batched.fit_lr(ro["X"], ro["U"]))
+    print(f"fit_lr no prior  (14,7) N=50, B={B}: {ms:.1f} ms = {B * T / (ms * 1e-3):.0f} fits/s")

@@ -171,3 +171,30 @@ def test_warp_kernel_dims_vs_oracle(backend, dims, reverse):
         ref = oracle.ilqr_step(probs[b], float(etas[b]))
         assert relerr(r1.K[b, 0], ref.K) < TOL
         assert abs(float(r1.kl_div[b, 0]) - ref.kl_div) < 1e-9 * max(1.0, abs(ref.kl_div))
+
+
+def test_generic_kernel_config5_dims(backend):
+    """dX=64, dU=16 (BASELINE config 5): no warp instantiation, the generic CTA kernel with one slot per CTA."""
+    from donk_b200 import synthetic
+    from donk_b200.batched import BatchedILQR
+
+    dX, dU, T, N, B = 64, 16, 3, 100, 2
+    conds = [synthetic.condition(5, i, T, dX, dU, N) for i in range(B)]
+    fits = [oracle.fit_lr(c.X, c.U) for c in conds]
+    x0 = [oracle.state_fit(c.X[:, 0]) for c in conds]
+    st = lambda xs: np.stack(xs)  # noqa: E731
+    il = BatchedILQR(st([f[0] for f in fits]), st([f[1] for f in fits]), st([f[2] for f in fits]),
+                     st([c.prev_K for c in conds]), st([c.prev_k for c in conds]), st([c.C for c in conds]),
+                     st([c.c for c in conds]), st([c.cc for c in conds]), st([m for m, _ in x0]),
+                     st([S for _, S in x0]), prev_covar=st([c.prev_covar for c in conds]))
+    etas = np.array([0.5, 20.0])
+    r = il.step(torch.as_tensor(etas).expand(B, 2))
+    assert int(r.info.sum()) == 0
+    for b, c in enumerate(conds):
+        prob = ILQRProblem(*fits[b], c.C, c.c, c.cc, c.prev_K, c.prev_k, c.prev_covar,
+                           np.linalg.inv(c.prev_covar), *x0[b])
+        for e, eta in enumerate(etas):
+            ref = oracle.ilqr_step(prob, float(eta))
+            assert relerr(r.K[b, e], ref.K) < TOL and relerr(r.covar[b, e], ref.covar) < TOL
+            assert abs(float(r.kl_div[b, e]) - ref.kl_div) < 1e-9 * max(1.0, abs(ref.kl_div))
+            assert abs(float(r.expected_costs[b, e]) - ref.expected_costs) < 1e-9 * abs(ref.expected_costs)

@@ -160,3 +160,32 @@ def test_traj_opt_algorithm_two_iterations(backend):
     mult, *_ = oracle.step_adjust(1.0, (F1, f1, S1), (r1.K, r1.k, r1.covar), x01, (c0.C, c0.c, c0.cc),
                                   (F0, f0, S0), (r0.K, r0.k, r0.covar), x00, (c0.C, c0.c, c0.cc))
     assert abs(algo.kl_step_mult - mult) < 1e-6
+
+
+def test_batched_gps_iteration_matches_per_condition_api(backend):
+    """BatchedTrajOpt (full GPS inner iteration, BASELINE config 5 shape) == TrajOptAlgorithm per condition."""
+    import torch
+
+    from donk_b200 import synthetic
+    from donk_b200.batched import BatchedTrajOpt
+    from donk_b200.costs import QuadraticCosts
+    from donk_b200.policy import LinearGaussianPolicy
+    from donk_b200.traj_opt import TrajOptAlgorithm
+
+    T, dX, dU, N, B = 8, 6, 2, 12, 3
+    it0 = [synthetic.condition(30, i, T, dX, dU, N) for i in range(B)]
+    it1 = [synthetic.condition(31, i, T, dX, dU, N) for i in range(B)]
+    st = lambda xs: np.stack(xs)  # noqa: E731
+    algo = BatchedTrajOpt(kl_step=0.7)
+    C, c, cc = st([x.C for x in it0]), st([x.c for x in it0]), st([x.cc for x in it0])
+    algo.iteration(st([x.X for x in it0]), st([x.U for x in it0]), C, c, cc, st([x.prev_K for x in it0]),
+                   st([x.prev_k for x in it0]), st([x.prev_covar for x in it0]))
+    algo.iteration(st([x.X for x in it1]), st([x.U for x in it1]), C, c, cc)
+    for b in range(B):
+        single = TrajOptAlgorithm(kl_step=0.7)
+        costs = QuadraticCosts(it0[b].C, it0[b].c, it0[b].cc)
+        single.iteration(it0[b].X, it0[b].U, costs,
+                         prev_pol=LinearGaussianPolicy(it0[b].prev_K, it0[b].prev_k, it0[b].prev_covar))
+        single.iteration(it1[b].X, it1[b].U, costs)
+        assert relerr(algo.pol[0][b], single.pol.K) < 1e-9 and relerr(algo.pol[2][b], single.pol.covar) < 1e-9
+        assert abs(float(algo.kl_step_mult[b]) - single.kl_step_mult) < 1e-9
