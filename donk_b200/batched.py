@@ -205,6 +205,40 @@ class BatchedILQR:
         return BatchedStepResult(eta, ws["K"], ws["k"], ws["covar"], ws["inv_covar"], ws["kl"], ws["cost"],
                                  ws["info"], ws["tmean"], ws["tcov"])
 
+    def step_f32(self, eta) -> BatchedStepResult:
+        """``ILQR.step`` in single precision (``donk_ilqr_step_f32``): same kernel, float storage and FFMA math.
+
+        Inputs are cast once and cached.  Stated tolerance against the fp64 path / the reference for
+        well-conditioned problems (tests/test_ilqr_kernels.py::test_step_f32_tolerance): gains ``K`` within
+        2e-3 max-norm relative, KL and expected cost within 5e-3 relative, for eta in [1e-2, 1e2].  At the extremes
+        of the eta range ``C/eta + C_kl`` loses ``C_kl`` (or ``C``) entirely in fp32 — use fp64 there.
+        """
+        nat = _lib.native()
+        f32 = torch.float32
+        if getattr(self, "_f32", None) is None:
+            self._f32 = {k: getattr(self, k).to(f32).contiguous() for k in
+                         ("F", "f", "dyn_covar", "C", "c", "cc", "C_kl", "c_kl", "prev_K", "prev_k", "prev_inv_covar",
+                          "prev_hld", "x0_mean", "x0_covar")}
+        d = self._f32
+        eta = torch.as_tensor(eta, dtype=f32).to(self.F.device)
+        if eta.ndim == 0:
+            eta = eta.expand(self.B, 1)
+        elif eta.ndim == 1:
+            eta = eta[:, None]
+        eta = eta.contiguous()
+        E = eta.shape[1]
+        B, T, dX, dU = self.B, self.T, self.dX, self.dU
+        o = dict(dtype=f32, device=self.F.device)
+        K, k = torch.empty(B, E, T, dU, dX, **o), torch.empty(B, E, T, dU, **o)
+        cov, inv = torch.empty(B, E, T, dU, dU, **o), torch.empty(B, E, T, dU, dU, **o)
+        kl, cost = torch.zeros(B, E, **o), torch.zeros(B, E, **o)
+        info = torch.zeros(B, E, dtype=torch.int32, device=self.F.device)
+        nat.call("ilqr_step_f32", B, E, T, dX, dU, ILQR_BACKWARD | ILQR_FORWARD | ILQR_KL | ILQR_COST,
+                 d["F"], d["f"], d["dyn_covar"], d["C"], d["c"], d["cc"], d["C_kl"], d["c_kl"], d["prev_K"], d["prev_k"],
+                 d["prev_inv_covar"], d["prev_hld"], d["x0_mean"], d["x0_covar"], eta, 1.0, 1e-6, None, K, k, cov, inv,
+                 kl, cost, None, None, info)
+        return BatchedStepResult(eta, K, k, cov, inv, kl, cost, info)
+
     def sample_surface(self, min_eta: float = 1e-6, max_eta: float = 1e16, N: int = 100) -> BatchedStepResult:
         """``ILQR.sample_surface`` (lqg.py:77-88): N log-spaced eta candidates for every condition."""
         etas = np.logspace(np.log10(min_eta), np.log10(max_eta), num=N)

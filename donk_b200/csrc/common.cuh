@@ -210,7 +210,7 @@ DONK_D void warp_mma_pre(const WCtx& w, const R* __restrict__ A, int lda, const 
   if (sizeof(R) == 8) {
     const R* ap = A + tq * lda + g;
     const R* bp = Bm + tq * ldb + g;
-#pragma unroll 2
+#pragma unroll 8
     for (int k4 = 0; k4 < K4; ++k4) {
       R af[RA], bf[RB];
 #pragma unroll
@@ -222,7 +222,7 @@ DONK_D void warp_mma_pre(const WCtx& w, const R* __restrict__ A, int lda, const 
 #pragma unroll
         for (int rb = 0; rb < RB; ++rb) {
           double d0 = (double)c[ra][rb][0], d1 = (double)c[ra][rb][1];
-          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+          asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                        : "+d"(d0), "+d"(d1)
                        : "d"((double)af[ra]), "d"((double)bf[rb]));
           c[ra][rb][0] = (R)d0;

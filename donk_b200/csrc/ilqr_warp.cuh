@@ -520,7 +520,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
               for (int rb = 0; rb < D::NBX; ++rb) {
                 if (sizeof(R) == 8) {
                   double d0 = (double)c[ra][rb][0], d1 = (double)c[ra][rb][1];
-                  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                                : "+d"(d0), "+d"(d1)
                                : "d"((double)af[ra]), "d"((double)bf[rb]));
                   c[ra][rb][0] = (R)d0;

@@ -29,17 +29,50 @@ static int env_int(const char* name) {
   return v ? atoi(v) : 0;
 }
 
-template <int DX, int DU>
-static int emu_ilqr_warp(const IlqrArgs<double>& a) {
+template <typename R, int DX, int DU>
+static int emu_ilqr_warp(const IlqrArgs<R>& a) {
   int G, ES, grid;
   size_t bytes;
-  int rc = ilqr_warp_plan<double, DX, DU>(a.B, a.E, kSmemCap, env_int("DONK_ILQR_WARPS"), G, ES, grid, bytes);
+  int rc = ilqr_warp_plan<R, DX, DU>(a.B, a.E, kSmemCap, env_int("DONK_ILQR_WARPS"), G, ES, grid, bytes);
   if (rc != DONK_OK) return rc;
-  std::vector<double> smem(bytes / sizeof(double) + 2);
+  std::vector<R> smem(bytes / sizeof(R) + 4);
   WCtx w{0, 1, 0, 0, G};
   for (int cta = 0; cta < grid; ++cta) {
-    memset(smem.data(), 0xFF, smem.size() * sizeof(double));
-    ilqr_warp_cta<double, DX, DU>(w, a, cta, ES, smem.data());
+    memset(smem.data(), 0xFF, smem.size() * sizeof(R));
+    ilqr_warp_cta<R, DX, DU>(w, a, cta, ES, smem.data());
+  }
+  return DONK_OK;
+}
+
+template <typename R>
+static int emu_ilqr_step(IlqrArgs<R> a) {
+  if (a.B < 0 || a.E < 1 || a.T < 1 || a.dX < 1 || a.dU < 1) return DONK_BAD_SHAPE;
+  if ((a.flags & ILQR_KL) && (a.flags & (ILQR_BACKWARD | ILQR_FORWARD)) != (ILQR_BACKWARD | ILQR_FORWARD))
+    return DONK_BAD_SHAPE;
+  if (a.B == 0) return DONK_OK;
+  if (!env_int("DONK_ILQR_GENERIC")) {
+    if (a.dX == 20 && a.dU == 6) return emu_ilqr_warp<R, 20, 6>(a);
+    if (a.dX == 14 && a.dU == 7) return emu_ilqr_warp<R, 14, 7>(a);
+    if (a.dX == 6 && a.dU == 2) return emu_ilqr_warp<R, 6, 2>(a);
+  }
+  IlqrPlan pl;
+  int rc;
+  if (env_int("DONK_ILQR_TEAM_MODE")) {  // team launch: one slot per team, "cta" index = problem index
+    rc = ilqr_plan_team(a.B, a.E, a.dX, a.dU, sizeof(R), kSmemCap, 0, 0, pl);
+    if (rc != DONK_OK) return rc;
+    pl.smem = IlqrLayout(a.dX, a.dU).bytes(1, 1, sizeof(R));
+    pl.grid = a.B * a.E;
+  } else {
+    rc = ilqr_plan(a.B, a.E, a.dX, a.dU, sizeof(R), kSmemCap, env_int("DONK_ILQR_SLOTS"), 0, pl);
+    if (rc != DONK_OK) return rc;
+  }
+  a.S = pl.S;
+  a.ES = pl.ES;
+  std::vector<R> smem(pl.smem / sizeof(R) + 4);
+  Ctx ctx{0, 1};
+  for (int cta = 0; cta < pl.grid; ++cta) {
+    memset(smem.data(), 0xFF, smem.size() * sizeof(R));  // poison: kernels must not depend on initial contents
+    ilqr_cta<R>(ctx, a, cta, smem.data());
   }
   return DONK_OK;
 }
@@ -64,52 +97,25 @@ extern "C" {
 
 void donk_emu_set_reverse(int r) { g_emu_reverse = r; }
 
-int donk_emu_ilqr_step_f64(int B, int E, int T, int dX, int dU, int flags, const double* F, const double* f,
-                           const double* dyn_covar, const double* C, const double* c, const double* cc,
-                           const double* C_kl, const double* c_kl, const double* prevK, const double* prevk,
-                           const double* prevLam, const double* prev_hld, const double* x0_mean,
-                           const double* x0_covar, const double* eta, double gamma, double fwd_reg,
-                           const int* active, double* K, double* k, double* pol_covar, double* pol_inv_covar,
-                           double* kl, double* cost, double* traj_mean, double* traj_covar, int* info, void*) {
-  IlqrArgs<double> a;
-  memset(&a, 0, sizeof(a));
-  a.B = B; a.E = E; a.T = T; a.dX = dX; a.dU = dU; a.flags = flags;
-  a.F = F; a.f = f; a.dyn_covar = dyn_covar; a.C = C; a.c = c; a.cc = cc; a.C_kl = C_kl; a.c_kl = c_kl;
-  a.prevK = prevK; a.prevk = prevk; a.prevLam = prevLam; a.prev_hld = prev_hld;
-  a.x0m = x0_mean; a.x0S = x0_covar; a.eta = eta; a.gamma = gamma; a.fwd_reg = fwd_reg;
-  a.K = K; a.k = k; a.pcov = pol_covar; a.pinv = pol_inv_covar; a.kl = kl; a.cost = cost;
-  a.tmean = traj_mean; a.tcov = traj_covar; a.info = info; a.active = active;
-  if (B < 0 || E < 1 || T < 1 || dX < 1 || dU < 1) return DONK_BAD_SHAPE;
-  if ((flags & ILQR_KL) && (flags & (ILQR_BACKWARD | ILQR_FORWARD)) != (ILQR_BACKWARD | ILQR_FORWARD))
-    return DONK_BAD_SHAPE;
-  if (B == 0) return DONK_OK;
-  IlqrPlan pl;
-  int rc;
-  if (!env_int("DONK_ILQR_GENERIC")) {
-    if (dX == 20 && dU == 6) return emu_ilqr_warp<20, 6>(a);
-    if (dX == 14 && dU == 7) return emu_ilqr_warp<14, 7>(a);
-    if (dX == 6 && dU == 2) return emu_ilqr_warp<6, 2>(a);
+#define EMU_ILQR_STEP(SUFFIX, R)                                                                                  \
+  int donk_emu_ilqr_step_##SUFFIX(int B, int E, int T, int dX, int dU, int flags, const R* F, const R* f,        \
+                                  const R* dyn_covar, const R* C, const R* c, const R* cc, const R* C_kl,        \
+                                  const R* c_kl, const R* prevK, const R* prevk, const R* prevLam,               \
+                                  const R* prev_hld, const R* x0_mean, const R* x0_covar, const R* eta, R gamma, \
+                                  R fwd_reg, const int* active, R* K, R* k, R* pol_covar, R* pol_inv_covar,      \
+                                  R* kl, R* cost, R* traj_mean, R* traj_covar, int* info, void*) {               \
+    IlqrArgs<R> a;                                                                                               \
+    memset(&a, 0, sizeof(a));                                                                                    \
+    a.B = B; a.E = E; a.T = T; a.dX = dX; a.dU = dU; a.flags = flags;                                            \
+    a.F = F; a.f = f; a.dyn_covar = dyn_covar; a.C = C; a.c = c; a.cc = cc; a.C_kl = C_kl; a.c_kl = c_kl;        \
+    a.prevK = prevK; a.prevk = prevk; a.prevLam = prevLam; a.prev_hld = prev_hld;                                \
+    a.x0m = x0_mean; a.x0S = x0_covar; a.eta = eta; a.gamma = gamma; a.fwd_reg = fwd_reg;                        \
+    a.K = K; a.k = k; a.pcov = pol_covar; a.pinv = pol_inv_covar; a.kl = kl; a.cost = cost;                      \
+    a.tmean = traj_mean; a.tcov = traj_covar; a.info = info; a.active = active;                                  \
+    return emu_ilqr_step<R>(a);                                                                                  \
   }
-  if (env_int("DONK_ILQR_TEAM_MODE")) {  // team launch: one slot per team, "cta" index = problem index
-    rc = ilqr_plan_team(B, E, dX, dU, sizeof(double), kSmemCap, 0, 0, pl);
-    if (rc != DONK_OK) return rc;
-    pl.smem = IlqrLayout(dX, dU).bytes(1, 1, sizeof(double));
-    pl.grid = B * E;
-  } else {
-    rc = ilqr_plan(B, E, dX, dU, sizeof(double), kSmemCap, env_int("DONK_ILQR_SLOTS"), 0, pl);
-    if (rc != DONK_OK) return rc;
-  }
-  a.S = pl.S;
-  a.ES = pl.ES;
-  std::vector<double> smem(pl.smem / sizeof(double) + 2);
-  Ctx ctx{0, 1};
-  for (int cta = 0; cta < pl.grid; ++cta) {
-    // poison shared memory: kernels must not depend on its initial contents
-    memset(smem.data(), 0xFF, smem.size() * sizeof(double));
-    ilqr_cta<double>(ctx, a, cta, smem.data());
-  }
-  return DONK_OK;
-}
+EMU_ILQR_STEP(f64, double)
+EMU_ILQR_STEP(f32, float)
 
 int donk_emu_extended_costs_kl_f64(int n, int dX, int dU, const double* K, const double* k, const double* Lam,
                                    double* C_kl, double* c_kl, void*) {

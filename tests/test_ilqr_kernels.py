@@ -198,3 +198,32 @@ def test_generic_kernel_config5_dims(backend):
             assert relerr(r.K[b, e], ref.K) < TOL and relerr(r.covar[b, e], ref.covar) < TOL
             assert abs(float(r.kl_div[b, e]) - ref.kl_div) < 1e-9 * max(1.0, abs(ref.kl_div))
             assert abs(float(r.expected_costs[b, e]) - ref.expected_costs) < 1e-9 * abs(ref.expected_costs)
+
+
+@pytest.mark.parametrize("dims", [(20, 6), (5, 3)])
+def test_step_f32_tolerance(backend, dims):
+    """Single-precision step (donk_ilqr_step_f32) against the fp64 oracle: the stated fp32 tolerance."""
+    from donk_b200 import synthetic
+    from donk_b200.batched import BatchedILQR
+
+    dX, dU = dims
+    T, N, B = 10, dX + dU + 10, 2
+    conds = [synthetic.condition(14, i, T, dX, dU, N) for i in range(B)]
+    fits = [oracle.fit_lr(c.X, c.U) for c in conds]
+    x0 = [oracle.state_fit(c.X[:, 0]) for c in conds]
+    st = lambda xs: np.stack(xs)  # noqa: E731
+    il = BatchedILQR(st([f[0] for f in fits]), st([f[1] for f in fits]), st([f[2] for f in fits]),
+                     st([c.prev_K for c in conds]), st([c.prev_k for c in conds]), st([c.C for c in conds]),
+                     st([c.c for c in conds]), st([c.cc for c in conds]), st([m for m, _ in x0]),
+                     st([S for _, S in x0]), prev_covar=st([c.prev_covar for c in conds]))
+    etas = np.array([1e-2, 1.0, 1e2])
+    r = il.step_f32(torch.as_tensor(etas).expand(B, 3))
+    assert r.K.dtype == torch.float32 and int(r.info.sum()) == 0
+    for b, c in enumerate(conds):
+        prob = ILQRProblem(*fits[b], c.C, c.c, c.cc, c.prev_K, c.prev_k, c.prev_covar,
+                           np.linalg.inv(c.prev_covar), *x0[b])
+        for e, eta in enumerate(etas):
+            ref = oracle.ilqr_step(prob, float(eta))
+            assert relerr(r.K[b, e].double(), ref.K) < 2e-3
+            assert abs(float(r.kl_div[b, e]) - ref.kl_div) < 5e-3 * max(1.0, abs(ref.kl_div))
+            assert abs(float(r.expected_costs[b, e]) - ref.expected_costs) < 5e-3 * abs(ref.expected_costs)
