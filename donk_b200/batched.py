@@ -666,3 +666,77 @@ class BatchedTrajOpt:
             self.kl_step_mult = torch.clamp(mult, self.min_step_mult, self.max_step_mult)
             self.last.update(previous_costs=previous, predicted_new_costs=predicted, actual_new_costs=actual)
         return res
+
+
+# =====================================================================================================
+# Device k-means: initial labelling for GMMPrior.update on pools that live on the GPU
+# =====================================================================================================
+class DeviceKMeans:
+    """Lloyd's algorithm with k-means++ seeding on the device (``donk_kmeans_assign/update_f64``).
+
+    Stands in for the ``sklearn.cluster.KMeans(n_clusters, n_init=1, random_state)`` call that scikit-learn's
+    ``GaussianMixture`` uses to initialise EM (sklearn/mixture/_base.py:119-128).  Same algorithm and stopping
+    rule (``tol = 1e-4`` x mean feature variance, ``max_iter = 300``) but a different random stream, so labels
+    agree with scikit-learn statistically, not bit for bit.  Rows may be sharded over ranks: the per-cluster sums
+    are all-reduced every Lloyd step; seeding uses rank 0's rows and broadcasts the centres.
+    """
+
+    def __init__(self, n_clusters: int, random_state=None, max_iter: int = 300, tol: float = 1e-4):
+        self.K, self.max_iter, self.tol = int(n_clusters), max_iter, tol
+        self.seed = 0 if random_state is None else int(random_state)
+        self.centers = None
+        self.n_iter = 0
+
+    def _assign(self, X, centers, want_d2=False):
+        nat = _lib.native()
+        n, d = X.shape
+        labels = torch.empty(n, dtype=torch.int32, device=X.device)
+        d2 = torch.empty(n, dtype=X.dtype, device=X.device) if want_d2 else None
+        nat.call("kmeans_assign_f64", n, d, centers.shape[0], X, centers.contiguous(), labels, d2)
+        return labels, d2
+
+    def fit(self, X_local, group=None):
+        import torch.distributed as dist
+
+        nat = _lib.native()
+        X = _dev(X_local)
+        n, d = X.shape
+        K = self.K
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        rank = dist.get_rank(group) if multi else 0
+        o = dict(dtype=X.dtype, device=X.device)
+        # ---- k-means++ seeding (rank 0's rows) ----
+        centers = torch.empty(K, d, **o)
+        if rank == 0:
+            g = torch.Generator(device=X.device)
+            g.manual_seed(self.seed)
+            centers[0] = X[int(torch.randint(0, n, (1,), device=X.device, generator=g).item())]
+            for i in range(1, K):
+                _, d2 = self._assign(X, centers[:i], want_d2=True)
+                total = d2.sum()
+                idx = int(torch.multinomial(d2 / total, 1, generator=g).item()) if float(total) > 0 else i % n
+                centers[i] = X[idx]
+        if multi:
+            dist.broadcast(centers, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        # ---- Lloyd ----
+        stat = torch.stack([X.sum(0), (X * X).sum(0), torch.full((d,), float(n), **o)])
+        DeviceGMM._allreduce(stat, group)
+        var = stat[1] / stat[2] - (stat[0] / stat[2]) ** 2
+        tol = self.tol * float(var.mean())
+        ws = torch.empty(nat.size("kmeans_workspace_bytes", d, K) // 8 + 1, **o)
+        sums = torch.empty(K * d + K, **o)
+        labels = None
+        for it in range(1, self.max_iter + 1):
+            labels, _ = self._assign(X, centers)
+            nat.call("kmeans_update_f64", n, d, K, X, labels, sums, ws, ws.numel() * ws.element_size())
+            DeviceGMM._allreduce(sums, group)
+            cnt = sums[K * d:]
+            new = torch.where(cnt[:, None] > 0, sums[:K * d].reshape(K, d) / cnt.clamp(min=1)[:, None], centers)
+            shift = float(((new - centers) ** 2).sum())
+            centers = new
+            self.n_iter = it
+            if shift <= tol:
+                break
+        self.centers = centers
+        self.labels, _ = self._assign(X, centers)
+        return self

@@ -13,6 +13,7 @@
 #include "gmm.cuh"
 #include "gmm_mma.cuh"
 #include "ilqr.cuh"
+#include "kmeans.cuh"
 #include "ilqr_warp.cuh"
 
 using namespace donk;
@@ -415,6 +416,28 @@ int gmm_e_launch(GmmArgs<double>& a, void* stream) {
 
 
 // ---------------------------------------------------------------------------------------------
+// k-means passes (device initialisation of the GMM prior)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) kmeans_assign_kernel(int n, int d, int K, const double* X, const double* centers,
+                                                            int* labels, double* mind2) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Ctx ctx{(int)threadIdx.x, (int)blockDim.x};
+  kmeans_assign_cta<double>(ctx, n, d, K, X, centers, labels, mind2, (int)blockIdx.x, (int)gridDim.x,
+                            reinterpret_cast<double*>(smem_raw));
+}
+__global__ void __launch_bounds__(256) kmeans_update_kernel(int n, int d, int K, const double* X, const int* labels,
+                                                            double* part) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Ctx ctx{(int)threadIdx.x, (int)blockDim.x};
+  kmeans_update_cta<double>(ctx, n, d, K, X, labels, part, (int)blockIdx.x, (int)gridDim.x,
+                            reinterpret_cast<double*>(smem_raw));
+}
+__global__ void kmeans_reduce_kernel(int ncta, int len, const double* part, double* out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < len) kmeans_reduce_item<double>(ncta, len, part, out, idx);
+}
+
+// ---------------------------------------------------------------------------------------------
 // FP64 pipe probes (roofline denominators for the FP64-bound kernels; MEASURED_PEAKS.json only holds
 // HBM and bf16 tensor peaks).  mode 0: dependent-chain-free DFMA on CUDA cores; mode 1: DMMA
 // (mma.sync.m8n8k4.f64) to see whether the tensor path offers more FP64 throughput on sm_100a.
@@ -702,6 +725,45 @@ int donk_fp64_probe(int mode, int blocks, int iters, double* scratch, double* fl
   fp64_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(mode, iters, scratch);
   LAUNCHED("fp64_probe_kernel");
   if (flops) *flops = mode == 0 ? (double)blocks * 256 * iters * 32.0 : (double)blocks * 8 * iters * 8 * 512.0;
+  return DONK_OK;
+}
+
+enum { KM_UPDATE_CTAS = 296 };
+size_t donk_kmeans_workspace_bytes(int d, int K) { return (size_t)KM_UPDATE_CTAS * ((size_t)K * d + K) * sizeof(double); }
+
+int donk_kmeans_assign_f64(int n, int d, int K, const double* X, const double* centers, int* labels, double* mind2,
+                           void* stream) {
+  if (n < 0 || d < 1 || K < 1) return DONK_BAD_SHAPE;
+  if (n == 0) return DONK_OK;
+  const size_t smem = kmeans_assign_smem(d, K) * sizeof(double);
+  if (smem > smem_optin_cap()) return DONK_SMEM_LIMIT;
+  int rc = allow_smem(kmeans_assign_kernel, smem);
+  if (rc != DONK_OK) return rc;
+  int grid = 148 * 2;
+  const int nblocks = (n + KM_TS - 1) / KM_TS;
+  if (grid > nblocks) grid = nblocks;
+  kmeans_assign_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(n, d, K, X, centers, labels, mind2);
+  LAUNCHED("kmeans_assign_kernel");
+  return DONK_OK;
+}
+
+int donk_kmeans_update_f64(int n, int d, int K, const double* X, const int* labels, double* sums, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  if (n < 0 || d < 1 || K < 1) return DONK_BAD_SHAPE;
+  if (workspace_bytes < donk_kmeans_workspace_bytes(d, K)) return DONK_BAD_SHAPE;
+  const int len = K * d + K;
+  const size_t smem = kmeans_update_smem(d, K) * sizeof(double);
+  if (smem > smem_optin_cap() || d + 1 > 256) return DONK_SMEM_LIMIT;
+  int rc = allow_smem(kmeans_update_kernel, smem);
+  if (rc != DONK_OK) return rc;
+  int grid = KM_UPDATE_CTAS;
+  const int nblocks = (n + KM_TS - 1) / KM_TS;
+  if (grid > nblocks) grid = nblocks > 0 ? nblocks : 1;
+  double* part = static_cast<double*>(workspace);
+  kmeans_update_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(n, d, K, X, labels, part);
+  LAUNCHED("kmeans_update_kernel");
+  kmeans_reduce_kernel<<<(len + 127) / 128, 128, 0, (cudaStream_t)stream>>>(grid, len, part, sums);
+  LAUNCHED("kmeans_reduce_kernel");
   return DONK_OK;
 }
 

@@ -39,10 +39,14 @@ class _MixtureView:
 class GMMPrior(DynamicsPrior):
     """A Gaussian-mixture based prior: ``GMMPrior(n_clusters, random_state=None)``."""
 
-    def __init__(self, n_clusters: int, random_state=None) -> None:
+    def __init__(self, n_clusters: int, random_state=None, init: str = "auto") -> None:
+        """``init``: where the k-means labels of the first ``update`` come from — ``"sklearn"`` (host, the
+        reference's exact labels), ``"device"`` (``batched.DeviceKMeans``, statistical parity) or ``"auto"``
+        (device for CUDA tensors and pools of >= 100 000 rows, else sklearn)."""
         from donk_b200.batched import DeviceGMM
 
         self.random_state = random_state
+        self.init = init
         self._gmm = DeviceGMM(n_clusters)
         self.gmm = _MixtureView(self._gmm, self)
 
@@ -64,14 +68,22 @@ class GMMPrior(DynamicsPrior):
                 w, m, prec = init
                 g.set_params(w, m, precisions=prec)
             else:
-                g.init_from_labels(XUX, self._kmeans_labels(XUX, g.K), group)
+                on_device = hasattr(XUX, "is_cuda") and XUX.is_cuda
+                use_device = self.init == "device" or (self.init == "auto" and (on_device or XUX.shape[0] >= 100_000))
+                if use_device:
+                    from donk_b200.batched import DeviceKMeans
+
+                    km = DeviceKMeans(g.K, self.random_state).fit(XUX, group)
+                    g.init_from_labels(XUX, km.labels, group)
+                else:
+                    g.init_from_labels(XUX, self._kmeans_labels(XUX, g.K), group)
         g.fit(XUX, warm_start=warm, group=group)
         self.N = g.N
         self.gmm.warm_start = True
 
     def _kmeans_labels(self, XUX, K):
-        # Host-side initial labelling, once per prior (the EM iterations themselves run on the device).
-        # A device k-means is a listed follow-up.
+        # Host-side initial labelling with scikit-learn's own KMeans: reproduces the reference's labels exactly
+        # (its random stream).  Large / device-resident pools use batched.DeviceKMeans instead (init="device").
         from sklearn.cluster import KMeans
         from sklearn.utils import check_random_state
 

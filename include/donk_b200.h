@@ -186,6 +186,19 @@ int donk_gmm_predict_proba_f64(int n, int d, int K, const double* X, const doubl
 int donk_gmm_prec_chol_from_precisions_f64(int d, int K, const double* precisions, double* prec_chol,
                                            int* info, void* stream);
 
+/* ---- k-means initialisation of the GMM prior ------------------------------------------------ */
+
+/* The reference's first GMMPrior.update starts EM from k-means labels (sklearn/mixture/_base.py:119-128 via
+ * donk/dynamics/prior/prior_gmm.py:21).  Lloyd passes on the device for pools that live there:
+ *   assign: nearest centre of every row X (n,d) among centers (K,d) -> labels (n) int32, mind2 (n) squared
+ *           distance to it (optional, used for k-means++ seeding);
+ *   update: per-cluster sums and counts of the rows -> sums (K*d + K): [sum x (K,d) | count (K)]. */
+size_t donk_kmeans_workspace_bytes(int d, int K);
+int donk_kmeans_assign_f64(int n, int d, int K, const double* X, const double* centers, int* labels,
+                           double* mind2, void* stream);
+int donk_kmeans_update_f64(int n, int d, int K, const double* X, const int* labels, double* sums,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- diagnostics ------------------------------------------------------------------------ */
 
 /* FP64 pipe throughput probe (roofline denominator of the FP64-bound kernels): mode 0 = DFMA on the

@@ -153,3 +153,28 @@ def test_fit_lr_warp_kernel_dims(backend, dims, N, reverse):
         assert relerr(F[b], Fo) < 1e-8 and relerr(f[b], fo) < 1e-8 and relerr(covar[b], co) < 1e-8
     cv = covar.cpu().numpy()
     assert np.array_equal(cv, np.swapaxes(cv, -1, -2))
+
+
+def test_device_kmeans_and_prior_init(backend):
+    """Device Lloyd passes: exact against a numpy Lloyd step; k-means++ seeded fit recovers separated clusters;
+    GMMPrior(init="device") fits a mixture whose log-likelihood matches sklearn's fit (statistical parity)."""
+    from donk_b200 import synthetic
+    from donk_b200.batched import DeviceKMeans
+    from donk_b200.dynamics.prior import GMMPrior
+
+    X, _, _, _ = synthetic.gmm_pool(1800, 9, 4, seed=3)
+    km = DeviceKMeans(4, random_state=0)
+    c0 = torch.as_tensor(X[:4]).to(backend.device)
+    labels, d2 = km._assign(torch.as_tensor(X).to(backend.device), c0, want_d2=True)
+    dist = ((X[:, None, :] - X[None, :4, :]) ** 2).sum(-1)
+    assert np.array_equal(labels.cpu().numpy(), dist.argmin(1))
+    assert relerr(d2, dist.min(1)) < 1e-10
+    km.fit(X)
+    counts = np.bincount(km.labels.cpu().numpy(), minlength=4)
+    assert counts.min() > 300 and km.n_iter < 50  # four well separated clusters of ~450 rows each
+    prior = GMMPrior(4, random_state=0, init="device")
+    prior.update(X)
+    from sklearn.mixture import GaussianMixture
+
+    ref = GaussianMixture(4, random_state=0).fit(X)
+    assert abs(prior.gmm.lower_bound_ - ref.lower_bound_) < 1e-3 * abs(ref.lower_bound_)
