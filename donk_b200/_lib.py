@@ -40,8 +40,7 @@ SIGNATURES = {
     "gmm_predict_proba_f64": [c_int] * 3 + [P] * 5 + [P],
     "gmm_prec_chol_from_precisions_f64": [c_int] * 2 + [P] * 3 + [P],
     "fp64_probe": [c_int, c_int, c_int, P, ctypes.POINTER(c_double), P],
-    "kmeans_assign_f64": [c_int] * 3 + [P] * 4 + [P],
-    "kmeans_update_f64": [c_int] * 3 + [P] * 3 + [P, c_size_t, P],
+    "kmeans_pass_f64": [c_int] * 3 + [P] * 6 + [P, c_size_t, P],
 }
 _SIZE_FUNCS = {
     "gmm_stats_size": [c_int, c_int],

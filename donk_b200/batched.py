@@ -672,28 +672,62 @@ class BatchedTrajOpt:
 # Device k-means: initial labelling for GMMPrior.update on pools that live on the GPU
 # =====================================================================================================
 class DeviceKMeans:
-    """Lloyd's algorithm with k-means++ seeding on the device (``donk_kmeans_assign/update_f64``).
+    """Lloyd's algorithm with greedy k-means++ seeding on the device (``donk_kmeans_pass_f64``).
 
     Stands in for the ``sklearn.cluster.KMeans(n_clusters, n_init=1, random_state)`` call that scikit-learn's
-    ``GaussianMixture`` uses to initialise EM (sklearn/mixture/_base.py:119-128).  Same algorithm and stopping
-    rule (``tol = 1e-4`` x mean feature variance, ``max_iter = 300``) but a different random stream, so labels
-    agree with scikit-learn statistically, not bit for bit.  Rows may be sharded over ranks: the per-cluster sums
-    are all-reduced every Lloyd step; seeding uses rank 0's rows and broadcasts the centres.
+    ``GaussianMixture`` uses to initialise EM (sklearn/mixture/_base.py:119-128).  Same algorithm — greedy
+    k-means++ with ``2 + log(K)`` candidates per centre, Lloyd iterations until the centres move by less than
+    ``tol = 1e-4`` x mean feature variance, ``max_iter = 300`` — but a different random stream, so labels agree with
+    scikit-learn statistically, not bit for bit.  One Lloyd iteration is one pass over the rows (labels and the
+    per-cluster sums come out of the same kernel).  Rows may be sharded over ranks: the sums are all-reduced every
+    iteration; seeding uses rank 0's rows and broadcasts the centres.
     """
 
     def __init__(self, n_clusters: int, random_state=None, max_iter: int = 300, tol: float = 1e-4):
         self.K, self.max_iter, self.tol = int(n_clusters), max_iter, tol
         self.seed = 0 if random_state is None else int(random_state)
         self.centers = None
+        self.labels = None
         self.n_iter = 0
 
-    def _assign(self, X, centers, want_d2=False):
+    @staticmethod
+    def _pass(X, centers, labels=False, mind2=False, dist=False, sums=None, ws=None):
         nat = _lib.native()
         n, d = X.shape
-        labels = torch.empty(n, dtype=torch.int32, device=X.device)
-        d2 = torch.empty(n, dtype=X.dtype, device=X.device) if want_d2 else None
-        nat.call("kmeans_assign_f64", n, d, centers.shape[0], X, centers.contiguous(), labels, d2)
-        return labels, d2
+        K = centers.shape[0]
+        o = dict(dtype=X.dtype, device=X.device)
+        lab = torch.empty(n, dtype=torch.int32, device=X.device) if labels else None
+        m2 = torch.empty(n, **o) if mind2 else None
+        D = torch.empty(n, K, **o) if dist else None
+        nat.call("kmeans_pass_f64", n, d, K, X, centers.contiguous(), lab, m2, D, sums, ws,
+                 ws.numel() * ws.element_size() if ws is not None else 0)
+        return lab, m2, D
+
+    def _seed(self, X):
+        """Greedy k-means++ (sklearn/cluster/_kmeans.py:_kmeans_plusplus): each new centre is the best of
+        ``2 + log K`` candidates drawn with probability proportional to the current squared distance."""
+        import math
+
+        n, d = X.shape
+        K = self.K
+        g = torch.Generator(device=X.device)
+        g.manual_seed(self.seed)
+        trials = 2 + int(math.log(K))
+        centers = torch.empty(K, d, dtype=X.dtype, device=X.device)
+        centers[0] = X[int(torch.randint(0, n, (1,), device=X.device, generator=g).item())]
+        _, closest, _ = self._pass(X, centers[:1], mind2=True)
+        for i in range(1, K):
+            total = closest.sum()
+            if float(total) <= 0:  # fewer distinct rows than clusters
+                centers[i] = X[i % n]
+                continue
+            cand = torch.multinomial(closest / total, trials, replacement=True, generator=g)
+            _, _, D = self._pass(X, X[cand], dist=True)
+            D = torch.minimum(D, closest[:, None])
+            best = int(D.sum(0).argmin())
+            closest = D[:, best].contiguous()
+            centers[i] = X[cand[best]]
+        return centers
 
     def fit(self, X_local, group=None):
         import torch.distributed as dist
@@ -705,30 +739,17 @@ class DeviceKMeans:
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         rank = dist.get_rank(group) if multi else 0
         o = dict(dtype=X.dtype, device=X.device)
-        # ---- k-means++ seeding (rank 0's rows) ----
-        centers = torch.empty(K, d, **o)
-        if rank == 0:
-            g = torch.Generator(device=X.device)
-            g.manual_seed(self.seed)
-            centers[0] = X[int(torch.randint(0, n, (1,), device=X.device, generator=g).item())]
-            for i in range(1, K):
-                _, d2 = self._assign(X, centers[:i], want_d2=True)
-                total = d2.sum()
-                idx = int(torch.multinomial(d2 / total, 1, generator=g).item()) if float(total) > 0 else i % n
-                centers[i] = X[idx]
+        centers = self._seed(X) if rank == 0 else torch.empty(K, d, **o)
         if multi:
             dist.broadcast(centers, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
-        # ---- Lloyd ----
         stat = torch.stack([X.sum(0), (X * X).sum(0), torch.full((d,), float(n), **o)])
         DeviceGMM._allreduce(stat, group)
         var = stat[1] / stat[2] - (stat[0] / stat[2]) ** 2
         tol = self.tol * float(var.mean())
         ws = torch.empty(nat.size("kmeans_workspace_bytes", d, K) // 8 + 1, **o)
         sums = torch.empty(K * d + K, **o)
-        labels = None
         for it in range(1, self.max_iter + 1):
-            labels, _ = self._assign(X, centers)
-            nat.call("kmeans_update_f64", n, d, K, X, labels, sums, ws, ws.numel() * ws.element_size())
+            self._pass(X, centers, sums=sums, ws=ws)
             DeviceGMM._allreduce(sums, group)
             cnt = sums[K * d:]
             new = torch.where(cnt[:, None] > 0, sums[:K * d].reshape(K, d) / cnt.clamp(min=1)[:, None], centers)
@@ -738,5 +759,5 @@ class DeviceKMeans:
             if shift <= tol:
                 break
         self.centers = centers
-        self.labels, _ = self._assign(X, centers)
+        self.labels, _, _ = self._pass(X, centers, labels=True)
         return self

@@ -418,19 +418,12 @@ int gmm_e_launch(GmmArgs<double>& a, void* stream) {
 // ---------------------------------------------------------------------------------------------
 // k-means passes (device initialisation of the GMM prior)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) kmeans_assign_kernel(int n, int d, int K, const double* X, const double* centers,
-                                                            int* labels, double* mind2) {
+__global__ void __launch_bounds__(256, 3) kmeans_pass_kernel(int n, int d, int K, const double* X, const double* centers,
+                                                             int* labels, double* mind2, double* dist, double* part) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Ctx ctx{(int)threadIdx.x, (int)blockDim.x};
-  kmeans_assign_cta<double>(ctx, n, d, K, X, centers, labels, mind2, (int)blockIdx.x, (int)gridDim.x,
-                            reinterpret_cast<double*>(smem_raw));
-}
-__global__ void __launch_bounds__(256) kmeans_update_kernel(int n, int d, int K, const double* X, const int* labels,
-                                                            double* part) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Ctx ctx{(int)threadIdx.x, (int)blockDim.x};
-  kmeans_update_cta<double>(ctx, n, d, K, X, labels, part, (int)blockIdx.x, (int)gridDim.x,
-                            reinterpret_cast<double*>(smem_raw));
+  kmeans_pass_cta<double>(ctx, n, d, K, X, centers, labels, mind2, dist, part, (int)blockIdx.x, (int)gridDim.x,
+                          reinterpret_cast<double*>(smem_raw));
 }
 __global__ void kmeans_reduce_kernel(int ncta, int len, const double* part, double* out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -728,42 +721,28 @@ int donk_fp64_probe(int mode, int blocks, int iters, double* scratch, double* fl
   return DONK_OK;
 }
 
-enum { KM_UPDATE_CTAS = 296 };
-size_t donk_kmeans_workspace_bytes(int d, int K) { return (size_t)KM_UPDATE_CTAS * ((size_t)K * d + K) * sizeof(double); }
+enum { KM_PASS_CTAS = 148 * 3 };
+size_t donk_kmeans_workspace_bytes(int d, int K) { return (size_t)KM_PASS_CTAS * ((size_t)K * d + K) * sizeof(double); }
 
-int donk_kmeans_assign_f64(int n, int d, int K, const double* X, const double* centers, int* labels, double* mind2,
-                           void* stream) {
+int donk_kmeans_pass_f64(int n, int d, int K, const double* X, const double* centers, int* labels, double* mind2,
+                         double* dist, double* sums, void* workspace, size_t workspace_bytes, void* stream) {
   if (n < 0 || d < 1 || K < 1) return DONK_BAD_SHAPE;
-  if (n == 0) return DONK_OK;
-  const size_t smem = kmeans_assign_smem(d, K) * sizeof(double);
-  if (smem > smem_optin_cap()) return DONK_SMEM_LIMIT;
-  int rc = allow_smem(kmeans_assign_kernel, smem);
-  if (rc != DONK_OK) return rc;
-  int grid = 148 * 2;
-  const int nblocks = (n + KM_TS - 1) / KM_TS;
-  if (grid > nblocks) grid = nblocks;
-  kmeans_assign_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(n, d, K, X, centers, labels, mind2);
-  LAUNCHED("kmeans_assign_kernel");
-  return DONK_OK;
-}
-
-int donk_kmeans_update_f64(int n, int d, int K, const double* X, const int* labels, double* sums, void* workspace,
-                           size_t workspace_bytes, void* stream) {
-  if (n < 0 || d < 1 || K < 1) return DONK_BAD_SHAPE;
-  if (workspace_bytes < donk_kmeans_workspace_bytes(d, K)) return DONK_BAD_SHAPE;
+  if (sums && workspace_bytes < donk_kmeans_workspace_bytes(d, K)) return DONK_BAD_SHAPE;
   const int len = K * d + K;
-  const size_t smem = kmeans_update_smem(d, K) * sizeof(double);
+  const size_t smem = kmeans_pass_smem(d, K) * sizeof(double);
   if (smem > smem_optin_cap() || d + 1 > 256) return DONK_SMEM_LIMIT;
-  int rc = allow_smem(kmeans_update_kernel, smem);
+  int rc = allow_smem(kmeans_pass_kernel, smem);
   if (rc != DONK_OK) return rc;
-  int grid = KM_UPDATE_CTAS;
+  int grid = KM_PASS_CTAS;
   const int nblocks = (n + KM_TS - 1) / KM_TS;
   if (grid > nblocks) grid = nblocks > 0 ? nblocks : 1;
-  double* part = static_cast<double*>(workspace);
-  kmeans_update_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(n, d, K, X, labels, part);
-  LAUNCHED("kmeans_update_kernel");
-  kmeans_reduce_kernel<<<(len + 127) / 128, 128, 0, (cudaStream_t)stream>>>(grid, len, part, sums);
-  LAUNCHED("kmeans_reduce_kernel");
+  double* part = sums ? static_cast<double*>(workspace) : nullptr;
+  kmeans_pass_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(n, d, K, X, centers, labels, mind2, dist, part);
+  LAUNCHED("kmeans_pass_kernel");
+  if (sums) {
+    kmeans_reduce_kernel<<<(len + 127) / 128, 128, 0, (cudaStream_t)stream>>>(grid, len, part, sums);
+    LAUNCHED("kmeans_reduce_kernel");
+  }
   return DONK_OK;
 }
 

@@ -190,14 +190,15 @@ int donk_gmm_prec_chol_from_precisions_f64(int d, int K, const double* precision
 
 /* The reference's first GMMPrior.update starts EM from k-means labels (sklearn/mixture/_base.py:119-128 via
  * donk/dynamics/prior/prior_gmm.py:21).  Lloyd passes on the device for pools that live there:
- *   assign: nearest centre of every row X (n,d) among centers (K,d) -> labels (n) int32, mind2 (n) squared
- *           distance to it (optional, used for k-means++ seeding);
- *   update: per-cluster sums and counts of the rows -> sums (K*d + K): [sum x (K,d) | count (K)]. */
+ * One pass over the rows X (n,d) with centres centers (K,d); every output is optional (NULL):
+ *   labels (n) int32  nearest centre;   mind2 (n)  squared distance to it (k-means++ potential);
+ *   dist (n,K)        squared distance to every centre (greedy k-means++ candidate scoring);
+ *   sums (K*d + K)    [sum of the rows of each cluster (K,d) | row count (K)] of the labelling just computed, i.e.
+ *                     the numerators of the next centres: one Lloyd iteration reads X once.  Needs `workspace`
+ *                     of donk_kmeans_workspace_bytes(d, K) bytes.  Rows sharded over ranks: all-reduce `sums`. */
 size_t donk_kmeans_workspace_bytes(int d, int K);
-int donk_kmeans_assign_f64(int n, int d, int K, const double* X, const double* centers, int* labels,
-                           double* mind2, void* stream);
-int donk_kmeans_update_f64(int n, int d, int K, const double* X, const int* labels, double* sums,
-                           void* workspace, size_t workspace_bytes, void* stream);
+int donk_kmeans_pass_f64(int n, int d, int K, const double* X, const double* centers, int* labels, double* mind2,
+                         double* dist, double* sums, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- diagnostics ------------------------------------------------------------------------ */
 

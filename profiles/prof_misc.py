@@ -58,3 +58,19 @@ elif what == "config2":
     print(f"fit_lr + GMM prior (14,7) N=50 K=4, B={B}: {ms:.1f} ms = {B * T / (ms * 1e-3):.0f} fits/s, info {int(info.sum())}")
     ms, _ = timed(lambda: batched.fit_lr(ro["X"], ro["U"]))
     print(f"fit_lr no prior  (14,7) N=50, B={B}: {ms:.1f} ms = {B * T / (ms * 1e-3):.0f} fits/s")
+elif what == "kmeans":
+    n, d, K = int(sys.argv[2]), 72, 16
+    X, _, _, _ = synthetic.gmm_pool_torch(n, d, K, seed=5, device=dev)
+    km = batched.DeviceKMeans(K, random_state=0)
+    c0 = X[:K].contiguous()
+    nat = _lib.native()
+    ws = torch.empty(nat.size("kmeans_workspace_bytes", d, K) // 8 + 1, dtype=torch.float64, device=dev)
+    sums = torch.empty(K * d + K, dtype=torch.float64, device=dev)
+    ms_a, _ = timed(lambda: km._pass(X, c0, labels=True))
+    ms_u, _ = timed(lambda: km._pass(X, c0, sums=sums, ws=ws))
+    gb = n * d * 8 / 1e9
+    print(f"kmeans n={n} d={d} K={K}: labels-only pass {ms_a:.2f} ms ({gb / ms_a * 1e3:.0f} GB/s), Lloyd pass (labels+sums) {ms_u:.2f} ms ({gb / ms_u * 1e3:.0f} GB/s)")
+    t0 = time.perf_counter(); c = km._seed(X); torch.cuda.synchronize()
+    print(f"  greedy k-means++ seeding: {1e3 * (time.perf_counter() - t0):.1f} ms")
+    t0 = time.perf_counter(); km.fit(X); torch.cuda.synchronize()
+    print(f"  DeviceKMeans.fit: {km.n_iter} Lloyd iterations, {1e3 * (time.perf_counter() - t0):.1f} ms, counts", torch.bincount(km.labels.long(), minlength=K).tolist())

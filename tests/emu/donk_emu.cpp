@@ -355,33 +355,21 @@ int donk_emu_gmm_prec_chol_from_precisions_f64(int d, int K, const double* preci
 
 extern "C" {
 
-size_t donk_emu_kmeans_workspace_bytes(int d, int K) { return (size_t)296 * ((size_t)K * d + K) * sizeof(double); }
+size_t donk_emu_kmeans_workspace_bytes(int d, int K) { return (size_t)444 * ((size_t)K * d + K) * sizeof(double); }
 
-int donk_emu_kmeans_assign_f64(int n, int d, int K, const double* X, const double* centers, int* labels, double* mind2,
-                               void*) {
-  if (n == 0) return DONK_OK;
-  std::vector<double> smem(kmeans_assign_smem(d, K) + 2);
+int donk_emu_kmeans_pass_f64(int n, int d, int K, const double* X, const double* centers, int* labels, double* mind2,
+                             double* dist, double* sums, void* workspace, size_t workspace_bytes, void*) {
+  if (sums && workspace_bytes < donk_emu_kmeans_workspace_bytes(d, K)) return DONK_BAD_SHAPE;
+  const int len = K * d + K, ncta = 3;
+  std::vector<double> smem(kmeans_pass_smem(d, K) + 2);
   Ctx ctx{0, 1};
-  const int ncta = 3;
+  double* part = sums ? static_cast<double*>(workspace) : nullptr;
   for (int cta = 0; cta < ncta; ++cta) {
     memset(smem.data(), 0xFF, smem.size() * sizeof(double));
-    kmeans_assign_cta<double>(ctx, n, d, K, X, centers, labels, mind2, cta, ncta, smem.data());
+    kmeans_pass_cta<double>(ctx, n, d, K, X, centers, labels, mind2, dist, part, cta, ncta, smem.data());
   }
-  return DONK_OK;
-}
-
-int donk_emu_kmeans_update_f64(int n, int d, int K, const double* X, const int* labels, double* sums, void* workspace,
-                               size_t workspace_bytes, void*) {
-  if (workspace_bytes < donk_emu_kmeans_workspace_bytes(d, K)) return DONK_BAD_SHAPE;
-  const int len = K * d + K, ncta = 5;
-  std::vector<double> smem(kmeans_update_smem(d, K) + 2);
-  Ctx ctx{0, 1};
-  double* part = static_cast<double*>(workspace);
-  for (int cta = 0; cta < ncta; ++cta) {
-    memset(smem.data(), 0xFF, smem.size() * sizeof(double));
-    kmeans_update_cta<double>(ctx, n, d, K, X, labels, part, cta, ncta, smem.data());
-  }
-  for (int i = 0; i < len; ++i) kmeans_reduce_item<double>(ncta, len, part, sums, i);
+  if (sums)
+    for (int i = 0; i < len; ++i) kmeans_reduce_item<double>(ncta, len, part, sums, i);
   return DONK_OK;
 }
 

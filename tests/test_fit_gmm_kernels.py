@@ -164,11 +164,19 @@ def test_device_kmeans_and_prior_init(backend):
 
     X, _, _, _ = synthetic.gmm_pool(1800, 9, 4, seed=3)
     km = DeviceKMeans(4, random_state=0)
-    c0 = torch.as_tensor(X[:4]).to(backend.device)
-    labels, d2 = km._assign(torch.as_tensor(X).to(backend.device), c0, want_d2=True)
+    Xd = torch.as_tensor(X).to(backend.device)
+    ws = torch.empty(backend.size("kmeans_workspace_bytes", 9, 4) // 8 + 1, dtype=torch.float64, device=backend.device)
+    sums = torch.empty(4 * 9 + 4, dtype=torch.float64, device=backend.device)
+    labels, d2, D = km._pass(Xd, Xd[:4], labels=True, mind2=True, dist=True, sums=sums, ws=ws)
     dist = ((X[:, None, :] - X[None, :4, :]) ** 2).sum(-1)
-    assert np.array_equal(labels.cpu().numpy(), dist.argmin(1))
-    assert relerr(d2, dist.min(1)) < 1e-10
+    lab = dist.argmin(1)
+    assert np.array_equal(labels.cpu().numpy(), lab)
+    assert relerr(d2, dist.min(1)) < 1e-10 and relerr(D, dist) < 1e-10
+    want = np.concatenate([np.stack([X[lab == k].sum(0) for k in range(4)]).ravel(), np.bincount(lab, minlength=4)])
+    assert relerr(sums, want) < 1e-13
+    for K3 in (3, 5):  # centre counts that are not a multiple of the 4-centre register tile
+        l3, _, _ = km._pass(Xd, Xd[:K3], labels=True)
+        assert np.array_equal(l3.cpu().numpy(), ((X[:, None, :] - X[None, :K3, :]) ** 2).sum(-1).argmin(1))
     km.fit(X)
     counts = np.bincount(km.labels.cpu().numpy(), minlength=4)
     assert counts.min() > 300 and km.n_iter < 50  # four well separated clusters of ~450 rows each
