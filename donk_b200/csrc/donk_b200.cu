@@ -136,6 +136,8 @@ int ilqr_warp_launch(const IlqrArgs<R>& a, void* stream) {
   size_t bytes;
   int rc = ilqr_warp_plan<R, DX, DU>(a.B, a.E, smem_optin_cap(), env_int("DONK_ILQR_WARPS"), G, ES, grid, bytes);
   if (rc != DONK_OK) return rc;
+  bytes += (size_t)env_int("DONK_ILQR_SMEM_PAD_KB") * 1024;  // occupancy experiments (profiles/prof_phases.py)
+  if (bytes > smem_optin_cap()) return DONK_SMEM_LIMIT;
   if (G <= 8) {
     rc = allow_smem(ilqr_warp_kernel<R, DX, DU>, bytes);
     if (rc != DONK_OK) return rc;
@@ -720,6 +722,18 @@ int donk_fp64_probe(int mode, int blocks, int iters, double* scratch, double* fl
   if (flops) *flops = mode == 0 ? (double)blocks * 256 * iters * 32.0 : (double)blocks * 8 * iters * 8 * 512.0;
   return DONK_OK;
 }
+
+#if defined(DONK_PHASE_PROF)
+// profiling builds only (profiles/prof_phases.py): read / reset the per-phase cycle counters of the warp kernel
+int donk_phase_prof_read(unsigned long long* out32, int reset) {
+  if (out32) cudaMemcpyFromSymbol(out32, donk::donk_phase_cycles, 32 * sizeof(unsigned long long));
+  if (reset) {
+    unsigned long long z[32] = {0};
+    cudaMemcpyToSymbol(donk::donk_phase_cycles, z, sizeof(z));
+  }
+  return DONK_OK;
+}
+#endif
 
 enum { KM_PASS_CTAS = 148 * 3 };
 size_t donk_kmeans_workspace_bytes(int d, int K) { return (size_t)KM_PASS_CTAS * ((size_t)K * d + K) * sizeof(double); }

@@ -28,6 +28,24 @@
 
 namespace donk {
 
+// Per-phase cycle counters of the warp kernel (profiling builds only: profiles/prof_phases.py compiles a separate
+// library with -DDONK_PHASE_PROF; the shipped library has no trace of it).
+#if defined(DONK_PHASE_PROF) && !defined(DONK_EMU)
+__device__ unsigned long long donk_phase_cycles[32];
+#endif
+#if defined(DONK_PHASE_PROF) && defined(__CUDA_ARCH__)
+#define PHASE_INIT long long ph_t0 = clock64();
+#define PHASE_MARK(id)                                                                            \
+  do {                                                                                            \
+    const long long ph_now = clock64();                                                           \
+    if (w.lane == 0) atomicAdd(&donk_phase_cycles[id], (unsigned long long)(ph_now - ph_t0));     \
+    ph_t0 = ph_now;                                                                               \
+  } while (0)
+#else
+#define PHASE_INIT
+#define PHASE_MARK(id)
+#endif
+
 template <int DX, int DU>
 struct WarpDims {
   static_assert(DU <= 8 && DX + 1 <= 32, "warp kernel: dU <= 8, dX <= 31");
@@ -91,6 +109,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
 #define STAGEP(tm) (stages + (size_t)((tm) / ES) * D::STAGE)
 #define PIDX(tm) ((size_t)team_b(tm) * E + team_e(tm))
 
+  PHASE_INIT
   // zero everything once: K paddings must be exact zeros, over-read rows/columns must be finite
   CTA_FOR(idx, G * D::TEAM + NC * D::STAGE) smem[idx] = R(0);
   w.cta_sync();
@@ -133,6 +152,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
     }
     cp_async_wait_all();
     w.cta_sync();
+    PHASE_MARK(12);
 
     for (int t = T - 1; t >= 0; --t) {
       TEAMS_DO(tm) {
@@ -156,6 +176,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
           }
         });
         w.team_sync();
+        PHASE_MARK(0);
         // ---- B2: Q_ext = C_ext + gamma [F|f]^T W_ext, upper blocks; column P is q.  Only the xu block is mirrored
         //      (Qux feeds the gains and the value update); Qxx / Quu are consumed from their upper triangles. ----------
         {
@@ -201,11 +222,13 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
 #undef DONK_B2_ROW
         }
         w.team_sync();
+        PHASE_MARK(1);
       }
       // all teams are done with the staged inputs of step t: fetch step t-1 while the factorisation, gains and
       // value update (team-private data only) run
       w.cta_sync();
       if (t > 0) stage_bwd(t - 1);
+      PHASE_MARK(2);
       TEAMS_DO(tm) {
         if (!team_valid(tm)) continue;
         R* tp = TEAMP(tm);
@@ -300,6 +323,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
           }
         }
         w.team_sync();
+        PHASE_MARK(3);
         // ---- B5: [V | v] = [Qxx | q_x] + Qxu [K | k] (upper blocks, mirrored) (lqg.py:178-180) ---------------
         {
           auto epi = [&](int i, int j, R v0, R v1) {
@@ -343,9 +367,11 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
           tp[D::oScal + 3] += ld;
         }
         w.team_sync();
+        PHASE_MARK(4);
       }
       cp_async_wait_all();
       w.cta_sync();
+      PHASE_MARK(5);
     }
   }
 
@@ -411,6 +437,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
     }
     cp_async_wait_all();
     w.cta_sync();
+    PHASE_MARK(12);
 
     for (int t = 0; t < T; ++t) {
       TEAMS_DO(tm) {
@@ -456,6 +483,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
           });
         }
         w.team_sync();
+        PHASE_MARK(6);
         // ---- F2: Sigma_uu = Sigma_ux K^T + pol_covar (upper, mirrored) (lqg.py:231); delta_u ---------------------
         warp_mma<R, 1, 1>(w, tp + D::oM + DX, PP, tp + D::oK, KTL, DX4 / 4, [&](int a2, int j, R v0, R v1) {
 #pragma unroll
@@ -472,6 +500,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
           LANE_FOR(a2, DU) tp[D::oDel + a2] -= tp[D::oM + (DX + a2) * PP + P];  // (K_prev mu_x + k_prev) - mu_u
         }
         w.team_sync();
+        PHASE_MARK(7);
         // ---- F3: Rt_ext = ([F] [Sigma | mu])^T (PE x DX).  The expected cost of step t rides on the A fragments:
         //      every lane sees 1/32 of [Sigma | mu] anyway and adds C_kj (Sigma_kj + mu_k mu_j [+ reg]) for it --------
         {
@@ -578,6 +607,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
           }
 #endif
         }
+        PHASE_MARK(8);
         if (a.tcov) {
           LANE_FOR(idx, P * P) {
             const int i = idx / P, j = idx % P;
@@ -588,6 +618,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
           LANE_FOR(i, P) a.tmean[(PIDX(tm) * (T + 1) + t) * P + i] = tp[D::oM + i * PP + P];
         }
         w.team_sync();
+        PHASE_MARK(9);
         // ---- F4: Sigma'_xx = (F Sigma) F^T + dyn_covar (upper blocks, mirrored); mu' = F mu + f; scalars -------------
         {
           const R* Dg = a.dyn_covar + ((size_t)b * T + t) * DX * DX;
@@ -641,6 +672,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
           if (do_cost) tp[D::oScal + 2] += st[oCc];
         }
         if (t + 1 < T) stage_policy(tm, t + 1);
+        PHASE_MARK(10);
       }
       w.cta_sync();  // everyone is done with the staged inputs of step t
       if (t + 1 < T) {
@@ -648,6 +680,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
         cp_async_wait_all();
         w.cta_sync();
       }
+      PHASE_MARK(11);
     }
 
     // ---- final row T: state block only (lqg.py:221-222,242) ---------------------------------------------------
