@@ -64,6 +64,7 @@ struct WCtx {
        ++i##_it, i = donk::emu_idx(i##_it, i##_n))
 #define LANE_FOR(i, n) CTA_FOR(i, n)
 #define TEAMS_DO(tm) for (int tm = 0; tm < w.G; ++tm)
+#define WARP_ROWS_FOR(r, n) for (int r = 0; r < (n); ++r)
 #else
 struct WCtx {
   int tid, nthreads, team, lane, G;
@@ -73,6 +74,8 @@ struct WCtx {
 #define CTA_FOR(i, n) for (int i = w.tid; i < (n); i += w.nthreads)
 #define LANE_FOR(i, n) for (int i = w.lane; i < (n); i += 32)
 #define TEAMS_DO(tm) for (int tm = w.team, tm##_once = 0; tm##_once == 0; tm##_once = 1)
+// rows of a staged matrix dealt to the warps of the CTA (the lanes then walk the row: no div/mod per element)
+#define WARP_ROWS_FOR(r, n) for (int r = w.team; r < (n); r += w.G)
 #endif
 
 DONK_HD int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -189,24 +192,50 @@ DONK_HD void tile_km(const R* __restrict__ A, int lda, const R* __restrict__ Bm,
 // make the fragment loads bank-conflict free.  Rows/columns beyond the valid range may be over-read
 // (their outputs are discarded by the epilogue); the k range must be zero-padded in one operand and
 // finite in the other.  float has no such instruction: each lane computes its two outputs with FFMA.
-struct NoPre {};
+// Values a lane fetches for the epilogue of a product (addends read from global memory): NP raw values per fragment.
+// frag_pre issues the loads (raw loads only, no arithmetic on the loaded values: they stay in flight while other
+// work runs — possibly a whole earlier product); warp_mma_ep runs the product and hands them to the epilogue.
+template <typename R, int RA, int RB, int NP>
+struct FragVals {
+#if defined(__CUDA_ARCH__)
+  R v[RA][RB][NP];
+#else
+  R v[8 * RA][4 * RB][NP];
+#endif
+};
 
-template <typename R, int RA, int RB, int NP, class Pre, class Epi>
-DONK_D void warp_mma_pre(const WCtx& w, const R* __restrict__ A, int lda, const R* __restrict__ Bm, int ldb, int K4,
-                         Pre&& pre, Epi&& epi) {
+template <typename R, int RA, int RB, int NP, class Pre>
+DONK_D void frag_pre(const WCtx& w, FragVals<R, RA, RB, NP>& fv, Pre&& pre) {
 #if defined(__CUDA_ARCH__)
   const int g = w.lane >> 2, tq = w.lane & 3;
-  R c[RA][RB][2], pv[RA][RB][NP];
 #pragma unroll
   for (int ra = 0; ra < RA; ++ra)
 #pragma unroll
     for (int rb = 0; rb < RB; ++rb) {
-      c[ra][rb][0] = R(0); c[ra][rb][1] = R(0);
 #pragma unroll
-      for (int q = 0; q < NP; ++q) pv[ra][rb][q] = R(0);
-      // raw loads only (no arithmetic on the loaded values): they stay in flight while the product runs
-      pre(8 * ra + g, 8 * rb + 2 * tq, pv[ra][rb]);
+      for (int q = 0; q < NP; ++q) fv.v[ra][rb][q] = R(0);
+      pre(8 * ra + g, 8 * rb + 2 * tq, fv.v[ra][rb]);
     }
+#else
+  (void)w;
+  for (int i = 0; i < 8 * RA; ++i)
+    for (int j = 0; j < 8 * RB; j += 2) {
+      for (int q = 0; q < NP; ++q) fv.v[i][j / 2][q] = R(0);
+      pre(i, j, fv.v[i][j / 2]);
+    }
+#endif
+}
+
+template <typename R, int RA, int RB, int NP, class Epi>
+DONK_D void warp_mma_ep(const WCtx& w, const R* __restrict__ A, int lda, const R* __restrict__ Bm, int ldb, int K4,
+                        const FragVals<R, RA, RB, NP>& fv, Epi&& epi) {
+#if defined(__CUDA_ARCH__)
+  const int g = w.lane >> 2, tq = w.lane & 3;
+  R c[RA][RB][2];
+#pragma unroll
+  for (int ra = 0; ra < RA; ++ra)
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb) { c[ra][rb][0] = R(0); c[ra][rb][1] = R(0); }
   if (sizeof(R) == 8) {
     const R* ap = A + tq * lda + g;
     const R* bp = Bm + tq * ldb + g;
@@ -248,22 +277,27 @@ DONK_D void warp_mma_pre(const WCtx& w, const R* __restrict__ A, int lda, const 
   for (int ra = 0; ra < RA; ++ra)
 #pragma unroll
     for (int rb = 0; rb < RB; ++rb)
-      epi(8 * ra + g, 8 * rb + 2 * tq, c[ra][rb][0], c[ra][rb][1], pv[ra][rb]);
+      epi(8 * ra + g, 8 * rb + 2 * tq, c[ra][rb][0], c[ra][rb][1], fv.v[ra][rb]);
 #else
   (void)w;
   for (int i = 0; i < 8 * RA; ++i)
     for (int j = 0; j < 8 * RB; j += 2) {
-      R pv[NP];
-      for (int q = 0; q < NP; ++q) pv[q] = R(0);
-      pre(i, j, pv);
       R v0 = R(0), v1 = R(0);
       for (int k = 0; k < 4 * K4; ++k) {
         v0 = fma(A[k * lda + i], Bm[k * ldb + j], v0);
         v1 = fma(A[k * lda + i], Bm[k * ldb + j + 1], v1);
       }
-      epi(i, j, v0, v1, pv);
+      epi(i, j, v0, v1, fv.v[i][j / 2]);
     }
 #endif
+}
+
+template <typename R, int RA, int RB, int NP, class Pre, class Epi>
+DONK_D void warp_mma_pre(const WCtx& w, const R* __restrict__ A, int lda, const R* __restrict__ Bm, int ldb, int K4,
+                         Pre&& pre, Epi&& epi) {
+  FragVals<R, RA, RB, NP> fv;
+  frag_pre<R, RA, RB, NP>(w, fv, pre);
+  warp_mma_ep<R, RA, RB, NP>(w, A, lda, Bm, ldb, K4, fv, epi);
 }
 
 template <typename R, int RA, int RB, class Epi>
@@ -318,6 +352,40 @@ DONK_HD void ld2(const R* p, R& v0, R& v1) {
 #endif
   v0 = p[0]; v1 = p[1];
 }
+// The same pair, for rows that are `ld` apart with ld % 16 in {4, 12} (the fragment-friendly leading dimensions):
+// a 16-byte access per lane would put the two rows of a quarter-warp on overlapping banks (2-way conflict on every
+// accumulator store).  Two 8-byte accesses whose order alternates with the row parity touch every bank exactly once.
+// Measured (B200, config 3): the conflict-free form is SLOWER (58.8 vs 53.9 ms per launch) - the kernel is bound by
+// issued instructions, not by shared-memory wavefronts - so it is off unless DONK_PAIR_SPLIT is defined.
+template <typename R>
+DONK_HD void st2s(R* p, R v0, R v1, int row) {
+#if defined(__CUDA_ARCH__) && !defined(DONK_PAIR_SPLIT)
+  (void)row;
+  st2(p, v0, v1);
+#elif defined(__CUDA_ARCH__)
+  const int odd = row & 1;
+  p[odd] = odd ? v1 : v0;
+  p[odd ^ 1] = odd ? v0 : v1;
+#else
+  (void)row;
+  p[0] = v0; p[1] = v1;
+#endif
+}
+template <typename R>
+DONK_HD void ld2s(const R* p, R& v0, R& v1, int row) {
+#if defined(__CUDA_ARCH__) && !defined(DONK_PAIR_SPLIT)
+  (void)row;
+  ld2(p, v0, v1);
+#elif defined(__CUDA_ARCH__)
+  const int odd = row & 1;
+  const R a = p[odd], b = p[odd ^ 1];
+  v0 = odd ? b : a;
+  v1 = odd ? a : b;
+#else
+  (void)row;
+  v0 = p[0]; v1 = p[1];
+#endif
+}
 
 // *slot += sum_{r < n} f(r), n <= 32: one item per lane on the device (every lane joins the shuffle), a plain loop
 // under emulation.  The caller synchronises the team before reading *slot.
@@ -365,9 +433,34 @@ DONK_D void cp_async(R* dst, const R* src) {
   *dst = *src;
 #endif
 }
+// 16-byte variant (two adjacent reals of a double row; both addresses 16-byte aligned)
+template <typename R>
+DONK_D void cp_async_pair(R* dst, const R* src) {
+#if defined(__CUDA_ARCH__)
+  const unsigned s = (unsigned)__cvta_generic_to_shared(dst);
+  if (sizeof(R) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s), "l"(src) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(src) : "memory");
+#else
+  dst[0] = src[0]; dst[1] = src[1];
+#endif
+}
 DONK_D void cp_async_wait_all() {
 #if defined(__CUDA_ARCH__)
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+#endif
+}
+// close the copies issued so far into one group / wait until at most N of this thread's groups are still pending
+// (groups complete in issue order): lets a later group (next step's shared inputs) stay in flight while an earlier one
+// (this step's policy) is consumed
+DONK_D void cp_async_commit() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+DONK_D void cp_async_wait_group() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 #endif
 }
 

@@ -14,6 +14,7 @@
 #include "gmm_mma.cuh"
 #include "ilqr.cuh"
 #include "kmeans.cuh"
+#include <cstdint>
 #include "ilqr_warp.cuh"
 
 using namespace donk;
@@ -117,17 +118,32 @@ __global__ void __launch_bounds__(512, 1) ilqr_team_kernel_big(const IlqrArgs<R>
 }
 
 // Warp-per-problem fast path with compile-time dimensions (ilqr_warp.cuh).
-template <typename R, int DX, int DU>
+template <typename R, int DX, int DU, bool FULL>
 __global__ void __launch_bounds__(512, 1) ilqr_warp_kernel_big(const IlqrArgs<R> a, int ES) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WCtx w{(int)threadIdx.x, (int)blockDim.x, (int)threadIdx.x >> 5, (int)threadIdx.x & 31, (int)blockDim.x >> 5};
-  ilqr_warp_cta<R, DX, DU>(w, a, (int)blockIdx.x, ES, reinterpret_cast<R*>(smem_raw));
+  ilqr_warp_cta<R, DX, DU, FULL>(w, a, (int)blockIdx.x, ES, reinterpret_cast<R*>(smem_raw));
 }
-template <typename R, int DX, int DU>
+template <typename R, int DX, int DU, bool FULL>
 __global__ void __launch_bounds__(256, 2) ilqr_warp_kernel(const IlqrArgs<R> a, int ES) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WCtx w{(int)threadIdx.x, (int)blockDim.x, (int)threadIdx.x >> 5, (int)threadIdx.x & 31, (int)blockDim.x >> 5};
-  ilqr_warp_cta<R, DX, DU>(w, a, (int)blockIdx.x, ES, reinterpret_cast<R*>(smem_raw));
+  ilqr_warp_cta<R, DX, DU, FULL>(w, a, (int)blockIdx.x, ES, reinterpret_cast<R*>(smem_raw));
+}
+
+template <typename R, int DX, int DU, bool FULL>
+int ilqr_warp_launch_v(const IlqrArgs<R>& a, int G, int ES, int grid, size_t bytes, void* stream) {
+  int rc;
+  if (G <= 8) {
+    rc = allow_smem(ilqr_warp_kernel<R, DX, DU, FULL>, bytes);
+    if (rc != DONK_OK) return rc;
+    ilqr_warp_kernel<R, DX, DU, FULL><<<grid, 32 * G, bytes, (cudaStream_t)stream>>>(a, ES);
+  } else {
+    rc = allow_smem(ilqr_warp_kernel_big<R, DX, DU, FULL>, bytes);
+    if (rc != DONK_OK) return rc;
+    ilqr_warp_kernel_big<R, DX, DU, FULL><<<grid, 32 * G, bytes, (cudaStream_t)stream>>>(a, ES);
+  }
+  return DONK_OK;
 }
 
 template <typename R, int DX, int DU>
@@ -138,15 +154,10 @@ int ilqr_warp_launch(const IlqrArgs<R>& a, void* stream) {
   if (rc != DONK_OK) return rc;
   bytes += (size_t)env_int("DONK_ILQR_SMEM_PAD_KB") * 1024;  // occupancy experiments (profiles/prof_phases.py)
   if (bytes > smem_optin_cap()) return DONK_SMEM_LIMIT;
-  if (G <= 8) {
-    rc = allow_smem(ilqr_warp_kernel<R, DX, DU>, bytes);
-    if (rc != DONK_OK) return rc;
-    ilqr_warp_kernel<R, DX, DU><<<grid, 32 * G, bytes, (cudaStream_t)stream>>>(a, ES);
-  } else {
-    rc = allow_smem(ilqr_warp_kernel_big<R, DX, DU>, bytes);
-    if (rc != DONK_OK) return rc;
-    ilqr_warp_kernel_big<R, DX, DU><<<grid, 32 * G, bytes, (cudaStream_t)stream>>>(a, ES);
-  }
+  // the everything-enabled call (ILQR.step / .optimize) runs the instantiation with the options folded at compile time
+  rc = ilqr_warp_is_full<R, DX, DU>(a) ? ilqr_warp_launch_v<R, DX, DU, true>(a, G, ES, grid, bytes, stream)
+                                      : ilqr_warp_launch_v<R, DX, DU, false>(a, G, ES, grid, bytes, stream);
+  if (rc != DONK_OK) return rc;
   LAUNCHED("ilqr_warp_kernel");
   return DONK_OK;
 }
@@ -492,6 +503,7 @@ unsigned long long donk_launch_count(void) { return g_launches.load(); }
     a.x0m = x0_mean; a.x0S = x0_covar; a.eta = eta; a.gamma = gamma; a.fwd_reg = fwd_reg;                     \
     a.K = K; a.k = k; a.pcov = pol_covar; a.pinv = pol_inv_covar; a.kl = kl; a.cost = cost;                   \
     a.tmean = traj_mean; a.tcov = traj_covar; a.info = info; a.active = active;                               \
+    a.aligned16 = (((uintptr_t)F | (uintptr_t)C_kl | (uintptr_t)dyn_covar) & 15) == 0;                        \
     return ilqr_step_launch<R>(a, stream);                                                                    \
   }
 ILQR_STEP_IMPL(f64, double)

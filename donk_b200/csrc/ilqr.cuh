@@ -43,6 +43,7 @@ struct IlqrArgs {
   R *tmean, *tcov;                               // optional (B,E,T+1,p) (B,E,T+1,p,p)
   int *info;                                     // (B,E): 0 ok, 1+t = Quu not PD at step t
   const int *active;                             // optional (B): 0 = skip this condition
+  int aligned16;                                 // set by the launcher: F, C_kl, dyn_covar are 16-byte aligned
 };
 
 // Shared-memory layout, in units of R.  Every sub-array starts 16-byte aligned.

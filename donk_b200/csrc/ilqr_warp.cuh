@@ -46,6 +46,13 @@ __device__ unsigned long long donk_phase_cycles[32];
 #define PHASE_MARK(id)
 #endif
 
+// experiment switch (profiles only): drop the per-step CTA barriers to see what decoupled warps would gain (racy!)
+#if defined(DONK_EXPERIMENT_NOSYNC)
+#define LOOP_SYNC w.team_sync()
+#else
+#define LOOP_SYNC w.cta_sync()
+#endif
+
 template <int DX, int DU>
 struct WarpDims {
   static_assert(DU <= 8 && DX + 1 <= 32, "warp kernel: dU <= 8, dX <= 31");
@@ -65,21 +72,40 @@ struct WarpDims {
   static constexpr int KSZ = (DU4 * KLD > DX4 * KTL ? DU4 * KLD : DX4 * KTL) + 8;
   static constexpr int oM = 0, oR = oM + MSZ, oK = oR + RSZ, oKv = oK + KSZ;
   static constexpr int oPc = oKv + 8, oLds = oPc + (DU * DU + 3) / 4 * 4, oDel = oLds + 8, oRow = oDel + 8;
-  static constexpr int oScal = oRow + 32, TEAM = oScal + 8;  // scal: 0 1/eta 1 kl 2 cost 3 logdet 4 notpd
-  // stage area per condition (reals): backward and forward views share the storage.  Only what the products
-  // read many times is staged (F_t, K_prev_t); C_t, C_kl_t, dyn_covar_t are read once per problem and step and
-  // come straight from global memory, prefetched into registers ahead of the product they are added to.
+  // oRow: forward: compact copy of mu (P values, conflict-free reads in the cost phase); end: per-lane cost partials
+  static constexpr int oScal = oRow + (P4 > 32 ? P4 : 32), TEAM = oScal + 8;  // scal: 0 1/eta 1 kl 2 cost 3 logdet 4 notpd
+  // stage area per condition (reals): backward and forward views share the storage.  Everything the teams of a
+  // condition share and that does not depend on eta is staged one step ahead with cp.async: F_t, C_kl_t (backward);
+  // F_t^T, K_prev_t, Lam_prev_t, dyn_covar_t (forward).  C_t (scaled by 1/eta, and the cost weights) is the one input
+  // that does not fit: it comes straight from global memory into registers, issued a whole product ahead of its use.
   static constexpr int oFx = 0;  // bwd: F_ext (DX4 x PP); fwd: F^T (P4 x DXP)
   static constexpr int FXS = (DX4 * PP > P4 * DXP ? DX4 * PP : P4 * DXP) + 8;
+  static constexpr int PKL = PP, DXE = DXP;                // row strides % 16 in {4, 12}: conflict-free pair reads
+  static constexpr int oCk = oFx + FXS;                    // bwd: [C_kl_t | c_kl_t] (P x PKL), vector in column P
+  static constexpr int BWD_END = oCk + P * PKL;
   static constexpr int oPK = oFx + FXS;                    // fwd: K_prev^T (DX4 x KTL)
   static constexpr int oPL = oPK + DX4 * KTL + 8;          // fwd: Lam_prev (DU x DU)
   static constexpr int oVec = oPL + (DU * DU + 3) / 4 * 4; // fwd: f (DXP) | k_prev (8) | cc, phld (4)
-  static constexpr int STAGE = oVec + DXP + 8 + 4;
+  static constexpr int oD = oVec + DXP + 8 + 4;            // fwd: dyn_covar_t (DX x DXE)
+  static constexpr int FWD_END = oD + DX * DXE;
+  static constexpr int STAGE = ((BWD_END > FWD_END ? BWD_END : FWD_END) + 1) / 2 * 2;
 };
 
+// FULL: the call computes everything (backward + forward + KL + cost, eta given, no trajectory outputs) - the
+// ILQR.step / ILQR.optimize case.  The option tests then fold at compile time instead of being re-read from the
+// kernel parameters in every phase (the kernel is bound by issued instructions).
 template <typename R, int DX, int DU>
+DONK_HD bool ilqr_warp_is_full(const IlqrArgs<R>& a) {
+  return a.flags == (ILQR_BACKWARD | ILQR_FORWARD | ILQR_KL | ILQR_COST) && a.C_kl && a.c_kl && a.eta && a.kl &&
+         a.cost && !a.tcov && !a.tmean;
+}
+
+template <typename R, int DX, int DU, bool FULL>
 DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, R* smem) {
   using D = WarpDims<DX, DU>;
+  const bool opt_bwd = FULL || (a.flags & ILQR_BACKWARD) != 0, opt_fwd = FULL || (a.flags & ILQR_FORWARD) != 0;
+  const bool has_ckl = FULL || a.C_kl != nullptr, has_cklv = FULL || a.c_kl != nullptr, has_eta = FULL || a.eta != nullptr;
+  const bool want_tcov = !FULL && a.tcov != nullptr, want_tmean = !FULL && a.tmean != nullptr;
   constexpr int P = D::P, PE = D::PE, PP = D::PP, DXP = D::DXP, KLD = D::KLD, KTL = D::KTL;
   constexpr int DX4 = D::DX4, P4 = D::P4, DU4 = D::DU4;
   const int G = w.G, T = a.T, E = a.E;
@@ -92,14 +118,24 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
 
   auto team_b = [&](int tm) { return cg * NC + tm / ES; };
   auto team_e = [&](int tm) { return ec * ES + tm % ES; };
-  auto team_valid = [&](int tm) {
+  auto team_valid_raw = [&](int tm) {
     const int b = team_b(tm), e = team_e(tm);
     return b < a.B && e < E && (a.active == nullptr || a.active[b] != 0);
   };
-  auto cond_b = [&](int ci) {  // condition ci of this CTA, or -1
+  auto cond_b_raw = [&](int ci) {  // condition ci of this CTA, or -1
     const int b = cg * NC + ci;
     return (b < a.B && ec * ES < E && (a.active == nullptr || a.active[b] != 0)) ? b : -1;
   };
+#if defined(__CUDA_ARCH__)
+  // looked up once: the flags live in global memory and these predicates guard every phase
+  const bool tv_mine = team_valid_raw(w.team);
+  const int cb0 = cond_b_raw(0);
+  auto team_valid = [&](int) { return tv_mine; };
+  auto cond_b = [&](int ci) { return ci == 0 ? cb0 : cond_b_raw(ci); };
+#else
+  auto team_valid = team_valid_raw;
+  auto cond_b = cond_b_raw;
+#endif
   {
     bool any = false;
     for (int ci = 0; ci < NC; ++ci) any = any || cond_b(ci) >= 0;
@@ -116,13 +152,13 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
   TEAMS_DO(tm) {
     if (!team_valid(tm)) continue;
     R* tp = TEAMP(tm);
-    LANE_FOR(one, 1) tp[D::oScal + 0] = a.eta ? R(1) / a.eta[PIDX(tm)] : R(1);
+    LANE_FOR(one, 1) tp[D::oScal + 0] = has_eta ? R(1) / a.eta[PIDX(tm)] : R(1);
   }
 
   // =========================================================================================
   // Backward pass
   // =========================================================================================
-  if (a.flags & ILQR_BACKWARD) {
+  if (opt_bwd) {
     // async staging of step t: F_ext = [F_t | f_t | 0] (rows DX..DX4-1 stay zero), C_t, C_kl_t, c_t, c_kl_t
     auto stage_bwd = [&](int t) {
       for (int ci = 0; ci < NC; ++ci) {
@@ -130,10 +166,34 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
         if (b < 0) continue;
         R* st = stages + (size_t)ci * D::STAGE;
         const size_t bt = (size_t)b * T + t;
-        CTA_FOR(idx, DX * PE) {
-          const int k = idx / PE, j = idx % PE;  // compile-time divisors
-          if (j < P) cp_async(st + D::oFx + k * PP + j, a.F + bt * szF + (size_t)k * P + j);
-          else cp_async(st + D::oFx + k * PP + P, a.f + bt * DX + k);
+        // rows of [F_t | f_t] and [C_kl_t | c_kl_t]: 16-byte copies where the row length is even
+        if (P % 2 == 0 && a.aligned16) {
+          constexpr int HP = (P + 1) / 2;
+          CTA_FOR(idx, DX * HP) {
+            const int k = idx / HP, j = 2 * (idx % HP);  // compile-time divisors
+            cp_async_pair(st + D::oFx + k * PP + j, a.F + bt * szF + (size_t)k * P + j);
+          }
+          if (has_ckl) {
+            CTA_FOR(idx, P * HP) {
+              const int i = idx / HP, j = 2 * (idx % HP);
+              cp_async_pair(st + D::oCk + i * D::PKL + j, a.C_kl + bt * szC + (size_t)i * P + j);
+            }
+          }
+        } else {
+          CTA_FOR(idx, DX * P) {
+            const int k = idx / P, j = idx % P;
+            cp_async(st + D::oFx + k * PP + j, a.F + bt * szF + idx);
+          }
+          if (has_ckl) {
+            CTA_FOR(idx, P * P) {
+              const int i = idx / P, j = idx % P;
+              cp_async(st + D::oCk + i * D::PKL + j, a.C_kl + bt * szC + idx);
+            }
+          }
+        }
+        CTA_FOR(k, DX) cp_async(st + D::oFx + k * PP + P, a.f + bt * DX + k);
+        if (has_cklv) {
+          CTA_FOR(i, P) cp_async(st + D::oCk + i * D::PKL + P, a.c_kl + bt * P + i);
         }
       }
     };
@@ -142,13 +202,14 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
     TEAMS_DO(tm) {
       if (!team_valid(tm)) continue;
       R* tp = TEAMP(tm);
-      const R ie = a.eta ? R(1) / a.eta[PIDX(tm)] : R(1);
+      const R ie = has_eta ? R(1) / a.eta[PIDX(tm)] : R(1);
       const size_t bT = (size_t)team_b(tm) * (T + 1) + T;
       LANE_FOR(idx, DX * DX) {
         const int i = idx / DX, j = idx % DX;
         tp[D::oM + i * PP + j] = ldg(a.C + bT * szC + (size_t)i * P + j) * ie;
       }
       LANE_FOR(i, DX) tp[D::oM + i * PP + P] = ldg(a.c + bT * P + i) * ie;
+      LANE_FOR(j, DU) tp[D::oLds + j] = R(1);
     }
     cp_async_wait_all();
     w.cta_sync();
@@ -159,50 +220,61 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
         if (!team_valid(tm)) continue;
         R* tp = TEAMP(tm);
         const R* st = STAGEP(tm);
-        if (t > 0) {  // pull next step's C / C_kl rows into L2 while this step computes (one 128-byte line per lane)
-          const int b = team_b(tm);
+        const int b = team_b(tm);
+        if (t > 0) {  // pull next step's C rows into L2 while this step computes (one 128-byte line per lane)
           constexpr int LINES = (P * P * (int)sizeof(R) + 127) / 128;
           LANE_FOR(ln, LINES) {
-            if ((tm % ES) * 2 < ES) prefetch_l2(a.C + ((size_t)b * (T + 1) + t - 1) * szC + (size_t)ln * (128 / sizeof(R)));
-            else if (a.C_kl) prefetch_l2(a.C_kl + ((size_t)b * T + t - 1) * szC + (size_t)ln * (128 / sizeof(R)));
+            if (tm % ES == t % ES) prefetch_l2(a.C + ((size_t)b * (T + 1) + t - 1) * szC + (size_t)ln * (128 / sizeof(R)));
           }
         }
+        // C_t entries (i, j), (i, j+1) of the Q fragments: raw loads, issued a whole product ahead of the epilogue that
+        // adds them (row blocks 1.. before B1, row block 0 before the first B2 product)
+        const R ie = tp[D::oScal + 0];
+        const R* Cg = a.C + ((size_t)b * (T + 1) + t) * szC;
+        const R* cg = a.c + ((size_t)b * (T + 1) + t) * P;
+        const bool has_kl = has_ckl;
+        auto pre = [&](int i, int j, R* pv) {
+          if (i >= P || i > j + 1) return;
+          if (j + 1 < P) {
+            ldg2(Cg + i * P + j, P % 2 == 0, pv[0], pv[1]);
+          } else {
+            if (j < P) pv[0] = ldg(Cg + i * P + j);
+            const int h = j == P ? 0 : 1;  // which of the two columns is the vector column P
+            if (j == P || j + 1 == P) pv[h] = ldg(cg + i);
+          }
+        };
+#define DONK_RBN(RB_ROW) (D::NBP - (RB_ROW) > 0 ? D::NBP - (RB_ROW) : 1)
+        FragVals<R, 1, DONK_RBN(0), 2> fv0;
+        FragVals<R, 1, DONK_RBN(1), 2> fv1;
+        FragVals<R, 1, DONK_RBN(2), 2> fv2;
+        FragVals<R, 1, DONK_RBN(3), 2> fv3;
+        FragVals<R, 1, DONK_RBN(4), 2> fv4;
+#define DONK_B2_PRE(RB_ROW)                                                                                      \
+  if (RB_ROW < D::NBP)                                                                                           \
+    frag_pre<R, 1, DONK_RBN(RB_ROW), 2>(w, fv##RB_ROW, [&](int i, int j, R* pv) { pre(8 * RB_ROW + i, 8 * RB_ROW + j, pv); });
+        DONK_B2_PRE(1) DONK_B2_PRE(2) DONK_B2_PRE(3) DONK_B2_PRE(4)
         // ---- B1: W_ext = V [F | f] (+ v in column P) ----------------------------------------------------
         warp_mma<R, D::NBX, D::NBP>(w, tp + D::oM, PP, st + D::oFx, PP, DX4 / 4, [&](int i, int j, R v0, R v1) {
           if (i < DX && j < PP) {
             if (j == P) v0 += tp[D::oM + i * PP + P];
             if (j + 1 == P) v1 += tp[D::oM + i * PP + P];
-            st2(tp + D::oR + i * PP + j, v0, v1);  // j even, PP even: 16-byte aligned
+            st2s(tp + D::oR + i * PP + j, v0, v1, i);
           }
         });
+        DONK_B2_PRE(0)
         w.team_sync();
         PHASE_MARK(0);
-        // ---- B2: Q_ext = C_ext + gamma [F|f]^T W_ext, upper blocks; column P is q.  Only the xu block is mirrored
-        //      (Qux feeds the gains and the value update); Qxx / Quu are consumed from their upper triangles. ----------
+        // ---- B2: Q_ext = C_ext / eta + C_kl + gamma [F|f]^T W_ext, upper blocks; column P is q.  Only the xu block is
+        //      mirrored (Qux feeds the gains and the value update); Qxx / Quu are consumed from their upper triangles.
+        //      C_kl comes from the staged copy of the condition, C from the registers loaded above. ------------------
         {
-          const R ie = tp[D::oScal + 0];
-          const int b = team_b(tm);
-          const R* Cg = a.C + ((size_t)b * (T + 1) + t) * szC;
-          const R* Kg = a.C_kl ? a.C_kl + ((size_t)b * T + t) * szC : nullptr;
-          const R* cg = a.c + ((size_t)b * (T + 1) + t) * P;
-          const R* kg = a.c_kl ? a.c_kl + ((size_t)b * T + t) * P : nullptr;
-          // C and C_kl entries (i, j), (i, j+1) of the fragment: raw loads issued before the product starts
-          auto pre = [&](int i, int j, R* pv) {
-            if (i >= P || i > j + 1) return;
-            if (j + 1 < P) {
-              ldg2(Cg + i * P + j, P % 2 == 0, pv[0], pv[1]);
-              if (Kg) ldg2(Kg + i * P + j, P % 2 == 0, pv[2], pv[3]);
-            } else {
-              if (j < P) { pv[0] = ldg(Cg + i * P + j); if (Kg) pv[2] = ldg(Kg + i * P + j); }
-              const int h = j == P ? 0 : 1;  // which of the two columns is the vector column P
-              if (j == P || j + 1 == P) { pv[h] = ldg(cg + i); if (kg) pv[2 + h] = ldg(kg + i); }
-            }
-          };
           auto epi = [&](int i, int j, R v0, R v1, const R* pv) {
             if (i >= P || i > j + 1 || j > P) return;
-            const R q0 = fma(gamma, v0, fma(pv[0], ie, pv[2])), q1 = fma(gamma, v1, fma(pv[1], ie, pv[3]));
+            R k0 = R(0), k1 = R(0);
+            if (has_kl) ld2s(st + D::oCk + i * D::PKL + j, k0, k1, i);  // column P holds c_kl, beyond it zeros
+            const R q0 = fma(gamma, v0, fma(pv[0], ie, k0)), q1 = fma(gamma, v1, fma(pv[1], ie, k1));
             if (i <= j && j + 1 <= P) {
-              st2(tp + D::oM + i * PP + j, q0, q1);
+              st2s(tp + D::oM + i * PP + j, q0, q1, i);
             } else {
               if (i <= j) tp[D::oM + i * PP + j] = q0;
               if (j + 1 <= P) tp[D::oM + i * PP + j + 1] = q1;
@@ -214,19 +286,20 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
           };
 #define DONK_B2_ROW(RB_ROW)                                                                                      \
   if (RB_ROW < D::NBP)                                                                                           \
-    warp_mma_pre<R, 1, (D::NBP - RB_ROW > 0 ? D::NBP - RB_ROW : 1), 4>(                                           \
-        w, st + D::oFx + 8 * RB_ROW, PP, tp + D::oR + 8 * RB_ROW, PP, DX4 / 4,                                    \
-        [&](int i, int j, R* pv) { pre(8 * RB_ROW + i, 8 * RB_ROW + j, pv); },                                    \
+    warp_mma_ep<R, 1, DONK_RBN(RB_ROW), 2>(                                                                       \
+        w, st + D::oFx + 8 * RB_ROW, PP, tp + D::oR + 8 * RB_ROW, PP, DX4 / 4, fv##RB_ROW,                         \
         [&](int i, int j, R v0, R v1, const R* pv) { epi(8 * RB_ROW + i, 8 * RB_ROW + j, v0, v1, pv); });
-          DONK_B2_ROW(0) DONK_B2_ROW(1) DONK_B2_ROW(2) DONK_B2_ROW(3) DONK_B2_ROW(4)
+          DONK_B2_ROW(4) DONK_B2_ROW(3) DONK_B2_ROW(2) DONK_B2_ROW(1) DONK_B2_ROW(0)
 #undef DONK_B2_ROW
+#undef DONK_B2_PRE
+#undef DONK_RBN
         }
         w.team_sync();
         PHASE_MARK(1);
       }
       // all teams are done with the staged inputs of step t: fetch step t-1 while the factorisation, gains and
       // value update (team-private data only) run
-      w.cta_sync();
+      LOOP_SYNC;
       if (t > 0) stage_bwd(t - 1);
       PHASE_MARK(2);
       TEAMS_DO(tm) {
@@ -263,62 +336,55 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
             R dsel = Lm[0][0];
 #pragma unroll
             for (int j = 1; j < DU; ++j) dsel = ln == j ? Lm[j][j] : dsel;
-            tp[D::oLds + ln] = log(dsel);
+            // log det: the diagonals are multiplied up over 8 steps and the logarithm taken once (a double-precision
+            // log costs ~80 instructions); oDel holds the per-lane sums of the backward pass
+            R pr = tp[D::oLds + ln] * dsel;
+            if ((t & 7) == 0) {
+              tp[D::oDel + ln] += log(pr);
+              pr = R(1);
+            }
+            tp[D::oLds + ln] = pr;
           }
           if (ln == 31 && bad && tp[D::oScal + 4] == R(0)) tp[D::oScal + 4] = R(t + 1);
-#pragma unroll
-          for (int c = 0; c < DU; ++c) {  // in-place inverse of the lower factor: Li = L^-1
-            Lm[c][c] = idg[c];
-#pragma unroll
-            for (int i = c + 1; i < DU; ++i) {
-              R acc = R(0);
-#pragma unroll
-              for (int k = c; k < i; ++k) acc = fma(Lm[i][k], Lm[k][c], acc);
-              Lm[i][c] = -acc * idg[i];
-            }
+          // pol_inv_covar = Quu (lqg.py:168): one entry per lane
+          for (int e = ln; e < DU * DU; e += 32) {
+            const int i = e / DU, j = e % DU;
+            a.pinv[pt * szS + e] = tp[D::oM + (DX + (i < j ? i : j)) * PP + DX + (i < j ? j : i)];
           }
-          {  // pol_covar = Quu^-1 = Li^T Li (symmetric by construction, lqg.py:165-166); lane e stores entry e
-            int e = 0;
+          // One right-hand side per lane, two triangular substitutions each (scipy.linalg.solve(assume_a="pos"),
+          // lqg.py:165-167):  column ln of Qux -> column ln of K;  q_u -> k;  column c of -I -> column c of
+          // pol_covar = Quu^-1.  out = -Quu^-1 x in every case.
 #pragma unroll
-            for (int i = 0; i < DU; ++i)
+          for (int c0 = 0; c0 < DX + 1 + DU; c0 += 32) {
+            const int col = c0 + ln;
+            if (col < DX + 1 + DU) {
+              R x[DU];
+              const int mcol = col < DX ? col : P;
 #pragma unroll
-              for (int j = 0; j <= i; ++j, ++e) {
-                R acc = R(0);
+              for (int b2 = 0; b2 < DU; ++b2)
+                x[b2] = col <= DX ? tp[D::oM + (DX + b2) * PP + mcol] : (b2 == col - DX - 1 ? R(-1) : R(0));
 #pragma unroll
-                for (int k = i; k < DU; ++k) acc = fma(Lm[k][i], Lm[k][j], acc);
-                if (ln == (e & 31)) {
-                  a.pcov[pt * szS + i * DU + j] = acc;
-                  a.pcov[pt * szS + j * DU + i] = acc;
-                  const R quu = tp[D::oM + (DX + j) * PP + DX + i];
-                  a.pinv[pt * szS + i * DU + j] = quu;
-                  a.pinv[pt * szS + j * DU + i] = quu;
-                }
+              for (int i = 0; i < DU; ++i) {  // L y = x
+                R acc = x[i];
+#pragma unroll
+                for (int k = 0; k < i; ++k) acc = fma(-Lm[i][k], x[k], acc);
+                x[i] = acc * idg[i];
               }
-          }
-          if (ln <= DX) {  // column ln of K (ln < DX) or k (ln == DX): z = -Li^T (Li x), x = Qux[:, ln] / q_u
-            const int col = ln < DX ? ln : P;
-            R x[DU];
 #pragma unroll
-            for (int b2 = 0; b2 < DU; ++b2) x[b2] = tp[D::oM + (DX + b2) * PP + col];
+              for (int i = DU - 1; i >= 0; --i) {  // L^T z = y
+                R acc = x[i];
 #pragma unroll
-            for (int i = DU - 1; i >= 0; --i) {
-              R acc = R(0);
+                for (int k = i + 1; k < DU; ++k) acc = fma(-Lm[k][i], x[k], acc);
+                x[i] = acc * idg[i];
+              }
 #pragma unroll
-              for (int k = 0; k <= i; ++k) acc = fma(Lm[i][k], x[k], acc);
-              x[i] = acc;
-            }
-#pragma unroll
-            for (int i = 0; i < DU; ++i) {
-              R acc = R(0);
-#pragma unroll
-              for (int k = i; k < DU; ++k) acc = fma(Lm[k][i], x[k], acc);
-              x[i] = -acc;
-            }
-#pragma unroll
-            for (int a2 = 0; a2 < DU; ++a2) {
-              tp[D::oK + a2 * KLD + ln] = x[a2];
-              if (ln < DX) a.K[pt * szK + a2 * DX + ln] = x[a2];
-              else a.k[pt * DU + a2] = x[a2];
+              for (int a2 = 0; a2 < DU; ++a2) {
+                const R val = -x[a2];
+                if (col <= DX) tp[D::oK + a2 * KLD + col] = val;
+                if (col < DX) a.K[pt * szK + a2 * DX + col] = val;
+                else if (col == DX) a.k[pt * DU + a2] = val;
+                else a.pcov[pt * szS + a2 * DU + (col - DX - 1)] = val;
+              }
             }
           }
         }
@@ -330,9 +396,9 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
             if (i >= DX || i > j + 1 || j > DX) return;
             if (i <= j && j + 1 < DX) {
               R m0, m1;
-              ld2(tp + D::oM + i * PP + j, m0, m1);
+              ld2s(tp + D::oM + i * PP + j, m0, m1, i);
               m0 += v0; m1 += v1;
-              st2(tp + D::oM + i * PP + j, m0, m1);
+              st2s(tp + D::oM + i * PP + j, m0, m1, i);
               tp[D::oM + j * PP + i] = m0;
               tp[D::oM + (j + 1) * PP + i] = m1;
             } else {
@@ -360,27 +426,32 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
           DONK_B5_ROW(0) DONK_B5_ROW(1) DONK_B5_ROW(2) DONK_B5_ROW(3)
 #undef DONK_B5_ROW
         }
-        LANE_FOR(one, 1) {
-          R ld = R(0);
-#pragma unroll
-          for (int j = 0; j < DU; ++j) ld += tp[D::oLds + j];
-          tp[D::oScal + 3] += ld;
-        }
         w.team_sync();
         PHASE_MARK(4);
       }
       cp_async_wait_all();
-      w.cta_sync();
+      LOOP_SYNC;
       PHASE_MARK(5);
+    }
+    TEAMS_DO(tm) {  // sum_t log det chol(Quu_t)  (t = 0 flushed the running products)
+      if (!team_valid(tm)) continue;
+      R* tp = TEAMP(tm);
+      LANE_FOR(one, 1) {
+        R ld = R(0);
+#pragma unroll
+        for (int j = 0; j < DU; ++j) ld += tp[D::oDel + j];
+        tp[D::oScal + 3] = ld;
+      }
+      w.team_sync();
     }
   }
 
   // =========================================================================================
   // Forward pass with KL and expected cost
   // =========================================================================================
-  if (a.flags & ILQR_FORWARD) {
+  if (opt_fwd) {
     const R reg = a.fwd_reg;
-    const bool do_kl = (a.flags & ILQR_KL) != 0, do_cost = (a.flags & ILQR_COST) != 0;
+    const bool do_kl = FULL || (a.flags & ILQR_KL) != 0, do_cost = FULL || (a.flags & ILQR_COST) != 0;
     constexpr int oPK = D::oPK, oPL = D::oPL, oFv = D::oVec, oPk = oFv + DXP, oCc = oPk + 8;  // inside the stage area
     // the stage and K areas change layout: clear the paddings the forward products rely on
     CTA_FOR(idx, NC * D::STAGE) stages[idx] = R(0);
@@ -412,14 +483,25 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
           CTA_FOR(i, DU) cp_async(st + oPk + i, a.prevk + bt * DU + i);
           CTA_FOR(one, 1) cp_async(st + oCc + 1, a.prev_hld + bt);
         }
+        if (DX % 2 == 0 && a.aligned16) {
+          CTA_FOR(idx, DX * (DX / 2)) {
+            const int i = idx / (DX / 2), j = 2 * (idx % (DX / 2));
+            cp_async_pair(st + D::oD + i * D::DXE + j, a.dyn_covar + bt * DX * DX + (size_t)i * DX + j);
+          }
+        } else {
+          CTA_FOR(idx, DX * DX) {
+            const int i = idx / DX, j = idx % DX;
+            cp_async(st + D::oD + i * D::DXE + j, a.dyn_covar + bt * DX * DX + idx);
+          }
+        }
       }
     };
     auto stage_policy = [&](int tm, int t) {  // K_t^T, k_t, pol_covar_t of this team's problem (async)
       R* tp = TEAMP(tm);
       const size_t pt = PIDX(tm) * T + t;
-      LANE_FOR(idx, DU * DX) {
-        const int a2 = idx / DX, k = idx % DX;
-        cp_async(tp + D::oK + k * KTL + a2, a.K + pt * szK + idx);
+#pragma unroll
+      for (int a2 = 0; a2 < DU; ++a2) {
+        LANE_FOR(k, DX) cp_async(tp + D::oK + k * KTL + a2, a.K + pt * szK + (size_t)a2 * DX + k);
       }
       LANE_FOR(i, DU) cp_async(tp + D::oKv + i, a.k + pt * DU + i);
       LANE_FOR(idx, DU * DU) cp_async(tp + D::oPc + idx, a.pcov + pt * szS + idx);
@@ -432,7 +514,11 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
       LANE_FOR(idx, D::MSZ) tp[D::oM + idx] = R(0);
       w.team_sync();
       LANE_FOR(idx, DX * DX) tp[D::oM + (idx / DX) * PP + idx % DX] = ldg(a.x0S + (size_t)b * DX * DX + idx);
-      LANE_FOR(i, DX) tp[D::oM + i * PP + P] = ldg(a.x0m + (size_t)b * DX + i);
+      LANE_FOR(i, DX) {
+        const R m0 = ldg(a.x0m + (size_t)b * DX + i);
+        tp[D::oM + i * PP + P] = m0;
+        tp[D::oRow + i] = m0;
+      }
       stage_policy(tm, 0);
     }
     cp_async_wait_all();
@@ -440,23 +526,40 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
     PHASE_MARK(12);
 
     for (int t = 0; t < T; ++t) {
+      // ---- first half of step t: team-private data only (policy of step t was fetched during step t-1); the shared
+      //      inputs of step t (F_t^T, dyn_covar_t, previous policy) are still in flight ---------------------------------
       TEAMS_DO(tm) {
         if (!team_valid(tm)) continue;
         R* tp = TEAMP(tm);
-        const R* st = STAGEP(tm);
         const int b = team_b(tm);
-        if (t + 1 < T) {  // pull next step's C / dyn_covar rows into L2
-          constexpr int LINES = (P * P * (int)sizeof(R) + 127) / 128, LINESD = (DX * DX * (int)sizeof(R) + 127) / 128;
-          LANE_FOR(ln, LINES + LINESD) {
-            if (ln < LINES) { if (do_cost) prefetch_l2(a.C + ((size_t)b * (T + 1) + t + 1) * szC + (size_t)ln * (128 / sizeof(R))); }
-            else prefetch_l2(a.dyn_covar + ((size_t)b * T + t + 1) * DX * DX + (size_t)(ln - LINES) * (128 / sizeof(R)));
+        const R* Cg = a.C + ((size_t)b * (T + 1) + t) * szC;
+        const R* cg = a.c + ((size_t)b * (T + 1) + t) * P;
+        if (do_cost && t + 1 < T) {  // pull next step's C rows into L2
+          constexpr int LINES = (P * P * (int)sizeof(R) + 127) / 128;
+          LANE_FOR(ln, LINES) {
+            if (tm % ES == t % ES) prefetch_l2(a.C + ((size_t)b * (T + 1) + t + 1) * szC + (size_t)ln * (128 / sizeof(R)));
           }
         }
-        // ---- F1: [Sigma_ux | mu_u] = K [Sigma_xx | mu_x] (+ k); K_prev mu_x (lqg.py:227-230, 294) --------------
+#if defined(__CUDA_ARCH__)
+        // cost weights of this step: lane j holds column j of C_t (P values, row-wise coalesced loads), issued now,
+        // consumed after F2
+        static_assert(P <= 32, "cost phase: one column of C per lane");
+        R creg[P], cvec = R(0), cdiag = R(0);
+        if (do_cost) {
+          const int jc = w.lane < P ? w.lane : 0;
+#pragma unroll
+          for (int k = 0; k < P; ++k) creg[k] = ldg(Cg + k * P + jc);
+          cvec = ldg(cg + jc);
+          cdiag = ldg(Cg + jc * P + jc);
+        }
+#endif
+        cp_async_wait_group<1>();  // this lane's share of the policy of step t has landed
+        w.team_sync();
+        // ---- F1: [Sigma_ux | mu_u] = K [Sigma_xx | mu_x] (+ k) (lqg.py:227-230) -----------------------------------
         warp_mma<R, 1, D::NBP>(w, tp + D::oK, KTL, tp + D::oM, PP, DX4 / 4, [&](int a2, int j, R v0, R v1) {
           if (a2 < DU) {
             if (j + 1 < DX) {
-              st2(tp + D::oM + (DX + a2) * PP + j, v0, v1);
+              st2s(tp + D::oM + (DX + a2) * PP + j, v0, v1, a2);
               tp[D::oM + j * PP + DX + a2] = v0;
               tp[D::oM + (j + 1) * PP + DX + a2] = v1;
             } else {
@@ -468,23 +571,17 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
                   tp[D::oM + (DX + a2) * PP + jj] = acc;
                   tp[D::oM + jj * PP + DX + a2] = acc;
                 } else if (jj == P) {
-                  tp[D::oM + (DX + a2) * PP + P] = acc + tp[D::oKv + a2];
+                  const R mu_u = acc + tp[D::oKv + a2];
+                  tp[D::oM + (DX + a2) * PP + P] = mu_u;
+                  tp[D::oRow + DX + a2] = mu_u;
                 }
               }
             }
           }
         });
-        if (do_kl) {
-          warp_mma<R, 1, 1>(w, st + oPK, KTL, tp + D::oM + 8 * D::BP, PP, DX4 / 4, [&](int a2, int j, R v0, R v1) {
-            if (a2 < DU) {
-              if (8 * D::BP + j == P) tp[D::oDel + a2] = v0 + st[oPk + a2];
-              if (8 * D::BP + j + 1 == P) tp[D::oDel + a2] = v1 + st[oPk + a2];
-            }
-          });
-        }
         w.team_sync();
         PHASE_MARK(6);
-        // ---- F2: Sigma_uu = Sigma_ux K^T + pol_covar (upper, mirrored) (lqg.py:231); delta_u ---------------------
+        // ---- F2: Sigma_uu = Sigma_ux K^T + pol_covar (upper, mirrored) (lqg.py:231) ------------------------------
         warp_mma<R, 1, 1>(w, tp + D::oM + DX, PP, tp + D::oK, KTL, DX4 / 4, [&](int a2, int j, R v0, R v1) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -496,159 +593,117 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
             }
           }
         });
-        if (do_kl) {
-          LANE_FOR(a2, DU) tp[D::oDel + a2] -= tp[D::oM + (DX + a2) * PP + P];  // (K_prev mu_x + k_prev) - mu_u
-        }
         w.team_sync();
         PHASE_MARK(7);
-        // ---- F3: Rt_ext = ([F] [Sigma | mu])^T (PE x DX).  The expected cost of step t rides on the A fragments:
-        //      every lane sees 1/32 of [Sigma | mu] anyway and adds C_kj (Sigma_kj + mu_k mu_j [+ reg]) for it --------
-        {
-          const R* Cg = a.C + ((size_t)b * (T + 1) + t) * szC;
-          const R* cg = a.c + ((size_t)b * (T + 1) + t) * P;
+        // ---- expected cost of step t: 1/2 sum_kj C_kj (Sigma_kj + mu_k mu_j [+ reg]) + c^T mu (quadratic_costs.py:106-119)
+        if (do_cost) {
 #if defined(__CUDA_ARCH__)
-          const int g = w.lane >> 2, tq = w.lane & 3;
-          R c[D::NBP][D::NBX][2];
+          // lane j: sum_k C_kj Sigma_kj and sum_k C_kj mu_k  (Sigma row k at consecutive addresses, mu_k broadcast)
+          R acc1 = R(0), acc2 = R(0);
+          const R* mrow = tp + D::oM + w.lane;
 #pragma unroll
-          for (int ra = 0; ra < D::NBP; ++ra)
-#pragma unroll
-            for (int rb = 0; rb < D::NBX; ++rb) { c[ra][rb][0] = R(0); c[ra][rb][1] = R(0); }
-          R muj[D::NBP], cn[D::NBP], cn2[D::NBP];
-          auto loadC = [&](int k, int ra) {
-            const int j = 8 * ra + g;
-            return (do_cost && k < P && j < P) ? ldg(Cg + k * P + j) : R(0);
-          };
-#pragma unroll
-          for (int ra = 0; ra < D::NBP; ++ra) {
-            muj[ra] = 8 * ra + g < P ? tp[D::oM + (8 * ra + g) * PP + P] : R(0);
-            cn[ra] = loadC(tq, ra);
-            cn2[ra] = loadC(tq + 4, ra);
+          for (int k = 0; k < P; k += 2) {
+            R mk0, mk1;
+            ld2(tp + D::oRow + k, mk0, mk1);
+            acc1 = fma(creg[k], mrow[k * PP], acc1);
+            acc2 = fma(creg[k], mk0, acc2);
+            if (k + 1 < P) {
+              acc1 = fma(creg[k + 1], mrow[(k + 1) * PP], acc1);
+              acc2 = fma(creg[k + 1], mk1, acc2);
+            }
           }
           R cost = R(0);
-          const R* ap = tp + D::oM + tq * PP + g;
-          const R* bp = st + D::oFx + tq * DXP + g;
-          for (int k4 = 0; k4 < P4 / 4; ++k4) {
-            const int k = 4 * k4 + tq;
-            R cc_[D::NBP], af[D::NBP], bf[D::NBX];
-#pragma unroll
-            for (int ra = 0; ra < D::NBP; ++ra) { cc_[ra] = cn[ra]; cn[ra] = cn2[ra]; cn2[ra] = loadC(k + 8, ra); af[ra] = ap[8 * ra]; }
-#pragma unroll
-            for (int rb = 0; rb < D::NBX; ++rb) bf[rb] = bp[8 * rb];
-            if (do_cost) {
-              const R muk = k < P ? tp[D::oM + k * PP + P] : R(0);
-#pragma unroll
-              for (int ra = 0; ra < D::NBP; ++ra) {
-                R sv = fma(muk, muj[ra], af[ra]);
-                if (k == 8 * ra + g) sv += reg;
-                cost = fma(cc_[ra], sv, cost);
-              }
-            }
-#pragma unroll
-            for (int ra = 0; ra < D::NBP; ++ra)
-#pragma unroll
-              for (int rb = 0; rb < D::NBX; ++rb) {
-                if (sizeof(R) == 8) {
-                  double d0 = (double)c[ra][rb][0], d1 = (double)c[ra][rb][1];
-                  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                               : "+d"(d0), "+d"(d1)
-                               : "d"((double)af[ra]), "d"((double)bf[rb]));
-                  c[ra][rb][0] = (R)d0;
-                  c[ra][rb][1] = (R)d1;
-                }
-              }
-            ap += 4 * PP;
-            bp += 4 * DXP;
+          if (w.lane < P) {
+            const R mj = tp[D::oRow + w.lane];
+            cost = fma(R(0.5), fma(mj, acc2, fma(reg, cdiag, acc1)), mj * cvec);
           }
-          if (sizeof(R) != 8) {  // float: no tensor path, each lane computes its two outputs per fragment
-            for (int k = 0; k < P4; ++k)
-#pragma unroll
-              for (int ra = 0; ra < D::NBP; ++ra) {
-                const R av = tp[D::oM + k * PP + 8 * ra + g];
-#pragma unroll
-                for (int rb = 0; rb < D::NBX; ++rb) {
-                  c[ra][rb][0] = fma(av, st[D::oFx + k * DXP + 8 * rb + 2 * tq], c[ra][rb][0]);
-                  c[ra][rb][1] = fma(av, st[D::oFx + k * DXP + 8 * rb + 2 * tq + 1], c[ra][rb][1]);
-                }
-              }
-          }
-#pragma unroll
-          for (int ra = 0; ra < D::NBP; ++ra)
-#pragma unroll
-            for (int rb = 0; rb < D::NBX; ++rb) {
-              const int j = 8 * ra + g, i = 8 * rb + 2 * tq;
-              if (j < PE) {
-                if (i + 1 < DX) st2(tp + D::oR + j * DXP + i, c[ra][rb][0], c[ra][rb][1]);
-                else if (i < DX) tp[D::oR + j * DXP + i] = c[ra][rb][0];
-              }
-            }
-          if (do_cost) {
-            cost *= R(0.5);
-            if (w.lane < P) cost = fma(tp[D::oM + w.lane * PP + P], ldg(cg + w.lane), cost);
-            team_accumulate(w, tp + D::oScal + 2, cost);
-          }
+          team_accumulate(w, tp + D::oScal + 2, cost);
 #else
-          for (int j = 0; j < PE; ++j)
-            for (int i = 0; i < DX; ++i) {
-              R acc = R(0);
-              for (int k = 0; k < P4; ++k) acc = fma(tp[D::oM + k * PP + j], st[D::oFx + k * DXP + i], acc);
-              tp[D::oR + j * DXP + i] = acc;
+          R cost = R(0);
+          for (int k = 0; k < P; ++k)
+            for (int j = 0; j < P; ++j) {
+              R sv = fma(tp[D::oRow + k], tp[D::oRow + j], tp[D::oM + k * PP + j]);
+              if (k == j) sv += reg;
+              cost = fma(Cg[k * P + j], sv, cost);
             }
-          if (do_cost) {
-            R cost = R(0);
-            for (int k = 0; k < P; ++k)
-              for (int j = 0; j < P; ++j) {
-                R sv = fma(tp[D::oM + k * PP + P], tp[D::oM + j * PP + P], tp[D::oM + k * PP + j]);
-                if (k == j) sv += reg;
-                cost = fma(Cg[k * P + j], sv, cost);
-              }
-            cost *= R(0.5);
-            for (int i = 0; i < P; ++i) cost = fma(tp[D::oM + i * PP + P], cg[i], cost);
-            tp[D::oScal + 2] += cost;
-          }
+          cost *= R(0.5);
+          for (int i = 0; i < P; ++i) cost = fma(tp[D::oRow + i], cg[i], cost);
+          tp[D::oScal + 2] += cost;
 #endif
         }
-        PHASE_MARK(8);
-        if (a.tcov) {
+        if (want_tcov) {
           LANE_FOR(idx, P * P) {
             const int i = idx / P, j = idx % P;
             a.tcov[(PIDX(tm) * (T + 1) + t) * szC + idx] = tp[D::oM + i * PP + j] + (i == j ? reg : R(0));
           }
         }
-        if (a.tmean) {
+        if (want_tmean) {
           LANE_FOR(i, P) a.tmean[(PIDX(tm) * (T + 1) + t) * P + i] = tp[D::oM + i * PP + P];
         }
+        PHASE_MARK(8);
+      }
+      cp_async_wait_all();
+      LOOP_SYNC;  // the shared inputs of step t are in place
+      PHASE_MARK(9);
+      // ---- second half of step t --------------------------------------------------------------------------------
+      TEAMS_DO(tm) {
+        if (!team_valid(tm)) continue;
+        R* tp = TEAMP(tm);
+        const R* st = STAGEP(tm);
+        if (do_kl) {  // delta_u = (K_prev mu_x + k_prev) - mu_u  (lqg.py:294)
+          warp_mma<R, 1, 1>(w, st + oPK, KTL, tp + D::oM + 8 * D::BP, PP, DX4 / 4, [&](int a2, int j, R v0, R v1) {
+            if (a2 < DU) {
+              if (8 * D::BP + j == P) tp[D::oDel + a2] = v0 + st[oPk + a2] - tp[D::oM + (DX + a2) * PP + P];
+              if (8 * D::BP + j + 1 == P) tp[D::oDel + a2] = v1 + st[oPk + a2] - tp[D::oM + (DX + a2) * PP + P];
+            }
+          });
+        }
+        // ---- F3: Rt_ext = ([F] [Sigma | mu])^T (PE x DX) (lqg.py:236-240) -----------------------------------------
+        warp_mma<R, D::NBP, D::NBX>(w, tp + D::oM, PP, st + D::oFx, DXP, P4 / 4, [&](int j, int i, R v0, R v1) {
+          if (j < PE) {
+            if (i + 1 < DX) st2s(tp + D::oR + j * DXP + i, v0, v1, j);
+            else if (i < DX) tp[D::oR + j * DXP + i] = v0;
+          }
+        });
         w.team_sync();
-        PHASE_MARK(9);
+        PHASE_MARK(10);
         // ---- F4: Sigma'_xx = (F Sigma) F^T + dyn_covar (upper blocks, mirrored); mu' = F mu + f; scalars -------------
         {
-          const R* Dg = a.dyn_covar + ((size_t)b * T + t) * DX * DX;
-          auto pre = [&](int i, int j, R* pv) {
+          auto epi = [&](int i, int j, R v0, R v1) {
             if (i >= DX || i > j + 1 || j >= DX) return;
-            if (j + 1 < DX) ldg2(Dg + i * DX + j, DX % 2 == 0, pv[0], pv[1]);
-            else pv[0] = ldg(Dg + i * DX + j);
-          };
-          auto epi = [&](int i, int j, R v0, R v1, const R* pv) {
-            if (i >= DX || i > j + 1 || j >= DX) return;
-            const R s0 = v0 + pv[0], s1 = v1 + pv[1];
             if (i <= j && j + 1 < DX) {
-              st2(tp + D::oM + i * PP + j, s0, s1);
+              R d0, d1;
+              ld2s(st + D::oD + i * D::DXE + j, d0, d1, i);
+              const R s0 = v0 + d0, s1 = v1 + d1;
+              st2s(tp + D::oM + i * PP + j, s0, s1, i);
               tp[D::oM + j * PP + i] = s0;
               tp[D::oM + (j + 1) * PP + i] = s1;
             } else {
-              if (i <= j) { tp[D::oM + i * PP + j] = s0; tp[D::oM + j * PP + i] = s0; }
-              if (j + 1 < DX) { tp[D::oM + i * PP + j + 1] = s1; tp[D::oM + (j + 1) * PP + i] = s1; }
+              if (i <= j) {
+                const R s0 = v0 + st[D::oD + i * D::DXE + j];
+                tp[D::oM + i * PP + j] = s0;
+                tp[D::oM + j * PP + i] = s0;
+              }
+              if (j + 1 < DX) {
+                const R s1 = v1 + st[D::oD + i * D::DXE + j + 1];
+                tp[D::oM + i * PP + j + 1] = s1;
+                tp[D::oM + (j + 1) * PP + i] = s1;
+              }
             }
           };
 #define DONK_F4_ROW(RB_ROW)                                                                                        \
   if (RB_ROW < D::NBX)                                                                                             \
-    warp_mma_pre<R, 1, (D::NBX - RB_ROW > 0 ? D::NBX - RB_ROW : 1), 2>(                                             \
+    warp_mma<R, 1, (D::NBX - RB_ROW > 0 ? D::NBX - RB_ROW : 1)>(                                                    \
         w, tp + D::oR + 8 * RB_ROW, DXP, st + D::oFx + 8 * RB_ROW, DXP, P4 / 4,                                     \
-        [&](int i, int j, R* pv) { pre(8 * RB_ROW + i, 8 * RB_ROW + j, pv); },                                      \
-        [&](int i, int j, R v0, R v1, const R* pv) { epi(8 * RB_ROW + i, 8 * RB_ROW + j, v0, v1, pv); });
+        [&](int i, int j, R v0, R v1) { epi(8 * RB_ROW + i, 8 * RB_ROW + j, v0, v1); });
           DONK_F4_ROW(0) DONK_F4_ROW(1) DONK_F4_ROW(2) DONK_F4_ROW(3)
 #undef DONK_F4_ROW
         }
-        LANE_FOR(i, DX) tp[D::oM + i * PP + P] = tp[D::oR + P * DXP + i] + st[oFv + i];
+        LANE_FOR(i, DX) {
+          const R mu_n = tp[D::oR + P * DXP + i] + st[oFv + i];
+          tp[D::oM + i * PP + P] = mu_n;
+          tp[D::oRow + i] = mu_n;
+        }
         if (do_kl) {
           LANE_FOR(ln, DU) {  // row ln of  tr(Lam_prev Sigma_new) + delta^T Lam_prev delta  (lqg.py:295-304)
             R tr = R(0), row = R(0);
@@ -672,15 +727,13 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
           if (do_cost) tp[D::oScal + 2] += st[oCc];
         }
         if (t + 1 < T) stage_policy(tm, t + 1);
-        PHASE_MARK(10);
+        cp_async_commit();
+        PHASE_MARK(11);
       }
-      w.cta_sync();  // everyone is done with the staged inputs of step t
-      if (t + 1 < T) {
-        stage_fwd(t + 1);
-        cp_async_wait_all();
-        w.cta_sync();
-      }
-      PHASE_MARK(11);
+      LOOP_SYNC;  // everyone is done with the shared inputs of step t: fetch those of step t+1 behind F1 / F2 / cost
+      if (t + 1 < T) stage_fwd(t + 1);
+      cp_async_commit();
+      PHASE_MARK(13);
     }
 
     // ---- final row T: state block only (lqg.py:221-222,242) ---------------------------------------------------
@@ -701,13 +754,13 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
           tp[D::oRow + ln] = acc;
         }
       }
-      if (a.tcov) {
+      if (want_tcov) {
         LANE_FOR(idx, P * P) {
           const int i = idx / P, j = idx % P;
           a.tcov[(PIDX(tm) * (T + 1) + T) * szC + idx] = (i < DX && j < DX) ? tp[D::oM + i * PP + j] : R(0);
         }
       }
-      if (a.tmean) {
+      if (want_tmean) {
         LANE_FOR(i, P) a.tmean[(PIDX(tm) * (T + 1) + T) * P + i] = i < DX ? tp[D::oM + i * PP + P] : R(0);
       }
       w.team_sync();
@@ -720,12 +773,12 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
     R* tp = TEAMP(tm);
     LANE_FOR(one, 1) {
       const size_t pi = PIDX(tm);
-      if ((a.flags & ILQR_FORWARD) && (a.flags & ILQR_COST) && a.cost) {
+      if (FULL || ((a.flags & ILQR_FORWARD) && (a.flags & ILQR_COST) && a.cost)) {
         R acc = R(0);
         for (int i = 0; i < 32; ++i) acc += tp[D::oRow + i];
         a.cost[pi] = tp[D::oScal + 2] + acc + ldg(a.cc + (size_t)team_b(tm) * (T + 1) + T);
       }
-      if ((a.flags & ILQR_FORWARD) && (a.flags & ILQR_KL) && a.kl) a.kl[pi] = (tp[D::oScal + 1] + tp[D::oScal + 3]) / R(T);
+      if (FULL || ((a.flags & ILQR_FORWARD) && (a.flags & ILQR_KL) && a.kl)) a.kl[pi] = (tp[D::oScal + 1] + tp[D::oScal + 3]) / R(T);
       if (a.info) a.info[pi] = (int)tp[D::oScal + 4];
     }
   }

@@ -37,13 +37,14 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record(); il.step(eta); e1.record(); torch.cuda.synchronize()
 out = (ctypes.c_ulonglong * 32)()
 nat.lib.donk_phase_prof_read(out, 0)
-names = {0: "B1  W=V[F|f]", 1: "B2  Q=C+F'W", 2: "bwd cta_sync+stage issue", 3: "B34 chol/gains", 4: "B5  V update",
-         5: "bwd cp.async wait+cta_sync", 6: "F1  K[S|mu] (+KL product)", 7: "F2  Suu", 8: "F3  (F[S|mu])' + cost",
-         9: "tcov/tmean + sync", 10: "F4  F S F' + D, KL tail, policy stage", 11: "fwd cta_sync+stage+wait", 12: "prologues"}
+names = {0: "B1  W=V[F|f] (+C loads issued)", 1: "B2  Q=C/eta+C_kl+F'W", 2: "bwd cta_sync+stage issue", 3: "B34 chol/gains", 4: "B5  V update",
+         5: "bwd cp.async wait+cta_sync", 6: "F1  K[S|mu] (+policy wait, C loads issued)", 7: "F2  Suu", 8: "cost + tcov/tmean",
+         9: "fwd mid wait+cta_sync", 10: "KL product + F3 (F[S|mu])'", 11: "F4  F S F' + D, KL tail, policy stage",
+         12: "prologues", 13: "fwd end cta_sync+stage issue"}
 warps = B * E
 tot = sum(out)
 print(f"B={B} E={E}: {e0.elapsed_time(e1):.2f} ms (profiling build); cycles per warp and step:")
-for i in range(13):
+for i in range(14):
     per = out[i] / warps / T
     print(f"  {i:2d} {names[i]:40s} {per:9.0f}  {100 * out[i] / tot:5.1f} %")
 print(f"  total per warp and step pair: {tot / warps / T:.0f} cycles")

@@ -40,7 +40,8 @@ static int emu_ilqr_warp(const IlqrArgs<R>& a) {
   WCtx w{0, 1, 0, 0, G};
   for (int cta = 0; cta < grid; ++cta) {
     memset(smem.data(), 0xFF, smem.size() * sizeof(R));
-    ilqr_warp_cta<R, DX, DU>(w, a, cta, ES, smem.data());
+    if (ilqr_warp_is_full<R, DX, DU>(a)) ilqr_warp_cta<R, DX, DU, true>(w, a, cta, ES, smem.data());
+    else ilqr_warp_cta<R, DX, DU, false>(w, a, cta, ES, smem.data());
   }
   return DONK_OK;
 }
@@ -112,7 +113,7 @@ void donk_emu_set_reverse(int r) { g_emu_reverse = r; }
     a.prevK = prevK; a.prevk = prevk; a.prevLam = prevLam; a.prev_hld = prev_hld;                                \
     a.x0m = x0_mean; a.x0S = x0_covar; a.eta = eta; a.gamma = gamma; a.fwd_reg = fwd_reg;                        \
     a.K = K; a.k = k; a.pcov = pol_covar; a.pinv = pol_inv_covar; a.kl = kl; a.cost = cost;                      \
-    a.tmean = traj_mean; a.tcov = traj_covar; a.info = info; a.active = active;                                  \
+    a.tmean = traj_mean; a.tcov = traj_covar; a.info = info; a.active = active; a.aligned16 = 1;                                  \
     return emu_ilqr_step<R>(a);                                                                                  \
   }
 EMU_ILQR_STEP(f64, double)
