@@ -300,6 +300,87 @@ DONK_D void warp_mma_pre(const WCtx& w, const R* __restrict__ A, int lda, const 
   warp_mma_ep<R, RA, RB, NP>(w, A, lda, Bm, ldb, K4, fv, epi);
 }
 
+// Block-upper-triangular variant: only the fragments with rb >= ra are computed (symmetric results: Q, V, Sigma).
+// One call instead of one call per block row: the A and B fragments of a k-step are loaded once for all of its
+// fragments (RA + RB loads instead of sum_r (1 + RB - r)), all accumulators are independent, one prologue / epilogue.
+template <typename R, int RA, int RB, int NP, class Pre, class Epi>
+DONK_D void warp_mma_tri(const WCtx& w, const R* __restrict__ A, int lda, const R* __restrict__ Bm, int ldb, int K4,
+                         Pre&& pre, Epi&& epi) {
+#if defined(__CUDA_ARCH__)
+  const int g = w.lane >> 2, tq = w.lane & 3;
+  R c[RA][RB][2], pv[RA][RB][NP];
+#pragma unroll
+  for (int ra = 0; ra < RA; ++ra)
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb)
+      if (rb >= ra) {
+        c[ra][rb][0] = R(0); c[ra][rb][1] = R(0);
+#pragma unroll
+        for (int q = 0; q < NP; ++q) pv[ra][rb][q] = R(0);
+        pre(8 * ra + g, 8 * rb + 2 * tq, pv[ra][rb]);
+      }
+  if (sizeof(R) == 8) {
+    const R* ap = A + tq * lda + g;
+    const R* bp = Bm + tq * ldb + g;
+#pragma unroll 8
+    for (int k4 = 0; k4 < K4; ++k4) {
+      R af[RA], bf[RB];
+#pragma unroll
+      for (int ra = 0; ra < RA; ++ra) af[ra] = ap[8 * ra];
+#pragma unroll
+      for (int rb = 0; rb < RB; ++rb) bf[rb] = bp[8 * rb];
+#pragma unroll
+      for (int ra = 0; ra < RA; ++ra)
+#pragma unroll
+        for (int rb = 0; rb < RB; ++rb)
+          if (rb >= ra) {
+            double d0 = (double)c[ra][rb][0], d1 = (double)c[ra][rb][1];
+            asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                : "+d"(d0), "+d"(d1)
+                : "d"((double)af[ra]), "d"((double)bf[rb]));
+            c[ra][rb][0] = (R)d0;
+            c[ra][rb][1] = (R)d1;
+          }
+      ap += 4 * lda;
+      bp += 4 * ldb;
+    }
+  } else {
+    for (int k = 0; k < 4 * K4; ++k) {
+#pragma unroll
+      for (int ra = 0; ra < RA; ++ra) {
+        const R av = A[k * lda + 8 * ra + g];
+#pragma unroll
+        for (int rb = 0; rb < RB; ++rb)
+          if (rb >= ra) {
+            c[ra][rb][0] = fma(av, Bm[k * ldb + 8 * rb + 2 * tq], c[ra][rb][0]);
+            c[ra][rb][1] = fma(av, Bm[k * ldb + 8 * rb + 2 * tq + 1], c[ra][rb][1]);
+          }
+      }
+    }
+  }
+#pragma unroll
+  for (int ra = 0; ra < RA; ++ra)
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb)
+      if (rb >= ra) epi(8 * ra + g, 8 * rb + 2 * tq, c[ra][rb][0], c[ra][rb][1], pv[ra][rb]);
+#else
+  (void)w;
+  for (int i = 0; i < 8 * RA; ++i)
+    for (int j = 0; j < 8 * RB; j += 2) {
+      if (j / 8 < i / 8) continue;
+      R pv[NP];
+      for (int q = 0; q < NP; ++q) pv[q] = R(0);
+      pre(i, j, pv);
+      R v0 = R(0), v1 = R(0);
+      for (int k = 0; k < 4 * K4; ++k) {
+        v0 = fma(A[k * lda + i], Bm[k * ldb + j], v0);
+        v1 = fma(A[k * lda + i], Bm[k * ldb + j + 1], v1);
+      }
+      epi(i, j, v0, v1, pv);
+    }
+#endif
+}
+
 template <typename R, int RA, int RB, class Epi>
 DONK_D void warp_mma(const WCtx& w, const R* __restrict__ A, int lda, const R* __restrict__ Bm, int ldb, int K4,
                      Epi&& epi) {

@@ -38,7 +38,8 @@ __device__ unsigned long long donk_phase_cycles[32];
 #define PHASE_MARK(id)                                                                            \
   do {                                                                                            \
     const long long ph_now = clock64();                                                           \
-    if (w.lane == 0) atomicAdd(&donk_phase_cycles[id], (unsigned long long)(ph_now - ph_t0));     \
+    if (w.lane == 0 && (blockIdx.x & 7) == 0)  /* every 8th CTA records: keeps the perturbation small */ \
+      atomicAdd(&donk_phase_cycles[id], (unsigned long long)(ph_now - ph_t0));                    \
     ph_t0 = ph_now;                                                                               \
   } while (0)
 #else
@@ -141,6 +142,13 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
     for (int ci = 0; ci < NC; ++ci) any = any || cond_b(ci) >= 0;
     if (!any) return;  // CTA-uniform
   }
+  // L2 prefetch of the next C_t: the 128-byte lines of the matrix are dealt to the ES teams that share the condition
+  constexpr int PF_LINES = (P * P * (int)sizeof(R) + 127) / 128;
+#if defined(__CUDA_ARCH__)
+  const int pf_lo = ((w.team % ES) * PF_LINES) / ES, pf_hi = ((w.team % ES + 1) * PF_LINES) / ES;
+#else
+  const int pf_lo = 0, pf_hi = 0;  // hint only
+#endif
 #define TEAMP(tm) (teams + (size_t)(tm) * D::TEAM)
 #define STAGEP(tm) (stages + (size_t)((tm) / ES) * D::STAGE)
 #define PIDX(tm) ((size_t)team_b(tm) * E + team_e(tm))
@@ -221,14 +229,12 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
         R* tp = TEAMP(tm);
         const R* st = STAGEP(tm);
         const int b = team_b(tm);
-        if (t > 0) {  // pull next step's C rows into L2 while this step computes (one 128-byte line per lane)
-          constexpr int LINES = (P * P * (int)sizeof(R) + 127) / 128;
-          LANE_FOR(ln, LINES) {
-            if (tm % ES == t % ES) prefetch_l2(a.C + ((size_t)b * (T + 1) + t - 1) * szC + (size_t)ln * (128 / sizeof(R)));
-          }
+        if (t > 0) {  // pull next step's C rows into L2 while this step computes: this team's share of the lines
+          for (int ln = pf_lo + w.lane; ln < pf_hi; ln += 32)
+            prefetch_l2(a.C + ((size_t)b * (T + 1) + t - 1) * szC + (size_t)ln * (128 / sizeof(R)));
         }
-        // C_t entries (i, j), (i, j+1) of the Q fragments: raw loads, issued a whole product ahead of the epilogue that
-        // adds them (row blocks 1.. before B1, row block 0 before the first B2 product)
+        // C_t entries (i, j), (i, j+1) of the Q fragments: raw loads issued right before the B2 product (50 DMMA at
+        // (20,6): long enough to cover an L2 hit), consumed by its epilogue
         const R ie = tp[D::oScal + 0];
         const R* Cg = a.C + ((size_t)b * (T + 1) + t) * szC;
         const R* cg = a.c + ((size_t)b * (T + 1) + t) * P;
@@ -243,16 +249,6 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
             if (j == P || j + 1 == P) pv[h] = ldg(cg + i);
           }
         };
-#define DONK_RBN(RB_ROW) (D::NBP - (RB_ROW) > 0 ? D::NBP - (RB_ROW) : 1)
-        FragVals<R, 1, DONK_RBN(0), 2> fv0;
-        FragVals<R, 1, DONK_RBN(1), 2> fv1;
-        FragVals<R, 1, DONK_RBN(2), 2> fv2;
-        FragVals<R, 1, DONK_RBN(3), 2> fv3;
-        FragVals<R, 1, DONK_RBN(4), 2> fv4;
-#define DONK_B2_PRE(RB_ROW)                                                                                      \
-  if (RB_ROW < D::NBP)                                                                                           \
-    frag_pre<R, 1, DONK_RBN(RB_ROW), 2>(w, fv##RB_ROW, [&](int i, int j, R* pv) { pre(8 * RB_ROW + i, 8 * RB_ROW + j, pv); });
-        DONK_B2_PRE(1) DONK_B2_PRE(2) DONK_B2_PRE(3) DONK_B2_PRE(4)
         // ---- B1: W_ext = V [F | f] (+ v in column P) ----------------------------------------------------
         warp_mma<R, D::NBX, D::NBP>(w, tp + D::oM, PP, st + D::oFx, PP, DX4 / 4, [&](int i, int j, R v0, R v1) {
           if (i < DX && j < PP) {
@@ -261,7 +257,6 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
             st2s(tp + D::oR + i * PP + j, v0, v1, i);
           }
         });
-        DONK_B2_PRE(0)
         w.team_sync();
         PHASE_MARK(0);
         // ---- B2: Q_ext = C_ext / eta + C_kl + gamma [F|f]^T W_ext, upper blocks; column P is q.  Only the xu block is
@@ -284,15 +279,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
               if (j + 1 >= DX && j + 1 < P) tp[D::oM + (j + 1) * PP + i] = q1;
             }
           };
-#define DONK_B2_ROW(RB_ROW)                                                                                      \
-  if (RB_ROW < D::NBP)                                                                                           \
-    warp_mma_ep<R, 1, DONK_RBN(RB_ROW), 2>(                                                                       \
-        w, st + D::oFx + 8 * RB_ROW, PP, tp + D::oR + 8 * RB_ROW, PP, DX4 / 4, fv##RB_ROW,                         \
-        [&](int i, int j, R v0, R v1, const R* pv) { epi(8 * RB_ROW + i, 8 * RB_ROW + j, v0, v1, pv); });
-          DONK_B2_ROW(4) DONK_B2_ROW(3) DONK_B2_ROW(2) DONK_B2_ROW(1) DONK_B2_ROW(0)
-#undef DONK_B2_ROW
-#undef DONK_B2_PRE
-#undef DONK_RBN
+          warp_mma_tri<R, D::NBP, D::NBP, 2>(w, st + D::oFx, PP, tp + D::oR, PP, DX4 / 4, pre, epi);
         }
         w.team_sync();
         PHASE_MARK(1);
@@ -418,13 +405,8 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
               }
             }
           };
-#define DONK_B5_ROW(RB_ROW)                                                                                        \
-  if (RB_ROW < D::NBX)                                                                                             \
-    warp_mma<R, 1, (D::NBX1 - RB_ROW > 0 ? D::NBX1 - RB_ROW : 1)>(                                                  \
-        w, tp + D::oM + DX * PP + 8 * RB_ROW, PP, tp + D::oK + 8 * RB_ROW, KLD, DU4 / 4,                            \
-        [&](int i, int j, R v0, R v1) { epi(8 * RB_ROW + i, 8 * RB_ROW + j, v0, v1); });
-          DONK_B5_ROW(0) DONK_B5_ROW(1) DONK_B5_ROW(2) DONK_B5_ROW(3)
-#undef DONK_B5_ROW
+          warp_mma_tri<R, D::NBX, D::NBX1, 1>(w, tp + D::oM + DX * PP, PP, tp + D::oK, KLD, DU4 / 4, [](int, int, R*) {},
+                                              [&](int i, int j, R v0, R v1, const R*) { epi(i, j, v0, v1); });
         }
         w.team_sync();
         PHASE_MARK(4);
@@ -534,11 +516,9 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
         const int b = team_b(tm);
         const R* Cg = a.C + ((size_t)b * (T + 1) + t) * szC;
         const R* cg = a.c + ((size_t)b * (T + 1) + t) * P;
-        if (do_cost && t + 1 < T) {  // pull next step's C rows into L2
-          constexpr int LINES = (P * P * (int)sizeof(R) + 127) / 128;
-          LANE_FOR(ln, LINES) {
-            if (tm % ES == t % ES) prefetch_l2(a.C + ((size_t)b * (T + 1) + t + 1) * szC + (size_t)ln * (128 / sizeof(R)));
-          }
+        if (do_cost && t + 1 < T) {  // pull next step's C rows into L2: this team's share of the lines
+          for (int ln = pf_lo + w.lane; ln < pf_hi; ln += 32)
+            prefetch_l2(a.C + ((size_t)b * (T + 1) + t + 1) * szC + (size_t)ln * (128 / sizeof(R)));
         }
 #if defined(__CUDA_ARCH__)
         // cost weights of this step: lane j holds column j of C_t (P values, row-wise coalesced loads), issued now,
@@ -691,13 +671,8 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
               }
             }
           };
-#define DONK_F4_ROW(RB_ROW)                                                                                        \
-  if (RB_ROW < D::NBX)                                                                                             \
-    warp_mma<R, 1, (D::NBX - RB_ROW > 0 ? D::NBX - RB_ROW : 1)>(                                                    \
-        w, tp + D::oR + 8 * RB_ROW, DXP, st + D::oFx + 8 * RB_ROW, DXP, P4 / 4,                                     \
-        [&](int i, int j, R v0, R v1) { epi(8 * RB_ROW + i, 8 * RB_ROW + j, v0, v1); });
-          DONK_F4_ROW(0) DONK_F4_ROW(1) DONK_F4_ROW(2) DONK_F4_ROW(3)
-#undef DONK_F4_ROW
+          warp_mma_tri<R, D::NBX, D::NBX, 1>(w, tp + D::oR, DXP, st + D::oFx, DXP, P4 / 4, [](int, int, R*) {},
+                                             [&](int i, int j, R v0, R v1, const R*) { epi(i, j, v0, v1); });
         }
         LANE_FOR(i, DX) {
           const R mu_n = tp[D::oR + P * DXP + i] + st[oFv + i];
@@ -794,20 +769,38 @@ inline size_t ilqr_warp_bytes(int G, int NC) {
   return ((size_t)G * D::TEAM + (size_t)NC * D::STAGE) * sizeof(R);
 }
 
-// teams per CTA: as many eta candidates of one condition as fit (<= 16 warps), else several conditions
+// Teams (warps) per CTA.  A CTA holds ES eta candidates of NC = G / ES conditions and one stage area per condition.
+// Pick the G that puts the most warps on an SM (shared memory and 128 registers per thread allow 16); ties go to the
+// smaller CTA: two 8-warp CTAs drift apart, so the tensor-heavy products of one overlap the factorisation / epilogue /
+// staging phases of the other (one 16-warp CTA runs its warps in lock-step).
 template <typename R, int DX, int DU>
 inline int ilqr_warp_plan(int B, int E, size_t smem_cap, int force_G, int& G, int& ES, int& grid, size_t& bytes) {
-  // 8 warps per CTA by default: two CTAs share an SM and drift apart, so the tensor-heavy products of one overlap
-  // the factorisation / epilogue / staging phases of the other (one 16-warp CTA runs its warps in lock-step)
-  int g = force_G > 0 ? force_G : 8;
-  for (; g >= 1; --g) {
-    ES = E < g ? E : g;
-    G = (g / ES) * ES;
-    if (G < 1) continue;
-    bytes = ilqr_warp_bytes<R, DX, DU>(G, G / ES);
-    if (bytes <= smem_cap) break;
+  const size_t sm_total = 228 * 1024, cta_reserved = 1024;
+  int best_g = 0, best_warps = 0, best_es = 0;
+  for (int g = force_G > 0 ? force_G : 16; g >= 1; --g) {
+    const int es = E < g ? E : g, gg = (g / es) * es;
+    if (gg < 1) continue;
+    const size_t by = ilqr_warp_bytes<R, DX, DU>(gg, gg / es);
+    if (by > smem_cap) continue;
+    int ctas = (int)(sm_total / (by + cta_reserved));
+    if (ctas * gg > 16) ctas = 16 / gg;  // register file: 128 registers x 32 lanes x 16 warps
+    if (gg > 8 && ctas > 1) ctas = 1;    // the large-CTA kernel is built for one CTA per SM
+    const int warps = ctas * gg;
+    // ties: CTAs of at most 8 warps (several per SM, out of phase; measured 56 vs 60 ms at config 3), then more eta
+    // candidates per staged condition (fewer copies of the shared inputs), then the smaller CTA
+    const bool small = gg <= 8, best_small = best_g <= 8;
+    const bool better = warps != best_warps ? warps > best_warps
+                        : small != best_small ? small
+                        : es != best_es ? es > best_es
+                                        : gg < best_g;
+    if (best_g == 0 || better) { best_warps = warps; best_g = gg; best_es = es; }
+    if (force_G > 0) break;
   }
-  if (g < 1) return DONK_SMEM_LIMIT;
+  if (best_g < 1) return DONK_SMEM_LIMIT;
+  G = best_g;
+  ES = E < G ? E : G;
+  G = (G / ES) * ES;
+  bytes = ilqr_warp_bytes<R, DX, DU>(G, G / ES);
   const int NC = G / ES, n_ech = (E + ES - 1) / ES;
   grid = ((B + NC - 1) / NC) * n_ech;
   return DONK_OK;

@@ -41,7 +41,7 @@ names = {0: "B1  W=V[F|f] (+C loads issued)", 1: "B2  Q=C/eta+C_kl+F'W", 2: "bwd
          5: "bwd cp.async wait+cta_sync", 6: "F1  K[S|mu] (+policy wait, C loads issued)", 7: "F2  Suu", 8: "cost + tcov/tmean",
          9: "fwd mid wait+cta_sync", 10: "KL product + F3 (F[S|mu])'", 11: "F4  F S F' + D, KL tail, policy stage",
          12: "prologues", 13: "fwd end cta_sync+stage issue"}
-warps = B * E
+warps = B * E / 8  # every 8th CTA records (PHASE_MARK)
 tot = sum(out)
 print(f"B={B} E={E}: {e0.elapsed_time(e1):.2f} ms (profiling build); cycles per warp and step:")
 for i in range(14):
