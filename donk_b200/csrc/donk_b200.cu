@@ -124,8 +124,13 @@ __global__ void __launch_bounds__(512, 1) ilqr_warp_kernel_big(const IlqrArgs<R>
   WCtx w{(int)threadIdx.x, (int)blockDim.x, (int)threadIdx.x >> 5, (int)threadIdx.x & 31, (int)blockDim.x >> 5};
   ilqr_warp_cta<R, DX, DU, FULL>(w, a, (int)blockIdx.x, ES, reinterpret_cast<R*>(smem_raw));
 }
+#if defined(DONK_LB_EXPERIMENT)  // profiles only: 4-warp CTAs x 3 per SM with 168 registers per thread
+#define DONK_WARP_LB __launch_bounds__(128, 3)
+#else
+#define DONK_WARP_LB __launch_bounds__(256, 2)
+#endif
 template <typename R, int DX, int DU, bool FULL>
-__global__ void __launch_bounds__(256, 2) ilqr_warp_kernel(const IlqrArgs<R> a, int ES) {
+__global__ void DONK_WARP_LB ilqr_warp_kernel(const IlqrArgs<R> a, int ES) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WCtx w{(int)threadIdx.x, (int)blockDim.x, (int)threadIdx.x >> 5, (int)threadIdx.x & 31, (int)blockDim.x >> 5};
   ilqr_warp_cta<R, DX, DU, FULL>(w, a, (int)blockIdx.x, ES, reinterpret_cast<R*>(smem_raw));
