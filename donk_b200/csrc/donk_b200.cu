@@ -300,18 +300,40 @@ __global__ void __launch_bounds__(128, 3) fit_warp_kernel(const FitArgs<R> a) {
   WCtx w{(int)threadIdx.x, (int)blockDim.x, (int)threadIdx.x >> 5, (int)threadIdx.x & 31, (int)blockDim.x >> 5};
   fit_warp_cta<R, DX, DU>(w, a, (int)blockIdx.x, reinterpret_cast<R*>(smem_raw));
 }
+template <typename R>
+__global__ void gmm_prior_consts_kernel(int d, int K, const R* gw, const R* gmeans, const R* gpc, R* out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < K * d + K) gmm_prior_consts_item<R>(d, K, gw, gmeans, gpc, out, idx);
+}
+
 template <typename R, int DX, int DU>
-int fit_warp_launch(const FitArgs<R>& a, void* stream) {
+int fit_warp_launch(FitArgs<R> a, void* stream) {
   int G;
   size_t bytes;
-  int rc = fit_warp_plan<R, DX, DU>(smem_optin_cap() / 3 - 1024, env_int("DONK_FIT_WARPS"), G, bytes);
-  if (rc != DONK_OK) rc = fit_warp_plan<R, DX, DU>(smem_optin_cap(), env_int("DONK_FIT_WARPS"), G, bytes);
+  const int forced = env_int("DONK_FIT_WARPS");
+  int rc = fit_warp_plan<R, DX, DU>(smem_optin_cap() / 3 - 1024, forced, a.N, a.K, G, bytes);
+  if (rc != DONK_OK) rc = fit_warp_plan<R, DX, DU>(smem_optin_cap(), forced, a.N, a.K, G, bytes);
   if (rc != DONK_OK) return rc;
-  if (G > 4) G = 4, bytes = (size_t)4 * FitWarpDims<DX, DU>::TEAM * sizeof(R);  // kernel is compiled for <= 128 threads
+  if (G > 4) {  // the kernel is compiled for <= 128 threads
+    G = 4;
+    bytes = (size_t)4 * (FitWarpDims<DX, DU>::TEAM + FitWarpDims<DX, DU>::prior_tail(a.N, a.K)) * sizeof(R);
+  }
   rc = allow_smem(fit_warp_kernel<R, DX, DU>, bytes);
   if (rc != DONK_OK) return rc;
+  R* consts = nullptr;
+  if (a.K > 0) {  // per-cluster constants of the log-probabilities: stream-ordered scratch, freed after the fit launch
+    const int d = 2 * DX + DU, len = a.K * d + a.K;
+    if (cudaMallocAsync(reinterpret_cast<void**>(&consts), (size_t)len * sizeof(R), (cudaStream_t)stream) != cudaSuccess) {
+      snprintf(g_err, sizeof(g_err), "fit_lr: cudaMallocAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return DONK_CUDA_ERROR;
+    }
+    gmm_prior_consts_kernel<R><<<(len + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d, a.K, a.gw, a.gmeans, a.gpc, consts);
+    LAUNCHED("gmm_prior_consts_kernel");
+    a.gconst = consts;
+  }
   const long long nfits = (long long)a.B * a.T;
   fit_warp_kernel<R, DX, DU><<<(unsigned)((nfits + G - 1) / G), 32 * G, bytes, (cudaStream_t)stream>>>(a);
+  if (consts) cudaFreeAsync(consts, (cudaStream_t)stream);
   LAUNCHED("fit_warp_kernel");
   return DONK_OK;
 }
@@ -586,7 +608,8 @@ int donk_fit_lr_f64(int B, int N, int T, int dX, int dU, const double* X, const 
   a.gw = gmm_weights; a.gmeans = gmm_means; a.gcov = gmm_covariances; a.gpc = gmm_prec_chol;
   a.n_pool = n_pool; a.prior_weight = prior_weight; a.reg = regularization;
   a.F = F; a.f = f; a.covar = covar; a.info = info;
-  if (gmm_K == 0 && !env_int("DONK_FIT_GENERIC")) {  // warp-per-fit fast path for the instantiated dimensions
+  // warp-per-fit fast path for the instantiated dimensions (with the prior: partial sums for at most 64 samples)
+  if ((gmm_K == 0 || N <= 64) && !env_int("DONK_FIT_GENERIC")) {
 #define DONK_TRY_FITW(DXV, DUV) \
   if (dX == DXV && dU == DUV) return fit_warp_launch<double, DXV, DUV>(a, stream);
     DONK_WARP_DIMS(DONK_TRY_FITW)

@@ -28,6 +28,7 @@ struct FitArgs {
   int K;           // GMM clusters (0: no prior)
   const R *gw, *gmeans, *gcov, *gpc;  // (K) (K,d) (K,d,d) (K,d,d)
   R n_pool, prior_weight, reg;
+  const R* gconst;   // warp kernel with prior: per-cluster constants from gmm_prior_consts_item, (K*d + K)
   R *F, *f, *covar;  // (B,T,dX,p) (B,T,dX) (B,T,dX,dX)
   int* info;         // (B,T)
 };
@@ -86,6 +87,27 @@ DONK_HD R sig_get(const R* sm, const FitLayout& L, int i, int j) {  // i <= j
 }
 
 // One sample value of the joint vector [x_t | u_t | x_{t+1}] from the roll-out arrays.
+// Per-cluster constants of the sample log-probabilities (sklearn _estimate_log_gaussian_prob, _gaussian_mixture.py:
+// 530-545: y = X P_k - mu_k P_k, logp = -(d log 2pi + |y|^2)/2 + sum log diag P_k + log w_k): they depend on the
+// mixture only, not on the fit, so one tiny launch computes them for all (condition, t) fits of a call.
+//   out[k*d + j] = -sum_{i<=j} mu_k[i] P_k[i][j]        (k < K, j < d)
+//   out[K*d + k] = -d/2 log(2 pi) + sum_i log P_k[i][i] + log w_k
+template <typename R>
+DONK_HD void gmm_prior_consts_item(int d, int K, const R* gw, const R* gmeans, const R* gpc, R* out, int idx) {
+  const size_t dd = (size_t)d * d;
+  if (idx < K * d) {
+    const int k = idx / d, j = idx % d;
+    R acc = R(0);
+    for (int i = 0; i <= j; ++i) acc = fma(gmeans[(size_t)k * d + i], gpc[k * dd + (size_t)i * d + j], acc);
+    out[idx] = -acc;
+  } else if (idx < K * d + K) {
+    const int k = idx - K * d;
+    R ldet = R(0);
+    for (int i = 0; i < d; ++i) ldet += log(gpc[k * dd + (size_t)i * d + i]);
+    out[idx] = -R(d) * R(1.8378770664093453) / 2 + ldet + log(gw[k]);
+  }
+}
+
 template <typename R>
 DONK_HD R xux_load(const FitArgs<R>& a, int b, int n, int t, int j) {
   const int dX = a.dX, dU = a.dU, p = dX + dU;

@@ -1,4 +1,4 @@
-// donk_b200 — fit_lr, warp-per-fit variant with compile-time dimensions (fast path, no prior).
+// donk_b200 — fit_lr, warp-per-fit variant with compile-time dimensions (fast path, with or without the GMM prior).
 //
 // Same math and reference lines as fitlr.cuh (fit_lr, donk/dynamics/linear_dynamics.py:137-189).  The generic
 // kernel spends a CTA and ~200 __syncthreads on every (condition, t); here one warp owns a fit and needs only
@@ -12,6 +12,11 @@
 //      (succeeds iff lambda_min > reg, i.e. iff the reference would not regularise); only if it fails the smallest
 //      eigenvalue is computed (Householder tridiagonalisation + Sturm multisection) and the diagonal lifted.
 //      All factorisations work in the lower triangle of Sigma_pp; the upper triangle keeps the original;
+//   1b. optional GMM prior (GMMPrior.eval, prior_gmm.py:26-41): log-probabilities of the N samples under the K
+//      clusters as Y^T = P_k^T X^T on the tensor path - the fragments of P_k for one block of output features stay
+//      in registers while the sample blocks stream past (samples read from global memory in the order
+//      [x_t | x_{t+1} | u_t], which is contiguous; rows of the upper-triangular P_k that cannot contribute are
+//      skipped at compile time); softmax, mixture moments, NIW posterior MAP covariance (prior.py:29-45);
 //   3. Cholesky, forward solve Y = L^-1 Sigma_px (one right-hand side per lane), Schur complement
 //      Sigma_x'x' - Y^T Y as DMMA blocks (symmetric and PSD by construction), backward solve F^T = L^-T Y.
 #pragma once
@@ -33,6 +38,11 @@ struct FitWarpDims {
   static constexpr int oMu = oSxx + DX * DXP + 8;  // mean (D8)
   static constexpr int oTd = oMu + D8, oTe = oTd + PA + 4, oV = oTe + PA + 4, oWw = oV + PA + 4;
   static constexpr int oScal = oWw + PA + 4, TEAM = oScal + 8;
+  // prior: runtime-sized tail behind TEAM: resp (N8 x K) | wts (K8) | mu_prior (D8)
+  static constexpr int NSB_MAX = 8;  // sample blocks of 8 the prior path holds partial sums for (N <= 64)
+  static_assert(DX % 2 == 0, "prior path: [x_t | x_{t+1}] is read as one run of 2 dX values in blocks of 4");
+  static constexpr int KX4 = 2 * DX / 4, KU4 = (DU + 3) / 4, KT4 = KX4 + KU4;
+  DONK_HD static int prior_tail(int N, int K) { return K > 0 ? ((N + 7) / 8 * 8) * K + (K + 7) / 8 * 8 + D8 : 0; }
 };
 
 template <typename R, int DX, int DU>
@@ -47,7 +57,8 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
     const long long fit = (long long)cta * w.G + tm;
     if (fit >= nfits) continue;
     const int b = (int)(fit / T), t = (int)(fit % T);
-    R* tp = smem + (size_t)tm * D::TEAM;
+    const int team_sz = D::TEAM + D::prior_tail(N, a.K);
+    R* tp = smem + (size_t)tm * team_sz;
     R* Spp = tp + D::oSpp;  // upper triangle + diagonal: Sigma_pp; strict lower triangle: work space for factors
     R* Spx = tp + D::oSpx;  // Sigma_px, then Y = L^-1 Sigma_px, then Z = F^T
     R* Sxx = tp + D::oSxx;
@@ -57,7 +68,7 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
     R* vv = tp + D::oV;
     R* ww = tp + D::oWw;
     R* scal = tp + D::oScal;
-    LANE_FOR(idx, D::TEAM) tp[idx] = R(0);
+    LANE_FOR(idx, team_sz) tp[idx] = R(0);
     w.team_sync();
 
     // ---- 1. S = sum_n (x_n - x_0)(x_n - x_0)^T (upper blocks) and column sums, fragments straight from global ----
@@ -151,6 +162,163 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
     }
 #endif
     w.team_sync();
+
+    // ---- 1b. GMM prior -> NIW posterior MAP covariance (prior_gmm.py:26-41, prior.py:18-45) -------------------------
+    if (a.K > 0) {
+      const int K = a.K, N8 = (N + 7) / 8 * 8, K8 = (K + 7) / 8 * 8;
+      const size_t dd = (size_t)d * d;
+      R* resp = tp + D::TEAM;  // [N8][K]: log-probabilities, then responsibilities
+      R* wts = resp + (size_t)N8 * K;
+      R* mup = wts + K8;
+      auto load_sigma = [&](int i, int j) {  // element (i <= j) of the blocked joint covariance
+        if (j < P) return Spp[i * PA + j];
+        if (i < P) return Spx[i * DXP + (j - P)];
+        return Sxx[(i - P) * DXP + (j - P)];
+      };
+#if !defined(DONK_EMU)
+      {
+        constexpr int NBD = D::NBD, KX4 = D::KX4, KT4 = D::KT4, NSB = D::NSB_MAX;
+        const int g = w.lane >> 2, tq = w.lane & 3;
+        const R* Xb = a.X + (((size_t)b * N) * (T + 1) + t) * DX;  // sample n: [x_t | x_{t+1}] = Xb[n * sx + 0 .. 2 DX)
+        const R* Ub = a.U + (((size_t)b * N) * T + t) * DU;
+        const size_t sx = (size_t)(T + 1) * DX, su = (size_t)T * DU;
+        for (int k = 0; k < K; ++k) {
+          const R* Pk = a.gpc + k * dd;
+          R ssp[NSB][2];
+#pragma unroll
+          for (int rb = 0; rb < NSB; ++rb) { ssp[rb][0] = R(0); ssp[rb][1] = R(0); }
+#pragma unroll
+          for (int ra = 0; ra < NBD; ++ra) {
+            // fragments of P_k for the output features 8 ra .. 8 ra + 7.  k-order of the product: [x_t | x_{t+1} | u_t];
+            // block k4 holds the original rows o(4 k4 + tq).  P_k is upper triangular: a block whose smallest original row
+            // index exceeds 8 ra + 7 contributes nothing and is skipped (compile-time test)
+            const int col = 8 * ra + g;
+            R pa[KT4];
+#pragma unroll
+            for (int k4 = 0; k4 < KT4; ++k4) {
+              const int kk = 4 * k4 + tq;
+              const int orig = k4 < DX / 4 + (DX % 4 ? 1 : 0) && kk < DX ? kk : (kk < 2 * DX ? kk + DU : kk - DX);
+              const int omin = 4 * k4 < DX ? 4 * k4 : (4 * k4 < 2 * DX ? 4 * k4 + DU : 4 * k4 - DX);
+              pa[k4] = R(0);
+              if (omin <= 8 * ra + 7) {
+                if (orig < d && col < d && orig <= col) pa[k4] = ldg(Pk + (size_t)orig * d + col);
+              }
+            }
+            const R cj = col < d ? ldg(a.gconst + (size_t)k * d + col) : R(0);
+#pragma unroll
+            for (int rb = 0; rb < NSB; rb += 2) {
+              if (8 * rb < N) {  // warp-uniform
+                const int n0 = 8 * rb + g, n1 = n0 + 8;
+                const bool v0 = n0 < N, v1 = n1 < N;
+                const R* x0p = Xb + (size_t)n0 * sx + tq;
+                const R* x1p = Xb + (size_t)n1 * sx + tq;
+                const R* u0p = Ub + (size_t)n0 * su + tq;
+                const R* u1p = Ub + (size_t)n1 * su + tq;
+                double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
+#pragma unroll
+                for (int k4 = 0; k4 < KT4; ++k4) {
+                  const int omin = 4 * k4 < DX ? 4 * k4 : (4 * k4 < 2 * DX ? 4 * k4 + DU : 4 * k4 - DX);
+                  if (omin <= 8 * ra + 7) {
+                    R b0, b1;
+                    if (k4 < KX4) {
+                      b0 = v0 ? ldg(x0p + 4 * k4) : R(0);
+                      b1 = v1 ? ldg(x1p + 4 * k4) : R(0);
+                    } else {
+                      const bool fv = 4 * (k4 - KX4) + tq < DU;
+                      b0 = (v0 && fv) ? ldg(u0p + 4 * (k4 - KX4)) : R(0);
+                      b1 = (v1 && fv) ? ldg(u1p + 4 * (k4 - KX4)) : R(0);
+                    }
+                    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                        : "+d"(c00), "+d"(c01) : "d"((double)pa[k4]), "d"((double)b0));
+                    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                        : "+d"(c10), "+d"(c11) : "d"((double)pa[k4]), "d"((double)b1));
+                  }
+                }
+                // the lane holds y[j = 8 ra + g][n = 8 rb + 2 tq + h] (and the same for block rb + 1)
+                const R y00 = (R)c00 + cj, y01 = (R)c01 + cj, y10 = (R)c10 + cj, y11 = (R)c11 + cj;
+                ssp[rb][0] = fma(y00, y00, ssp[rb][0]);
+                ssp[rb][1] = fma(y01, y01, ssp[rb][1]);
+                if (rb + 1 < NSB) {
+                  ssp[rb + 1][0] = fma(y10, y10, ssp[rb + 1][0]);
+                  ssp[rb + 1][1] = fma(y11, y11, ssp[rb + 1][1]);
+                }
+              }
+            }
+          }
+          const R lc = ldg(a.gconst + (size_t)K * d + k);
+#pragma unroll
+          for (int rb = 0; rb < NSB; ++rb) {
+            if (8 * rb < N) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                R s = ssp[rb][h];
+                s += __shfl_xor_sync(0xffffffffu, s, 4);
+                s += __shfl_xor_sync(0xffffffffu, s, 8);
+                s += __shfl_xor_sync(0xffffffffu, s, 16);
+                const int n = 8 * rb + 2 * tq + h;
+                if (g == 0 && n < N) resp[(size_t)n * K + k] = lc - s / 2;
+              }
+            }
+          }
+        }
+      }
+#else
+      for (int k = 0; k < K; ++k) {
+        const R* Pk = a.gpc + k * dd;
+        for (int n = 0; n < N; ++n) {
+          R ss = R(0);
+          for (int j = 0; j < d; ++j) {
+            R y = a.gconst[(size_t)k * d + j];
+            for (int i = 0; i <= j; ++i) y = fma(xux_load(a, b, n, t, i), Pk[(size_t)i * d + j], y);
+            ss = fma(y, y, ss);
+          }
+          resp[(size_t)n * K + k] = a.gconst[(size_t)K * d + k] - ss / 2;
+        }
+      }
+#endif
+      w.team_sync();
+      LANE_FOR(n, N) {  // responsibilities: softmax over the clusters (sklearn/mixture/_base.py:552-582)
+        R m = resp[(size_t)n * K];
+        for (int k = 1; k < K; ++k) m = resp[(size_t)n * K + k] > m ? resp[(size_t)n * K + k] : m;
+        R s = R(0);
+        for (int k = 0; k < K; ++k) s += exp(resp[(size_t)n * K + k] - m);
+        const R lse = m + log(s);
+        for (int k = 0; k < K; ++k) resp[(size_t)n * K + k] = exp(resp[(size_t)n * K + k] - lse);
+      }
+      w.team_sync();
+      LANE_FOR(k, K) {
+        R acc = R(0);
+        for (int n = 0; n < N; ++n) acc += resp[(size_t)n * K + k];
+        wts[k] = acc / R(N);  // prior_gmm.py:33
+      }
+      w.team_sync();
+      LANE_FOR(j, d) {
+        R acc = R(0);
+        for (int k = 0; k < K; ++k) acc = fma(wts[k], ldg(a.gmeans + (size_t)k * d + j), acc);
+        mup[j] = acc;  // prior_gmm.py:35
+      }
+      LANE_FOR(one, 1) {
+        R acc = R(0);
+        for (int k = 0; k < K; ++k) acc = fma(wts[k], ldg(a.gw + k), acc);
+        scal[4] = acc * a.n_pool;  // prior_gmm.py:39: strength of the prior in samples
+      }
+      w.team_sync();
+      {
+        const R Np = scal[4];
+        const R nn = R(N) / a.prior_weight;  // linear_dynamics.py:172
+        const R coef = Np * nn / (Np + nn);
+        LANE_FOR(idx, d * d) {
+          const int i = idx / d, j = idx % d;
+          if (i > j) continue;
+          R phi = R(0);
+          for (int k = 0; k < K; ++k) phi = fma(wts[k], ldg(a.gcov + k * dd + idx), phi);  // prior_gmm.py:36
+          const R dm = (mu[i] - mup[i]) * (mu[j] - mup[j]);
+          // Phi' / (N_covar' + d + 1), Phi' = Np Phi_p + n S + Np n / (Np + n) dm dm^T  (prior.py:29-45)
+          store_sigma(i, j, (Np * phi + nn * load_sigma(i, j) + coef * dm) / (Np + nn));
+        }
+      }
+      w.team_sync();
+    }
 
     // In-place Cholesky of (A - shift I): A is read from the upper triangle + diagonal of Spp, the factor goes to
     // the strict lower triangle, its diagonal to dg.  *flag (shared) becomes 1 if a pivot is not positive.
@@ -337,9 +505,9 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
 }
 
 template <typename R, int DX, int DU>
-inline int fit_warp_plan(size_t smem_cap, int force_G, int& G, size_t& bytes) {
+inline int fit_warp_plan(size_t smem_cap, int force_G, int N, int K, int& G, size_t& bytes) {
   using D = FitWarpDims<DX, DU>;
-  const size_t per = (size_t)D::TEAM * sizeof(R);
+  const size_t per = (size_t)(D::TEAM + D::prior_tail(N, K)) * sizeof(R);
   G = force_G > 0 ? force_G : 4;
   while (G > 1 && (size_t)G * per > smem_cap) --G;
   bytes = (size_t)G * per;

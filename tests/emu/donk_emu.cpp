@@ -80,11 +80,18 @@ static int emu_ilqr_step(IlqrArgs<R> a) {
 }
 
 template <int DX, int DU>
-static int emu_fit_warp(const FitArgs<double>& a) {
+static int emu_fit_warp(FitArgs<double> a) {
   int G;
   size_t bytes;
-  int rc = fit_warp_plan<double, DX, DU>(kSmemCap, 0, G, bytes);
+  int rc = fit_warp_plan<double, DX, DU>(kSmemCap, 0, a.N, a.K, G, bytes);
   if (rc != DONK_OK) return rc;
+  std::vector<double> consts;
+  if (a.K > 0) {
+    const int d = 2 * DX + DU, len = a.K * d + a.K;
+    consts.resize(len);
+    for (int i = 0; i < len; ++i) gmm_prior_consts_item<double>(d, a.K, a.gw, a.gmeans, a.gpc, consts.data(), i);
+    a.gconst = consts.data();
+  }
   std::vector<double> smem(bytes / sizeof(double) + 2);
   WCtx w{0, 1, 0, 0, G};
   const long long nfits = (long long)a.B * a.T;
@@ -196,7 +203,7 @@ int donk_emu_fit_lr_f64(int B, int N, int T, int dX, int dU, const double* X, co
   a.gw = gmm_weights; a.gmeans = gmm_means; a.gcov = gmm_covariances; a.gpc = gmm_prec_chol;
   a.n_pool = n_pool; a.prior_weight = prior_weight; a.reg = regularization;
   a.F = F; a.f = f; a.covar = covar; a.info = info;
-  if (gmm_K == 0 && !env_int("DONK_FIT_GENERIC")) {
+  if ((gmm_K == 0 || N <= 64) && !env_int("DONK_FIT_GENERIC")) {
     if (dX == 20 && dU == 6) return emu_fit_warp<20, 6>(a);
     if (dX == 14 && dU == 7) return emu_fit_warp<14, 7>(a);
     if (dX == 6 && dU == 2) return emu_fit_warp<6, 2>(a);

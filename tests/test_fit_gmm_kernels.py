@@ -186,3 +186,43 @@ def test_device_kmeans_and_prior_init(backend):
 
     ref = GaussianMixture(4, random_state=0).fit(X)
     assert abs(prior.gmm.lower_bound_ - ref.lower_bound_) < 1e-3 * abs(ref.lower_bound_)
+
+
+def _synthetic_prior(dX, dU, K, seed):
+    """A K-cluster mixture over [x_t | u_t | x_{t+1}] with well-conditioned random covariances."""
+    from oracle.gmm import GMMParams, precision_cholesky
+
+    d = 2 * dX + dU
+    rng = np.random.default_rng(seed)
+    w = rng.uniform(0.5, 1.5, K)
+    w /= w.sum()
+    means = 0.3 * rng.standard_normal((K, d))
+    A = rng.standard_normal((K, d, d)) / np.sqrt(d)
+    cov = A @ np.swapaxes(A, -1, -2) + 0.5 * np.eye(d)
+    return GMMParams(w, means, cov, precision_cholesky(cov))
+
+
+@pytest.mark.parametrize("dims,N,K,generic", [((14, 7), 50, 4, 0), ((20, 6), 64, 3, 0), ((6, 2), 20, 5, 0), ((6, 2), 9, 2, 0),
+                                              ((6, 2), 70, 2, 0), ((14, 7), 20, 4, 1)])
+def test_fit_lr_warp_kernel_with_prior(backend, monkeypatch, dims, N, K, generic):
+    """GMM prior inside the warp-per-fit kernel (log-probabilities on the tensor path), N up to 64 samples; more
+    samples (N=70) and DONK_FIT_GENERIC=1 take the generic CTA kernel: same results."""
+    from donk_b200 import batched, synthetic
+    from donk_b200.batched import DeviceGMM
+    from oracle.gmm import gmm_eval_prior
+
+    if generic:
+        monkeypatch.setenv("DONK_FIT_GENERIC", "1")
+    dX, dU = dims
+    T, B, n_pool = 3, 2, 12345
+    conds = [synthetic.condition(33, i, T, dX, dU, N) for i in range(B)]
+    X, U = np.stack([c.X for c in conds]), np.stack([c.U for c in conds])
+    prm = _synthetic_prior(dX, dU, K, seed=5)
+    gm = DeviceGMM(K)
+    gm.set_params(prm.weights, prm.means, covariances=prm.covariances, precisions_cholesky=prm.precisions_cholesky)
+    gm.N = n_pool
+    F, f, covar, info = batched.fit_lr(X, U, gm, 1e-6, prior_weight=2.0)
+    assert int(info.sum()) == 0
+    for b, c in enumerate(conds):
+        Fo, fo, co = oracle.fit_lr(c.X, c.U, lambda xux: gmm_eval_prior(prm, n_pool, xux), 1e-6, 2.0)
+        assert relerr(F[b], Fo) < 1e-8 and relerr(f[b], fo) < 1e-8 and relerr(covar[b], co) < 1e-8
