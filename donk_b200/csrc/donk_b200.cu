@@ -389,6 +389,12 @@ __global__ void __launch_bounds__(256, 1) gmm_e_mma_kernel(const GmmArgs<double>
   WCtx w{(int)threadIdx.x, (int)blockDim.x, (int)threadIdx.x >> 5, (int)threadIdx.x & 31, (int)blockDim.x >> 5};
   gmm_e_mma_cta<double, NB, RA>(w, a, (int)blockIdx.x, (int)gridDim.x, reinterpret_cast<double*>(smem_raw));
 }
+template <int NB, int RA>
+__global__ void __launch_bounds__(256, 2) gmm_e_mma_kernel_occ2(const GmmArgs<double> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WCtx w{(int)threadIdx.x, (int)blockDim.x, (int)threadIdx.x >> 5, (int)threadIdx.x & 31, (int)blockDim.x >> 5};
+  gmm_e_mma_cta<double, NB, RA>(w, a, (int)blockIdx.x, (int)gridDim.x, reinterpret_cast<double*>(smem_raw));
+}
 template <int NBW, int KC>
 __global__ void __launch_bounds__(NBW <= 6 ? 256 : 512, NBW <= 6 ? 2 : 1) gmm_m_mma_kernel(const GmmArgs<double> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -402,11 +408,15 @@ int gmm_e_mma_launch(GmmArgs<double>& a, const GmmMmaPlan& pl, void* stream) {
   a.nblocks = (a.n + TS - 1) / TS;
   const size_t smem = gmm_e_mma_smem<NB, RA>(a.K, pl.Ge) * sizeof(double);
   if (smem > smem_optin_cap()) return DONK_SMEM_LIMIT;
-  int rc = allow_smem(gmm_e_mma_kernel<NB, RA>, smem);
+  // two CTAs per SM when they fit: the staging / softmax / barrier phases of one overlap the products of the other
+  // (113.4 -> 107.0 ms per EM iteration at 10 M x 72, K = 16; DONK_GMM_E_CTAS=1 restores one CTA per SM)
+  const bool occ2 = 2 * (smem + 1024) <= (size_t)228 * 1024 && 32 * pl.Ge <= 256 && env_int("DONK_GMM_E_CTAS") != 1;
+  int rc = occ2 ? allow_smem(gmm_e_mma_kernel_occ2<NB, RA>, smem) : allow_smem(gmm_e_mma_kernel<NB, RA>, smem);
   if (rc != DONK_OK) return rc;
-  int grid = 148;  // one CTA per SM: the rest of the SM's memory is L1 for the P_k all warps walk together
+  int grid = occ2 ? 296 : 148;  // persistent CTAs walking the row tiles
   if (grid > a.nblocks) grid = a.nblocks;
-  gmm_e_mma_kernel<NB, RA><<<grid, 32 * pl.Ge, smem, (cudaStream_t)stream>>>(a);
+  if (occ2) gmm_e_mma_kernel_occ2<NB, RA><<<grid, 32 * pl.Ge, smem, (cudaStream_t)stream>>>(a);
+  else gmm_e_mma_kernel<NB, RA><<<grid, 32 * pl.Ge, smem, (cudaStream_t)stream>>>(a);
   LAUNCHED("gmm_e_mma_kernel");
   return DONK_OK;
 }
