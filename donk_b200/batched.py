@@ -761,3 +761,87 @@ class DeviceKMeans:
         self.centers = centers
         self.labels, _, _ = self._pass(X, centers, labels=True)
         return self
+
+
+# =====================================================================================================
+# Device-resident transition pool
+# =====================================================================================================
+class DeviceTransitionPool:
+    """``donk.samples.TransitionPool`` (donk/samples/pool.py:6-56) with the rows kept in device memory.
+
+    Same semantics — rows ``[x_t | u_t | x_{t+1}]`` in roll-out order, the newest ``capacity`` rows are kept,
+    ``get_transitions(N)`` returns the ``N`` newest — but ``add`` takes roll-outs that may already live on the GPU and
+    writes their transitions straight into a ring buffer (``donk_to_transitions_f64``), so a GPS iteration uploads only
+    its new roll-outs instead of the whole pool (5.76 GB at 10 M x 72).  ``get_transitions`` returns a view of the
+    buffer when the requested window is contiguous and one device-to-device gather otherwise (2 ms per 5.76 GB: noise
+    next to an EM iteration).  With roll-outs sharded over ranks every rank keeps its own pool;
+    ``GMMPrior.update(pool.get_transitions())`` then all-reduces the EM statistics (``DeviceGMM.fit``).
+    """
+
+    def __init__(self, capacity: int = None) -> None:
+        self.capacity = capacity
+        self._buf = None   # (rows_allocated, d)
+        self._start = 0    # ring start (oldest row) when capacity is set
+        self._size = 0
+
+    def __len__(self) -> int:
+        return self._size
+
+    def add(self, X, U) -> None:
+        assert X.shape[0] == U.shape[0], f"{X.shape[0]} != {U.shape[0]}"
+        assert X.shape[1] == U.shape[1] + 1, f"{X.shape[1]} != {U.shape[1] + 1}"
+        X, U = _dev(X), _dev(U)
+        if self._buf is None:
+            self.dX, self.dU = X.shape[-1], U.shape[-1]
+        else:
+            assert X.shape[-1] == self.dX, f"{X.shape[-1]} != {self.dX}"
+            assert U.shape[-1] == self.dU, f"{U.shape[-1]} != {self.dU}"
+        d = 2 * self.dX + self.dU
+        N, T = U.shape[0], U.shape[1]
+        rows = N * T
+        nat = _lib.native()
+        if self.capacity is None:  # growing buffer, geometric reallocation
+            need = self._size + rows
+            if self._buf is None or need > self._buf.shape[0]:
+                grown = torch.empty(max(need, 2 * (self._buf.shape[0] if self._buf is not None else 0)), d,
+                                    dtype=X.dtype, device=X.device)
+                if self._size:
+                    grown[:self._size] = self._buf[:self._size]
+                self._buf = grown
+            nat.call("to_transitions_f64", N, T, self.dX, self.dU, X, U, self._buf[self._size:need])
+            self._size = need
+            return
+        cap = self.capacity
+        if self._buf is None:
+            self._buf = torch.empty(cap, d, dtype=X.dtype, device=X.device)
+        if rows >= cap:  # only the newest `cap` rows of this batch survive
+            new = torch.empty(rows, d, dtype=X.dtype, device=X.device)
+            nat.call("to_transitions_f64", N, T, self.dX, self.dU, X, U, new)
+            self._buf.copy_(new[rows - cap:])
+            self._start, self._size = 0, cap
+            return
+        end = (self._start + self._size) % cap
+        if end + rows <= cap:  # fits without wrapping: the kernel writes in place
+            nat.call("to_transitions_f64", N, T, self.dX, self.dU, X, U, self._buf[end:end + rows])
+        else:
+            new = torch.empty(rows, d, dtype=X.dtype, device=X.device)
+            nat.call("to_transitions_f64", N, T, self.dX, self.dU, X, U, new)
+            first = cap - end
+            self._buf[end:] = new[:first]
+            self._buf[:rows - first] = new[first:]
+        overflow = max(0, self._size + rows - cap)
+        self._start = (self._start + overflow) % cap
+        self._size = min(cap, self._size + rows)
+
+    def get_transitions(self, N: int = None) -> torch.Tensor:
+        """All, or the ``N`` newest, transitions ``(n, d)`` on the device, oldest first (pool.py:44-56)."""
+        if self._buf is None:
+            raise ValueError("pool is empty")
+        n = self._size if N is None else min(int(N), self._size)
+        if self.capacity is None:
+            return self._buf[self._size - n:self._size]
+        cap = self.capacity
+        lo = (self._start + self._size - n) % cap
+        if lo + n <= cap:
+            return self._buf[lo:lo + n]
+        return torch.cat([self._buf[lo:], self._buf[:lo + n - cap]], dim=0)

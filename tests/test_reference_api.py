@@ -8,7 +8,7 @@ import pickle
 import numpy as np
 import pytest
 
-from donk_testutil import load_golden, relerr
+from donk_testutil import load_golden, relerr, to_np
 
 
 def test_lqg_module_functions(backend):
@@ -189,3 +189,25 @@ def test_batched_gps_iteration_matches_per_condition_api(backend):
         single.iteration(it1[b].X, it1[b].U, costs)
         assert relerr(algo.pol[0][b], single.pol.K) < 1e-9 and relerr(algo.pol[2][b], single.pol.covar) < 1e-9
         assert abs(float(algo.kl_step_mult[b]) - single.kl_step_mult) < 1e-9
+
+
+def test_device_transition_pool_matches_reference_semantics(backend):
+    """batched.DeviceTransitionPool against the host TransitionPool (donk/samples/pool.py:6-56): growing pool, FIFO
+    capacity with wrap-around, a batch larger than the capacity, newest-N windows."""
+    from donk_b200.batched import DeviceTransitionPool
+    from donk_b200.samples import TransitionPool
+
+    rng = np.random.default_rng(0)
+    dX, dU, T = 3, 2, 4
+    for cap in (None, 23, 8):
+        host, dev = TransitionPool(cap), DeviceTransitionPool(cap)
+        for N in (2, 3, 1, 4, 2):
+            X, U = rng.standard_normal((N, T + 1, dX)), rng.standard_normal((N, T, dU))
+            host.add(X, U)
+            dev.add(X, U)
+            assert len(dev) == host.get_transitions().shape[0]
+            assert np.array_equal(to_np(dev.get_transitions()), host.get_transitions())
+            for n in (1, 5, 100):
+                assert np.array_equal(to_np(dev.get_transitions(n)), host.get_transitions(n))
+    with pytest.raises(AssertionError):
+        dev.add(rng.standard_normal((2, T + 1, dX + 1)), rng.standard_normal((2, T, dU)))
