@@ -322,6 +322,34 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
 
     // In-place Cholesky of (A - shift I): A is read from the upper triangle + diagonal of Spp, the factor goes to
     // the strict lower triangle, its diagonal to dg.  *flag (shared) becomes 1 if a pivot is not positive.
+#if !defined(DONK_EMU)
+    // Device form: lane i owns row i of the factor and keeps it in registers (compile-time indices after unrolling);
+    // column j needs row j, which lane j has already published to shared memory - one broadcast load per term instead
+    // of two dependent loads, no loop overhead.  Every lane recomputes the pivot (no cross-lane dependency in a column).
+    auto chol = [&](R shift, R* dg, R* flag) {
+      R Lr[P];
+      bool bad = false;
+      const int li = w.lane;
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        R sj = Spp[j * PA + j] - shift;
+        R si = (li > j && li < P) ? Spp[j * PA + li] : R(0);  // A[i][j] from the upper triangle
+#pragma unroll
+        for (int k = 0; k < j; ++k) {
+          const R ljk = Spp[j * PA + k];
+          sj = fma(-ljk, ljk, sj);
+          si = fma(-Lr[k], ljk, si);
+        }
+        bad = bad || !(sj > R(0));
+        Lr[j] = si * rsqrt_r(sj);
+        if (li == j) dg[j] = sqrt(sj);
+        if (li > j && li < P) Spp[li * PA + j] = Lr[j];
+        w.team_sync();
+      }
+      if (li == 0) *flag = bad ? R(1) : R(0);
+      w.team_sync();
+    };
+#else
     auto chol = [&](R shift, R* dg, R* flag) {
       LANE_FOR(one, 1) *flag = R(0);
       w.team_sync();
@@ -344,6 +372,7 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
         w.team_sync();
       }
     };
+#endif
 
     // ---- 2. does the reference regularise?  lambda_min(Sigma_pp) < reg  <=>  Sigma_pp - reg I is not PD ------------
     chol(a.reg, ww, scal + 0);
@@ -445,6 +474,25 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
 
     // ---- 3. Cholesky of Sigma_pp; Y = L^-1 Sigma_px; covar = Sigma_x'x' - Y^T Y; Z = L^-T Y = F^T ----------------------
     chol(R(0), td, scal + 3);
+#if !defined(DONK_EMU)
+    LANE_FOR(i, P) ww[i] = R(1) / td[i];  // reciprocal pivots: the substitutions multiply
+    w.team_sync();
+    if (w.lane < DX) {  // forward substitution, one right-hand side per lane, the solution in registers
+      const int c = w.lane;
+      R y[P];
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        R a0 = Spx[i * DXP + c], a1 = R(0);
+#pragma unroll
+        for (int k = 0; k < i; k += 2) {
+          a0 = fma(-Spp[i * PA + k], y[k], a0);
+          if (k + 1 < i) a1 = fma(-Spp[i * PA + k + 1], y[k + 1], a1);
+        }
+        y[i] = (a0 + a1) * ww[i];
+        Spx[i * DXP + c] = y[i];
+      }
+    }
+#else
     LANE_FOR(c, DX) {  // forward substitution, one right-hand side per lane
       for (int i = 0; i < P; ++i) {
         R acc = Spx[i * DXP + c];
@@ -452,6 +500,7 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
         Spx[i * DXP + c] = acc / td[i];
       }
     }
+#endif
     w.team_sync();
     const size_t bt = (size_t)b * T + t;
     {
@@ -479,6 +528,23 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
 #undef DONK_FIT_ROW
     }
     w.team_sync();
+#if !defined(DONK_EMU)
+    if (w.lane < DX) {  // backward substitution
+      const int c = w.lane;
+      R z[P];
+#pragma unroll
+      for (int i = P - 1; i >= 0; --i) {
+        R a0 = Spx[i * DXP + c], a1 = R(0);
+#pragma unroll
+        for (int k = i + 1; k < P; k += 2) {
+          a0 = fma(-Spp[k * PA + i], z[k], a0);
+          if (k + 1 < P) a1 = fma(-Spp[(k + 1) * PA + i], z[k + 1], a1);
+        }
+        z[i] = (a0 + a1) * ww[i];
+        Spx[i * DXP + c] = z[i];
+      }
+    }
+#else
     LANE_FOR(c, DX) {  // backward substitution
       for (int i = P - 1; i >= 0; --i) {
         R acc = Spx[i * DXP + c];
@@ -486,6 +552,7 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
         Spx[i * DXP + c] = acc / td[i];
       }
     }
+#endif
     w.team_sync();
     // outputs F[i][j] = Z[j][i], f = mu_x' - F mu_p   (linear_dynamics.py:184-185)
     LANE_FOR(idx, DX * P) {

@@ -74,3 +74,12 @@ elif what == "kmeans":
     print(f"  greedy k-means++ seeding: {1e3 * (time.perf_counter() - t0):.1f} ms")
     t0 = time.perf_counter(); km.fit(X); torch.cuda.synchronize()
     print(f"  DeviceKMeans.fit: {km.n_iter} Lloyd iterations, {1e3 * (time.perf_counter() - t0):.1f} ms, counts", torch.bincount(km.labels.long(), minlength=K).tolist())
+elif what == "config1":
+    # BASELINE configs[0]: T=50, dX=6, dU=2, N=20 - one condition (latency) and a 4096-condition batch (throughput)
+    for B in (1, 4096):
+        ro, il, fit_ms = build(B, 50, 6, 2, 20)
+        ms, (res, status, n_steps) = timed(lambda: il.optimize(1.0, raise_on_failure=False), 5)
+        eta = torch.ones(B, 1, dtype=torch.float64, device=dev)
+        ms_s, _ = timed(lambda: il.step(eta), 20)
+        print(f"config1 B={B}: fit_lr {fit_ms * 1e3:.0f} us, ILQR.step {ms_s * 1e3:.0f} us, ILQR.optimize {ms * 1e3:.0f} us "
+              f"({n_steps} steps) = {B / (ms * 1e-3):.0f} optimize/s, status", torch.bincount(status, minlength=4).tolist())
