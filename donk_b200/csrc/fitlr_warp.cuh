@@ -81,6 +81,7 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
     {
       constexpr int NBD = D::NBD, NTRI = NBD * (NBD + 1) / 2;
       const int g = w.lane >> 2, tq = w.lane & 3;
+      const R invN = R(1) / R(N);
       const R* ptr[NBD];   // address of column 8 ib + g of sample 0
       size_t stride[NBD];  // distance between consecutive samples
       bool ok[NBD];
@@ -102,11 +103,13 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
 #pragma unroll
         for (int ib = 0; ib < NBD; ++ib) dst[ib] = (ok[ib] && n < N) ? ldg(ptr[ib] + (size_t)n * stride[ib]) : sh[ib];
       };
+      R nx2[NBD];
       load(tq, nxt);
+      load(4 + tq, nx2);
       for (int k4 = 0; k4 < (N + 3) / 4; ++k4) {
 #pragma unroll
-        for (int ib = 0; ib < NBD; ++ib) cur[ib] = nxt[ib];
-        load(4 * (k4 + 1) + tq, nxt);  // the next sample row is in flight while this one is multiplied
+        for (int ib = 0; ib < NBD; ++ib) { cur[ib] = nxt[ib]; nxt[ib] = nx2[ib]; }
+        load(4 * (k4 + 2) + tq, nx2);  // two sample rows are in flight while this one is multiplied
 #pragma unroll
         for (int ib = 0; ib < NBD; ++ib) { cur[ib] -= sh[ib]; csum[ib] += cur[ib]; }
         int q = 0;
@@ -127,7 +130,7 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
         R s = csum[ib];
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
-        csum[ib] = s / R(N);  // every lane of the quad now holds the shifted mean of column 8 ib + g
+        csum[ib] = s * invN;  // every lane of the quad now holds the shifted mean of column 8 ib + g
         if (tq == 0 && ok[ib]) mu[8 * ib + g] = sh[ib] + csum[ib];
       }
       // Sigma = S / N - m m^T, biased (linear_dynamics.py:165): the lane holds row 8 ib + g, columns 8 jb + 2 tq + h;
@@ -141,7 +144,7 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
           for (int h = 0; h < 2; ++h) {
             const R mj = __shfl_sync(0xffffffffu, csum[jb], 4 * (2 * tq + h));
             const int i = 8 * ib + g, j = 8 * jb + 2 * tq + h;
-            if (i <= j && j < d) store_sigma(i, j, acc[q][h] / R(N) - csum[ib] * mj);
+            if (i <= j && j < d) store_sigma(i, j, fma(acc[q][h], invN, -csum[ib] * mj));
           }
         }
     }
@@ -341,8 +344,9 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
           si = fma(-Lr[k], ljk, si);
         }
         bad = bad || !(sj > R(0));
-        Lr[j] = si * rsqrt_r(sj);
-        if (li == j) dg[j] = sqrt(sj);
+        const R rs = rsqrt_r(sj);
+        Lr[j] = si * rs;
+        if (li == j) dg[j] = rs;  // the device form stores the RECIPROCAL pivots: the substitutions multiply
         if (li > j && li < P) Spp[li * PA + j] = Lr[j];
         w.team_sync();
       }
@@ -475,8 +479,6 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
     // ---- 3. Cholesky of Sigma_pp; Y = L^-1 Sigma_px; covar = Sigma_x'x' - Y^T Y; Z = L^-T Y = F^T ----------------------
     chol(R(0), td, scal + 3);
 #if !defined(DONK_EMU)
-    LANE_FOR(i, P) ww[i] = R(1) / td[i];  // reciprocal pivots: the substitutions multiply
-    w.team_sync();
     if (w.lane < DX) {  // forward substitution, one right-hand side per lane, the solution in registers
       const int c = w.lane;
       R y[P];
@@ -488,7 +490,7 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
           a0 = fma(-Spp[i * PA + k], y[k], a0);
           if (k + 1 < i) a1 = fma(-Spp[i * PA + k + 1], y[k + 1], a1);
         }
-        y[i] = (a0 + a1) * ww[i];
+        y[i] = (a0 + a1) * td[i];
         Spx[i * DXP + c] = y[i];
       }
     }
@@ -540,7 +542,7 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
           a0 = fma(-Spp[k * PA + i], z[k], a0);
           if (k + 1 < P) a1 = fma(-Spp[(k + 1) * PA + i], z[k + 1], a1);
         }
-        z[i] = (a0 + a1) * ww[i];
+        z[i] = (a0 + a1) * td[i];
         Spx[i * DXP + c] = z[i];
       }
     }
