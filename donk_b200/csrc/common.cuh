@@ -36,17 +36,10 @@ static inline int emu_idx(int it, int n) { return g_emu_reverse ? n - 1 - it : i
   for (int i##_it = 0, i##_n = (n), i = donk::emu_idx(0, i##_n); i##_it < i##_n;     \
        ++i##_it, i = donk::emu_idx(i##_it, i##_n))
 #else
-// A "team" is the group of threads that executes one kernel body: the whole CTA (bar == 0), a group of
-// warps synchronised by a named barrier (bar > 0), or a (sub-)warp synchronised by __syncwarp (bar < 0).
+// The "team" that executes one generic kernel body is the whole CTA.
 struct Ctx {
   int tid, nt;
-  int bar;
-  unsigned mask;
-  DONK_D void sync() const {
-    if (bar == 0) __syncthreads();
-    else if (bar < 0) __syncwarp(mask);
-    else asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nt) : "memory");
-  }
+  DONK_D void sync() const { __syncthreads(); }
 };
 #define TEAM_FOR(i, n) for (int i = ctx.tid; i < (n); i += ctx.nt)
 #endif

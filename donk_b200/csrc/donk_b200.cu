@@ -85,38 +85,6 @@ __global__ void __launch_bounds__(320, 2) ilqr_step_kernel_occ2(const IlqrArgs<R
   ilqr_cta<R>(ctx, a, (int)blockIdx.x, reinterpret_cast<R*>(smem_raw));
 }
 
-// One team of L threads per (condition, eta) problem; see ilqr_plan_team.
-template <typename R>
-__device__ __forceinline__ void ilqr_team_body(const IlqrArgs<R>& a, int L, int G, size_t team_bytes,
-                                               long long n_teams) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int team = (int)threadIdx.x / L, lane = (int)threadIdx.x % L;
-  const long long g = (long long)blockIdx.x * G + team;
-  if (team >= G || g >= n_teams) return;  // whole teams leave together; no CTA-wide barrier is used
-  Ctx ctx;
-  ctx.tid = lane;
-  ctx.nt = L;
-  if (L > 32) {
-    ctx.bar = 1 + team;
-    ctx.mask = 0;
-  } else {
-    ctx.bar = -1;
-    const int w = (int)threadIdx.x & 31;
-    ctx.mask = L == 32 ? 0xffffffffu : (((1u << L) - 1u) << (w - (w % L)));
-  }
-  ilqr_cta<R>(ctx, a, (int)g, reinterpret_cast<R*>(smem_raw + (size_t)team * team_bytes));
-}
-template <typename R>
-__global__ void __launch_bounds__(256, 2) ilqr_team_kernel(const IlqrArgs<R> a, int L, int G, size_t team_bytes,
-                                                            long long n_teams) {
-  ilqr_team_body<R>(a, L, G, team_bytes, n_teams);
-}
-template <typename R>
-__global__ void __launch_bounds__(512, 1) ilqr_team_kernel_big(const IlqrArgs<R> a, int L, int G, size_t team_bytes,
-                                                                long long n_teams) {
-  ilqr_team_body<R>(a, L, G, team_bytes, n_teams);
-}
-
 // Warp-per-problem fast path with compile-time dimensions (ilqr_warp.cuh).
 template <typename R, int DX, int DU, bool FULL>
 __global__ void __launch_bounds__(512, 1) ilqr_warp_kernel_big(const IlqrArgs<R> a, int ES) {
@@ -124,13 +92,8 @@ __global__ void __launch_bounds__(512, 1) ilqr_warp_kernel_big(const IlqrArgs<R>
   WCtx w{(int)threadIdx.x, (int)blockDim.x, (int)threadIdx.x >> 5, (int)threadIdx.x & 31, (int)blockDim.x >> 5};
   ilqr_warp_cta<R, DX, DU, FULL>(w, a, (int)blockIdx.x, ES, reinterpret_cast<R*>(smem_raw));
 }
-#if defined(DONK_LB_EXPERIMENT)  // profiles only: 4-warp CTAs x 3 per SM with 168 registers per thread
-#define DONK_WARP_LB __launch_bounds__(128, 3)
-#else
-#define DONK_WARP_LB __launch_bounds__(256, 2)
-#endif
 template <typename R, int DX, int DU, bool FULL>
-__global__ void DONK_WARP_LB ilqr_warp_kernel(const IlqrArgs<R> a, int ES) {
+__global__ void __launch_bounds__(256, 2) ilqr_warp_kernel(const IlqrArgs<R> a, int ES) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WCtx w{(int)threadIdx.x, (int)blockDim.x, (int)threadIdx.x >> 5, (int)threadIdx.x & 31, (int)blockDim.x >> 5};
   ilqr_warp_cta<R, DX, DU, FULL>(w, a, (int)blockIdx.x, ES, reinterpret_cast<R*>(smem_raw));
@@ -181,28 +144,6 @@ int ilqr_step_launch(IlqrArgs<R> a, void* stream) {
   if (a.dX == DXV && a.dU == DUV) return ilqr_warp_launch<R, DXV, DUV>(a, stream);
     DONK_WARP_DIMS(DONK_TRY_WARP)
 #undef DONK_TRY_WARP
-  }
-  if (env_int("DONK_ILQR_TEAM_MODE")) {
-    rc = ilqr_plan_team(a.B, a.E, a.dX, a.dU, sizeof(R), smem_optin_cap(), env_int("DONK_ILQR_LANES"),
-                        env_int("DONK_ILQR_TEAMS"), pl);
-    if (rc == DONK_OK) {
-      a.S = 1;
-      a.ES = 1;
-      const IlqrLayout lay(a.dX, a.dU);
-      if (pl.threads <= 256) {
-        rc = allow_smem(ilqr_team_kernel<R>, pl.smem);
-        if (rc != DONK_OK) return rc;
-        ilqr_team_kernel<R><<<pl.grid, pl.threads, pl.smem, (cudaStream_t)stream>>>(
-            a, pl.L, pl.G, lay.bytes(1, 1, sizeof(R)), (long long)a.B * a.E);
-      } else {
-        rc = allow_smem(ilqr_team_kernel_big<R>, pl.smem);
-        if (rc != DONK_OK) return rc;
-        ilqr_team_kernel_big<R><<<pl.grid, pl.threads, pl.smem, (cudaStream_t)stream>>>(
-            a, pl.L, pl.G, lay.bytes(1, 1, sizeof(R)), (long long)a.B * a.E);
-      }
-      LAUNCHED("ilqr_team_kernel");
-      return DONK_OK;
-    }
   }
   rc = ilqr_plan(a.B, a.E, a.dX, a.dU, sizeof(R), smem_optin_cap(), env_int("DONK_ILQR_SLOTS"),
                  env_int("DONK_ILQR_THREADS"), pl);

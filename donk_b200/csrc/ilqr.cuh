@@ -880,41 +880,7 @@ namespace donk {
 struct IlqrPlan {
   int S, ES, NC, threads, grid;
   size_t smem;
-  int L, G;  // team launch: lanes per team (one slot each), teams per CTA
 };
-
-// Team launch: every (condition, eta) problem gets its own team of L threads and its own shared-memory
-// region; teams never wait for each other (no CTA-wide barrier), so their serial phases and memory
-// latencies overlap.  L <= 32: sub-warp/warp teams (__syncwarp); L > 32: named barriers (<= 15 teams).
-inline int ilqr_plan_team(int B, int E, int dX, int dU, size_t sz, size_t smem_cap, int force_L, int force_G,
-                          IlqrPlan& pl) {
-  const IlqrLayout L(dX, dU);
-  const size_t per_team = L.bytes(1, 1, sz);
-  if (per_team > smem_cap) return DONK_SMEM_LIMIT;
-  const int tiles = (L.dXp / 4) * (L.pp / 4);
-  int lanes = force_L;
-  if (lanes <= 0) {
-    if (tiles <= 6) lanes = 8;
-    else if (tiles <= 12) lanes = 16;
-    else if (tiles <= 48) lanes = 32;
-    else lanes = round_up(tiles, 32) > 512 ? 512 : round_up(tiles, 32);
-  }
-  const size_t half = (smem_cap + 1024) / 2 - 1024;
-  int G = (int)(half / per_team);           // two CTAs per SM when possible
-  if (G < 1) G = (int)(smem_cap / per_team);
-  if (G * lanes > 512) G = 512 / lanes;
-  if (lanes > 32 && G > 15) G = 15;
-  if (G < 1) G = 1;
-  if (force_G > 0) G = force_G;
-  if ((size_t)G * per_team > smem_cap || G * lanes > 1024) return DONK_SMEM_LIMIT;
-  pl.S = 1; pl.ES = 1; pl.NC = 1;
-  pl.L = lanes; pl.G = G;
-  pl.threads = round_up(G * lanes, 32);
-  pl.smem = (size_t)G * per_team;
-  const long long teams = (long long)B * E;
-  pl.grid = (int)((teams + G - 1) / G);
-  return DONK_OK;
-}
 
 // Choose slots per CTA.  Prefer a footprint that lets two CTAs share an SM (their sync stalls
 // overlap); fall back to the full 227 KB for large state dimensions.  force_S/force_threads > 0

@@ -47,13 +47,6 @@ __device__ unsigned long long donk_phase_cycles[32];
 #define PHASE_MARK(id)
 #endif
 
-// experiment switch (profiles only): drop the per-step CTA barriers to see what decoupled warps would gain (racy!)
-#if defined(DONK_EXPERIMENT_NOSYNC)
-#define LOOP_SYNC w.team_sync()
-#else
-#define LOOP_SYNC w.cta_sync()
-#endif
-
 template <int DX, int DU>
 struct WarpDims {
   static_assert(DU <= 8 && DX + 1 <= 32, "warp kernel: dU <= 8, dX <= 31");
@@ -286,7 +279,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
       }
       // all teams are done with the staged inputs of step t: fetch step t-1 while the factorisation, gains and
       // value update (team-private data only) run
-      LOOP_SYNC;
+      w.cta_sync();
       if (t > 0) stage_bwd(t - 1);
       PHASE_MARK(2);
       TEAMS_DO(tm) {
@@ -412,7 +405,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
         PHASE_MARK(4);
       }
       cp_async_wait_all();
-      LOOP_SYNC;
+      w.cta_sync();
       PHASE_MARK(5);
     }
     TEAMS_DO(tm) {  // sum_t log det chol(Quu_t)  (t = 0 flushed the running products)
@@ -623,7 +616,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
         PHASE_MARK(8);
       }
       cp_async_wait_all();
-      LOOP_SYNC;  // the shared inputs of step t are in place
+      w.cta_sync();  // the shared inputs of step t are in place
       PHASE_MARK(9);
       // ---- second half of step t --------------------------------------------------------------------------------
       TEAMS_DO(tm) {
@@ -705,7 +698,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
         cp_async_commit();
         PHASE_MARK(11);
       }
-      LOOP_SYNC;  // everyone is done with the shared inputs of step t: fetch those of step t+1 behind F1 / F2 / cost
+      w.cta_sync();  // everyone is done with the shared inputs of step t: fetch those of step t+1 behind F1 / F2 / cost
       if (t + 1 < T) stage_fwd(t + 1);
       cp_async_commit();
       PHASE_MARK(13);

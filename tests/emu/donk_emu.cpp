@@ -59,15 +59,8 @@ static int emu_ilqr_step(IlqrArgs<R> a) {
   }
   IlqrPlan pl;
   int rc;
-  if (env_int("DONK_ILQR_TEAM_MODE")) {  // team launch: one slot per team, "cta" index = problem index
-    rc = ilqr_plan_team(a.B, a.E, a.dX, a.dU, sizeof(R), kSmemCap, 0, 0, pl);
-    if (rc != DONK_OK) return rc;
-    pl.smem = IlqrLayout(a.dX, a.dU).bytes(1, 1, sizeof(R));
-    pl.grid = a.B * a.E;
-  } else {
-    rc = ilqr_plan(a.B, a.E, a.dX, a.dU, sizeof(R), kSmemCap, env_int("DONK_ILQR_SLOTS"), 0, pl);
-    if (rc != DONK_OK) return rc;
-  }
+  rc = ilqr_plan(a.B, a.E, a.dX, a.dU, sizeof(R), kSmemCap, env_int("DONK_ILQR_SLOTS"), 0, pl);
+  if (rc != DONK_OK) return rc;
   a.S = pl.S;
   a.ES = pl.ES;
   std::vector<R> smem(pl.smem / sizeof(R) + 4);
