@@ -226,3 +226,26 @@ def test_fit_lr_warp_kernel_with_prior(backend, monkeypatch, dims, N, K, generic
     for b, c in enumerate(conds):
         Fo, fo, co = oracle.fit_lr(c.X, c.U, lambda xux: gmm_eval_prior(prm, n_pool, xux), 1e-6, 2.0)
         assert relerr(F[b], Fo) < 1e-8 and relerr(f[b], fo) < 1e-8 and relerr(covar[b], co) < 1e-8
+
+
+@pytest.mark.parametrize("dims,N,T", [((6, 2), 2, 1), ((6, 2), 3, 2), ((5, 3), 2, 1), ((14, 7), 64, 1)])
+def test_fit_lr_edge_shapes(backend, dims, N, T):
+    """Smallest legal sample count (N=2: rank-1 covariance, the eigenvalue lift carries the fit), a single time step,
+    the largest N of the prior fast path; warp kernel dimensions and a generic one."""
+    from donk_b200 import batched, synthetic
+    from donk_b200.batched import DeviceGMM
+    from oracle.gmm import gmm_eval_prior
+
+    dX, dU = dims
+    c = synthetic.condition(41, 0, T, dX, dU, N)
+    F, f, covar, info = batched.fit_lr(c.X[None], c.U[None])
+    Fo, fo, co = oracle.fit_lr(c.X, c.U)
+    assert int(info.sum()) == 0
+    assert relerr(F[0], Fo) < 1e-8 and relerr(f[0], fo) < 1e-8 and relerr(covar[0], co) < 1e-8
+    prm = _synthetic_prior(dX, dU, 1, seed=2)  # a single-cluster "mixture"
+    gm = DeviceGMM(1)
+    gm.set_params(prm.weights, prm.means, covariances=prm.covariances, precisions_cholesky=prm.precisions_cholesky)
+    gm.N = 77
+    F, f, covar, info = batched.fit_lr(c.X[None], c.U[None], gm)
+    Fo, fo, co = oracle.fit_lr(c.X, c.U, lambda xux: gmm_eval_prior(prm, 77, xux))
+    assert relerr(F[0], Fo) < 1e-8 and relerr(f[0], fo) < 1e-8 and relerr(covar[0], co) < 1e-8

@@ -227,3 +227,31 @@ def test_step_f32_tolerance(backend, dims):
             assert relerr(r.K[b, e].double(), ref.K) < 2e-3
             assert abs(float(r.kl_div[b, e]) - ref.kl_div) < 5e-3 * max(1.0, abs(ref.kl_div))
             assert abs(float(r.expected_costs[b, e]) - ref.expected_costs) < 5e-3 * abs(ref.expected_costs)
+
+
+@pytest.mark.parametrize("B,E,T", [(1, 1, 1), (3, 17, 2), (5, 3, 4), (2, 9, 3)])
+def test_warp_kernel_edge_shapes(backend, B, E, T):
+    """Ragged launches of the everything-enabled (FULL) warp kernel at (6,2): one problem with a single time step,
+    E that is not a multiple of the eta candidates per CTA (17 = 8 + 8 + 1), fewer candidates than a CTA holds."""
+    from donk_b200 import synthetic
+    from donk_b200.batched import BatchedILQR
+
+    dX, dU, N = 6, 2, 12
+    conds = [synthetic.condition(17, i, T, dX, dU, N) for i in range(B)]
+    fits = [oracle.fit_lr(c.X, c.U) for c in conds]
+    x0 = [oracle.state_fit(c.X[:, 0]) for c in conds]
+    st = lambda xs: np.stack(xs)  # noqa: E731
+    il = BatchedILQR(st([f[0] for f in fits]), st([f[1] for f in fits]), st([f[2] for f in fits]),
+                     st([c.prev_K for c in conds]), st([c.prev_k for c in conds]), st([c.C for c in conds]),
+                     st([c.c for c in conds]), st([c.cc for c in conds]), st([m for m, _ in x0]),
+                     st([S for _, S in x0]), prev_covar=st([c.prev_covar for c in conds]))
+    etas = np.logspace(-2, 3, E)
+    r = il.step(torch.as_tensor(etas).expand(B, E))
+    assert int(r.info.sum()) == 0
+    for b, c in enumerate(conds):
+        prob = ILQRProblem(*fits[b], c.C, c.c, c.cc, c.prev_K, c.prev_k, c.prev_covar, np.linalg.inv(c.prev_covar), *x0[b])
+        for e in range(E):
+            ref = oracle.ilqr_step(prob, float(etas[e]))
+            assert relerr(r.K[b, e], ref.K) < TOL and relerr(r.covar[b, e], ref.covar) < TOL
+            assert abs(float(r.kl_div[b, e]) - ref.kl_div) < 1e-9 * max(1.0, abs(ref.kl_div))
+            assert abs(float(r.expected_costs[b, e]) - ref.expected_costs) < 1e-9 * abs(ref.expected_costs)
