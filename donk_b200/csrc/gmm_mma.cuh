@@ -89,7 +89,7 @@ DONK_D void gmm_e_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, int ncta,
 #pragma unroll
               for (int ra = 0; ra < RA; ++ra) {
                 double d0 = (double)c[ra][jb][0], d1 = (double)c[ra][jb][1];
-                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                              : "+d"(d0), "+d"(d1)
                              : "d"((double)af[ra]), "d"((double)bf));
                 c[ra][jb][0] = (R)d0;
@@ -210,6 +210,13 @@ DONK_D void gmm_m_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, R* sm) {
 #pragma unroll
     for (int c = 0; c < KC; ++c) { acc[i][c][0] = R(0); acc[i][c][1] = R(0); }
   }
+  R xbA[NBW], xbB[NBW];  // x_bar of the lane's fragment columns
+  int offA[NBW], offB[NBW];
+#pragma unroll
+  for (int i = 0; i < NBW; ++i) {
+    offA[i] = 8 * ib[i] + g; offB[i] = 8 * jb[i] + g;
+    xbA[i] = xbar[offA[i]]; xbB[i] = xbar[offB[i]];
+  }
   R side[KC];  // thread tid < d: sum_n r_nc (x - x_bar)[tid]; thread tid == d: sum_n r_nc
 #pragma unroll
   for (int c = 0; c < KC; ++c) side[c] = R(0);
@@ -220,10 +227,19 @@ DONK_D void gmm_m_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, R* sm) {
   auto stage = [&](size_t n0, int buf) {
     R* xs = Xs + (size_t)buf * TS * ld;
     R* rk = rr + (size_t)buf * TS * KC;
-    CTA_FOR(idx, TS * d) {
-      const int r = idx / d, j = idx % d;
-      if (n0 + r < row1) cp_async(xs + r * ld + j, a.X + (n0 + r) * d + j);
-      else xs[r * ld + j] = R(0);
+    if (d % 2 == 0 && (reinterpret_cast<size_t>(a.X) & 15) == 0) {  // rows are 16-byte aligned: copy pairs
+      const int hd = d / 2;
+      CTA_FOR(idx, TS * hd) {
+        const int r = idx / hd, j = 2 * (idx % hd);
+        if (n0 + r < row1) cp_async_pair(xs + r * ld + j, a.X + (n0 + r) * d + j);
+        else { xs[r * ld + j] = R(0); xs[r * ld + j + 1] = R(0); }
+      }
+    } else {
+      CTA_FOR(idx, TS * d) {
+        const int r = idx / d, j = idx % d;
+        if (n0 + r < row1) cp_async(xs + r * ld + j, a.X + (n0 + r) * d + j);
+        else xs[r * ld + j] = R(0);
+      }
     }
     CTA_FOR(idx, TS * KC) {
       const int r = idx / KC, c = idx % KC;
@@ -241,43 +257,45 @@ DONK_D void gmm_m_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, R* sm) {
     if (n0 + TS < row1) stage(n0 + TS, buf ^ 1);  // next tile lands while this one is multiplied
     R* xs = Xs + (size_t)buf * TS * ld;
     const R* rk = rr + (size_t)buf * TS * KC;
-    // centre the freshly landed tile on x_bar (in place; rows beyond the range stay zero)
-    CTA_FOR(idx, TS * d) {
-      const int r = idx / d, j = idx % d;
-      if (n0 + r < row1) xs[r * ld + j] -= xbar[j];
-    }
-    w.cta_sync();
 #if !defined(DONK_EMU)
+    // the tile is centred on x_bar in registers (rows beyond the range carry r = 0 and contribute nothing)
+#pragma unroll 2
     for (int k4 = 0; k4 < TS / 4; ++k4) {
-      const int n = 4 * k4 + tq;
-      R rv[KC];
+      const R* xrow = xs + (4 * k4 + tq) * ld;
+      // all fragment loads of the k-step first (unconditional, fixed offsets), then the products: the loads of
+      // one step overlap the products of the previous one instead of stalling each product on its own operand
+      R rv[KC], av[NBW], bv[NBW];
 #pragma unroll
-      for (int c = 0; c < KC; ++c) rv[c] = rk[n * KC + c];
-      R av = R(0), bv;
+      for (int c = 0; c < KC; ++c) rv[c] = rk[(4 * k4 + tq) * KC + c];
+#pragma unroll
+      for (int i = 0; i < NBW; ++i) { av[i] = xrow[offA[i]] - xbA[i]; bv[i] = xrow[offB[i]] - xbB[i]; }
 #pragma unroll
       for (int i = 0; i < NBW; ++i) {
         if (!ok[i]) continue;
-        if (i == 0 || ib[i] != ib[i - 1]) av = xs[n * ld + 8 * ib[i] + g];
-        bv = xs[n * ld + 8 * jb[i] + g];
 #pragma unroll
         for (int c = 0; c < KC; ++c) {
           double d0 = (double)acc[i][c][0], d1 = (double)acc[i][c][1];
-          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+          asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                        : "+d"(d0), "+d"(d1)
-                       : "d"((double)(av * rv[c])), "d"((double)bv));
+                       : "d"((double)(av[i] * rv[c])), "d"((double)bv[i]));
           acc[i][c][0] = (R)d0;
           acc[i][c][1] = (R)d1;
         }
       }
     }
     if (w.tid <= d) {
+      const R xb = w.tid < d ? xbar[w.tid] : R(0);
       for (int r = 0; r < TS; ++r) {
-        const R xv = w.tid < d ? xs[r * ld + w.tid] : R(1);
+        const R xv = w.tid < d ? xs[r * ld + w.tid] - xb : R(1);
 #pragma unroll
         for (int c = 0; c < KC; ++c) side[c] = fma(rk[r * KC + c], xv, side[c]);
       }
     }
 #else
+    CTA_FOR(idx, TS * d) {  // centre the tile on x_bar (in place; rows beyond the range stay zero)
+      const int r = idx / d, j = idx % d;
+      if (n0 + r < row1) xs[r * ld + j] -= xbar[j];
+    }
     for (int c = 0; c < KC; ++c)
       for (int r = 0; r < TS; ++r) {
         const R rv = rk[r * KC + c];
@@ -289,8 +307,8 @@ DONK_D void gmm_m_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, R* sm) {
         }
       }
 #endif
-    buf ^= 1;
-    w.cta_sync();
+    buf ^= 1;  // no barrier here: the one at the top of the next iteration orders this tile's reads before the
+               // copies that overwrite its buffer (they are issued after that barrier)
   }
   cp_async_wait_all();
 
