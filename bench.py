@@ -204,6 +204,8 @@ def run_ours(args):
         dev = torch.device("cuda", local)
         if world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            # NCCL's own log lines (version banner, NCCL_DEBUG output) go to stderr: stdout carries the one JSON line
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
             dist.init_process_group("nccl", device_id=dev)
     nat = _lib.native()
     w = WORKLOAD

@@ -12,6 +12,7 @@
 // GPU; it is never loaded by the product path (donk_b200/_lib.py loads the CUDA
 // library only and raises if it is missing).
 #pragma once
+#include <cstring>
 #include <math.h>
 #include <stdint.h>
 
@@ -535,6 +536,57 @@ template <int N>
 DONK_D void cp_async_wait_group() {
 #if defined(__CUDA_ARCH__)
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
+// ---- bulk asynchronous copies (the TMA engine's 1-D form, UBLKCP) with an mbarrier as completion object -------------
+// One instruction moves a whole contiguous row (global -> shared, both 16-byte aligned, size a multiple of 16) and
+// reports its bytes to the mbarrier; the consumers wait on the barrier's phase.  Under emulation: a plain copy.
+DONK_D void mbar_init(unsigned long long* bar, int arrivals) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(arrivals) : "memory");
+#else
+  (void)bar; (void)arrivals;
+#endif
+}
+// the single expected arrival of a phase, announcing how many bytes the bulk copies of the phase will deliver
+DONK_D void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+#else
+  (void)bar; (void)bytes;
+#endif
+}
+DONK_D void bulk_copy_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(dst)),
+               "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+#else
+  (void)bar;
+  memcpy(dst, src, bytes);
+#endif
+}
+// wait for the phase with the given parity; a protocol error (byte count mismatch) traps instead of hanging the GPU
+DONK_D void mbar_wait(unsigned long long* bar, unsigned parity) {
+#if defined(__CUDA_ARCH__)
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  for (unsigned spin = 0;; ++spin) {
+    unsigned ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    if (ok) return;
+    if (spin > (1u << 24)) __trap();
+  }
+#else
+  (void)bar; (void)parity;
+#endif
+}
+// orders earlier generic-proxy writes to shared memory (zero fill) before later async-proxy writes (bulk copies)
+DONK_D void fence_proxy_async() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #endif
 }
 

@@ -156,7 +156,7 @@ enum { GMM_MTS = 64 };  // rows per staged tile of the M pass
 
 DONK_HD size_t gmm_m_mma_smem(int d, int KC) {
   const int D8 = round_up(d, 8), ld = ld_pad(D8);
-  return (size_t)2 * GMM_MTS * ld + (size_t)2 * GMM_MTS * KC + D8 + 8;
+  return (size_t)2 * GMM_MTS * ld + (size_t)2 * GMM_MTS * KC + D8 + 8 + 2;  // + two mbarriers
 }
 
 // block q of the row-major enumeration of the upper triangle of an nb x nb block grid
@@ -176,6 +176,9 @@ DONK_D void gmm_m_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, R* sm) {
   R* Xs = sm;                                   // [2][TS][ld]  rows minus x_bar (double buffered)
   R* rr = Xs + (size_t)2 * TS * ld;             // [2][TS][KC]  responsibilities of the KC clusters
   R* xbar = rr + (size_t)2 * TS * KC;           // [D8]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(xbar + D8 + 8);  // completion of the row copies
+  // rows are 16-byte aligned multiples of 16 bytes: each row of a tile is ONE bulk copy (TMA engine, 1-D form)
+  const bool bulk = sizeof(R) == 8 && d % 2 == 0 && (reinterpret_cast<size_t>(a.X) & 15) == 0;
   const size_t rows_per = ((size_t)a.n + a.nch - 1) / a.nch;
   const size_t row0 = (size_t)ch * rows_per;
   const size_t row1 = row0 + rows_per < (size_t)a.n ? row0 + rows_per : (size_t)a.n;
@@ -188,7 +191,9 @@ DONK_D void gmm_m_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, R* sm) {
     xbar[j] = acc;
   }
   CTA_FOR(idx, 2 * TS * ld) Xs[idx] = R(0);
+  CTA_FOR(i, 2) mbar_init(bars + i, 1);
   w.cta_sync();
+  fence_proxy_async();  // the zero fill above (generic proxy) precedes the bulk copies (async proxy) into the same rows
   if (cta == 0 && a.shift_out) {
     CTA_FOR(idx, K * d) a.shift_out[idx] = xbar[idx % d];
   }
@@ -227,12 +232,16 @@ DONK_D void gmm_m_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, R* sm) {
   auto stage = [&](size_t n0, int buf) {
     R* xs = Xs + (size_t)buf * TS * ld;
     R* rk = rr + (size_t)buf * TS * KC;
-    if (d % 2 == 0 && (reinterpret_cast<size_t>(a.X) & 15) == 0) {  // rows are 16-byte aligned: copy pairs
-      const int hd = d / 2;
-      CTA_FOR(idx, TS * hd) {
-        const int r = idx / hd, j = 2 * (idx % hd);
-        if (n0 + r < row1) cp_async_pair(xs + r * ld + j, a.X + (n0 + r) * d + j);
-        else { xs[r * ld + j] = R(0); xs[r * ld + j + 1] = R(0); }
+    if (bulk) {
+      const size_t left = row1 - n0;
+      const int valid = left < (size_t)TS ? (int)left : TS;
+      CTA_FOR(one, 1) mbar_arrive_expect_tx(bars + buf, (unsigned)((size_t)valid * d * sizeof(R)));
+      CTA_FOR(r, TS) {
+        if (r < valid) {
+          bulk_copy_g2s(xs + r * ld, a.X + (n0 + r) * d, (unsigned)(d * sizeof(R)), bars + buf);
+        } else {
+          for (int j = 0; j < d; ++j) xs[r * ld + j] = R(0);
+        }
       }
     } else {
       CTA_FOR(idx, TS * d) {
@@ -250,9 +259,11 @@ DONK_D void gmm_m_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, R* sm) {
   };
 
   int buf = 0;
+  unsigned tile = 0;
   if (row0 < row1) stage(row0, 0);
-  for (size_t n0 = row0; n0 < row1; n0 += TS) {
+  for (size_t n0 = row0; n0 < row1; n0 += TS, ++tile) {
     cp_async_wait_all();
+    if (bulk) mbar_wait(bars + buf, (tile >> 1) & 1);  // the rows of this tile have landed
     w.cta_sync();
     if (n0 + TS < row1) stage(n0 + TS, buf ^ 1);  // next tile lands while this one is multiplied
     R* xs = Xs + (size_t)buf * TS * ld;
