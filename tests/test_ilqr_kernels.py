@@ -255,3 +255,32 @@ def test_warp_kernel_edge_shapes(backend, B, E, T):
             assert relerr(r.K[b, e], ref.K) < TOL and relerr(r.covar[b, e], ref.covar) < TOL
             assert abs(float(r.kl_div[b, e]) - ref.kl_div) < 1e-9 * max(1.0, abs(ref.kl_div))
             assert abs(float(r.expected_costs[b, e]) - ref.expected_costs) < 1e-9 * abs(ref.expected_costs)
+
+
+def test_warp_kernel_reports_quu_not_positive_definite(backend):
+    """lqg.py:165: scipy's solve(assume_a="pos") raises LinAlgError; the kernel flags the problem in ``info`` with
+    1 + t of the first failing step (the backward pass starts at t = T-1) and the healthy problems stay correct."""
+    from donk_b200 import synthetic
+    from donk_b200.batched import BatchedILQR
+
+    dX, dU, T, N = 6, 2, 5, 12
+    conds = [synthetic.condition(19, i, T, dX, dU, N) for i in range(3)]
+    fits = [oracle.fit_lr(c.X, c.U) for c in conds]
+    x0 = [oracle.state_fit(c.X[:, 0]) for c in conds]
+    st = lambda xs: np.stack(xs)  # noqa: E731
+    C = st([c.C for c in conds])
+    C[1] = -C[1]  # negative-definite costs for condition 1: Quu = C_uu / eta + C_kl,uu + ... fails for small eta
+    il = BatchedILQR(st([f[0] for f in fits]), st([f[1] for f in fits]), st([f[2] for f in fits]),
+                     st([c.prev_K for c in conds]), st([c.prev_k for c in conds]), C,
+                     st([c.c for c in conds]), st([c.cc for c in conds]), st([m for m, _ in x0]),
+                     st([S for _, S in x0]), prev_covar=st([c.prev_covar for c in conds]))
+    etas = np.array([1e-3, 1.0])
+    r = il.step(torch.as_tensor(etas).expand(3, 2))
+    info = r.info.cpu().numpy()
+    assert info[0].tolist() == [0, 0] and info[2].tolist() == [0, 0]
+    assert info[1, 0] == T  # eta = 1e-3: -C_uu / eta dominates at the very first step (t = T-1)
+    for b in (0, 2):
+        c = conds[b]
+        prob = ILQRProblem(*fits[b], c.C, c.c, c.cc, c.prev_K, c.prev_k, c.prev_covar, np.linalg.inv(c.prev_covar), *x0[b])
+        ref = oracle.ilqr_step(prob, 1.0)
+        assert relerr(r.K[b, 1], ref.K) < TOL and abs(float(r.kl_div[b, 1]) - ref.kl_div) < 1e-9 * max(1.0, abs(ref.kl_div))
