@@ -220,7 +220,10 @@ DONK_D void frag_pre(const WCtx& w, FragVals<R, RA, RB, NP>& fv, Pre&& pre) {
 #endif
 }
 
-template <typename R, int RA, int RB, int NP, class Epi>
+// AT / BT: the operand is stored the other way round (A[i*lda + k] / Bm[j*ldb + k]).  Both orientations are
+// conflict-free for the fragment loads at leading dimensions with ld % 16 in {4, 12}, so a matrix that one product
+// produces row by row can feed the next product in either role without a transposed copy.
+template <typename R, int RA, int RB, int NP, bool AT = false, bool BT = false, class Epi>
 DONK_D void warp_mma_ep(const WCtx& w, const R* __restrict__ A, int lda, const R* __restrict__ Bm, int ldb, int K4,
                         const FragVals<R, RA, RB, NP>& fv, Epi&& epi) {
 #if defined(__CUDA_ARCH__)
@@ -231,15 +234,16 @@ DONK_D void warp_mma_ep(const WCtx& w, const R* __restrict__ A, int lda, const R
 #pragma unroll
     for (int rb = 0; rb < RB; ++rb) { c[ra][rb][0] = R(0); c[ra][rb][1] = R(0); }
   if (sizeof(R) == 8) {
-    const R* ap = A + tq * lda + g;
-    const R* bp = Bm + tq * ldb + g;
+    const R* ap = AT ? A + g * lda + tq : A + tq * lda + g;
+    const R* bp = BT ? Bm + g * ldb + tq : Bm + tq * ldb + g;
+    const int sa = AT ? 8 * lda : 8, sb = BT ? 8 * ldb : 8;  // step to the next 8-row / 8-column fragment
 #pragma unroll 8
     for (int k4 = 0; k4 < K4; ++k4) {
       R af[RA], bf[RB];
 #pragma unroll
-      for (int ra = 0; ra < RA; ++ra) af[ra] = ap[8 * ra];
+      for (int ra = 0; ra < RA; ++ra) af[ra] = ap[sa * ra];
 #pragma unroll
-      for (int rb = 0; rb < RB; ++rb) bf[rb] = bp[8 * rb];
+      for (int rb = 0; rb < RB; ++rb) bf[rb] = bp[sb * rb];
 #pragma unroll
       for (int ra = 0; ra < RA; ++ra)
 #pragma unroll
@@ -251,18 +255,19 @@ DONK_D void warp_mma_ep(const WCtx& w, const R* __restrict__ A, int lda, const R
           c[ra][rb][0] = (R)d0;
           c[ra][rb][1] = (R)d1;
         }
-      ap += 4 * lda;
-      bp += 4 * ldb;
+      ap += AT ? 4 : 4 * lda;
+      bp += BT ? 4 : 4 * ldb;
     }
   } else {
     for (int k = 0; k < 4 * K4; ++k) {
 #pragma unroll
       for (int ra = 0; ra < RA; ++ra) {
-        const R av = A[k * lda + 8 * ra + g];
+        const R av = AT ? A[(8 * ra + g) * lda + k] : A[k * lda + 8 * ra + g];
 #pragma unroll
         for (int rb = 0; rb < RB; ++rb) {
-          c[ra][rb][0] = fma(av, Bm[k * ldb + 8 * rb + 2 * tq], c[ra][rb][0]);
-          c[ra][rb][1] = fma(av, Bm[k * ldb + 8 * rb + 2 * tq + 1], c[ra][rb][1]);
+          const int j0 = 8 * rb + 2 * tq;
+          c[ra][rb][0] = fma(av, BT ? Bm[j0 * ldb + k] : Bm[k * ldb + j0], c[ra][rb][0]);
+          c[ra][rb][1] = fma(av, BT ? Bm[(j0 + 1) * ldb + k] : Bm[k * ldb + j0 + 1], c[ra][rb][1]);
         }
       }
     }
@@ -278,26 +283,27 @@ DONK_D void warp_mma_ep(const WCtx& w, const R* __restrict__ A, int lda, const R
     for (int j = 0; j < 8 * RB; j += 2) {
       R v0 = R(0), v1 = R(0);
       for (int k = 0; k < 4 * K4; ++k) {
-        v0 = fma(A[k * lda + i], Bm[k * ldb + j], v0);
-        v1 = fma(A[k * lda + i], Bm[k * ldb + j + 1], v1);
+        const R av = AT ? A[i * lda + k] : A[k * lda + i];
+        v0 = fma(av, BT ? Bm[j * ldb + k] : Bm[k * ldb + j], v0);
+        v1 = fma(av, BT ? Bm[(j + 1) * ldb + k] : Bm[k * ldb + j + 1], v1);
       }
       epi(i, j, v0, v1, fv.v[i][j / 2]);
     }
 #endif
 }
 
-template <typename R, int RA, int RB, int NP, class Pre, class Epi>
+template <typename R, int RA, int RB, int NP, bool AT = false, bool BT = false, class Pre, class Epi>
 DONK_D void warp_mma_pre(const WCtx& w, const R* __restrict__ A, int lda, const R* __restrict__ Bm, int ldb, int K4,
                          Pre&& pre, Epi&& epi) {
   FragVals<R, RA, RB, NP> fv;
   frag_pre<R, RA, RB, NP>(w, fv, pre);
-  warp_mma_ep<R, RA, RB, NP>(w, A, lda, Bm, ldb, K4, fv, epi);
+  warp_mma_ep<R, RA, RB, NP, AT, BT>(w, A, lda, Bm, ldb, K4, fv, epi);
 }
 
 // Block-upper-triangular variant: only the fragments with rb >= ra are computed (symmetric results: Q, V, Sigma).
 // One call instead of one call per block row: the A and B fragments of a k-step are loaded once for all of its
 // fragments (RA + RB loads instead of sum_r (1 + RB - r)), all accumulators are independent, one prologue / epilogue.
-template <typename R, int RA, int RB, int NP, class Pre, class Epi>
+template <typename R, int RA, int RB, int NP, bool AT = false, bool BT = false, class Pre, class Epi>
 DONK_D void warp_mma_tri(const WCtx& w, const R* __restrict__ A, int lda, const R* __restrict__ Bm, int ldb, int K4,
                          Pre&& pre, Epi&& epi) {
 #if defined(__CUDA_ARCH__)
@@ -314,15 +320,16 @@ DONK_D void warp_mma_tri(const WCtx& w, const R* __restrict__ A, int lda, const 
         pre(8 * ra + g, 8 * rb + 2 * tq, pv[ra][rb]);
       }
   if (sizeof(R) == 8) {
-    const R* ap = A + tq * lda + g;
-    const R* bp = Bm + tq * ldb + g;
+    const R* ap = AT ? A + g * lda + tq : A + tq * lda + g;
+    const R* bp = BT ? Bm + g * ldb + tq : Bm + tq * ldb + g;
+    const int sa = AT ? 8 * lda : 8, sb = BT ? 8 * ldb : 8;
 #pragma unroll 8
     for (int k4 = 0; k4 < K4; ++k4) {
       R af[RA], bf[RB];
 #pragma unroll
-      for (int ra = 0; ra < RA; ++ra) af[ra] = ap[8 * ra];
+      for (int ra = 0; ra < RA; ++ra) af[ra] = ap[sa * ra];
 #pragma unroll
-      for (int rb = 0; rb < RB; ++rb) bf[rb] = bp[8 * rb];
+      for (int rb = 0; rb < RB; ++rb) bf[rb] = bp[sb * rb];
 #pragma unroll
       for (int ra = 0; ra < RA; ++ra)
 #pragma unroll
@@ -335,19 +342,20 @@ DONK_D void warp_mma_tri(const WCtx& w, const R* __restrict__ A, int lda, const 
             c[ra][rb][0] = (R)d0;
             c[ra][rb][1] = (R)d1;
           }
-      ap += 4 * lda;
-      bp += 4 * ldb;
+      ap += AT ? 4 : 4 * lda;
+      bp += BT ? 4 : 4 * ldb;
     }
   } else {
     for (int k = 0; k < 4 * K4; ++k) {
 #pragma unroll
       for (int ra = 0; ra < RA; ++ra) {
-        const R av = A[k * lda + 8 * ra + g];
+        const R av = AT ? A[(8 * ra + g) * lda + k] : A[k * lda + 8 * ra + g];
 #pragma unroll
         for (int rb = 0; rb < RB; ++rb)
           if (rb >= ra) {
-            c[ra][rb][0] = fma(av, Bm[k * ldb + 8 * rb + 2 * tq], c[ra][rb][0]);
-            c[ra][rb][1] = fma(av, Bm[k * ldb + 8 * rb + 2 * tq + 1], c[ra][rb][1]);
+            const int j0 = 8 * rb + 2 * tq;
+            c[ra][rb][0] = fma(av, BT ? Bm[j0 * ldb + k] : Bm[k * ldb + j0], c[ra][rb][0]);
+            c[ra][rb][1] = fma(av, BT ? Bm[(j0 + 1) * ldb + k] : Bm[k * ldb + j0 + 1], c[ra][rb][1]);
           }
       }
     }
@@ -367,18 +375,19 @@ DONK_D void warp_mma_tri(const WCtx& w, const R* __restrict__ A, int lda, const 
       pre(i, j, pv);
       R v0 = R(0), v1 = R(0);
       for (int k = 0; k < 4 * K4; ++k) {
-        v0 = fma(A[k * lda + i], Bm[k * ldb + j], v0);
-        v1 = fma(A[k * lda + i], Bm[k * ldb + j + 1], v1);
+        const R av = AT ? A[i * lda + k] : A[k * lda + i];
+        v0 = fma(av, BT ? Bm[j * ldb + k] : Bm[k * ldb + j], v0);
+        v1 = fma(av, BT ? Bm[(j + 1) * ldb + k] : Bm[k * ldb + j + 1], v1);
       }
       epi(i, j, v0, v1, pv);
     }
 #endif
 }
 
-template <typename R, int RA, int RB, class Epi>
+template <typename R, int RA, int RB, bool AT = false, bool BT = false, class Epi>
 DONK_D void warp_mma(const WCtx& w, const R* __restrict__ A, int lda, const R* __restrict__ Bm, int ldb, int K4,
                      Epi&& epi) {
-  warp_mma_pre<R, RA, RB, 1>(w, A, lda, Bm, ldb, K4, [](int, int, R*) {},
+  warp_mma_pre<R, RA, RB, 1, AT, BT>(w, A, lda, Bm, ldb, K4, [](int, int, R*) {},
                              [&](int i, int j, R v0, R v1, const R*) { epi(i, j, v0, v1); });
 }
 
