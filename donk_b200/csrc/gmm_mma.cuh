@@ -126,6 +126,42 @@ DONK_D void gmm_e_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, int ncta,
       }
     }
     w.cta_sync();
+#if !defined(DONK_EMU)
+    {
+      // responsibilities (softmax over the clusters, sklearn/mixture/_base.py:552-582): two threads per row, each
+      // taking every other cluster (TS = blockDim / 2); exp is evaluated once per entry (resp = e_k / sum e_k);
+      // the tile's sum of log-sum-exp is reduced by warp shuffles instead of one thread walking the rows
+      const int r = w.tid >> 1, h = w.tid & 1;
+      const bool live = n0 + r < (size_t)a.n;
+      R* lp = logp + r * K;
+      R m = -INFINITY;
+      for (int k = h; k < K; k += 2) m = lp[k] > m ? lp[k] : m;
+      const R mo = __shfl_xor_sync(0xffffffffu, m, 1);
+      m = mo > m ? mo : m;
+      R sum = R(0);
+      for (int k = h; k < K; k += 2) {
+        const R e = exp(lp[k] - m);
+        lp[k] = e;
+        sum += e;
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      const R inv = R(1) / sum;
+      if (live)
+        for (int k = h; k < K; k += 2) a.resp[(n0 + r) * K + k] = lp[k] * inv;
+      R lse = (live && h == 0) ? m + log(sum) : R(0);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) lse += __shfl_xor_sync(0xffffffffu, lse, o);
+      if (w.lane == 0) logp[TS * K + w.team] = lse;  // the 8 spare slots behind the tile
+    }
+    w.cta_sync();
+    if (a.lse_part) {
+      CTA_FOR(one, 1) {
+        R acc = R(0);
+        for (int wp = 0; wp < G; ++wp) acc += logp[TS * K + wp];
+        a.lse_part[blk] = acc;
+      }
+    }
+#else
     CTA_FOR(r, TS) {
       if (n0 + r >= (size_t)a.n) { logp[r * K] = R(0); continue; }
       R* lp = logp + r * K;
@@ -145,6 +181,7 @@ DONK_D void gmm_e_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, int ncta,
         a.lse_part[blk] = acc;
       }
     }
+#endif
     w.cta_sync();
   }
 }
