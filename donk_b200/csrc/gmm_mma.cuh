@@ -235,12 +235,16 @@ DONK_D void gmm_m_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, R* sm) {
     CTA_FOR(idx, K * d) a.shift_out[idx] = xbar[idx % d];
   }
 
-  // block range of every warp (contiguous in row-major order: consecutive blocks share their A fragment)
-  const int per = (nblk + G - 1) / G;
+  // block range of every warp (contiguous in row-major order: consecutive blocks share their A fragment).  The
+  // remainder goes to the LAST warps: the first ones also carry the first-moment sums (threads 0..d), and the
+  // barrier of every tile waits for the slowest warp (45 blocks over 8 warps: 5,5,5,6,6,6,6,6 instead of 6 x 7 + 3)
+  const int base = nblk / G, rem = nblk % G;
 
 #if !defined(DONK_EMU)
   const int g = w.lane >> 2, tq = w.lane & 3;
-  const int q0 = w.team * per;
+  const int extra = w.team - (G - rem);
+  const int per = base + (extra >= 0 ? 1 : 0);
+  const int q0 = w.team * base + (extra > 0 ? extra : 0);
   int ib[NBW], jb[NBW];
   bool ok[NBW];
   R acc[NBW][KC][2];
