@@ -306,10 +306,25 @@ __global__ void __launch_bounds__(384) gmm_m_kernel(const GmmArgs<R> a) {
   Ctx ctx{(int)threadIdx.x, (int)blockDim.x};
   gmm_m_cta<R>(ctx, a, (int)blockIdx.x, reinterpret_cast<R*>(smem_raw));
 }
+// The last block sums the per-tile log-sum-exp totals cooperatively (78 k of them at 10 M rows: one thread walking
+// them took 2 ms); every thread adds a strided slice in a fixed order, then a fixed-order tree: deterministic.
 template <typename R>
-__global__ void gmm_reduce_kernel(const GmmArgs<R> a, size_t total, R* stats) {
+__global__ void __launch_bounds__(128) gmm_reduce_kernel(const GmmArgs<R> a, size_t total, R* stats) {
+  if (blockIdx.x + 1 == gridDim.x) {
+    __shared__ R part[128];
+    R acc = R(0);
+    for (int bI = threadIdx.x; bI < a.nblocks; bI += 128) acc += a.lse_part[bI];
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) stats[total - 1] = part[0];
+    return;
+  }
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < total) gmm_reduce_item<R>(a, idx, stats);
+  if (idx + 1 < total) gmm_reduce_item<R>(a, idx, stats);
 }
 template <typename R>
 __global__ void __launch_bounds__(256) gmm_finalize_kernel(const GmmFinArgs<R> a) {
@@ -646,7 +661,7 @@ int donk_gmm_em_step_f64(int n_local, int d, int K, const double* X, const doubl
     a.shift_out = shift;
     rc = gmm_m_mma_dispatch(a, pl, stream);
     if (rc != DONK_OK) return rc;
-    gmm_reduce_kernel<double><<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a, total, stats);
+    gmm_reduce_kernel<double><<<(unsigned)((total - 1 + 127) / 128) + 1, 128, 0, (cudaStream_t)stream>>>(a, total, stats);
     LAUNCHED("gmm_reduce_kernel");
     return DONK_OK;
   }
@@ -658,7 +673,7 @@ int donk_gmm_em_step_f64(int n_local, int d, int K, const double* X, const doubl
   if (rc != DONK_OK) return rc;
   gmm_m_kernel<double><<<K * a.nch, threads, smem, (cudaStream_t)stream>>>(a);
   LAUNCHED("gmm_m_kernel");
-  gmm_reduce_kernel<double><<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a, total, stats);
+  gmm_reduce_kernel<double><<<(unsigned)((total - 1 + 127) / 128) + 1, 128, 0, (cudaStream_t)stream>>>(a, total, stats);
   LAUNCHED("gmm_reduce_kernel");
   return DONK_OK;
 }
