@@ -25,6 +25,30 @@ class LinearDynamics(DynamicsModel, TimeVaryingLinearGaussian):
     def __str__(self) -> str:
         return f"LinearDynamics[T={self.T}, dX={self.dX}, dU={self.dU}]"
 
+    def log_prob(self, X, U):
+        """Log-probabilities of transitions under this model (linear_dynamics.py:54-64): ``X (..., T+1, dX)``,
+        ``U (..., T, dU)`` -> ``(..., T)``.
+
+        Host-side diagnostic (not on the device path).  Restates ``scipy.stats.multivariate_normal.logpdf`` as the
+        reference calls it (``allow_singular=False``): eigendecomposition of every ``covar_t``, eigenvalues below
+        ``1e6 * eps * max|lambda|`` count as zero and make the call fail, as scipy does.
+        """
+        X, U = np.asarray(X, dtype=np.float64), np.asarray(U, dtype=np.float64)
+        means = self.predict(X[..., :-1, :], U, t=None)
+        diff = X[..., 1:, :] - means
+        out = np.empty(diff.shape[:-1])
+        for t in range(self.T):
+            s, u = np.linalg.eigh(self.covar[t])
+            eps = 1e6 * np.finfo(np.float64).eps * np.max(np.abs(s))
+            if np.min(s) < -eps:
+                raise ValueError("The input matrix must be symmetric positive semidefinite.")
+            if np.any(s <= eps):
+                raise np.linalg.LinAlgError("When `allow_singular is False`, the input matrix must be symmetric "
+                                            "positive definite.")
+            maha = np.sum(np.square((diff[..., t, :] @ u) / np.sqrt(s)), axis=-1)
+            out[..., t] = -0.5 * (self.dX * np.log(2 * np.pi) + np.sum(np.log(s)) + maha)
+        return out
+
 
 def fit_lr(X: np.ndarray, U: np.ndarray, prior=None, regularization: float = 1e-6,
            prior_weight: float = 1) -> LinearDynamics:

@@ -211,3 +211,23 @@ def test_device_transition_pool_matches_reference_semantics(backend):
                 assert np.array_equal(to_np(dev.get_transitions(n)), host.get_transitions(n))
     with pytest.raises(AssertionError):
         dev.add(rng.standard_normal((2, T + 1, dX + 1)), rng.standard_normal((2, T, dU)))
+
+
+def test_log_prob_known_answer(backend):
+    """tests/dynamics_test.py:180-204: fit_lr under GMMPrior(8, random_state=0) on the training roll-outs of
+    tests/data/traj_00.npz, LinearDynamics.log_prob of the three held-out roll-outs (the reference's literal values)."""
+    from donk_b200.dynamics import to_transitions
+    from donk_b200.dynamics.linear_dynamics import fit_lr
+    from donk_b200.dynamics.prior import GMMPrior
+
+    g = load_golden("fitlr_traj00")
+    X, U = g["X"], g["U"]
+    N, _, dX = X.shape
+    _, T, dU = U.shape
+    X_train, U_train, X_test, U_test = X[:-3], U[:-3], X[-3:], U[-3:]
+    prior = GMMPrior(8, random_state=0)
+    prior.update(to_transitions(X_train, U_train).reshape(-1, dX + dU + dX))
+    dyn = fit_lr(X_train, U_train, prior, regularization=0)
+    log_prob = dyn.log_prob(X_test, U_test)
+    assert log_prob.shape == (3, T)
+    np.testing.assert_allclose(np.mean(log_prob, axis=-1), [-2139.578291, -2076.051295, -911263.960917])
