@@ -273,7 +273,8 @@ int donk_emu_gmm_em_step_f64(int n_local, int d, int K, const double* X, const d
   double* ws = static_cast<double*>(workspace);
   a.resp = ws; a.lse_part = ws + (size_t)n_local * K; a.part = a.lse_part + a.nblocks;
   const GmmMmaPlan pl = gmm_mma_plan(n_local, d, K);
-  const bool mma = pl.ok && !env_int("DONK_GMM_GENERIC") && weights != nullptr;
+  const bool mma = pl.ok && !env_int("DONK_GMM_GENERIC") && weights != nullptr &&
+                   (n_local >= 65536 || env_int("DONK_GMM_MMA"));  // same rule as the CUDA launcher
   if (resp_in) {
     a.resp = const_cast<double*>(resp_in);
     memset(a.lse_part, 0, (size_t)a.nblocks * sizeof(double));

@@ -91,9 +91,14 @@ def test_fit_lr_batch_and_errors(backend):
     assert np.array_equal(T.cpu().numpy(), oracle.to_transitions(conds[0].X, conds[0].U))
 
 
-def test_gmm_em_iterations_match_sklearn(backend):
+@pytest.mark.parametrize("mma", [0, 1])
+def test_gmm_em_iterations_match_sklearn(backend, monkeypatch, mma):
+    """EM against live scikit-learn output, through the scalar kernels (what pools below 65 536 rows take) and through
+    the DMMA kernels (forced with DONK_GMM_MMA=1)."""
     from donk_b200.batched import DeviceGMM
 
+    if mma:
+        monkeypatch.setenv("DONK_GMM_MMA", "1")
     g = load_golden("gmm_em")
     X = g["X"]
     for it in (1, 3, 5):
@@ -115,9 +120,13 @@ def test_gmm_em_iterations_match_sklearn(backend):
     assert relerr(gm.predict_proba(g["pp_rows"]), g["pp"]) < 1e-9
 
 
-def test_gmm_label_init_and_prior_api(backend):
+@pytest.mark.parametrize("mma", [0, 1])
+def test_gmm_label_init_and_prior_api(backend, monkeypatch, mma):
     """GMMPrior(8, random_state=0).update(...) reproduces the sklearn fit of tests/dynamics_test.py:115-116."""
     from donk_b200.dynamics.linear_dynamics import fit_lr
+
+    if mma:
+        monkeypatch.setenv("DONK_GMM_MMA", "1")
     from donk_b200.dynamics.prior import GMMPrior
 
     g = load_golden("fitlr_traj00")

@@ -18,7 +18,7 @@ from donk_testutil import ROOT, relerr
 def _worker(rank, world, port, out_dir):
     sys.path.insert(0, str(ROOT))
     sys.path.insert(0, str(ROOT / "tests"))
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), DONK_GMM_MMA="1")  # the sharded DMMA path
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from donk_b200 import _lib, synthetic
     from donk_b200.batched import DeviceGMM
@@ -67,7 +67,7 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_em_sharded_rows_match_single_rank(tmp_path, backend):
+def test_em_sharded_rows_match_single_rank(tmp_path, backend, monkeypatch):
     if backend.device_type != "cpu":
         pytest.skip("multi-rank logic is covered on CPU with gloo; the GPU run uses torchrun + NCCL (bench.py)")
     import warnings
@@ -75,6 +75,7 @@ def test_em_sharded_rows_match_single_rank(tmp_path, backend):
     from donk_b200 import synthetic
     from donk_b200.batched import DeviceGMM
 
+    monkeypatch.setenv("DONK_GMM_MMA", "1")  # the sharded DMMA path, here on a small pool
     X, w0, m0, p0 = synthetic.gmm_pool(1200, 8, 3, seed=11)
     ref = DeviceGMM(3, tol=0.0, max_iter=4).set_params(w0, m0, precisions=p0)
     with warnings.catch_warnings():
