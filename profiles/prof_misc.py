@@ -83,3 +83,21 @@ elif what == "config1":
         ms_s, _ = timed(lambda: il.step(eta), 20)
         print(f"config1 B={B}: fit_lr {fit_ms * 1e3:.0f} us, ILQR.step {ms_s * 1e3:.0f} us, ILQR.optimize {ms * 1e3:.0f} us "
               f"({n_steps} steps) = {B / (ms * 1e-3):.0f} optimize/s, status", torch.bincount(status, minlength=4).tolist())
+elif what == "config3prior":
+    # config-3 dimensions with a K-cluster prior (d = 46): what a GPS iteration with GMMPrior costs in fit_lr
+    B, K = int(sys.argv[2]), int(sys.argv[3])
+    T, dX, dU, N = 100, 20, 6, 64
+    ro = synthetic.rollout_batch_torch(B, T, dX, dU, N, seed=7, device=dev)
+    pool = batched.to_transitions(ro["X"][:16].reshape(-1, T + 1, dX), ro["U"][:16].reshape(-1, T, dU))
+    d = 2 * dX + dU
+    rng = np.random.default_rng(0)
+    idx = rng.choice(pool.shape[0], K, replace=False)
+    gm = batched.DeviceGMM(K).set_params(np.full(K, 1 / K), pool[idx].cpu().numpy(), precisions=np.broadcast_to(np.eye(d), (K, d, d)).copy())
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gm.fit(pool)
+    ms, (F, f, S, info) = timed(lambda: batched.fit_lr(ro["X"], ro["U"], gm))
+    print(f"fit_lr + GMM prior (20,6) N=64 K={K}, B={B}: {ms:.1f} ms = {B * T / (ms * 1e-3):.0f} fits/s, info {int(info.sum())}")
+    ms, _ = timed(lambda: batched.fit_lr(ro["X"], ro["U"]))
+    print(f"fit_lr no prior  (20,6) N=64, B={B}: {ms:.1f} ms = {B * T / (ms * 1e-3):.0f} fits/s")
