@@ -1,5 +1,10 @@
-from donk_b200.dynamics.dynamics import DynamicsModel
-from donk_b200.dynamics.linear_dynamics import LinearDynamics
-from donk_b200.dynamics.utils import to_transitions
+"""Dynamics models of the hot path (public names of ``donk.dynamics``): ``fit_lr`` lives in ``.linear_dynamics``."""
+from . import dynamics as _dynamics
+from . import linear_dynamics as _linear
+from . import utils as _utils
 
-__all__ = ["DynamicsModel", "LinearDynamics", "to_transitions"]
+DynamicsModel = _dynamics.DynamicsModel
+LinearDynamics = _linear.LinearDynamics
+to_transitions = _utils.to_transitions
+
+__all__ = ("LinearDynamics", "DynamicsModel", "to_transitions")

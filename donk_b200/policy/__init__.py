@@ -1,3 +1,6 @@
-from donk_b200.policy.lin_gaussian import LinearGaussianPolicy
+"""Policies of the hot path (``donk.policy``): the time-varying linear-Gaussian controller iLQR produces."""
+from . import lin_gaussian as _lg
 
-__all__ = ["LinearGaussianPolicy"]
+LinearGaussianPolicy = _lg.LinearGaussianPolicy
+
+__all__ = ("LinearGaussianPolicy",)

@@ -1,5 +1,11 @@
-from donk_b200.samples.pool import TransitionPool
-from donk_b200.samples.state_dist import StateDistribution
-from donk_b200.samples.traj_dist import TrajectoryDistribution
+"""Sample containers (public names of ``donk.samples`` that the hot path touches); the device-resident pool is
+``donk_b200.batched.DeviceTransitionPool``."""
+from . import pool as _pool
+from . import state_dist as _state
+from . import traj_dist as _traj
 
-__all__ = ["TransitionPool", "StateDistribution", "TrajectoryDistribution"]
+TransitionPool = _pool.TransitionPool
+StateDistribution = _state.StateDistribution
+TrajectoryDistribution = _traj.TrajectoryDistribution
+
+__all__ = ("StateDistribution", "TrajectoryDistribution", "TransitionPool")

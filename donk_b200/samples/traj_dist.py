@@ -1,4 +1,8 @@
-"""Normally distributed trajectory (donk/samples/traj_dist.py:6-49)."""
+"""Gaussian trajectory distribution over ``[x_t | u_t]`` (container semantics of donk/samples/traj_dist.py:6-71).
+
+``mean (..., T+1, dX+dU)`` and ``covar (..., T+1, dX+dU, dX+dU)`` as produced by the forward pass; the state and action
+blocks are exposed as views.  Leading batch dimensions are allowed.
+"""
 from __future__ import annotations
 
 import numpy as np
@@ -6,41 +10,35 @@ import numpy as np
 
 class TrajectoryDistribution:
     def __init__(self, mean, covar, dX: int, dU: int = None) -> None:
-        if dU is None:
-            dU = mean.shape[-1] - dX
-        assert mean.shape[-1:] == (dX + dU,), f"{mean.shape[-1:]} != {(dX + dU,)}"
-        assert covar.shape[-2:] == (dX + dU, dX + dU), f"{covar.shape[-2:]} != {(dX + dU, dX + dU)}"
-        assert mean.shape[:-1] == covar.shape[:-2], f"{mean.shape[:-1]} != {covar.shape[:-2]}"
-        self.mean = mean
-        self.covar = covar
+        p = mean.shape[-1]
         self.dX = dX
-        self.dU = dU
+        self.dU = p - dX if dU is None else dU
+        width = self.dX + self.dU
+        assert mean.shape[-1:] == (width,), f"{mean.shape[-1:]} != {(width,)}"
+        assert covar.shape[-2:] == (width, width), f"{covar.shape[-2:]} != {(width, width)}"
+        assert mean.shape[:-1] == covar.shape[:-2], f"{mean.shape[:-1]} != {covar.shape[:-2]}"
+        self.mean, self.covar = mean, covar
 
-    @property
-    def X_mean(self):
-        return self.mean[..., : self.dX]
+    # ---- views of the state / action blocks (actions exist for t < T only) ---------------------------------------
+    def _states(self) -> slice:
+        return slice(None, self.dX)
 
-    @property
-    def X_covar(self):
-        return self.covar[..., : self.dX, : self.dX]
+    def _actions(self) -> slice:
+        return slice(self.dX, None)
 
-    @property
-    def U_mean(self):
-        return self.mean[..., :-1, self.dX :]
-
-    @property
-    def U_covar(self):
-        return self.covar[..., :-1, self.dX :, self.dX :]
+    X_mean = property(lambda self: self.mean[..., self._states()])
+    X_covar = property(lambda self: self.covar[..., self._states(), self._states()])
+    U_mean = property(lambda self: self.mean[..., :-1, self._actions()])
+    U_covar = property(lambda self: self.covar[..., :-1, self._actions(), self._actions()])
 
     def sample(self, size, rng):
-        """Roll-outs drawn step by step from the per-step Gaussians (traj_dist.py:51-71): ``X size+(T+1,dX)``,
-        ``U size+(T,dU)``; the random stream is consumed in the reference's order."""
-        T = self.mean.shape[-2] - 1
-        n = int(np.prod(size))
-        X = np.empty((n, T + 1, self.dX))
-        U = np.empty((n, T, self.dU))
-        for t in range(T):
-            xu = rng.multivariate_normal(self.mean[t], self.covar[t], size=n)
-            X[:, t], U[:, t] = xu[:, :self.dX], xu[:, self.dX:]
-        X[:, T] = rng.multivariate_normal(self.X_mean[T], self.X_covar[T], size=n)
-        return X.reshape(tuple(size) + (T + 1, self.dX)), U.reshape(tuple(size) + (T, self.dU))
+        """Roll-outs ``X size+(T+1,dX)``, ``U size+(T,dU)`` drawn from the per-step Gaussians.  One joint draw per
+        step t < T and one state draw at T, in that order, so a seeded generator yields the reference's samples."""
+        steps = self.mean.shape[-2] - 1
+        count = int(np.prod(size))
+        joint = np.stack([rng.multivariate_normal(self.mean[t], self.covar[t], size=count) for t in range(steps)], axis=1)
+        last = rng.multivariate_normal(self.X_mean[steps], self.X_covar[steps], size=count)
+        X = np.concatenate([joint[..., : self.dX], last[:, None, :]], axis=1)
+        U = joint[..., self.dX:]
+        shape = tuple(size)
+        return X.reshape(shape + X.shape[1:]), np.ascontiguousarray(U).reshape(shape + U.shape[1:])

@@ -1,4 +1,10 @@
-from donk_b200.traj_opt.lqg import ILQR, ILQRStepResult
-from donk_b200.traj_opt.traj_opt import TrajOptAlgorithm
+"""KL-constrained trajectory optimisation on the device (public names of ``donk.traj_opt``; the module functions
+``backward`` / ``forward`` / ``extended_costs_kl`` / ``kl_divergence_action`` / ``step_adjust`` are in ``.lqg``)."""
+from . import lqg as _lqg
+from . import traj_opt as _algo
 
-__all__ = ["ILQR", "ILQRStepResult", "TrajOptAlgorithm"]
+ILQR = _lqg.ILQR
+ILQRStepResult = _lqg.ILQRStepResult
+TrajOptAlgorithm = _algo.TrajOptAlgorithm
+
+__all__ = ("TrajOptAlgorithm", "ILQR", "ILQRStepResult")

@@ -1,3 +1,8 @@
-from donk_b200.utils.batched import regularize, symmetrize, trace_of_product
+"""Small batched helpers with the in-place semantics the reference's tests pin (public names of ``donk.utils``)."""
+from . import batched as _batched
 
-__all__ = ["symmetrize", "regularize", "trace_of_product"]
+symmetrize = _batched.symmetrize
+regularize = _batched.regularize
+trace_of_product = _batched.trace_of_product
+
+__all__ = ("trace_of_product", "regularize", "symmetrize")
