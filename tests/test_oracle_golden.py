@@ -169,3 +169,39 @@ def test_step_adjust_and_costs(golden):
     assert relerr(ec, m["expected"]) < TOL
     mean, cov = oracle.state_fit(m["X0"])
     assert relerr(mean, m["sd_mean"]) < TOL and relerr(cov, m["sd_covar"]) < TOL
+
+
+def test_brentq_restatement_matches_live_scipy_on_random_functions():
+    """Property test of the oracle's Brent restatement against the installed scipy (the third-party dependency of
+    lqg.py:121): random monotone and non-monotone bracketed functions, random tolerances - identical roots AND
+    identical sequences of evaluated abscissae."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+    from scipy.optimize import brentq as scipy_brentq
+
+    @settings(max_examples=150, deadline=None)
+    @given(a=st.floats(-5, 5), b=st.floats(0.05, 3), c=st.floats(-2, 2), kind=st.integers(0, 3),
+           rtol=st.sampled_from([1e-2, 1e-4, 1e-8, 4 * np.finfo(float).eps]))
+    def check(a, b, c, kind, rtol):
+        fns = [lambda x: b * (x - a), lambda x: np.tanh(b * (x - a)) + 1e-3 * c * (x - a),
+               lambda x: np.expm1(b * (x - a) / 8), lambda x: (x - a) ** 3 + c * 1e-2 * (x - a)]
+        fn = fns[kind]
+        lo, hi = a - 7.3, a + 11.1
+        if not np.sign(fn(lo)) * np.sign(fn(hi)) < 0:
+            return
+        seen = []
+
+        def traced(x):
+            seen.append(x)
+            return fn(x)
+
+        try:
+            want = scipy_brentq(traced, lo, hi, xtol=2e-12, rtol=rtol, maxiter=100)
+        except RuntimeError:  # no convergence in 100 iterations (a triple root): the restatement must say so too
+            with pytest.raises(RuntimeError):
+                oracle.brentq(fn, lo, hi, rtol=rtol)
+            return
+        got, trace = oracle.brentq(fn, lo, hi, rtol=rtol)
+        assert got == want and trace == seen
+
+    check()
