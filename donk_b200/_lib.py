@@ -36,6 +36,7 @@ SIGNATURES = {
     "to_transitions_f64": [c_int] * 4 + [P, P, P, P],
     "state_fit_f64": [c_int] * 3 + [P, c_size_t, c_size_t, P, P, P],
     "gmm_em_step_f64": [c_int] * 3 + [P] * 7 + [P, c_size_t, P],
+    "gmm_em_step_mode_f64": [c_int] * 3 + [P] * 7 + [P, c_size_t, c_int, P],
     "gmm_m_finalize_f64": [c_double, c_int, c_int, P, P, c_double, P, P, P, P, P, P, P],
     "gmm_predict_proba_f64": [c_int] * 3 + [P] * 5 + [P],
     "gmm_prec_chol_from_precisions_f64": [c_int] * 2 + [P] * 3 + [P],

@@ -393,6 +393,7 @@ class DeviceGMM:
 
     def __init__(self, n_clusters: int, tol: float = 1e-3, reg_covar: float = 1e-6, max_iter: int = 100):
         self.K = int(n_clusters)
+        self.kernels = "auto"  # "auto" | "scalar" | "dmma": see fit()
         self.tol, self.reg_covar, self.max_iter = tol, reg_covar, max_iter
         self.d = None
         self.weights = self.means = self.covariances = self.precisions_cholesky = None
@@ -406,10 +407,11 @@ class DeviceGMM:
     def set_params(self, weights, means, precisions=None, covariances=None, precisions_cholesky=None):
         """Explicit start (sklearn ``weights_init / means_init / precisions_init``)."""
         nat = _lib.native()
-        self.weights, self.means = _dev(weights), _dev(means)
+        # own copies: EM updates the parameters in place, the caller's arrays must stay untouched
+        self.weights, self.means = _dev(weights).clone(), _dev(means).clone()
         self.K, self.d = self.means.shape
         if precisions_cholesky is not None:
-            self.precisions_cholesky = _dev(precisions_cholesky)
+            self.precisions_cholesky = _dev(precisions_cholesky).clone()
         elif precisions is not None:
             prec = _dev(precisions)
             self.precisions_cholesky = torch.empty_like(prec)
@@ -417,7 +419,7 @@ class DeviceGMM:
             nat.call("gmm_prec_chol_from_precisions_f64", self.d, self.K, prec, self.precisions_cholesky, info)
             if int(info.sum().item()):
                 raise ValueError("'full precision' should be symmetric, positive-definite")
-        self.covariances = _dev(covariances) if covariances is not None else torch.zeros(
+        self.covariances = _dev(covariances).clone() if covariances is not None else torch.zeros(
             self.K, self.d, self.d, dtype=torch.float64, device=self.means.device)
         return self
 
@@ -473,8 +475,8 @@ class DeviceGMM:
         n, d = X.shape
         if getattr(self, "_shift", None) is None or self._shift.shape != self.means.shape:
             self._shift = torch.empty_like(self.means)
-        nat.call("gmm_em_step_f64", n, d, self.K, X, self.weights, self.means, self.precisions_cholesky, None, stats,
-                 self._shift, ws, ws.numel() * ws.element_size())
+        nat.call("gmm_em_step_mode_f64", n, d, self.K, X, self.weights, self.means, self.precisions_cholesky, None, stats,
+                 self._shift, ws, ws.numel() * ws.element_size(), int(getattr(self, "_mode", 0)))
         self._allreduce(stats, group)  # the one exchange step of the path (NCCL over NVLink)
         nat.call("gmm_m_finalize_f64", float(n_total), d, self.K, stats, self._shift, float(self.reg_covar),
                  self.weights, self.means, self.covariances, self.precisions_cholesky, self._lb, self._info)
@@ -503,6 +505,19 @@ class DeviceGMM:
         stats = torch.empty(nat.size("gmm_stats_size", d, self.K), **o)
         self._lb = torch.zeros(1, **o)
         self._info = torch.zeros(self.K, dtype=torch.int32, device=X.device)
+        # Kernel family: the DMMA pass centres its statistics on the mixture mean; its rounding error grows as
+        # eps (|mu_k - x_bar| / sigma_k)^2.  Where that would exceed ~1e-9 the scalar kernels (centred on every
+        # cluster's own mean) are used whatever the pool size: results first, speed second.
+        self._mode = 0
+        if self.kernels == "auto":
+            var = torch.diagonal(self.covariances, dim1=-2, dim2=-1)
+            if float(var.min()) > 0:  # covariances are known (not the placeholder of an explicit precision start)
+                xbar = (self.weights[:, None] * self.means).sum(0)
+                hard = float((((self.means - xbar) ** 2) / var).max())
+                if hard * np.finfo(np.float64).eps > 1e-9:
+                    self._mode = 1
+        elif self.kernels in ("scalar", "dmma"):
+            self._mode = 1 if self.kernels == "scalar" else 2
         lb = self.lower_bound if warm_start else -np.inf
         self.converged = False
         self.lower_bounds = []

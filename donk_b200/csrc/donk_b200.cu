@@ -627,10 +627,10 @@ int donk_state_fit_f64(int B, int N, int dX, const double* X0, size_t sample_str
 size_t donk_gmm_stats_size(int d, int K) { return gmm_stats_len(d, K); }
 size_t donk_gmm_workspace_bytes(int n_local, int d, int K) { return gmm_ws_reals(n_local, d, K) * sizeof(double); }
 
-int donk_gmm_em_step_f64(int n_local, int d, int K, const double* X, const double* weights, const double* means,
-                         const double* prec_chol, const double* resp_in, double* stats, double* shift,
-                         void* workspace, size_t workspace_bytes, void* stream) {
-  if (n_local < 0 || d < 1 || K < 1) return DONK_BAD_SHAPE;
+int donk_gmm_em_step_mode_f64(int n_local, int d, int K, const double* X, const double* weights, const double* means,
+                              const double* prec_chol, const double* resp_in, double* stats, double* shift,
+                              void* workspace, size_t workspace_bytes, int mode, void* stream) {
+  if (n_local < 0 || d < 1 || K < 1 || mode < 0 || mode > 2) return DONK_BAD_SHAPE;
   if (workspace_bytes < donk_gmm_workspace_bytes(n_local, d, K)) return DONK_BAD_SHAPE;
   const size_t total = gmm_stats_len(d, K);
   if (n_local == 0) {
@@ -652,8 +652,9 @@ int donk_gmm_em_step_f64(int n_local, int d, int K, const double* X, const doubl
   // keeps agreement with scikit-learn at rounding level even when the clusters sit 1e3 widths apart (the reference's
   // own known-answer test on 660 real transitions needs that); the DMMA kernels centre on the mixture mean (shared
   // B fragments), which costs a few digits on such data and nothing measurable on pools with overlapping clusters.
-  const bool mma = pl.ok && !env_int("DONK_GMM_GENERIC") && weights != nullptr &&
-                   (n_local >= 65536 || env_int("DONK_GMM_MMA"));
+  // mode 1 / 2 (or DONK_GMM_GENERIC / DONK_GMM_MMA) override the size rule.
+  const bool want_mma = mode == 2 || (mode == 0 && (n_local >= 65536 || env_int("DONK_GMM_MMA")));
+  const bool mma = pl.ok && !env_int("DONK_GMM_GENERIC") && weights != nullptr && want_mma;
   if (resp_in) {
     a.resp = const_cast<double*>(resp_in);
     CU(cudaMemsetAsync(a.lse_part, 0, (size_t)a.nblocks * sizeof(double), (cudaStream_t)stream));
@@ -681,6 +682,13 @@ int donk_gmm_em_step_f64(int n_local, int d, int K, const double* X, const doubl
   gmm_reduce_kernel<double><<<(unsigned)((total - 1 + 127) / 128) + 1, 128, 0, (cudaStream_t)stream>>>(a, total, stats);
   LAUNCHED("gmm_reduce_kernel");
   return DONK_OK;
+}
+
+int donk_gmm_em_step_f64(int n_local, int d, int K, const double* X, const double* weights, const double* means,
+                         const double* prec_chol, const double* resp_in, double* stats, double* shift,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  return donk_gmm_em_step_mode_f64(n_local, d, K, X, weights, means, prec_chol, resp_in, stats, shift, workspace,
+                                   workspace_bytes, 0, stream);
 }
 
 int donk_gmm_m_finalize_f64(double n_total, int d, int K, const double* stats, const double* shift, double reg_covar,

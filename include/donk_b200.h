@@ -167,6 +167,14 @@ int donk_gmm_em_step_f64(int n_local, int d, int K, const double* X,
                          const double* weights, const double* means, const double* prec_chol,
                          const double* resp_in,
                          double* stats, double* shift, void* workspace, size_t workspace_bytes, void* stream);
+/* Same, with the kernel family chosen by the caller: mode 0 = by pool size (scalar kernels below 65 536 rows), 1 = scalar
+ * kernels (statistics centred on every cluster's own mean: agreement with scikit-learn at rounding level whatever the
+ * spread of the clusters), 2 = DMMA kernels (centred on the mixture mean: fastest; error ~ eps (|mu_k - x_bar| / sigma)^2). */
+int donk_gmm_em_step_mode_f64(int n_local, int d, int K, const double* X,
+                              const double* weights, const double* means, const double* prec_chol,
+                              const double* resp_in,
+                              double* stats, double* shift, void* workspace, size_t workspace_bytes, int mode,
+                              void* stream);
 
 /* M-step finalisation from (all-reduced) statistics of n_total rows: new weights, means,
  * covariances (+ reg_covar I), precision Cholesky factors, mean log-likelihood.

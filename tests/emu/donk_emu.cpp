@@ -258,10 +258,10 @@ static void emu_gmm_e_mma(GmmArgs<double>& a, const GmmMmaPlan& pl) {
 
 extern "C" {
 
-int donk_emu_gmm_em_step_f64(int n_local, int d, int K, const double* X, const double* weights, const double* means,
-                             const double* prec_chol, const double* resp_in, double* stats, double* shift,
-                             void* workspace, size_t workspace_bytes, void*) {
-  if (n_local < 0 || d < 1 || K < 1) return DONK_BAD_SHAPE;
+int donk_emu_gmm_em_step_mode_f64(int n_local, int d, int K, const double* X, const double* weights, const double* means,
+                                  const double* prec_chol, const double* resp_in, double* stats, double* shift,
+                                  void* workspace, size_t workspace_bytes, int mode, void*) {
+  if (n_local < 0 || d < 1 || K < 1 || mode < 0 || mode > 2) return DONK_BAD_SHAPE;
   if (workspace_bytes < donk_emu_gmm_workspace_bytes(n_local, d, K)) return DONK_BAD_SHAPE;
   const size_t total = gmm_stats_len(d, K);
   if (n_local == 0) { memset(stats, 0, total * sizeof(double)); return DONK_OK; }
@@ -273,8 +273,8 @@ int donk_emu_gmm_em_step_f64(int n_local, int d, int K, const double* X, const d
   double* ws = static_cast<double*>(workspace);
   a.resp = ws; a.lse_part = ws + (size_t)n_local * K; a.part = a.lse_part + a.nblocks;
   const GmmMmaPlan pl = gmm_mma_plan(n_local, d, K);
-  const bool mma = pl.ok && !env_int("DONK_GMM_GENERIC") && weights != nullptr &&
-                   (n_local >= 65536 || env_int("DONK_GMM_MMA"));  // same rule as the CUDA launcher
+  const bool want_mma = mode == 2 || (mode == 0 && (n_local >= 65536 || env_int("DONK_GMM_MMA")));
+  const bool mma = pl.ok && !env_int("DONK_GMM_GENERIC") && weights != nullptr && want_mma;  // as the CUDA launcher
   if (resp_in) {
     a.resp = const_cast<double*>(resp_in);
     memset(a.lse_part, 0, (size_t)a.nblocks * sizeof(double));
@@ -313,6 +313,13 @@ int donk_emu_gmm_em_step_f64(int n_local, int d, int K, const double* X, const d
   }
   for (size_t i = 0; i < total; ++i) gmm_reduce_item<double>(a, i, stats);
   return DONK_OK;
+}
+
+int donk_emu_gmm_em_step_f64(int n_local, int d, int K, const double* X, const double* weights, const double* means,
+                             const double* prec_chol, const double* resp_in, double* stats, double* shift,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  return donk_emu_gmm_em_step_mode_f64(n_local, d, K, X, weights, means, prec_chol, resp_in, stats, shift, workspace,
+                                       workspace_bytes, 0, stream);
 }
 
 int donk_emu_gmm_m_finalize_f64(double n_total, int d, int K, const double* stats, const double* shift,

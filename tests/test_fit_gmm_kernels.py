@@ -258,3 +258,24 @@ def test_fit_lr_edge_shapes(backend, dims, N, T):
     F, f, covar, info = batched.fit_lr(c.X[None], c.U[None], gm)
     Fo, fo, co = oracle.fit_lr(c.X, c.U, lambda xux: gmm_eval_prior(prm, 77, xux))
     assert relerr(F[0], Fo) < 1e-8 and relerr(f[0], fo) < 1e-8 and relerr(covar[0], co) < 1e-8
+
+
+def test_em_kernel_family_follows_cluster_separation(backend):
+    """DeviceGMM.fit picks the scalar kernels (statistics centred on every cluster's own mean) when the clusters are so
+    far apart, relative to their widths, that the mixture-mean-centred DMMA pass would lose more than ~1e-9."""
+    from donk_b200.batched import DeviceGMM
+
+    rng = np.random.default_rng(0)
+    d, K, n = 4, 2, 400
+    for sep, want in ((3.0, 0), (1e5, 1)):
+        centers = np.stack([np.zeros(d), np.full(d, sep)])
+        X = centers[rng.integers(0, K, n)] + rng.standard_normal((n, d))
+        gm = DeviceGMM(K, tol=0.0, max_iter=2).set_params(np.full(K, 0.5), centers, covariances=np.stack([np.eye(d)] * K),
+                                                           precisions_cholesky=np.stack([np.eye(d)] * K))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            gm.fit(X)
+        assert gm._mode == want
+        ref = oracle.gmm_fit(X, GMMParams(np.full(K, 0.5), centers, np.stack([np.eye(d)] * K), np.stack([np.eye(d)] * K)),
+                             tol=0.0, max_iter=2)
+        assert relerr(gm.means, ref.means) < 1e-12 and relerr(gm.covariances, ref.covariances) < 1e-10
