@@ -279,3 +279,13 @@ def test_em_kernel_family_follows_cluster_separation(backend):
         ref = oracle.gmm_fit(X, GMMParams(np.full(K, 0.5), centers, np.stack([np.eye(d)] * K), np.stack([np.eye(d)] * K)),
                              tol=0.0, max_iter=2)
         assert relerr(gm.means, ref.means) < 1e-12 and relerr(gm.covariances, ref.covariances) < 1e-10
+        if sep < 10:  # the explicit switches: both kernel families agree with the oracle on benign data
+            for kernels, mode in (("scalar", 1), ("dmma", 2)):
+                g2 = DeviceGMM(K, tol=0.0, max_iter=2).set_params(np.full(K, 0.5), centers,
+                                                                  covariances=np.stack([np.eye(d)] * K),
+                                                                  precisions_cholesky=np.stack([np.eye(d)] * K))
+                g2.kernels = kernels
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    g2.fit(X)
+                assert g2._mode == mode and relerr(g2.covariances, ref.covariances) < 1e-10
