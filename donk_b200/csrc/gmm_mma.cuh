@@ -311,7 +311,7 @@ DONK_D void gmm_m_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, R* sm) {
     const R* rk = rr + (size_t)buf * TS * KC;
 #if !defined(DONK_EMU)
     // the tile is centred on x_bar in registers (rows beyond the range carry r = 0 and contribute nothing)
-#pragma unroll 2
+#pragma unroll 1
     for (int k4 = 0; k4 < TS / 4; ++k4) {
       const R* xrow = xs + (4 * k4 + tq) * ld;
       // all fragment loads of the k-step first (unconditional, fixed offsets), then the products: the loads of
