@@ -69,45 +69,60 @@ DONK_D void gmm_e_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, int ncta,
         const int i0 = 8 * RA * tm;
 #if !defined(DONK_EMU)
         const int g = w.lane >> 2, tq = w.lane & 3;
-        R c[RA][NB][2];
+        // Column blocks in groups of JG: the accumulators of a group (RA x JG fragments) fit the registers of a
+        // two-CTA-per-SM launch without spilling; the A fragments of the rows a group needs are re-read per group.
+        constexpr int JG = 3;
+        R ssr[RA];
 #pragma unroll
-        for (int ra = 0; ra < RA; ++ra)
+        for (int ra = 0; ra < RA; ++ra) ssr[ra] = R(0);
 #pragma unroll
-          for (int jb = 0; jb < NB; ++jb) { c[ra][jb][0] = R(0); c[ra][jb][1] = R(0); }
+        for (int j0 = 0; j0 < NB; j0 += JG) {
+          R c[RA][JG][2];
 #pragma unroll
-        for (int fb = 0; fb < NB; ++fb) {
+          for (int ra = 0; ra < RA; ++ra)
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int f = 8 * fb + 4 * h + tq;  // feature index = k dimension of the product
-            R af[RA];
+            for (int jj = 0; jj < JG; ++jj) { c[ra][jj][0] = R(0); c[ra][jj][1] = R(0); }
 #pragma unroll
-            for (int ra = 0; ra < RA; ++ra) af[ra] = Xt[f * ldt + i0 + 8 * ra + g];
+          for (int fb = 0; fb < NB; ++fb) {
+            if (fb >= j0 + JG) continue;  // P_k is upper triangular: no block of this group lies on or above row fb
 #pragma unroll
-            for (int jb = fb; jb < NB; ++jb) {  // P_k is upper triangular: blocks below the diagonal are zero
-              const int j = 8 * jb + g;
-              const R bf = (f < d && j < d) ? ldg(P + (size_t)f * d + j) : R(0);
+            for (int h = 0; h < 2; ++h) {
+              const int f = 8 * fb + 4 * h + tq;  // feature index = k dimension of the product
+              R af[RA];
 #pragma unroll
-              for (int ra = 0; ra < RA; ++ra) {
-                double d0 = (double)c[ra][jb][0], d1 = (double)c[ra][jb][1];
-                asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                             : "+d"(d0), "+d"(d1)
-                             : "d"((double)af[ra]), "d"((double)bf));
-                c[ra][jb][0] = (R)d0;
-                c[ra][jb][1] = (R)d1;
+              for (int ra = 0; ra < RA; ++ra) af[ra] = Xt[f * ldt + i0 + 8 * ra + g];
+#pragma unroll
+              for (int jj = 0; jj < JG; ++jj) {
+                const int jb = j0 + jj;
+                if (jb >= NB || jb < fb) continue;  // blocks below the diagonal are zero
+                const int j = 8 * jb + g;
+                const R bf = (f < d && j < d) ? ldg(P + (size_t)f * d + j) : R(0);
+#pragma unroll
+                for (int ra = 0; ra < RA; ++ra) {
+                  double d0 = (double)c[ra][jj][0], d1 = (double)c[ra][jj][1];
+                  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                      : "+d"(d0), "+d"(d1)
+                      : "d"((double)af[ra]), "d"((double)bf));
+                  c[ra][jj][0] = (R)d0;
+                  c[ra][jj][1] = (R)d1;
+                }
               }
             }
           }
+#pragma unroll
+          for (int ra = 0; ra < RA; ++ra)
+#pragma unroll
+            for (int jj = 0; jj < JG; ++jj) {
+              if (j0 + jj >= NB) continue;
+              const int j = 8 * (j0 + jj) + 2 * tq;
+              const R y0 = c[ra][jj][0] + sP[k * D8 + j], y1 = c[ra][jj][1] + sP[k * D8 + j + 1];
+              ssr[ra] = fma(y0, y0, ssr[ra]);  // padded columns: c = 0 and sP = 0
+              ssr[ra] = fma(y1, y1, ssr[ra]);
+            }
         }
 #pragma unroll
         for (int ra = 0; ra < RA; ++ra) {
-          R ss = R(0);
-#pragma unroll
-          for (int jb = 0; jb < NB; ++jb) {
-            const int j = 8 * jb + 2 * tq;
-            const R y0 = c[ra][jb][0] + sP[k * D8 + j], y1 = c[ra][jb][1] + sP[k * D8 + j + 1];
-            ss = fma(y0, y0, ss);  // padded columns: c = 0 and sP = 0
-            ss = fma(y1, y1, ss);
-          }
+          R ss = ssr[ra];
           ss += __shfl_xor_sync(0xffffffffu, ss, 1);
           ss += __shfl_xor_sync(0xffffffffu, ss, 2);
           if (tq == 0) logp[(i0 + 8 * ra + g) * K + k] = -(cst + ss) / 2 + ldet[k];
