@@ -12,6 +12,9 @@ import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from donk_b200 import _lib, batched, synthetic  # noqa: E402
+import os as _os
+if _os.environ.get("PROF_ALT_LIB"):  # experiments: time an alternative build of the library
+    _lib.LIB_PATH = (Path(__file__).resolve().parent.parent / _os.environ["PROF_ALT_LIB"]).resolve()
 
 what = sys.argv[1] if len(sys.argv) > 1 else "ilqr"
 dev = torch.device("cuda", 0)
