@@ -351,8 +351,8 @@ __global__ void __launch_bounds__(256, 2) gmm_e_mma_kernel_occ2(const GmmArgs<do
   WCtx w{(int)threadIdx.x, (int)blockDim.x, (int)threadIdx.x >> 5, (int)threadIdx.x & 31, (int)blockDim.x >> 5};
   gmm_e_mma_cta<double, NB, RA>(w, a, (int)blockIdx.x, (int)gridDim.x, reinterpret_cast<double*>(smem_raw));
 }
-template <int NBW, int KC>
-__global__ void __launch_bounds__(NBW <= 6 ? 256 : 512, NBW <= 6 ? 2 : 1) gmm_m_mma_kernel(const GmmArgs<double> a) {
+template <int NBW, int KC, int THREADS, int OCC>
+__global__ void __launch_bounds__(THREADS, OCC) gmm_m_mma_kernel(const GmmArgs<double> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WCtx w{(int)threadIdx.x, (int)blockDim.x, (int)threadIdx.x >> 5, (int)threadIdx.x & 31, (int)blockDim.x >> 5};
   gmm_m_mma_cta<double, NBW, KC>(w, a, (int)blockIdx.x, reinterpret_cast<double*>(smem_raw));
@@ -392,14 +392,18 @@ int gmm_m_mma_dispatch(GmmArgs<double>& a, const GmmMmaPlan& pl, void* stream) {
   if (smem > smem_optin_cap()) return DONK_SMEM_LIMIT;
   const int grid = ((a.K + pl.KC - 1) / pl.KC) * a.nch;
   int rc;
-  if (pl.NBW <= 6) {
-    rc = allow_smem(gmm_m_mma_kernel<6, 2>, smem);
+  if (pl.NBW == 3) {  // 16 warps x 3 blocks x 4 clusters, one CTA per SM
+    rc = allow_smem(gmm_m_mma_kernel<3, 4, 512, 1>, smem);
     if (rc != DONK_OK) return rc;
-    gmm_m_mma_kernel<6, 2><<<grid, 32 * pl.Gm, smem, (cudaStream_t)stream>>>(a);
+    gmm_m_mma_kernel<3, 4, 512, 1><<<grid, 32 * pl.Gm, smem, (cudaStream_t)stream>>>(a);
+  } else if (pl.NBW <= 6) {  // 8 warps x 6 blocks x 2 clusters, two CTAs per SM
+    rc = allow_smem(gmm_m_mma_kernel<6, 2, 256, 2>, smem);
+    if (rc != DONK_OK) return rc;
+    gmm_m_mma_kernel<6, 2, 256, 2><<<grid, 32 * pl.Gm, smem, (cudaStream_t)stream>>>(a);
   } else {
-    rc = allow_smem(gmm_m_mma_kernel<11, 2>, smem);
+    rc = allow_smem(gmm_m_mma_kernel<11, 2, 512, 1>, smem);
     if (rc != DONK_OK) return rc;
-    gmm_m_mma_kernel<11, 2><<<grid, 32 * pl.Gm, smem, (cudaStream_t)stream>>>(a);
+    gmm_m_mma_kernel<11, 2, 512, 1><<<grid, 32 * pl.Gm, smem, (cudaStream_t)stream>>>(a);
   }
   LAUNCHED("gmm_m_mma_kernel");
   return DONK_OK;

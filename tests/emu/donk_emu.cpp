@@ -297,7 +297,8 @@ int donk_emu_gmm_em_step_mode_f64(int n_local, int d, int K, const double* X, co
     const int grid = ((K + pl.KC - 1) / pl.KC) * a.nch;
     for (int cta = 0; cta < grid; ++cta) {
       memset(smem.data(), 0xFF, smem.size() * sizeof(double));
-      if (pl.NBW <= 6) gmm_m_mma_cta<double, 6, 2>(w, a, cta, smem.data());
+      if (pl.NBW == 3) gmm_m_mma_cta<double, 3, 4>(w, a, cta, smem.data());
+      else if (pl.NBW <= 6) gmm_m_mma_cta<double, 6, 2>(w, a, cta, smem.data());
       else gmm_m_mma_cta<double, 11, 2>(w, a, cta, smem.data());
     }
     for (size_t i = 0; i < total; ++i) gmm_reduce_item<double>(a, i, stats);

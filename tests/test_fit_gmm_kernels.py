@@ -289,3 +289,25 @@ def test_em_kernel_family_follows_cluster_separation(backend):
                     warnings.simplefilter("ignore")
                     g2.fit(X)
                 assert g2._mode == mode and relerr(g2.covariances, ref.covariances) < 1e-10
+
+
+@pytest.mark.parametrize("d,K,n", [(72, 6, 1501), (56, 5, 700), (49, 4, 333), (40, 3, 500), (80, 2, 300), (120, 3, 400)])
+def test_em_dmma_cta_shapes_match_oracle(backend, d, K, n):
+    """The DMMA passes at every M-pass CTA shape: 8 warps x 6 blocks x 2 clusters (d <= 48), 16 warps x 3 blocks x 4
+    clusters (d = 49..72, K not a multiple of 4 and ragged row ranges included), 16 warps x 11 blocks (d > 72)."""
+    from donk_b200.batched import DeviceGMM
+    from donk_b200 import synthetic
+
+    X, w0, m0, p0 = synthetic.gmm_pool(n, d, K, seed=d + K)
+    pc0 = np.stack([np.linalg.cholesky(np.linalg.inv(p)).T for p in p0])  # precisions are identity here
+    ref = oracle.gmm_fit(X, GMMParams(w0, m0, np.stack([np.linalg.inv(p) for p in p0]), pc0), tol=0.0, max_iter=2)
+    eye = np.stack([np.eye(d)] * K)  # the pool's initial precisions are identities
+    gm = DeviceGMM(K, tol=0.0, max_iter=2).set_params(w0, m0, covariances=eye, precisions_cholesky=eye)
+    gm.kernels = "dmma"
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gm.fit(X)
+    assert gm._mode == 2
+    assert relerr(gm.weights, ref.weights) < 1e-11 and relerr(gm.means, ref.means) < 1e-11
+    assert relerr(gm.covariances, ref.covariances) < 1e-9
+    assert abs(gm.lower_bound - ref.lower_bound) < 1e-10 * abs(ref.lower_bound)
