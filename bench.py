@@ -115,7 +115,7 @@ def run_reference(args):
                                    f"oracle ILQR.step, one process per core"},
         "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(n_gpus):
@@ -418,12 +418,33 @@ def run_ours(args):
             "parity_max_rel_err_vs_oracle": parity,
             "extra": extra,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def _reserve_stdout():
+    """stdout carries exactly one JSON line: keep the real stdout aside and point fd 1 at stderr, so that nothing a
+    library prints (the NCCL version banner is written to fd 1 from C) can land next to the result."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    _reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
