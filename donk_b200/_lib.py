@@ -33,6 +33,7 @@ SIGNATURES = {
     "brent_update_f64": [c_int, c_int, c_double, c_double, P, P, P, c_double, c_double, c_double, c_int]
     + [P] * 5 + [P],
     "fit_lr_f64": [c_int] * 5 + [P, P, c_int, P, P, P, P, c_double, c_double, c_double, P, P, P, P, P],
+    "fit_lr_niw_f64": [c_int] * 5 + [P] * 6 + [c_double, c_double, P, P, P, P, P],
     "to_transitions_f64": [c_int] * 4 + [P, P, P, P],
     "state_fit_f64": [c_int] * 3 + [P, c_size_t, c_size_t, P, P, P],
     "gmm_em_step_f64": [c_int] * 3 + [P] * 7 + [P, c_size_t, P],

@@ -379,6 +379,30 @@ def fit_lr(X, U, prior: "DeviceGMM | None" = None, regularization: float = 1e-6,
     return F, f, covar, info
 
 
+def fit_lr_niw(X, U, mu0, Phi, N_mean, N_covar, regularization: float = 1e-6, prior_weight: float = 1.0):
+    """``fit_lr`` under an explicit normal-inverse-Wishart prior per (condition, t) — the form any
+    ``DynamicsPrior.eval`` result takes (linear_dynamics.py:168-175, prior.py:18-45).
+
+    ``mu0 (B,T,d), Phi (B,T,d,d), N_mean (B,T), N_covar (B,T)`` with ``d = 2dX+dU``; returns as :func:`fit_lr`.
+    """
+    nat = _lib.native()
+    X, U = _dev(X), _dev(U)
+    B, N, T1, dX = X.shape
+    _, _, T, dU = U.shape
+    if N <= 1:
+        raise ValueError(f"Cannot fit dynamics to {N} sample(s)")
+    d, p = 2 * dX + dU, dX + dU
+    mu0, Phi, N_mean, N_covar = _dev(mu0), _dev(Phi), _dev(N_mean), _dev(N_covar)
+    if mu0.shape != (B, T, d) or Phi.shape != (B, T, d, d) or N_mean.shape != (B, T) or N_covar.shape != (B, T):
+        raise ValueError("NIW prior arrays must be (B,T,d), (B,T,d,d), (B,T), (B,T)")
+    o = dict(dtype=X.dtype, device=X.device)
+    F, f, covar = torch.empty(B, T, dX, p, **o), torch.empty(B, T, dX, **o), torch.empty(B, T, dX, dX, **o)
+    info = torch.zeros(B, T, dtype=torch.int32, device=X.device)
+    nat.call("fit_lr_niw_f64", B, N, T, dX, dU, X, U, mu0, Phi, N_mean, N_covar, float(prior_weight),
+             float(regularization), F, f, covar, info)
+    return F, f, covar, info
+
+
 # =====================================================================================================
 # GMM EM (GMMPrior.update)
 # =====================================================================================================
@@ -421,6 +445,7 @@ class DeviceGMM:
                 raise ValueError("'full precision' should be symmetric, positive-definite")
         self.covariances = _dev(covariances).clone() if covariances is not None else torch.zeros(
             self.K, self.d, self.d, dtype=torch.float64, device=self.means.device)
+        self._cov_known = covariances is not None  # else a placeholder until the first M step fills it
         return self
 
     def init_from_labels(self, X_local, labels_local, group=None):
@@ -480,7 +505,29 @@ class DeviceGMM:
         self._allreduce(stats, group)  # the one exchange step of the path (NCCL over NVLink)
         nat.call("gmm_m_finalize_f64", float(n_total), d, self.K, stats, self._shift, float(self.reg_covar),
                  self.weights, self.means, self.covariances, self.precisions_cholesky, self._lb, self._info)
+        self._cov_known = True
         return self._lb
+
+    def _centring_hardness(self) -> torch.Tensor:
+        """``max_kj (mu_kj - x_bar_j)^2 / var_kj`` of the current parameters (device scalar, no host sync).
+
+        ``var`` is the diagonal of the covariances; for an explicit precision start (``set_params(precisions=...)``,
+        covariances unknown) it is bounded from below by ``1 / (P P^T)_jj`` (``(A^-1)_jj >= 1 / A_jj`` for SPD A), which
+        over-estimates the hardness — the safe side.
+        """
+        if getattr(self, "_cov_known", True):
+            var = torch.diagonal(self.covariances, dim1=-2, dim2=-1)
+        else:
+            var = 1.0 / (self.precisions_cholesky ** 2).sum(-1)
+        xbar = (self.weights[:, None] * self.means).sum(0)
+        return (((self.means - xbar) ** 2) / var).max()
+
+    def _pick_mode(self, hardness: float) -> int:
+        if self.kernels == "scalar":
+            return 1
+        if self.kernels == "dmma":
+            return 2
+        return 1 if (not np.isfinite(hardness) or hardness * np.finfo(np.float64).eps > 1e-9) else 0
 
     def fit(self, X_local, warm_start: bool = False, group=None, check_every: int = 1):
         """EM until ``|delta lower bound| < tol`` or ``max_iter`` (sklearn/mixture/_base.py:241-305).
@@ -507,17 +554,9 @@ class DeviceGMM:
         self._info = torch.zeros(self.K, dtype=torch.int32, device=X.device)
         # Kernel family: the DMMA pass centres its statistics on the mixture mean; its rounding error grows as
         # eps (|mu_k - x_bar| / sigma_k)^2.  Where that would exceed ~1e-9 the scalar kernels (centred on every
-        # cluster's own mean) are used whatever the pool size: results first, speed second.
-        self._mode = 0
-        if self.kernels == "auto":
-            var = torch.diagonal(self.covariances, dim1=-2, dim2=-1)
-            if float(var.min()) > 0:  # covariances are known (not the placeholder of an explicit precision start)
-                xbar = (self.weights[:, None] * self.means).sum(0)
-                hard = float((((self.means - xbar) ** 2) / var).max())
-                if hard * np.finfo(np.float64).eps > 1e-9:
-                    self._mode = 1
-        elif self.kernels in ("scalar", "dmma"):
-            self._mode = 1 if self.kernels == "scalar" else 2
+        # cluster's own mean) are used whatever the pool size: results first, speed second.  The bound is evaluated
+        # from the parameters going INTO every iteration (clusters move during EM), see _centring_hardness.
+        self._mode = self._pick_mode(float(self._centring_hardness()))
         lb = self.lower_bound if warm_start else -np.inf
         self.converged = False
         self.lower_bounds = []
@@ -525,7 +564,9 @@ class DeviceGMM:
         for n_iter in range(1, self.max_iter + 1):
             prev = lb
             self.em_iteration(X, n_total, ws, stats, group)
-            lb = float(self._lb.item())
+            # one device->host read per iteration: the lower bound and the centring bound of the NEXT iteration
+            lb, hard = torch.cat([self._lb, self._centring_hardness().reshape(1)]).tolist()
+            self._mode = self._pick_mode(hard)
             if int(self._info.sum().item()):
                 raise ValueError("Fitting the mixture model failed because some components have ill-defined "
                                  "empirical covariance (for instance caused by singleton or collapsed samples).")
@@ -540,6 +581,16 @@ class DeviceGMM:
             warnings.warn("Best performing initialization did not converge. Try different init parameters, or "
                           "increase max_iter, tol, or check for degenerate data.", ConvergenceWarning)
         return self
+
+    def eval_prior(self, XUX):
+        """``GMMPrior.eval`` (prior_gmm.py:26-41) on the device: the NIW hyper-parameters the mixture assigns to the
+        transitions ``XUX (N,d)`` — ``(mu0 (d), Phi (d,d), N_mean, N_covar)`` as device tensors / floats."""
+        resp = self.predict_proba(XUX)
+        share = resp.mean(dim=0)                                   # average responsibility of every cluster
+        strength = float(torch.dot(share, self.weights)) * self.N  # the prior's weight in samples
+        mu0 = share @ self.means
+        Phi = torch.tensordot(share, self.covariances, dims=1) * strength
+        return mu0, Phi, strength, strength - (1 + self.d)
 
     def predict_proba(self, X) -> torch.Tensor:
         nat = _lib.native()

@@ -1,0 +1,64 @@
+// donk_b200 — pieces shared by the translation units of the CUDA library (error reporting, launch counter,
+// shared-memory opt-in).  The library is built from several .cu files so that nvcc compiles them in parallel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <cstdint>
+
+#include "../../include/donk_b200.h"
+#include "common.cuh"
+
+// (dX, dU) pairs with warp-kernel instantiations (ILQR step, fit_lr): the BASELINE.json configurations that
+// fit one warp per problem; other dimensions run the CTA-cooperative or the generic kernels.
+#define DONK_WARP_DIMS(X) X(20, 6) X(14, 7) X(6, 2)
+
+namespace donk_abi {
+
+extern thread_local char g_err[256];
+extern std::atomic<unsigned long long> g_launches;
+
+inline int cuda_fail(cudaError_t e, const char* where) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+  return DONK_CUDA_ERROR;
+}
+#define CU(call)                                                  \
+  do {                                                            \
+    cudaError_t e_ = (call);                                      \
+    if (e_ != cudaSuccess) return donk_abi::cuda_fail(e_, #call); \
+  } while (0)
+#define LAUNCHED(name)                                                    \
+  do {                                                                    \
+    donk_abi::g_launches.fetch_add(1, std::memory_order_relaxed);         \
+    cudaError_t e_ = cudaGetLastError();                                  \
+    if (e_ != cudaSuccess) return donk_abi::cuda_fail(e_, name);          \
+  } while (0)
+
+inline int env_int(const char* name) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : 0;
+}
+
+inline size_t smem_optin_cap() {
+  static size_t cap = 0;
+  if (!cap) {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cap = v > 0 ? (size_t)v : 48 * 1024;
+  }
+  return cap;
+}
+
+template <typename KernelT>
+int allow_smem(KernelT kernel, size_t bytes) {
+  if (bytes > 48 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  // ask for the full shared-memory carve-out so that several CTAs fit one SM
+  CU(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  return DONK_OK;
+}
+
+}  // namespace donk_abi

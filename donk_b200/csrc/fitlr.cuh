@@ -29,6 +29,8 @@ struct FitArgs {
   const R *gw, *gmeans, *gcov, *gpc;  // (K) (K,d) (K,d,d) (K,d,d)
   R n_pool, prior_weight, reg;
   const R* gconst;   // warp kernel with prior: per-cluster constants from gmm_prior_consts_item, (K*d + K)
+  // explicit normal-inverse-Wishart prior per (condition, t) (any DynamicsPrior evaluated by the caller, K == 0):
+  const R *niw_mu0, *niw_Phi, *niw_Nmean, *niw_Ncovar;  // (B,T,d) (B,T,d,d) (B,T) (B,T) or null
   R *F, *f, *covar;  // (B,T,dX,p) (B,T,dX) (B,T,dX,dX)
   int* info;         // (B,T)
 };
@@ -306,6 +308,25 @@ DONK_D void fit_lr_cta(const Ctx& ctx, const FitArgs<R>& a, int cta, R* sm) {
     ctx.sync();
   }
 
+  // ---- 2'. explicit NIW prior of this (condition, t): sigma = posterior(mu, S, N / prior_weight).map_covar()
+  //          (linear_dynamics.py:171-175, prior.py:18-45), for priors the caller evaluated itself ----------------
+  if (K == 0 && a.niw_Phi != nullptr) {
+    const size_t bt = (size_t)b * a.T + t;
+    const R Nm = a.niw_Nmean[bt], Nc = a.niw_Ncovar[bt];
+    const R n = R(N) / a.prior_weight;
+    const R coef = Nm * n / (Nm + n), den = Nc + n + R(d) + R(1);
+    const R* mu0 = a.niw_mu0 + bt * d;
+    const R* Phi = a.niw_Phi + bt * (size_t)d * d;
+    TEAM_FOR(idx, d * d) {
+      const int i = idx / d, j = idx % d;
+      if (i > j) continue;
+      const R S = sig_get(sm, L, i, j);
+      const R dm = (mu[i] - ldg(mu0 + i)) * (mu[j] - ldg(mu0 + j));
+      sig_add(sm, L, i, j, (ldg(Phi + idx) + n * S + coef * dm) / den, false);
+    }
+    ctx.sync();
+  }
+
   // ---- 3. smallest eigenvalue of Sigma_pp (linear_dynamics.py:178) -------------------------------
   R* A = sm + L.oWork;
   R* td = sm + L.oTd;
@@ -448,57 +469,26 @@ DONK_D void fit_lr_cta(const Ctx& ctx, const FitArgs<R>& a, int cta, R* sm) {
   }
   {
     R* Z = sm + L.oSpx;
-    TEAM_FOR(c, dX) {  // one right-hand side per item: L y = b, then L^T z = y
+    const size_t bt = (size_t)b * a.T + t;
+    TEAM_FOR(c, dX) {  // one right-hand side per item: L y = b
       for (int i = 0; i < p; ++i) {
         R acc = Z[i * dXp + c];
         for (int k = 0; k < i; ++k) acc = fma(-Lm[i * pa + k], Z[k * dXp + c], acc);
         Z[i * dXp + c] = acc / td[i];
       }
-      for (int i = p - 1; i >= 0; --i) {
-        R acc = Z[i * dXp + c];
-        for (int k = i + 1; k < p; ++k) acc = fma(-Lm[k * pa + i], Z[k * dXp + c], acc);
-        Z[i * dXp + c] = acc / td[i];
-      }
     }
     ctx.sync();
-    // outputs: F[i][j] = Z[j][i]; f = mu_x' - F mu_p   (linear_dynamics.py:184-185)
-    const size_t bt = (size_t)b * a.T + t;
-    TEAM_FOR(idx, dX * p) {
-      const int i = idx / p, j = idx % p;
-      a.F[bt * dX * p + idx] = Z[j * dXp + i];
-    }
-    TEAM_FOR(i, dX) {
-      R acc = R(0);
-      for (int j = 0; j < p; ++j) acc = fma(Z[j * dXp + i], mu[j], acc);
-      a.f[bt * dX + i] = mu[p + i] - acc;
-    }
-    // Gt = Sigma_pp Z (p x dX) over the dead Cholesky factor; covar = Sigma_x'x' - Z^T Gt (linear_dynamics.py:186)
-    ctx.sync();
-    R* Gt = sm + L.oWork;
-    {
-      const int nti = pa / 4, ntj = dXp / 4;
-      TEAM_FOR(idx, nti * ntj) {
-        const int ti = idx / ntj, tj = idx % ntj;
-        R acc[4][4];
-        tile4x4(sm + L.oSpp, pa, 4 * ti, Z, dXp, 4 * tj, p, acc);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int k = 4 * ti + r;
-          if (k < p) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) Gt[k * dXp + 4 * tj + c] = acc[r][c];
-          }
-        }
-      }
-    }
-    ctx.sync();
+    // covar = Sigma_x'x' - Y^T Y with Y = L^-1 Sigma_px: the Schur complement of linear_dynamics.py:186
+    // (F Sigma_pp F^T = Sigma_xp Sigma_pp^-1 Sigma_px = Y^T Y) as the difference of the sample block and ONE Gram
+    // matrix - no second product through F, whose rounding pushed the smallest eigenvalue of a singular result
+    // to -1.8e-16 (the reference's own test tolerates -1e-16, tests/dynamics_test.py:85-90).
     {
       const int nt = dXp / 4, ntri = nt * (nt + 1) / 2;
       TEAM_FOR(idx, ntri) {
         int ti, tj;
         tri_tile(idx, nt, ti, tj);
         R acc[4][4];
-        tile4x4(Gt, dXp, 4 * ti, Z, dXp, 4 * tj, p, acc);
+        tile4x4(Z, dXp, 4 * ti, Z, dXp, 4 * tj, p, acc);
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -511,6 +501,25 @@ DONK_D void fit_lr_cta(const Ctx& ctx, const FitArgs<R>& a, int cta, R* sm) {
             }
           }
       }
+    }
+    ctx.sync();
+    TEAM_FOR(c, dX) {  // L^T z = y: F^T = Sigma_pp^-1 Sigma_px
+      for (int i = p - 1; i >= 0; --i) {
+        R acc = Z[i * dXp + c];
+        for (int k = i + 1; k < p; ++k) acc = fma(-Lm[k * pa + i], Z[k * dXp + c], acc);
+        Z[i * dXp + c] = acc / td[i];
+      }
+    }
+    ctx.sync();
+    // outputs: F[i][j] = Z[j][i]; f = mu_x' - F mu_p   (linear_dynamics.py:184-185)
+    TEAM_FOR(idx, dX * p) {
+      const int i = idx / p, j = idx % p;
+      a.F[bt * dX * p + idx] = Z[j * dXp + i];
+    }
+    TEAM_FOR(i, dX) {
+      R acc = R(0);
+      for (int j = 0; j < p; ++j) acc = fma(Z[j * dXp + i], mu[j], acc);
+      a.f[bt * dX + i] = mu[p + i] - acc;
     }
     ctx.sync();
     if (ctx.tid == 0 && a.info) a.info[bt] = sm[L.oScal + 1] != R(0);

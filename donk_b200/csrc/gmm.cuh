@@ -435,12 +435,6 @@ inline int gmm_m_threads(int d) {
   }
   return 0;  // d too large for the register-tile M pass
 }
-// workspace layout in reals: resp (n,K) | lse_part (nblocks) | part (K,nch,1+d+d*d)
-inline size_t gmm_ws_reals(int n, int d, int K) {
-  const size_t nblocks = ((size_t)n + GMM_TS - 1) / GMM_TS;
-  int nch = gmm_nch(n, d, K);
-  if (nch < 160) nch = 160;  // the tensor-path M pass (gmm_mma.cuh) uses up to 148*4/ceil(K/2) ranges
-  return (size_t)n * K + nblocks + (size_t)K * nch * gmm_part_len(d);
-}
+// gmm_ws_reals (workspace size) lives in gmm_mma.cuh: it needs the plan of the tensor-path M pass as well.
 
 }  // namespace donk

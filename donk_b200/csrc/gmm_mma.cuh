@@ -457,4 +457,15 @@ inline GmmMmaPlan gmm_mma_plan(int n, int d, int K) {
   return p;
 }
 
+// workspace layout in reals: resp (n,K) | lse_part (nblocks) | part (K,nch,1+d+d*d).  Sized from the very plans the
+// launchers use: the scalar M pass writes K * gmm_nch partials, the tensor-path M pass K * gmm_mma_plan().nch.
+inline int gmm_ws_nch(int n, int d, int K) {
+  const int a = gmm_nch(n, d, K), b = gmm_mma_plan(n, d, K).nch;
+  return a > b ? a : b;
+}
+inline size_t gmm_ws_reals(int n, int d, int K) {
+  const size_t nblocks = ((size_t)n + GMM_TS - 1) / GMM_TS;
+  return (size_t)n * K + nblocks + (size_t)K * gmm_ws_nch(n, d, K) * gmm_part_len(d);
+}
+
 }  // namespace donk

@@ -55,8 +55,8 @@ def fit_lr(X: np.ndarray, U: np.ndarray, prior=None, regularization: float = 1e-
     """Fit dynamics by per-timestep linear regression under an optional NIW prior.
 
     Same signature and error behaviour as the reference (linear_dynamics.py:137-189): ``X (N,T+1,dX)``,
-    ``U (N,T,dU)``, ``ValueError`` when ``N <= 1``.  ``prior`` must be a ``donk_b200`` ``GMMPrior`` (its
-    mixture lives on the device and is evaluated inside the fit kernel).
+    ``U (N,T,dU)``, ``ValueError`` when ``N <= 1``.  A ``GMMPrior`` is evaluated inside the fit kernel (its mixture lives on the
+    device); any other ``DynamicsPrior`` is evaluated by its own ``eval`` and enters the kernel as explicit NIW parameters.
     """
     from donk_b200 import batched
     from donk_b200.dynamics.prior import GMMPrior
@@ -65,12 +65,18 @@ def fit_lr(X: np.ndarray, U: np.ndarray, prior=None, regularization: float = 1e-
     N = X.shape[0]
     if N <= 1:
         raise ValueError(f"Cannot fit dynamics to {N} sample(s)")
-    gmm = None
-    if prior is not None:
-        if not isinstance(prior, GMMPrior):
-            raise TypeError("fit_lr on the device supports GMMPrior (or None) as prior")
-        gmm = prior._gmm
-    F, f, covar, info = batched.fit_lr(X[None], U[None], gmm, regularization, prior_weight)
+    if prior is None or isinstance(prior, GMMPrior):
+        gmm = None if prior is None else prior._gmm
+        F, f, covar, info = batched.fit_lr(X[None], U[None], gmm, regularization, prior_weight)
+    else:
+        # any other DynamicsPrior (prior.py:62-82): its eval() is user code and runs on the host, one call per time
+        # step as in the reference (linear_dynamics.py:171); the regression itself still runs on the device
+        T = U.shape[1]
+        niw = [prior.eval(np.concatenate([X[:, t], U[:, t], X[:, t + 1]], axis=1)) for t in range(T)]
+        F, f, covar, info = batched.fit_lr_niw(
+            X[None], U[None], np.stack([q.mu0 for q in niw])[None], np.stack([q.Phi for q in niw])[None],
+            np.array([[float(q.N_mean) for q in niw]]), np.array([[float(q.N_covar) for q in niw]]),
+            regularization, prior_weight)
     if int(info.sum()) != 0:
         raise np.linalg.LinAlgError("Singular matrix")  # numpy.linalg.solve, linear_dynamics.py:184
     return LinearDynamics(F[0].cpu().numpy(), f[0].cpu().numpy(), covar[0].cpu().numpy())

@@ -40,13 +40,18 @@ class GMMPrior(DynamicsPrior):
     """A Gaussian-mixture based prior: ``GMMPrior(n_clusters, random_state=None)``."""
 
     def __init__(self, n_clusters: int, random_state=None, init: str = "auto") -> None:
-        """``init``: where the k-means labels of the first ``update`` come from — ``"sklearn"`` (host, the
-        reference's exact labels), ``"device"`` (``batched.DeviceKMeans``, statistical parity) or ``"auto"``
-        (device for CUDA tensors and pools of >= 100 000 rows, else sklearn)."""
+        """``init``: where the k-means labels of the first ``update`` come from — ``"device"`` / ``"auto"`` (the default:
+        ``batched.DeviceKMeans``, k-means++ and Lloyd on the GPU; labels agree with scikit-learn statistically, its
+        random stream cannot be reproduced) or ``"sklearn"`` (opt-in, single rank only: scikit-learn's own ``KMeans`` on the
+        host, the reference's exact labels — a test / migration aid, not part of the device path)."""
         from donk_b200.batched import DeviceGMM
 
+        import os
+
         self.random_state = random_state
-        self.init = init
+        # DONK_GMM_INIT=sklearn: process-wide opt-in used when the reference's own known-answer tests run against
+        # this package (they pin scikit-learn's random stream through the k-means labels)
+        self.init = os.environ.get("DONK_GMM_INIT", init) if init == "auto" else init
         self._gmm = DeviceGMM(n_clusters)
         self.gmm = _MixtureView(self._gmm, self)
 
@@ -68,8 +73,15 @@ class GMMPrior(DynamicsPrior):
                 w, m, prec = init
                 g.set_params(w, m, precisions=prec)
             else:
-                on_device = hasattr(XUX, "is_cuda") and XUX.is_cuda
-                use_device = self.init == "device" or (self.init == "auto" and (on_device or XUX.shape[0] >= 100_000))
+                import torch.distributed as dist
+
+                sharded = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+                if sharded and self.init == "sklearn":
+                    # every rank would label ITS rows with its own k-means: cluster k would mean different things on
+                    # different ranks and the all-reduced statistics would mix unrelated clusters
+                    raise ValueError("init='sklearn' labels a single-rank pool; with rows sharded over ranks use "
+                                     "init='device' (centres are seeded on rank 0 and broadcast)")
+                use_device = self.init in ("device", "auto") or sharded
                 if use_device:
                     from donk_b200.batched import DeviceKMeans
 
@@ -94,11 +106,10 @@ class GMMPrior(DynamicsPrior):
         return KMeans(n_clusters=K, n_init=1, random_state=check_random_state(self.random_state)).fit(Xh).labels_
 
     def eval(self, XUX) -> NormalInverseWishart:
-        """Mixture-weighted NIW prior for the transitions ``XUX (N, d)`` (prior_gmm.py:26-41)."""
-        XUX = np.asarray(XUX, dtype=np.float64)
-        d = XUX.shape[1]
-        wts = np.mean(self.gmm.predict_proba(XUX), axis=0)
-        mu0 = np.sum(wts[:, np.newaxis] * self.gmm.means_, axis=0)
-        Phi = np.sum(wts[:, np.newaxis, np.newaxis] * self.gmm.covariances_, axis=0)
-        N = np.sum(wts * self.gmm.weights_) * self.N
-        return NormalInverseWishart.non_informative_prior(d).posterior(mu0, Phi, N)
+        """Mixture-weighted NIW prior for the transitions ``XUX (N, d)`` (prior_gmm.py:26-41), evaluated on the device.
+
+        A non-informative NIW updated with the responsibility-weighted cluster mean / covariance at the prior's
+        strength ``N_p`` is ``NIW(mu_p, N_p Phi_p, N_p, N_p - (1 + d))``: built directly.
+        """
+        mu0, Phi, n_mean, n_covar = self._gmm.eval_prior(np.asarray(XUX, dtype=np.float64))
+        return NormalInverseWishart(mu0.cpu().numpy(), Phi.cpu().numpy(), n_mean, n_covar)

@@ -1,75 +1,81 @@
 """Time-varying linear-Gaussian model holder (donk/models/tvlg.py:6-129)."""
+from __future__ import annotations
+
 import numpy as np
+
+from donk_b200.utils.shapes import require_shape
+
+
+class _SpdForms:
+    """The three forms of a batch of SPD matrices — the matrix, its lower Cholesky factor and its inverse —
+    derived from whichever was given, on first use, by ``donk_spd_factor_f64`` on the device."""
+
+    def __init__(self, matrix=None, inverse=None):
+        self._forms = {"matrix": matrix, "inverse": inverse, "chol": None}
+
+    def _factor(self, of, **want):
+        from donk_b200.batched import spd_factor
+
+        inv, chol, _ = spd_factor(np.asarray(of, dtype=np.float64), want_hld=False, **want)
+        return inv, chol
+
+    def get(self, form: str):
+        have = self._forms
+        if have[form] is None:
+            if form == "matrix":  # only the inverse was given
+                have["matrix"] = self._factor(have["inverse"])[0].cpu().numpy()
+            elif form == "chol":
+                have["chol"] = self._factor(self.get("matrix"), want_inv=False, want_chol=True)[1].cpu().numpy()
+            else:
+                have["inverse"] = self._factor(self.get("matrix"))[0].cpu().numpy()
+        return have[form]
 
 
 class TimeVaryingLinearGaussian:
     """``p(y|t,x) = N(coefficients_t x + intercept_t, covar_t)`` with lazily derived factors.
 
-    Same contract as the reference: exactly ``(T,dY,dX)`` coefficients (tvlg.py:28-36), ``covar`` /
-    ``chol_covar`` / ``inv_covar`` computed on first use (tvlg.py:62-99) — here on the device by
-    ``donk_spd_factor_f64`` — and ``numpy.linalg.LinAlgError`` if a covariance is not positive definite.
+    Contract of the reference: coefficients are exactly ``(T,dY,dX)`` (tvlg.py:28-36), at least one of ``covar`` /
+    ``inv_covar`` is given, the missing forms and ``chol_covar`` appear on first use (tvlg.py:62-99), and a covariance
+    that is not positive definite raises ``numpy.linalg.LinAlgError``.
     """
 
     def __init__(self, coefficients, intercept, covar=None, inv_covar=None) -> None:
         if covar is None and inv_covar is None:
             raise ValueError("Must provide covar or inv_covar.")
-        self.T, dY, dX = coefficients.shape
-        assert coefficients.shape == (self.T, dY, dX), f"{coefficients.shape} != {(self.T, dY, dX)}"
-        assert intercept.shape == (self.T, dY), f"{intercept.shape} != {(self.T, dY)}"
-        if covar is not None:
-            assert covar.shape == (self.T, dY, dY), f"{covar.shape} != {(self.T, dY, dY)}"
-        if inv_covar is not None:
-            assert inv_covar.shape == (self.T, dY, dY), f"{inv_covar.shape} != {(self.T, dY, dY)}"
-        self._coefficients = coefficients
-        self._intercept = intercept
-        self._covar = covar
-        self._chol_covar = None
-        self._inv_covar = inv_covar
+        if coefficients.ndim != 3:
+            raise AssertionError(f"coefficients must be (T, dY, dX), got shape {tuple(coefficients.shape)}")
+        self.T, dY, _ = coefficients.shape
+        require_shape("intercept", intercept, (self.T, dY))
+        for name, m in (("covar", covar), ("inv_covar", inv_covar)):
+            if m is not None:
+                require_shape(name, m, (self.T, dY, dY))
+        self._lin = (coefficients, intercept)
+        self._spd = _SpdForms(matrix=covar, inverse=inv_covar)
 
-    @property
-    def coefficients(self):
-        return self._coefficients
+    coefficients = property(lambda self: self._lin[0])
+    intercept = property(lambda self: self._lin[1])
+    covar = property(lambda self: self._spd.get("matrix"))
+    chol_covar = property(lambda self: self._spd.get("chol"))
+    inv_covar = property(lambda self: self._spd.get("inverse"))
 
-    @property
-    def intercept(self):
-        return self._intercept
-
-    @staticmethod
-    def _factor(a, **kw):
-        from donk_b200.batched import spd_factor
-
-        return [None if r is None else r.cpu().numpy() for r in spd_factor(np.asarray(a, dtype=np.float64), **kw)]
-
-    @property
-    def covar(self):
-        if self._covar is None:
-            self._covar = self._factor(self._inv_covar, want_hld=False)[0]
-        return self._covar
-
-    @property
-    def chol_covar(self):
-        if self._chol_covar is None:
-            self._chol_covar = self._factor(self.covar, want_inv=False, want_chol=True, want_hld=False)[1]
-        return self._chol_covar
-
-    @property
-    def inv_covar(self):
-        if self._inv_covar is None:
-            self._inv_covar = self._factor(self.covar, want_hld=False)[0]
-        return self._inv_covar
+    def given_forms(self):
+        """``(covar, inv_covar)`` as known so far, ``None`` for a form that has not been given or derived yet
+        (lets a caller ship only what exists and derive the rest on the device in the same batch)."""
+        return self._spd._forms["matrix"], self._spd._forms["inverse"]
 
     def predict(self, X, t: int = None, noise=None):
-        """Model output for inputs ``X`` at step ``t`` (or all steps), tvlg.py:101-129."""
+        """Model output for inputs ``X (..., dX)`` at step ``t``, or ``X (..., T, dX)`` for all steps (tvlg.py:101-129);
+        ``noise`` (standard normal, output shaped) is coloured by ``chol_covar``."""
         X = np.asarray(X)
-        if t is not None:
-            Y = np.einsum("ux,...x->...u", self.coefficients[t], X) + self.intercept[t]
-            if noise is not None:
-                Y = Y + np.einsum("ij,...j->...i", self.chol_covar[t], noise)
+        A, b = self._lin
+        if t is None:
+            if X.shape[-2:] != A.shape[::2]:
+                raise ValueError(f"Input must have shape (..., {self.T}, {A.shape[2]}), not {X.shape}")
+            L = self.chol_covar if noise is not None else None
         else:
-            dX = self.coefficients.shape[-1]
-            if X.shape[-2:] != (self.T, dX):
-                raise ValueError(f"Input must have shape (..., {self.T}, {dX}), not {X.shape}")
-            Y = np.einsum("tyx,...tx->...ty", self.coefficients, X) + self.intercept
-            if noise is not None:
-                Y = Y + np.einsum("tij,...tj->...ti", self.chol_covar, noise)
+            A, b = A[t], b[t]
+            L = self.chol_covar[t] if noise is not None else None
+        Y = np.matmul(A, X[..., None])[..., 0] + b
+        if L is not None:
+            Y = Y + np.matmul(L, np.asarray(noise)[..., None])[..., 0]
         return Y

@@ -3,15 +3,16 @@ from __future__ import annotations
 
 import numpy as np
 
+from donk_b200.utils.shapes import require_shape
+
 
 class StateDistribution:
+    """``N(mean (..., dX), covar (..., dX, dX))``; leading axes are batch axes and must agree."""
+
     def __init__(self, mean, covar) -> None:
-        dX = mean.shape[-1]
-        assert covar.shape[-2:] == (dX, dX), f"{covar.shape[-2:]} != {(dX, dX)}"
-        assert mean.shape[:-1] == covar.shape[:-2], f"{mean.shape[:-1]} != {covar.shape[:-2]}"
-        self.mean = mean
-        self.covar = covar
-        self.dX = dX
+        self.dX = mean.shape[-1]
+        require_shape("covar", covar, mean.shape[:-1] + (self.dX, self.dX))
+        self.mean, self.covar = mean, covar
 
     @staticmethod
     def fit(X) -> "StateDistribution":

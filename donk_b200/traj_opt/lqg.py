@@ -45,8 +45,7 @@ class ILQR:
         self.initial_state = initial_state
         a = lambda x: np.asarray(x, dtype=np.float64)[None]  # noqa: E731
         # Only what the caller supplied is shipped; the missing factor is derived on the device.
-        covar = prev_pol._covar
-        inv = prev_pol._inv_covar
+        covar, inv = prev_pol.given_forms()
         self._b = batched.BatchedILQR(
             a(dynamics.F), a(dynamics.f), a(dynamics.covar), a(prev_pol.K), a(prev_pol.k), a(costs.C), a(costs.c),
             a(costs.cc), a(initial_state.mean), a(initial_state.covar),

@@ -137,6 +137,15 @@ int donk_fit_lr_f64(int B, int N, int T, int dX, int dU, const double* X, const 
                     const double* gmm_prec_chol, double n_pool, double prior_weight, double regularization,
                     double* F, double* f, double* covar, int* info, void* stream);
 
+/* fit_lr under an explicit normal-inverse-Wishart prior per (condition, t): what linear_dynamics.py:168-175 does
+ * with ANY DynamicsPrior (donk/dynamics/prior/prior.py:62-82) after the caller has run prior.eval(xux_t):
+ *   sigma_t = NIW(mu0, Phi, N_mean, N_covar).posterior(mean_t, cov_t, N / prior_weight).map_covar()  (prior.py:18-45).
+ *   niw_mu0 (B,T,d), niw_Phi (B,T,d,d), niw_N_mean (B,T), niw_N_covar (B,T); everything else as donk_fit_lr_f64. */
+int donk_fit_lr_niw_f64(int B, int N, int T, int dX, int dU, const double* X, const double* U, const double* niw_mu0,
+                        const double* niw_Phi, const double* niw_N_mean, const double* niw_N_covar,
+                        double prior_weight, double regularization, double* F, double* f, double* covar, int* info,
+                        void* stream);
+
 /* to_transitions: donk/dynamics/utils.py:4-17.  X (N,T+1,dX), U (N,T,dU) -> XUX (N*T, 2dX+dU). */
 int donk_to_transitions_f64(int N, int T, int dX, int dU, const double* X, const double* U, double* XUX,
                             void* stream);

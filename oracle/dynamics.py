@@ -46,7 +46,7 @@ def fit_lr(X, U, prior=None, regularization: float = 1e-6, prior_weight: float =
     X (N,T+1,dX), U (N,T,dU) -> F (T,dX,p), f (T,dX), covar (T,dX,dX).
     ``prior`` is None or a callable ``xux (N,d) -> (mu_p, Phi_p, N_p)`` giving the
     GMM-mixed prior mean, covariance and strength (prior_gmm.py:26-41; see
-    ``oracle.gmm.gmm_eval_prior``).
+    ``oracle.gmm.gmm_eval_prior``), or returning an object with ``mu0, Phi, N_mean, N_covar`` (an explicit NIW).
     """
     N, _, dX = X.shape
     _, T, dU = U.shape
@@ -64,9 +64,13 @@ def fit_lr(X, U, prior=None, regularization: float = 1e-6, prior_weight: float =
         diff = xux - mu
         sigma = diff.T @ diff / N  # biased, linear_dynamics.py:165
         if prior is not None:
-            mu_p, Phi_p, N_p = prior(xux)
-            # non_informative_prior(d).posterior(mu_p, Phi_p, N_p)  (prior_gmm.py:41)
-            m0, Ph, Nm, Nc = niw_posterior(np.zeros(d), np.zeros((d, d)), 0, -(1 + d), mu_p, Phi_p, N_p)
+            pr = prior(xux)
+            if hasattr(pr, "mu0"):  # an explicit NIW, as any DynamicsPrior.eval returns (prior.py:62-82)
+                m0, Ph, Nm, Nc = pr.mu0, pr.Phi, pr.N_mean, pr.N_covar
+            else:
+                mu_p, Phi_p, N_p = pr
+                # non_informative_prior(d).posterior(mu_p, Phi_p, N_p)  (prior_gmm.py:41)
+                m0, Ph, Nm, Nc = niw_posterior(np.zeros(d), np.zeros((d, d)), 0, -(1 + d), mu_p, Phi_p, N_p)
             # .posterior(empmu, empsig, N / prior_weight).map_covar()  (linear_dynamics.py:172-175)
             _, Ph, _, Nc = niw_posterior(m0, Ph, Nm, Nc, mu, sigma, N / prior_weight)
             sigma = niw_map_covar(Ph, Nc, d)

@@ -1,6 +1,6 @@
 """Per-phase cycle breakdown of ilqr_warp_kernel (profiling build of the library with -DDONK_PHASE_PROF).
 
-  nvcc ... -DDONK_PHASE_PROF -o profiles/_build/libdonk_prof.so donk_b200/csrc/donk_b200.cu   (done by this script
+  nvcc ... -DDONK_PHASE_PROF -o profiles/_build/libdonk_prof.so donk_b200/csrc/*.cu   (done by this script
   when the file is missing and nvcc exists);  python profiles/prof_phases.py [B]
 Each warp adds clock64() deltas between phase boundaries to a global counter; the table is cycles per warp and step.
 Numbers from this build are diagnostic only (the counters perturb the kernel a little), never bench values.
@@ -14,7 +14,7 @@ LIB = ROOT / "profiles" / "_build" / "libdonk_prof.so"
 if not LIB.exists():
     LIB.parent.mkdir(exist_ok=True)
     subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-                    "-shared", "-DDONK_PHASE_PROF", "-o", str(LIB), str(ROOT / "donk_b200/csrc/donk_b200.cu")], check=True)
+                    "-shared", "-DDONK_PHASE_PROF", "-o", str(LIB)] + [str(f) for f in sorted((ROOT / "donk_b200/csrc").glob("*.cu"))], check=True)
 from donk_b200 import _lib, batched, synthetic  # noqa: E402
 _lib.LIB_PATH = LIB
 nat = _lib.native()

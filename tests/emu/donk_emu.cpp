@@ -185,21 +185,14 @@ int donk_emu_brent_update_f64(int B, int phase, double xa, double xb, const doub
 // ---------------------------------------------------------------------------------------------
 extern "C" {
 
-int donk_emu_fit_lr_f64(int B, int N, int T, int dX, int dU, const double* X, const double* U, int gmm_K,
-                        const double* gmm_weights, const double* gmm_means, const double* gmm_covariances,
-                        const double* gmm_prec_chol, double n_pool, double prior_weight, double regularization,
-                        double* F, double* f, double* covar, int* info, void*) {
-  if (B < 0 || N <= 1 || T < 1 || dX < 1 || dU < 1 || gmm_K < 0) return DONK_BAD_SHAPE;
-  FitArgs<double> a;
-  memset(&a, 0, sizeof(a));
-  a.B = B; a.N = N; a.T = T; a.dX = dX; a.dU = dU; a.X = X; a.U = U; a.K = gmm_K;
-  a.gw = gmm_weights; a.gmeans = gmm_means; a.gcov = gmm_covariances; a.gpc = gmm_prec_chol;
-  a.n_pool = n_pool; a.prior_weight = prior_weight; a.reg = regularization;
-  a.F = F; a.f = f; a.covar = covar; a.info = info;
-  if ((gmm_K == 0 || N <= 64) && !env_int("DONK_FIT_GENERIC")) {
-    if (dX == 20 && dU == 6) return emu_fit_warp<20, 6>(a);
-    if (dX == 14 && dU == 7) return emu_fit_warp<14, 7>(a);
-    if (dX == 6 && dU == 2) return emu_fit_warp<6, 2>(a);
+static int emu_fit_lr_launch(FitArgs<double>& a) {
+  const int B = a.B, N = a.N, T = a.T, dX = a.dX, dU = a.dU, gmm_K = a.K;
+  if ((gmm_K == 0 || N <= 64) && !a.niw_Phi && !env_int("DONK_FIT_GENERIC")) {
+    int rc = DONK_SMEM_LIMIT;
+    if (dX == 20 && dU == 6) rc = emu_fit_warp<20, 6>(a);
+    else if (dX == 14 && dU == 7) rc = emu_fit_warp<14, 7>(a);
+    else if (dX == 6 && dU == 2) rc = emu_fit_warp<6, 2>(a);
+    if (rc != DONK_SMEM_LIMIT) return rc;  // as the CUDA launcher: a plan that does not fit falls through
   }
   size_t bytes = 0;
   const int force = env_int("DONK_FIT_CHUNK");
@@ -213,6 +206,33 @@ int donk_emu_fit_lr_f64(int B, int N, int T, int dX, int dU, const double* X, co
     fit_lr_cta<double>(ctx, a, cta, smem.data());
   }
   return DONK_OK;
+}
+
+int donk_emu_fit_lr_f64(int B, int N, int T, int dX, int dU, const double* X, const double* U, int gmm_K,
+                        const double* gmm_weights, const double* gmm_means, const double* gmm_covariances,
+                        const double* gmm_prec_chol, double n_pool, double prior_weight, double regularization,
+                        double* F, double* f, double* covar, int* info, void*) {
+  if (B < 0 || N <= 1 || T < 1 || dX < 1 || dU < 1 || gmm_K < 0) return DONK_BAD_SHAPE;
+  FitArgs<double> a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.N = N; a.T = T; a.dX = dX; a.dU = dU; a.X = X; a.U = U; a.K = gmm_K;
+  a.gw = gmm_weights; a.gmeans = gmm_means; a.gcov = gmm_covariances; a.gpc = gmm_prec_chol;
+  a.n_pool = n_pool; a.prior_weight = prior_weight; a.reg = regularization;
+  a.F = F; a.f = f; a.covar = covar; a.info = info;
+  return emu_fit_lr_launch(a);
+}
+
+int donk_emu_fit_lr_niw_f64(int B, int N, int T, int dX, int dU, const double* X, const double* U, const double* mu0,
+                            const double* Phi, const double* Nm, const double* Nc, double prior_weight,
+                            double regularization, double* F, double* f, double* covar, int* info, void*) {
+  if (B < 0 || N <= 1 || T < 1 || dX < 1 || dU < 1 || !mu0 || !Phi || !Nm || !Nc) return DONK_BAD_SHAPE;
+  FitArgs<double> a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.N = N; a.T = T; a.dX = dX; a.dU = dU; a.X = X; a.U = U; a.K = 0;
+  a.niw_mu0 = mu0; a.niw_Phi = Phi; a.niw_Nmean = Nm; a.niw_Ncovar = Nc;
+  a.prior_weight = prior_weight; a.reg = regularization;
+  a.F = F; a.f = f; a.covar = covar; a.info = info;
+  return emu_fit_lr_launch(a);
 }
 
 int donk_emu_to_transitions_f64(int N, int T, int dX, int dU, const double* X, const double* U, double* XUX, void*) {

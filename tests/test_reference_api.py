@@ -225,7 +225,7 @@ def test_log_prob_known_answer(backend):
     N, _, dX = X.shape
     _, T, dU = U.shape
     X_train, U_train, X_test, U_test = X[:-3], U[:-3], X[-3:], U[-3:]
-    prior = GMMPrior(8, random_state=0)
+    prior = GMMPrior(8, random_state=0, init="sklearn")  # the literal values pin scikit-learn's k-means stream
     prior.update(to_transitions(X_train, U_train).reshape(-1, dX + dU + dX))
     dyn = fit_lr(X_train, U_train, prior, regularization=0)
     log_prob = dyn.log_prob(X_test, U_test)

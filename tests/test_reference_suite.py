@@ -3,9 +3,8 @@
 When the reference checkout is present (``/root/reference``; it is not on the GPU box, so this is a CPU test), its
 hot-path test modules are executed in a subprocess in which the name ``donk`` is bound to ``donk_b200`` (over the
 host emulation of the kernels).  Nothing of the reference's implementation is imported: only its test files and their
-data.  Expected outcome: everything passes except one sub-test of ``Test_LinearDynamics.test_fit_lr`` that asserts
-``eigvalsh(covar[t]) >= 0`` on a covariance that is singular by construction (N = 15 samples, p = 17): the smallest
-eigenvalue is rounding noise (-1.8e-16 here at t = 21, a different sign pattern in the reference).
+data.  Expected outcome: all 25 test functions (88 sub-tests) pass, including the sub-tests of ``Test_LinearDynamics.test_fit_lr`` that
+assert ``eigvalsh(covar[t]) >= -1e-16`` on a covariance that is singular by construction (N = 15 samples, p = 17).
 """
 import os
 import subprocess
@@ -49,13 +48,14 @@ DRIVER = textwrap.dedent('''
 def test_reference_unit_tests_pass_against_this_package():
     env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
     env.pop("DONK_GMM_MMA", None)
+    # tests/dynamics_test.py:102-178 pins values that depend on scikit-learn's k-means random stream: the opt-in host
+    # initialisation reproduces them; the package default (device k-means) agrees statistically only
+    env["DONK_GMM_INIT"] = "sklearn"
     code = DRIVER.format(root=str(ROOT), modules=MODULES)
     out = subprocess.run([sys.executable, "-c", code], cwd=REF, env=env, capture_output=True, text=True, timeout=900)
     text = out.stdout + out.stderr
     failed = [ln for ln in text.splitlines() if ln.startswith(("FAILED", "SUBFAILED", "ERROR"))]
-    allowed = [ln for ln in failed if "test_fit_lr" in ln and "test_fit_lr_with_prior" not in ln and ln.startswith("SUBFAIL")]
-    assert failed == allowed, text[-3000:]
-    assert len(allowed) <= 1, text[-3000:]
+    assert failed == [], text[-3000:]
     summary = [ln for ln in text.splitlines() if " passed" in ln][-1]
     passed = int(summary.split(" passed")[0].split()[-1])
-    assert passed >= 25, summary  # 26 test functions; test_fit_lr counts as failed when its one sub-test does
+    assert passed >= 25 and "88 subtests passed" in summary, summary  # what the reference scores against itself
