@@ -16,6 +16,10 @@
 // fit one warp per problem; other dimensions run the CTA-cooperative or the generic kernels.
 #define DONK_WARP_DIMS(X) X(20, 6) X(14, 7) X(6, 2)
 
+// (dX, dU) pairs with CTA-per-problem iLQR instantiations (ilqr_coop.cuh): BASELINE config 5 and a small shape
+// that keeps the oracle comparisons of the test-suite short.
+#define DONK_COOP_DIMS(X) X(64, 16) X(16, 8)
+
 namespace donk_abi {
 
 extern thread_local char g_err[256];
@@ -62,3 +66,11 @@ int allow_smem(KernelT kernel, size_t bytes) {
 }
 
 }  // namespace donk_abi
+
+namespace donk {
+template <typename R>
+struct IlqrArgs;
+}
+namespace donk_abi {
+int ilqr_coop_try_launch(const donk::IlqrArgs<double>& a, void* stream);  // abi_ilqr_coop.cu; -1: no instantiation
+}

@@ -84,6 +84,10 @@ int ilqr_step_launch(IlqrArgs<R> a, void* stream) {
   if (a.dX == DXV && a.dU == DUV) return ilqr_warp_launch<R, DXV, DUV>(a, stream);
     DONK_WARP_DIMS(DONK_TRY_WARP)
 #undef DONK_TRY_WARP
+    if constexpr (sizeof(R) == 8) {  // large state dimensions: one problem per CTA, products on DMMA tiles (ilqr_coop.cuh)
+      const int rc_c = ilqr_coop_try_launch(reinterpret_cast<const IlqrArgs<double>&>(a), stream);
+      if (rc_c >= 0 && rc_c != DONK_SMEM_LIMIT) return rc_c;
+    }
   }
   rc = ilqr_plan(a.B, a.E, a.dX, a.dU, sizeof(R), smem_optin_cap(), env_int("DONK_ILQR_SLOTS"),
                  env_int("DONK_ILQR_THREADS"), pl);
@@ -126,7 +130,7 @@ extern "C" {
     a.x0m = x0_mean; a.x0S = x0_covar; a.eta = eta; a.gamma = gamma; a.fwd_reg = fwd_reg;                     \
     a.K = K; a.k = k; a.pcov = pol_covar; a.pinv = pol_inv_covar; a.kl = kl; a.cost = cost;                   \
     a.tmean = traj_mean; a.tcov = traj_covar; a.info = info; a.active = active;                               \
-    a.aligned16 = (((uintptr_t)F | (uintptr_t)C_kl | (uintptr_t)dyn_covar) & 15) == 0;                        \
+    a.aligned16 = (((uintptr_t)F | (uintptr_t)C_kl | (uintptr_t)dyn_covar | (uintptr_t)C | (uintptr_t)K) & 15) == 0;                      \
     return ilqr_step_launch<R>(a, stream);                                                                    \
   }
 ILQR_STEP_IMPL(f64, double)

@@ -17,6 +17,7 @@
 #include "../../donk_b200/csrc/ilqr.cuh"
 #include "../../donk_b200/csrc/kmeans.cuh"
 #include "../../donk_b200/csrc/ilqr_warp.cuh"
+#include "../../donk_b200/csrc/ilqr_coop.cuh"
 
 namespace donk {
 int g_emu_reverse = 0;
@@ -46,6 +47,23 @@ static int emu_ilqr_warp(const IlqrArgs<R>& a) {
   return DONK_OK;
 }
 
+template <int DX, int DU>
+static int emu_ilqr_coop(const IlqrArgs<double>& a) {
+  int G = env_int("DONK_COOP_WARPS");
+  if (G <= 0) G = 8;
+  if (G > 16) G = 16;
+  const size_t bytes = ilqr_coop_bytes<double, DX, DU>();
+  if (bytes > kSmemCap || !coop_schedule_fits<DX, DU>(G)) return DONK_SMEM_LIMIT;
+  std::vector<double> smem(bytes / sizeof(double) + 4);
+  WCtx w{0, 1, 0, 0, G};
+  for (int cta = 0; cta < a.B * a.E; ++cta) {
+    memset(smem.data(), 0xFF, smem.size() * sizeof(double));
+    if (ilqr_coop_is_full<double, DX, DU>(a)) ilqr_coop_cta<double, DX, DU, true>(w, a, cta, smem.data());
+    else ilqr_coop_cta<double, DX, DU, false>(w, a, cta, smem.data());
+  }
+  return DONK_OK;
+}
+
 template <typename R>
 static int emu_ilqr_step(IlqrArgs<R> a) {
   if (a.B < 0 || a.E < 1 || a.T < 1 || a.dX < 1 || a.dU < 1) return DONK_BAD_SHAPE;
@@ -56,6 +74,12 @@ static int emu_ilqr_step(IlqrArgs<R> a) {
     if (a.dX == 20 && a.dU == 6) return emu_ilqr_warp<R, 20, 6>(a);
     if (a.dX == 14 && a.dU == 7) return emu_ilqr_warp<R, 14, 7>(a);
     if (a.dX == 6 && a.dU == 2) return emu_ilqr_warp<R, 6, 2>(a);
+    if constexpr (sizeof(R) == 8) {
+      int rc_c = -1;
+      if (a.dX == 64 && a.dU == 16) rc_c = emu_ilqr_coop<64, 16>(a);
+      else if (a.dX == 16 && a.dU == 8) rc_c = emu_ilqr_coop<16, 8>(a);
+      if (rc_c >= 0 && rc_c != DONK_SMEM_LIMIT) return rc_c;
+    }
   }
   IlqrPlan pl;
   int rc;

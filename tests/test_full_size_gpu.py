@@ -176,7 +176,9 @@ def test_config4_em_full_size(backend):
 
 
 def test_config5_dims_long_horizon(backend):
-    """BASELINE configs[4] dimensions (T=500, dX=64, dU=16, N=128) on a few conditions: the generic kernels."""
+    """BASELINE configs[4] dimensions (T=500, dX=64, dU=16, N=128) on a few conditions: the CTA-per-problem iLQR kernel
+    over the full horizon against the oracle (500 sequential Riccati steps at p = 80 is where rounding accumulates), the
+    full `optimize` of one condition, and the dynamics fit."""
     from donk_b200 import synthetic
 
     dev = backend.device
@@ -193,3 +195,25 @@ def test_config5_dims_long_horizon(backend):
     assert torch.equal(r.kl_div[-1], r.kl_div[0]) and bool((r.kl_div[:, 1] < r.kl_div[:, 0]).all())
     Fo, fo, co = oracle.fit_lr(ro["X"][1].cpu().numpy()[:, :6], ro["U"][1].cpu().numpy()[:, :5])
     assert relerr(F[1, :5], Fo) < 1e-8 and relerr(S[1, :5], co) < 1e-8
+    # full horizon against the oracle: every policy output, KL and expected cost of two (condition, eta) problems
+    for b, e in ((1, 0), (4, 1)):
+        ref = oracle.ilqr_step(_oracle_problem(b, ro, dyn, costs, x0), float(eta[b, e]))
+        assert relerr(r.K[b, e], ref.K) < 1e-8 and relerr(r.k[b, e], ref.k) < 1e-8
+        assert relerr(r.covar[b, e], ref.covar) < 1e-8 and relerr(r.inv_covar[b, e], ref.inv_covar) < 1e-8
+        assert abs(float(r.kl_div[b, e]) - ref.kl_div) < 1e-8 * max(1.0, abs(ref.kl_div))
+        assert abs(float(r.expected_costs[b, e]) - ref.expected_costs) < 1e-8 * abs(ref.expected_costs)
+    # the cooperative kernel and the generic kernel agree over the whole horizon (different summation orders)
+    import os
+
+    K_coop = r.K.clone()
+    os.environ["DONK_ILQR_GENERIC"] = "1"
+    try:
+        rg = il.step(eta)
+    finally:
+        del os.environ["DONK_ILQR_GENERIC"]
+    assert relerr(rg.K, K_coop.cpu().numpy()) < 1e-9
+    # optimize (Brent over eta, E = 1 launches) for one condition against the oracle's search
+    res, status, n_steps = il.optimize(1.0)
+    assert int(status.abs().sum()) == 0
+    ref, visited = oracle.ilqr_optimize(_oracle_problem(2, ro, dyn, costs, x0), 1.0)
+    assert abs(float(res.eta[2, 0]) - ref.eta) < 1e-8 * ref.eta and relerr(res.K[2, 0], ref.K) < 1e-8

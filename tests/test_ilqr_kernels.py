@@ -173,13 +173,11 @@ def test_warp_kernel_dims_vs_oracle(backend, dims, reverse):
         assert abs(float(r1.kl_div[b, 0]) - ref.kl_div) < 1e-9 * max(1.0, abs(ref.kl_div))
 
 
-def test_generic_kernel_config5_dims(backend):
-    """dX=64, dU=16 (BASELINE config 5): no warp instantiation, the generic CTA kernel with one slot per CTA."""
+def _coop_case(dX, dU, T, N, B, cfg=5):
     from donk_b200 import synthetic
     from donk_b200.batched import BatchedILQR
 
-    dX, dU, T, N, B = 64, 16, 3, 100, 2
-    conds = [synthetic.condition(5, i, T, dX, dU, N) for i in range(B)]
+    conds = [synthetic.condition(cfg, i, T, dX, dU, N) for i in range(B)]
     fits = [oracle.fit_lr(c.X, c.U) for c in conds]
     x0 = [oracle.state_fit(c.X[:, 0]) for c in conds]
     st = lambda xs: np.stack(xs)  # noqa: E731
@@ -187,17 +185,73 @@ def test_generic_kernel_config5_dims(backend):
                      st([c.prev_K for c in conds]), st([c.prev_k for c in conds]), st([c.C for c in conds]),
                      st([c.c for c in conds]), st([c.cc for c in conds]), st([m for m, _ in x0]),
                      st([S for _, S in x0]), prev_covar=st([c.prev_covar for c in conds]))
-    etas = np.array([0.5, 20.0])
-    r = il.step(torch.as_tensor(etas).expand(B, 2))
+    probs = [ILQRProblem(*fits[b], c.C, c.c, c.cc, c.prev_K, c.prev_k, c.prev_covar, np.linalg.inv(c.prev_covar), *x0[b])
+             for b, c in enumerate(conds)]
+    return il, probs
+
+
+def _check_step(r, b, e, ref, traj=False):
+    assert relerr(r.K[b, e], ref.K) < TOL and relerr(r.k[b, e], ref.k) < TOL
+    assert relerr(r.covar[b, e], ref.covar) < TOL and relerr(r.inv_covar[b, e], ref.inv_covar) < TOL
+    assert abs(float(r.kl_div[b, e]) - ref.kl_div) < 1e-9 * max(1.0, abs(ref.kl_div))
+    assert abs(float(r.expected_costs[b, e]) - ref.expected_costs) < 1e-9 * abs(ref.expected_costs)
+    if traj:
+        assert relerr(r.traj_mean[b, e], ref.mean) < TOL and relerr(r.traj_covar[b, e], ref.traj_covar) < TOL
+        c = to_np(r.traj_covar[b, e])
+        assert np.array_equal(c, np.swapaxes(c, 1, 2))
+
+
+@pytest.mark.parametrize("dims,G,reverse", [((16, 8), 8, 0), ((16, 8), 3, 1), ((16, 8), 16, 0), ((16, 8), 1, 0)])
+def test_coop_kernel_small_dims_vs_oracle(backend, monkeypatch, dims, G, reverse):
+    """The CTA-per-problem kernel (ilqr_coop.cuh) at small instantiations: every output of ILQR.step incl. the
+    trajectory, several eta per condition, a masked condition, different warp counts (tile schedules)."""
+    set_reverse(backend, reverse)
+    monkeypatch.setenv("DONK_COOP_WARPS", str(G))
+    dX, dU = dims
+    T, B = 6, 3
+    il, probs = _coop_case(dX, dU, T, dX + dU + 9, B, cfg=15)
+    etas = np.array([1e-3, 0.7, 40.0, 1e6])
+    r = il.step(torch.as_tensor(etas).expand(B, len(etas)), want_traj=True)
     assert int(r.info.sum()) == 0
-    for b, c in enumerate(conds):
-        prob = ILQRProblem(*fits[b], c.C, c.c, c.cc, c.prev_K, c.prev_k, c.prev_covar,
-                           np.linalg.inv(c.prev_covar), *x0[b])
+    for b in (0, B - 1):
         for e, eta in enumerate(etas):
-            ref = oracle.ilqr_step(prob, float(eta))
-            assert relerr(r.K[b, e], ref.K) < TOL and relerr(r.covar[b, e], ref.covar) < TOL
-            assert abs(float(r.kl_div[b, e]) - ref.kl_div) < 1e-9 * max(1.0, abs(ref.kl_div))
-            assert abs(float(r.expected_costs[b, e]) - ref.expected_costs) < 1e-9 * abs(ref.expected_costs)
+            _check_step(r, b, e, oracle.ilqr_step(probs[b], float(eta)), traj=True)
+    active = torch.ones(B, dtype=torch.int32)
+    active[1] = 0
+    r1 = il.step(torch.as_tensor(etas[:B]), active=active.to(backend.device))  # the FULL instantiation (no trajectory)
+    for b in (0, 2):
+        _check_step(r1, b, 0, oracle.ilqr_step(probs[b], float(etas[b])))
+    # the plain LQR entry points run through the same kernel (partial flags)
+    from donk_b200 import batched
+
+    p0 = probs[0]
+    K, k, cov, inv, info = batched.lqr_backward(p0.F[None], p0.f[None], p0.C[None], p0.c[None], gamma=0.9)
+    ref = oracle.backward(p0.F, p0.f, p0.C, p0.c, gamma=0.9)
+    assert relerr(K[0], ref[0]) < TOL and relerr(k[0], ref[1]) < TOL and relerr(cov[0], ref[2]) < TOL
+
+
+def test_coop_kernel_config5_dims(backend):
+    """dX=64, dU=16 (BASELINE config 5) on the CTA-per-problem kernel, short horizon (the T=500 comparison is the
+    -m gpu test in test_full_size_gpu.py)."""
+    il, probs = _coop_case(64, 16, 3, 100, 2)
+    etas = np.array([0.5, 20.0])
+    r = il.step(torch.as_tensor(etas).expand(2, 2))
+    assert int(r.info.sum()) == 0
+    for b in range(2):
+        for e, eta in enumerate(etas):
+            _check_step(r, b, e, oracle.ilqr_step(probs[b], float(eta)))
+
+
+def test_generic_kernel_config5_dims(backend, monkeypatch):
+    """dX=64, dU=16 on the generic CTA kernel (what any dimension without an instantiation runs)."""
+    monkeypatch.setenv("DONK_ILQR_GENERIC", "1")
+    il, probs = _coop_case(64, 16, 3, 100, 2)
+    etas = np.array([0.5, 20.0])
+    r = il.step(torch.as_tensor(etas).expand(2, 2))
+    assert int(r.info.sum()) == 0
+    for b in range(2):
+        for e, eta in enumerate(etas):
+            _check_step(r, b, e, oracle.ilqr_step(probs[b], float(eta)))
 
 
 @pytest.mark.parametrize("dims", [(20, 6), (5, 3)])
