@@ -71,6 +71,13 @@ namespace donk {
 template <typename R>
 struct IlqrArgs;
 }
+namespace donk {
+template <typename R>
+struct FitArgs;
+}
 namespace donk_abi {
 int ilqr_coop_try_launch(const donk::IlqrArgs<double>& a, void* stream);  // abi_ilqr_coop.cu; -1: no instantiation
+int fit_coop_try_launch(donk::FitArgs<double>& a, void* stream);          // abi_fit_coop.cu; -1: no instantiation
+int gmm_predict_proba_launch(int n, int d, int K, const double* X, const double* weights, const double* means,
+                             const double* prec_chol, double* resp, void* stream);  // abi_gmm.cu
 }

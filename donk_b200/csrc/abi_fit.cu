@@ -83,6 +83,14 @@ static int fit_lr_launch(FitArgs<double>& a, void* stream) {
     DONK_WARP_DIMS(DONK_TRY_FITW)
 #undef DONK_TRY_FITW
   }
+  // large dimensions: one fit per CTA on DMMA tiles (fitlr_coop.cuh); it flags the fits whose eigenvalue test needs the
+  // eigen-solver (info == 2) and the generic kernel below redoes exactly those
+  if (!env_int("DONK_FIT_GENERIC") && a.info != nullptr) {
+    const int rc_c = fit_coop_try_launch(a, stream);
+    a.wts_in = nullptr;  // stream-ordered scratch of the cooperative launch, already released
+    if (rc_c == DONK_OK) a.redo = 1;
+    else if (rc_c >= 0 && rc_c != DONK_SMEM_LIMIT) return rc_c;
+  }
   size_t bytes = 0;
   const int force = env_int("DONK_FIT_CHUNK");
   a.NS = fit_plan(dX, dU, gmm_K, force > 0 ? force : N, sizeof(double), smem_optin_cap(), bytes);
@@ -115,6 +123,7 @@ int donk_fit_lr_f64(int B, int N, int T, int dX, int dU, const double* X, const 
   a.gw = gmm_weights; a.gmeans = gmm_means; a.gcov = gmm_covariances; a.gpc = gmm_prec_chol;
   a.n_pool = n_pool; a.prior_weight = prior_weight; a.reg = regularization;
   a.F = F; a.f = f; a.covar = covar; a.info = info;
+  a.aligned16 = (((uintptr_t)X | (uintptr_t)U) & 15) == 0;
   return fit_lr_launch(a, stream);
 }
 
@@ -130,6 +139,7 @@ int donk_fit_lr_niw_f64(int B, int N, int T, int dX, int dU, const double* X, co
   a.niw_mu0 = niw_mu0; a.niw_Phi = niw_Phi; a.niw_Nmean = niw_N_mean; a.niw_Ncovar = niw_N_covar;
   a.prior_weight = prior_weight; a.reg = regularization;
   a.F = F; a.f = f; a.covar = covar; a.info = info;
+  a.aligned16 = (((uintptr_t)X | (uintptr_t)U) & 15) == 0;
   return fit_lr_launch(a, stream);
 }
 

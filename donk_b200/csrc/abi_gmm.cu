@@ -144,6 +144,26 @@ int gmm_e_launch(GmmArgs<double>& a, void* stream) {
 
 }  // namespace
 
+namespace donk_abi {
+
+// responsibilities of n rows (sklearn predict_proba): the tensor-path E pass for pools of at least 4096 rows (the
+// fit_lr prior at config-5 size evaluates millions of rows per call), the scalar kernel below that
+int gmm_predict_proba_launch(int n, int d, int K, const double* X, const double* weights, const double* means,
+                             const double* prec_chol, double* resp, void* stream) {
+  if (n < 0 || d < 1 || K < 1) return DONK_BAD_SHAPE;
+  if (n == 0) return DONK_OK;
+  GmmArgs<double> a;
+  memset(&a, 0, sizeof(a));
+  a.n = n; a.d = d; a.K = K; a.X = X; a.w = weights; a.means = means; a.pc = prec_chol;
+  a.resp = resp;
+  const GmmMmaPlan pl = gmm_mma_plan(n, d, K);
+  if (pl.ok && n >= 4096 && !env_int("DONK_GMM_GENERIC")) return gmm_e_mma_dispatch(a, pl, stream);
+  a.nblocks = (n + GMM_TS - 1) / GMM_TS;
+  return gmm_e_launch(a, stream);
+}
+
+}  // namespace donk_abi
+
 extern "C" {
 
 size_t donk_gmm_stats_size(int d, int K) { return gmm_stats_len(d, K); }
@@ -231,14 +251,7 @@ int donk_gmm_m_finalize_f64(double n_total, int d, int K, const double* stats, c
 
 int donk_gmm_predict_proba_f64(int n, int d, int K, const double* X, const double* weights, const double* means,
                                const double* prec_chol, double* resp, void* stream) {
-  if (n < 0 || d < 1 || K < 1) return DONK_BAD_SHAPE;
-  if (n == 0) return DONK_OK;
-  GmmArgs<double> a;
-  memset(&a, 0, sizeof(a));
-  a.n = n; a.d = d; a.K = K; a.X = X; a.w = weights; a.means = means; a.pc = prec_chol;
-  a.nblocks = (n + GMM_TS - 1) / GMM_TS;
-  a.resp = resp;
-  return gmm_e_launch(a, stream);
+  return donk_abi::gmm_predict_proba_launch(n, d, K, X, weights, means, prec_chol, resp, stream);
 }
 
 int donk_gmm_prec_chol_from_precisions_f64(int d, int K, const double* precisions, double* prec_chol, int* info,

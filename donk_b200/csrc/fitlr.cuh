@@ -31,6 +31,9 @@ struct FitArgs {
   const R* gconst;   // warp kernel with prior: per-cluster constants from gmm_prior_consts_item, (K*d + K)
   // explicit normal-inverse-Wishart prior per (condition, t) (any DynamicsPrior evaluated by the caller, K == 0):
   const R *niw_mu0, *niw_Phi, *niw_Nmean, *niw_Ncovar;  // (B,T,d) (B,T,d,d) (B,T) (B,T) or null
+  const R* wts_in;   // cooperative kernel with GMM prior: per-fit cluster weights mean_n predict_proba, (B,T,K)
+  int aligned16;     // set by the launcher: X and U are 16-byte aligned
+  int redo;          // generic kernel as second pass: only the fits another kernel flagged with info == 2
   R *F, *f, *covar;  // (B,T,dX,p) (B,T,dX) (B,T,dX,dX)
   int* info;         // (B,T)
 };
@@ -123,6 +126,7 @@ DONK_D void fit_lr_cta(const Ctx& ctx, const FitArgs<R>& a, int cta, R* sm) {
   const FitLayout L(a.dX, a.dU, a.K, a.N, a.NS);
   const int dX = L.dX, p = L.p, d = L.d, dp = L.dp, pa = L.pa, dXp = L.dXp, N = a.N, NS = a.NS, K = a.K;
   const int b = cta / a.T, t = cta % a.T;
+  if (a.redo && a.info[cta] != 2) return;  // CTA-uniform: this fit was completed by the cooperative kernel
   const int nchunk = (N + NS - 1) / NS;
   R* xs = sm + L.oWork;
   R* mu = sm + L.oMu;

@@ -318,10 +318,16 @@ DONK_D void chol_cta(const Ctx& ctx, int d, const R* A, int lda, R* Lm, int ldl,
   }
 }
 
-// M-step finalisation for cluster k = cta.  shared: C (d x dp) | Lm (d x dp) | dg (dp) | dl (dp) | scal (4)
+// M-step finalisation for cluster k = cta.  shared: C (d x dp) | Lm (d x dp) | dg (dp) | dl (dp) | scal (4).
+// Above d = 116 two matrices do not fit 227 KB: the factor then overwrites the strict lower triangle of C in place and the
+// substitution for L^-1 keeps its vector in the output array (gmm_fin_inplace; d up to 160).
+DONK_HD bool gmm_fin_inplace(int d) {
+  const int dp = round_up(d, 4);
+  return ((size_t)2 * d * dp + 2 * dp + 4) * 8 > (size_t)220 * 1024;
+}
 DONK_HD size_t gmm_fin_smem(int d) {
   const int dp = round_up(d, 4);
-  return (size_t)2 * d * dp + 2 * dp + 4;
+  return (size_t)(gmm_fin_inplace(d) ? 1 : 2) * d * dp + 2 * dp + 4;
 }
 
 template <typename R>
@@ -337,8 +343,9 @@ struct GmmFinArgs {
 template <typename R>
 DONK_D void gmm_finalize_cta(const Ctx& ctx, const GmmFinArgs<R>& a, int k, R* sm) {
   const int d = a.d, K = a.K, dp = round_up(d, 4);
+  const bool inplace = gmm_fin_inplace(d);
   R* C = sm;
-  R* Lm = C + (size_t)d * dp;
+  R* Lm = inplace ? C : C + (size_t)d * dp;
   R* dg = Lm + (size_t)d * dp;
   R* dl = dg + dp;
   R* scal = dl + dp;
@@ -379,14 +386,17 @@ DONK_D void gmm_finalize_cta(const Ctx& ctx, const GmmFinArgs<R>& a, int k, R* s
   if (ctx.tid == 0 && a.info) a.info[k] = scal[0] != R(0);
   // P = (L^-1)^T: column c of L^-1 by forward substitution, written as row c of P
   TEAM_FOR(c, d) {
-    R* col = C + c;  // reuse C column c as scratch for x (stride dp)
+    // scratch for x: column c of C (stride dp), or - when the factor lives in C - row c of the output itself
+    R* col = inplace ? a.pc + (size_t)k * d * d + (size_t)c * d : C + c;
+    const int cs = inplace ? 1 : dp;
     for (int i = 0; i < d; ++i) {
-      if (i < c) { col[i * dp] = R(0); continue; }
+      if (i < c) { col[i * cs] = R(0); continue; }
       R acc = i == c ? R(1) : R(0);
-      for (int q = c; q < i; ++q) acc = fma(-Lm[i * dp + q], col[q * dp], acc);
-      col[i * dp] = acc / dg[i];
+      for (int q = c; q < i; ++q) acc = fma(-Lm[i * dp + q], col[q * cs], acc);
+      col[i * cs] = acc / dg[i];
     }
-    for (int i = 0; i < d; ++i) a.pc[(size_t)k * d * d + (size_t)c * d + i] = col[i * dp];
+    if (!inplace)
+      for (int i = 0; i < d; ++i) a.pc[(size_t)k * d * d + (size_t)c * d + i] = col[i * dp];
   }
 }
 
@@ -396,7 +406,7 @@ template <typename R>
 DONK_D void gmm_prec_chol_cta(const Ctx& ctx, int d, const R* prec, R* pc, int* info, int k, R* sm) {
   const int dp = round_up(d, 4);
   R* C = sm;
-  R* Lm = C + (size_t)d * dp;
+  R* Lm = gmm_fin_inplace(d) ? C : C + (size_t)d * dp;
   R* dg = Lm + (size_t)d * dp;
   R* scal = dg + 2 * dp;
   const R* A = prec + (size_t)k * d * d;

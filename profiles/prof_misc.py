@@ -43,6 +43,24 @@ elif what == "config5":
     print(f"ILQR.step (64,16) B={B} T={T} E=1: {ms:.1f} ms = {B / (ms * 1e-3):.1f} solves/s, info {int(r.info.sum())}")
     ms, (res, status, n_steps) = timed(lambda: il.optimize(1.0, raise_on_failure=False), 1)
     print(f"ILQR.optimize (64,16) B={B}: {ms:.1f} ms, {n_steps} steps, status", torch.bincount(status, minlength=4).tolist())
+elif what == "config5fit":
+    B, T = int(sys.argv[2]), int(sys.argv[3])
+    dX, dU, N, K = 64, 16, 128, 16
+    d = 2 * dX + dU
+    ro = synthetic.rollout_batch_torch(B, T, dX, dU, N, seed=7, device=dev)
+    ms, (F, f, S, info) = timed(lambda: batched.fit_lr(ro["X"], ro["U"]))
+    print(f"fit_lr (64,16) N=128 no prior B={B} T={T}: {ms:.1f} ms = {B * T / (ms * 1e-3):.0f} fits/s, info counts", torch.bincount(info.flatten(), minlength=3).tolist())
+    pool = batched.to_transitions(ro["X"][:min(B, 32)].reshape(-1, T + 1, dX), ro["U"][:min(B, 32)].reshape(-1, T, dU))
+    rng = np.random.default_rng(0)
+    idx = rng.choice(pool.shape[0], K, replace=False)
+    gm = batched.DeviceGMM(K, max_iter=5).set_params(np.full(K, 1 / K), pool[idx].cpu().numpy(), precisions=np.broadcast_to(np.eye(d), (K, d, d)).copy())
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        t0 = time.perf_counter(); gm.fit(pool); torch.cuda.synchronize()
+    print(f"GMM fit on {pool.shape[0]} rows d={d} K={K}: {gm.n_iter} iterations, {1e3 * (time.perf_counter() - t0):.1f} ms")
+    ms, (F, f, S, info) = timed(lambda: batched.fit_lr(ro["X"], ro["U"], gm), 2)
+    print(f"fit_lr (64,16) N=128 K=16 prior B={B} T={T}: {ms:.1f} ms = {B * T / (ms * 1e-3):.0f} fits/s, info counts", torch.bincount(info.flatten(), minlength=3).tolist())
 elif what == "config2":
     B = int(sys.argv[2])
     T, dX, dU, N, K = 100, 14, 7, 50, 4

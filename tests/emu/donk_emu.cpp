@@ -5,6 +5,7 @@
 // shared memory is a heap buffer.  It exists so kernel logic can be checked against the
 // oracle in the build container, which has no GPU.  The product (donk_b200/_lib.py) never
 // loads this library; entry points carry the donk_emu_ prefix and take HOST pointers.
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -12,6 +13,7 @@
 
 #include "../../donk_b200/csrc/fitlr.cuh"
 #include "../../donk_b200/csrc/fitlr_warp.cuh"
+#include "../../donk_b200/csrc/fitlr_coop.cuh"
 #include "../../donk_b200/csrc/gmm.cuh"
 #include "../../donk_b200/csrc/gmm_mma.cuh"
 #include "../../donk_b200/csrc/ilqr.cuh"
@@ -207,6 +209,47 @@ int donk_emu_brent_update_f64(int B, int phase, double xa, double xb, const doub
 // ---------------------------------------------------------------------------------------------
 // fit_lr / transitions / state fit / GMM EM under emulation
 // ---------------------------------------------------------------------------------------------
+// forward declaration: responsibilities through the emulated E pass (defined with the GMM entry points below)
+extern "C" int donk_emu_gmm_predict_proba_f64(int n, int d, int K, const double* X, const double* weights, const double* means,
+                                              const double* prec_chol, double* resp, void*);
+
+template <int DX, int DU>
+static int emu_fit_coop(FitArgs<double>& a) {
+  const size_t bytes = fit_coop_bytes<double, DX, DU>();
+  if (bytes > kSmemCap) return DONK_SMEM_LIMIT;
+  const int d = 2 * DX + DU;
+  std::vector<double> wts, rows, resp;
+  if (a.K > 0) {  // as the CUDA launcher: gather rows, E pass, average over the samples of every fit
+    const size_t nrows = (size_t)a.B * a.N * a.T;
+    rows.resize(nrows * d);
+    resp.resize(nrows * a.K);
+    wts.resize((size_t)a.B * a.T * a.K);
+    for (size_t i = 0; i < nrows * d; ++i) rows[i] = transitions_item<double>(a.T, DX, DU, a.X, a.U, i);
+    int rc = donk_emu_gmm_predict_proba_f64((int)nrows, d, a.K, rows.data(), a.gw, a.gmeans, a.gpc, resp.data(), nullptr);
+    if (rc != DONK_OK) return rc;
+    for (size_t idx = 0; idx < wts.size(); ++idx) {
+      const int k = (int)(idx % a.K);
+      const size_t bt = idx / a.K, t = bt % a.T, b = bt / a.T;
+      double acc = 0.0;
+      for (int n = 0; n < a.N; ++n) acc += resp[((b * a.N + n) * a.T + t) * a.K + k];
+      wts[idx] = acc / a.N;
+    }
+    a.wts_in = wts.data();
+  }
+  std::vector<double> smem(bytes / sizeof(double) + 4);
+  int G = env_int("DONK_COOP_WARPS");
+  if (G <= 0) G = 8;
+  if (env_int("DONK_EMU_TRACE")) fprintf(stderr, "[emu] fit_coop_cta<%d,%d> K=%d N=%d G=%d\n", DX, DU, a.K, a.N, G);
+  WCtx w{0, 1, 0, 0, G};
+  const int ncta = 3;  // a few persistent "CTAs", each striding over the fits
+  for (int cta = 0; cta < ncta; ++cta) {
+    memset(smem.data(), 0xFF, smem.size() * sizeof(double));
+    fit_coop_cta<double, DX, DU>(w, a, cta, ncta, smem.data());
+  }
+  a.wts_in = nullptr;
+  return DONK_OK;
+}
+
 extern "C" {
 
 static int emu_fit_lr_launch(FitArgs<double>& a) {
@@ -218,6 +261,13 @@ static int emu_fit_lr_launch(FitArgs<double>& a) {
     else if (dX == 6 && dU == 2) rc = emu_fit_warp<6, 2>(a);
     if (rc != DONK_SMEM_LIMIT) return rc;  // as the CUDA launcher: a plan that does not fit falls through
   }
+  if (!env_int("DONK_FIT_GENERIC") && a.info != nullptr) {  // cooperative kernel + generic redo of the flagged fits
+    int rc_c = -1;
+    if (dX == 64 && dU == 16) rc_c = emu_fit_coop<64, 16>(a);
+    else if (dX == 16 && dU == 8) rc_c = emu_fit_coop<16, 8>(a);
+    if (rc_c == DONK_OK) a.redo = 1;
+    else if (rc_c >= 0 && rc_c != DONK_SMEM_LIMIT) return rc_c;
+  }
   size_t bytes = 0;
   const int force = env_int("DONK_FIT_CHUNK");
   a.NS = fit_plan(dX, dU, gmm_K, force > 0 ? force : N, sizeof(double), kSmemCap, bytes);
@@ -225,6 +275,11 @@ static int emu_fit_lr_launch(FitArgs<double>& a) {
   FitLayout L(dX, dU, gmm_K, N, a.NS);
   std::vector<double> smem(L.total + 2);
   Ctx ctx{0, 1};
+  if (env_int("DONK_EMU_TRACE")) {
+    int redo = 0;
+    for (int i = 0; i < B * T; ++i) redo += a.redo && a.info[i] == 2;
+    fprintf(stderr, "[emu] fit_lr_cta generic: %d of %d fits\n", a.redo ? redo : B * T, B * T);
+  }
   for (int cta = 0; cta < B * T; ++cta) {
     memset(smem.data(), 0xFF, smem.size() * sizeof(double));
     fit_lr_cta<double>(ctx, a, cta, smem.data());
@@ -242,7 +297,7 @@ int donk_emu_fit_lr_f64(int B, int N, int T, int dX, int dU, const double* X, co
   a.B = B; a.N = N; a.T = T; a.dX = dX; a.dU = dU; a.X = X; a.U = U; a.K = gmm_K;
   a.gw = gmm_weights; a.gmeans = gmm_means; a.gcov = gmm_covariances; a.gpc = gmm_prec_chol;
   a.n_pool = n_pool; a.prior_weight = prior_weight; a.reg = regularization;
-  a.F = F; a.f = f; a.covar = covar; a.info = info;
+  a.F = F; a.f = f; a.covar = covar; a.info = info; a.aligned16 = 1;
   return emu_fit_lr_launch(a);
 }
 
@@ -255,7 +310,7 @@ int donk_emu_fit_lr_niw_f64(int B, int N, int T, int dX, int dU, const double* X
   a.B = B; a.N = N; a.T = T; a.dX = dX; a.dU = dU; a.X = X; a.U = U; a.K = 0;
   a.niw_mu0 = mu0; a.niw_Phi = Phi; a.niw_Nmean = Nm; a.niw_Ncovar = Nc;
   a.prior_weight = prior_weight; a.reg = regularization;
-  a.F = F; a.f = f; a.covar = covar; a.info = info;
+  a.F = F; a.f = f; a.covar = covar; a.info = info; a.aligned16 = 1;
   return emu_fit_lr_launch(a);
 }
 

@@ -393,3 +393,67 @@ def test_fit_lr_accepts_any_dynamics_prior(backend):
     dyn = fit_lr(c.X, c.U, prior, regularization=1e-6, prior_weight=2.0)
     Fo, fo, co = oracle.fit_lr(c.X, c.U, lambda xux: prior.niw, 1e-6, 2.0)
     assert relerr(dyn.F, Fo) < 1e-8 and relerr(dyn.f, fo) < 1e-8 and relerr(dyn.covar, co) < 1e-8
+
+
+@pytest.mark.parametrize("N,K,G", [(70, 0, 8), (37, 3, 8), (64, 2, 3), (9, 0, 8), (50, -1, 16)])
+def test_fit_lr_coop_kernel_small_dims(backend, monkeypatch, N, K, G):
+    """The CTA-per-fit kernel (fitlr_coop.cuh) at its small instantiation (dX=16, dU=8): without prior, with a GMM prior
+    (cluster weights from the E pass over all samples of the call), with explicit NIW parameters (K = -1), ragged
+    sample chunks (N not a multiple of 32), and N < p (N = 9): the Cholesky attempt of the eigenvalue test fails, the fit
+    is flagged and redone by the generic kernel with the eigenvalue lift."""
+    from donk_b200 import batched, synthetic
+    from donk_b200.batched import DeviceGMM
+    from oracle.gmm import gmm_eval_prior
+
+    monkeypatch.setenv("DONK_COOP_WARPS", str(G))
+    dX, dU, T, B, n_pool = 16, 8, 3, 2, 4321
+    d = 2 * dX + dU
+    conds = [synthetic.condition(35, i, T, dX, dU, N) for i in range(B)]
+    X, U = np.stack([c.X for c in conds]), np.stack([c.U for c in conds])
+    if K > 0:
+        prm = _synthetic_prior(dX, dU, K, seed=8)
+        gm = DeviceGMM(K)
+        gm.set_params(prm.weights, prm.means, covariances=prm.covariances, precisions_cholesky=prm.precisions_cholesky)
+        gm.N = n_pool
+        F, f, covar, info = batched.fit_lr(X, U, gm, 1e-6, prior_weight=1.5)
+        prior = lambda xux: gmm_eval_prior(prm, n_pool, xux)  # noqa: E731
+    elif K < 0:
+        from donk_b200.dynamics.prior.prior import NormalInverseWishart
+
+        r = np.random.default_rng(3)
+        A = r.standard_normal((d, d))
+        niw = NormalInverseWishart(0.1 * r.standard_normal(d), A @ A.T + d * np.eye(d), 6.5, 9.0)
+        bc = lambda v: np.broadcast_to(v, (B, T) + np.shape(v)).copy()  # noqa: E731
+        F, f, covar, info = batched.fit_lr_niw(X, U, bc(niw.mu0), bc(niw.Phi), bc(niw.N_mean), bc(niw.N_covar), 1e-6, 1.5)
+        prior = lambda xux: niw  # noqa: E731
+    else:
+        F, f, covar, info = batched.fit_lr(X, U, None, 1e-6)
+        prior = None
+    assert int(info.sum()) == 0
+    for b, c in enumerate(conds):
+        Fo, fo, co = oracle.fit_lr(c.X, c.U, prior, 1e-6, 1.5 if prior is not None else 1.0)
+        assert relerr(F[b], Fo) < 1e-8 and relerr(f[b], fo) < 1e-8 and relerr(covar[b], co) < 1e-8
+        cc = to_np(covar[b])
+        assert np.array_equal(cc, np.swapaxes(cc, 1, 2))
+
+
+def test_fit_lr_coop_kernel_config5_dims(backend):
+    """dX=64, dU=16, N=128 with a 16-cluster prior (BASELINE config 5), two time steps."""
+    from donk_b200 import batched, synthetic
+    from donk_b200.batched import DeviceGMM
+    from oracle.gmm import gmm_eval_prior
+
+    dX, dU, T, N, K, n_pool = 64, 16, 2, 128, 16, 2_000_000
+    c = synthetic.condition(5, 0, T, dX, dU, N)
+    prm = _synthetic_prior(dX, dU, K, seed=11)
+    gm = DeviceGMM(K)
+    gm.set_params(prm.weights, prm.means, covariances=prm.covariances, precisions_cholesky=prm.precisions_cholesky)
+    gm.N = n_pool
+    F, f, covar, info = batched.fit_lr(c.X[None], c.U[None], gm, 1e-6)
+    assert int(info.sum()) == 0
+    Fo, fo, co = oracle.fit_lr(c.X, c.U, lambda xux: gmm_eval_prior(prm, n_pool, xux), 1e-6)
+    assert relerr(F[0], Fo) < 1e-8 and relerr(f[0], fo) < 1e-8 and relerr(covar[0], co) < 1e-8
+    F, f, covar, info = batched.fit_lr(c.X[None], c.U[None])
+    Fo, fo, co = oracle.fit_lr(c.X, c.U)
+    assert int(info.sum()) == 0
+    assert relerr(F[0], Fo) < 1e-8 and relerr(f[0], fo) < 1e-8 and relerr(covar[0], co) < 1e-8
