@@ -32,6 +32,7 @@ SIGNATURES = {
     "kl_divergence_action_f64": [c_int] * 4 + [P] * 10 + [P],
     "brent_update_f64": [c_int, c_int, c_double, c_double, P, P, P, c_double, c_double, c_double, c_int]
     + [P] * 5 + [P],
+    "ilqr_optimize_f64": [c_int] * 4 + [P] * 15 + [c_double] * 7 + [c_int] + [P] * 14 + [c_size_t, P],
     "fit_lr_f64": [c_int] * 5 + [P, P, c_int, P, P, P, P, c_double, c_double, c_double, P, P, P, P, P],
     "fit_lr_niw_f64": [c_int] * 5 + [P] * 6 + [c_double, c_double, P, P, P, P, P],
     "to_transitions_f64": [c_int] * 4 + [P, P, P, P],
@@ -48,6 +49,7 @@ _SIZE_FUNCS = {
     "gmm_stats_size": [c_int, c_int],
     "gmm_workspace_bytes": [c_int, c_int, c_int],
     "kmeans_workspace_bytes": [c_int, c_int],
+    "ilqr_optimize_workspace_bytes": [c_int],
 }
 
 

@@ -246,69 +246,51 @@ class BatchedILQR:
 
     def optimize(self, kl_step, min_eta: float = 1e-6, max_eta: float = 1e16, rtol: float = 1e-2,
                  want_traj: bool = False, raise_on_failure: bool = True):
-        """``ILQR.optimize`` (lqg.py:90-123) for all B conditions in lock-step.
+        """``ILQR.optimize`` (lqg.py:90-123) for all B conditions in lock-step, as one CUDA-graph launch.
 
-        ``kl_step`` scalar or ``(B,)``.  Returns ``(BatchedStepResult with E=1, status (B,) int32,
-        n_steps)``; status 0 = root found, 1 = constraint inactive at ``min_eta`` (lqg.py:108-109),
-        2 = ``max_eta`` too low (the reference raises ValueError, lqg.py:112-113), 3 = Brent did not
-        converge in 100 iterations (scipy raises RuntimeError).
+        The whole search — the check at ``min_eta``, the check at ``max_eta``, brentq's two bracket evaluations, the
+        Brent rounds until the last condition has converged, the step at the root — runs on the device
+        (``donk_ilqr_optimize_f64``: a WHILE graph node around the Brent rounds); the host reads three counters once.
+
+        ``kl_step`` scalar or ``(B,)``.  Returns ``(BatchedStepResult with E=1, status (B,) int32, n_steps)``; status
+        0 = root found, 1 = constraint inactive at ``min_eta`` (lqg.py:108-109), 2 = ``max_eta`` too low (the
+        reference raises ValueError, lqg.py:112-113), 3 = Brent failed (scipy raises ValueError / RuntimeError).
+        ``n_steps`` counts the batched ``step`` evaluations the reference's control flow needs for the slowest
+        condition.  Results live in this object's workspace and are valid until the next ``step`` / ``optimize``.
         """
         nat = _lib.native()
         dev, dt, B = self.F.device, self.F.dtype, self.B
-        kl_step_t = torch.as_tensor(kl_step, dtype=dt).to(dev).expand(B).contiguous()
-        n_steps = 0
-
-        def kl_at(eta_t, active):
-            nonlocal n_steps
-            n_steps += 1
-            r = self.step(eta_t, active=active)
-            bad = (r.info[:, 0] != 0) & (active != 0 if active is not None else True)
-            if bool(bad.any()):
-                raise np.linalg.LinAlgError("Quu is not positive definite")
-            return r.kl_div[:, 0].clone()
-
-        full = lambda v: torch.full((B,), float(v), dtype=dt, device=dev)  # noqa: E731
-        all_active = torch.ones(B, dtype=torch.int32, device=dev)
-        kl_min = kl_at(full(min_eta), all_active)
-        inactive = kl_min <= kl_step_t  # lqg.py:108: constraint already met at maximum deviation
-        active = (~inactive).to(torch.int32).contiguous()
-        status = torch.where(inactive, 1, 0).to(torch.int32)
-        eta_final = full(min_eta)
-        if int(active.sum().item()) > 0:
-            kl_max = kl_at(full(max_eta), active)
-            too_low = (kl_max > kl_step_t) & (active != 0)  # lqg.py:112
-            if bool(too_low.any()):
-                if raise_on_failure:
-                    raise ValueError(f"max_eta eta to low ({max_eta})")
-                status = torch.where(too_low, 2, status).to(torch.int32)
-                active = (active * (~too_low).to(torch.int32)).contiguous()
-            # brentq evaluates f(log min_eta), f(log max_eta) itself (exp(log(x)) may differ from x by an ulp)
-            xa, xb = float(np.log(min_eta)), float(np.log(max_eta))
-            searched = active.clone()
-            # kl_step may differ per condition: fold it into the function values (scalar argument = 0)
-            fa = (kl_at(full(np.exp(xa)), active) - kl_step_t).contiguous()
-            fb = (kl_at(full(np.exp(xb)), active) - kl_step_t).contiguous()
-            state = torch.zeros(B, 12, dtype=dt, device=dev)
-            eta = full(min_eta)
-            bstat = torch.zeros(B, dtype=torch.int32, device=dev)
-            n_active = torch.zeros(1, dtype=torch.int32, device=dev)
-            nat.call("brent_update_f64", B, 0, xa, xb, fa, fb, None, 0.0, 2e-12, float(rtol), 100, state, eta, active,
-                     bstat, n_active)
-            while int(n_active.item()) > 0:
-                fnew = (kl_at(eta, active) - kl_step_t).contiguous()
-                nat.call("brent_update_f64", B, 1, xa, xb, None, None, fnew, 0.0, 2e-12, float(rtol), 100, state,
-                         eta, active, bstat, n_active)
-            bad_sign = (bstat == 2) & (searched != 0)
-            no_conv = (bstat == 3) & (searched != 0)
-            if raise_on_failure and bool(bad_sign.any()):
+        ws = self._buffers(1, want_traj)
+        opt = getattr(self, "_opt", None)
+        if opt is None:
+            i32 = dict(dtype=torch.int32, device=dev)
+            opt = self._opt = dict(
+                kl_step=torch.empty(B, dtype=dt, device=dev), eta=torch.empty(B, 1, dtype=dt, device=dev),
+                active=torch.zeros(B, **i32), status=torch.zeros(B, **i32), counters=torch.zeros(3, **i32),
+                work=torch.empty(nat.size("ilqr_optimize_workspace_bytes", B) // 8 + 1, dtype=dt, device=dev))
+        opt["kl_step"].copy_(torch.as_tensor(kl_step, dtype=dt).to(dev).expand(B))
+        # brentq evaluates f(log min_eta), f(log max_eta) itself (exp(log(x)) may differ from x by an ulp)
+        xa, xb = float(np.log(min_eta)), float(np.log(max_eta))
+        nat.call("ilqr_optimize_f64", B, self.T, self.dX, self.dU, self.F, self.f, self.dyn_covar, self.C, self.c,
+                 self.cc, self.C_kl, self.c_kl, self.prev_K, self.prev_k, self.prev_inv_covar, self.prev_hld,
+                 self.x0_mean, self.x0_covar, opt["kl_step"], float(min_eta), float(max_eta), float(np.exp(xa)),
+                 float(np.exp(xb)), xa, xb, float(rtol), 100, opt["eta"], opt["active"], ws["K"], ws["k"],
+                 ws["covar"], ws["inv_covar"], ws["kl"], ws["cost"], ws["tmean"], ws["tcov"], ws["info"],
+                 opt["status"], opt["counters"], opt["work"], opt["work"].numel() * opt["work"].element_size())
+        rounds, err, searched = opt["counters"].tolist()  # the one device->host read of the optimisation
+        if err & 1:
+            raise np.linalg.LinAlgError("Quu is not positive definite")
+        if raise_on_failure:
+            if err & 2:
+                raise ValueError(f"max_eta eta to low ({max_eta})")
+            if err & 4:
                 raise ValueError("f(a) and f(b) must have different signs")
-            if raise_on_failure and bool(no_conv.any()):
+            if err & 8:
                 raise RuntimeError("Failed to converge after 100 iterations.")
-            status = torch.where(no_conv | bad_sign, 3, status).to(torch.int32)
-            eta_final = torch.where((searched != 0) & (bstat == 1), eta, eta_final)
-        n_steps += 1
-        result = self.step(eta_final, want_traj=want_traj)
-        return result, status, n_steps
+        n_steps = 2 + (3 + rounds if searched > 0 else 0)
+        result = BatchedStepResult(opt["eta"], ws["K"], ws["k"], ws["covar"], ws["inv_covar"], ws["kl"], ws["cost"],
+                                   ws["info"], ws["tmean"], ws["tcov"])
+        return result, opt["status"], n_steps
 
 
 # =====================================================================================================

@@ -113,6 +113,11 @@ int ilqr_step_launch(IlqrArgs<R> a, void* stream) {
 
 }  // namespace
 
+namespace donk_abi {
+// the step launch for other translation units (abi_optimize.cu captures it into the graph of ILQR.optimize)
+int ilqr_step_launch_f64(const IlqrArgs<double>& a, void* stream) { return ilqr_step_launch<double>(a, stream); }
+}  // namespace donk_abi
+
 extern "C" {
 
 #define ILQR_STEP_IMPL(SUFFIX, R)                                                                             \

@@ -123,6 +123,30 @@ int donk_brent_update_f64(int B, int phase, double xa, double xb, const double* 
                           const double* fnew, double kl_step, double xtol, double rtol, int maxiter,
                           double* state, double* eta, int* active, int* status, int* n_active, void* stream);
 
+/* ILQR.optimize for B conditions in lock-step, entirely on the device: donk/traj_opt/lqg.py:90-123 (the constraint
+ * check at min_eta, the feasibility check at max_eta, scipy.optimize.brentq in log space, the step at the root).
+ * One CUDA-graph launch: four fixed evaluation rounds, a WHILE node around the Brent rounds whose condition a small
+ * controller kernel sets from the number of still-searching conditions, the final step.  Inputs as donk_ilqr_step_f64
+ * (E = 1, gamma = 1, forward regularisation 1e-6); kl_step (B) per-condition KL bound.
+ *   eta_a = exp(xa), eta_b = exp(xb) with xa = log(min_eta), xb = log(max_eta): the multipliers brentq evaluates first
+ *   (passed in so that they are the host libm's values, as in the reference).
+ *   eta (B) out: the multiplier of the returned policy; active (B) int32 scratch;
+ *   K,k,pol_covar,pol_inv_covar,kl,cost,traj_mean,traj_covar,info: results of the final step (E = 1);
+ *   status (B) int32: 0 root found, 1 constraint inactive at min_eta, 2 max_eta too low (ValueError in the reference),
+ *                     3 brentq failed (same sign / maxiter), 4 Quu not positive definite (LinAlgError);
+ *   counters (3) int32 device: Brent rounds executed, OR of error bits (1 not PD, 2 max_eta, 4 sign, 8 maxiter),
+ *                     number of conditions whose constraint is active at min_eta;
+ *   work: donk_ilqr_optimize_workspace_bytes(B) bytes of device scratch. */
+size_t donk_ilqr_optimize_workspace_bytes(int B);
+int donk_ilqr_optimize_f64(int B, int T, int dX, int dU, const double* F, const double* f, const double* dyn_covar,
+                           const double* C, const double* c, const double* cc, const double* C_kl, const double* c_kl,
+                           const double* prevK, const double* prevk, const double* prevLam, const double* prev_hld,
+                           const double* x0_mean, const double* x0_covar, const double* kl_step, double min_eta,
+                           double max_eta, double eta_a, double eta_b, double xa, double xb, double rtol, int maxiter,
+                           double* eta, int* active, double* K, double* k, double* pol_covar, double* pol_inv_covar,
+                           double* kl, double* cost, double* traj_mean, double* traj_covar, int* info, int* status,
+                           int* counters, void* work, size_t work_bytes, void* stream);
+
 /* ---- dynamics fit ---------------------------------------------------------------------- */
 
 /* fit_lr batched over B conditions: donk/dynamics/linear_dynamics.py:137-189, with the GMM /

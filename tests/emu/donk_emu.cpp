@@ -19,6 +19,7 @@
 #include "../../donk_b200/csrc/ilqr.cuh"
 #include "../../donk_b200/csrc/kmeans.cuh"
 #include "../../donk_b200/csrc/ilqr_warp.cuh"
+#include "../../donk_b200/csrc/optimize.cuh"
 #include "../../donk_b200/csrc/ilqr_coop.cuh"
 
 namespace donk {
@@ -183,6 +184,60 @@ int donk_emu_kl_divergence_action_f64(int B, int T, int dX, int dU, const double
     kl[b] = acc / T;
   }
   return DONK_OK;
+}
+
+size_t donk_emu_ilqr_optimize_workspace_bytes(int B) { return optimize_workspace_bytes(B); }
+
+// the graph of abi_optimize.cu as a host loop: the same rounds, the same controller items
+int donk_emu_ilqr_optimize_f64(int B, int T, int dX, int dU, const double* F, const double* f, const double* dyn_covar,
+                               const double* C, const double* c, const double* cc, const double* C_kl,
+                               const double* c_kl, const double* prevK, const double* prevk, const double* prevLam,
+                               const double* prev_hld, const double* x0_mean, const double* x0_covar,
+                               const double* kl_step, double min_eta, double max_eta, double eta_a, double eta_b,
+                               double xa, double xb, double rtol, int maxiter, double* eta, int* active, double* K,
+                               double* k, double* pol_covar, double* pol_inv_covar, double* kl, double* cost,
+                               double* traj_mean, double* traj_covar, int* info, int* status, int* counters, void* work,
+                               size_t work_bytes, void*) {
+  if (B < 0 || T < 1 || dX < 1 || dU < 1 || maxiter < 1 || work_bytes < optimize_workspace_bytes(B)) return DONK_BAD_SHAPE;
+  if (B == 0) return DONK_OK;
+  IlqrArgs<double> s;
+  memset(&s, 0, sizeof(s));
+  s.B = B; s.E = 1; s.T = T; s.dX = dX; s.dU = dU;
+  s.flags = ILQR_BACKWARD | ILQR_FORWARD | ILQR_KL | ILQR_COST;
+  s.F = F; s.f = f; s.dyn_covar = dyn_covar; s.C = C; s.c = c; s.cc = cc; s.C_kl = C_kl; s.c_kl = c_kl;
+  s.prevK = prevK; s.prevk = prevk; s.prevLam = prevLam; s.prev_hld = prev_hld;
+  s.x0m = x0_mean; s.x0S = x0_covar; s.eta = eta; s.gamma = 1.0; s.fwd_reg = 1e-6;
+  s.K = K; s.k = k; s.pcov = pol_covar; s.pinv = pol_inv_covar; s.kl = kl; s.cost = cost;
+  s.info = info; s.active = active; s.aligned16 = 1;
+  IlqrArgs<double> fin = s;
+  fin.tmean = traj_mean; fin.tcov = traj_covar;
+  uintptr_t wp = ((uintptr_t)work + 15) & ~(uintptr_t)15;
+  OptArgs<double> o;
+  memset(&o, 0, sizeof(o));
+  o.B = B; o.kl_step = kl_step; o.min_eta = min_eta; o.max_eta = max_eta; o.eta_a = eta_a; o.eta_b = eta_b;
+  o.xa = xa; o.xb = xb; o.xtol = 2e-12; o.rtol = rtol; o.maxiter = maxiter;
+  o.kl = kl; o.info = info; o.eta = eta; o.active = active; o.status = status;
+  o.st = reinterpret_cast<OptState<double>*>(wp);
+  o.ctl = reinterpret_cast<OptCtl*>(wp + (size_t)B * sizeof(OptState<double>));
+  memset(o.ctl, 0, sizeof(OptCtl));
+  auto round = [&](int phase) {
+    int rc = DONK_OK;
+    if (phase != OPT_FINAL && phase != OPT_INIT) rc = emu_ilqr_step<double>(s);
+    if (rc != DONK_OK) return rc;
+    int n = 0;
+    for (int it = 0; it < B; ++it) n += optimize_ctl_item<double>(o, phase, emu_idx(it, B), &o.ctl->err);
+    o.ctl->n_active = n;
+    if (phase == OPT_MIN) o.ctl->n_after_min = n;
+    if (phase == OPT_LOOP) o.ctl->loop_iters += 1;
+    return DONK_OK;
+  };
+  int rc = DONK_OK;
+  for (int ph = OPT_INIT; ph <= OPT_FB && rc == DONK_OK; ++ph) rc = round(ph);
+  while (rc == DONK_OK && o.ctl->n_active > 0 && o.ctl->loop_iters <= maxiter + 2) rc = round(OPT_LOOP);
+  if (rc == DONK_OK) rc = round(OPT_FINAL);
+  if (rc == DONK_OK) rc = emu_ilqr_step<double>(fin);
+  counters[0] = o.ctl->loop_iters; counters[1] = o.ctl->err; counters[2] = o.ctl->n_after_min;
+  return rc;
 }
 
 int donk_emu_brent_update_f64(int B, int phase, double xa, double xb, const double* fa, const double* fb,
