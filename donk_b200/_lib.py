@@ -33,6 +33,9 @@ SIGNATURES = {
     "brent_update_f64": [c_int, c_int, c_double, c_double, P, P, P, c_double, c_double, c_double, c_int]
     + [P] * 5 + [P],
     "ilqr_optimize_f64": [c_int] * 4 + [P] * 15 + [c_double] * 7 + [c_int] + [P] * 14 + [c_size_t, P],
+    "quadratic_cost_l2_f64": [c_int, c_int] + [P] * 5 + [P],
+    "quadratic_cost_l1_f64": [c_int, c_int, P, P, P, c_double, P, P, P, P],
+    "dynamics_log_prob_f64": [c_int] * 5 + [P] * 7 + [P],
     "fit_lr_f64": [c_int] * 5 + [P, P, c_int, P, P, P, P, c_double, c_double, c_double, P, P, P, P, P],
     "fit_lr_niw_f64": [c_int] * 5 + [P] * 6 + [c_double, c_double, P, P, P, P, P],
     "to_transitions_f64": [c_int] * 4 + [P, P, P, P],

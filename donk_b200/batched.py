@@ -385,6 +385,55 @@ def fit_lr_niw(X, U, mu0, Phi, N_mean, N_covar, regularization: float = 1e-6, pr
     return F, f, covar, info
 
 
+def dynamics_log_prob(X, U, F, f, covar):
+    """Batched ``LinearDynamics.log_prob`` (linear_dynamics.py:54-64).
+
+    ``X (B,N,T+1,dX), U (B,N,T,dU)``, dynamics ``F (B,T,dX,p), f (B,T,dX), covar (B,T,dX,dX)`` -> ``(B,N,T)``
+    log-densities of every observed transition.  Raises ``numpy.linalg.LinAlgError`` when a ``covar_t`` is not positive
+    definite (scipy's ``multivariate_normal.logpdf`` with ``allow_singular=False`` fails there too).
+    """
+    nat = _lib.native()
+    X, U, F, f, covar = _dev(X), _dev(U), _dev(F), _dev(f), _dev(covar)
+    B, N, T1, dX = X.shape
+    T, dU = U.shape[2], U.shape[3]
+    if T1 != T + 1 or F.shape != (B, T, dX, dX + dU):
+        raise ValueError(f"inconsistent shapes {tuple(X.shape)} / {tuple(U.shape)} / {tuple(F.shape)}")
+    inv, _, hld = spd_factor(covar)
+    out = torch.empty(B, N, T, dtype=X.dtype, device=X.device)
+    nat.call("dynamics_log_prob_f64", B, N, T, dX, dU, X, U, F, f, inv, hld, out)
+    return out
+
+
+def quadratic_cost_approximation_l2(t, w):
+    """``QuadraticCosts.quadratic_cost_approximation_l2`` (quadratic_costs.py:121-139) for targets / weights
+    ``t, w (..., p)`` -> ``C (...,p,p), c (...,p), cc (...)`` on the device."""
+    nat = _lib.native()
+    t, w = _dev(t), _dev(w)
+    if t.shape != w.shape:
+        raise ValueError(f"{tuple(t.shape)} != {tuple(w.shape)}")
+    p = t.shape[-1]
+    n = t.numel() // p
+    o = dict(dtype=t.dtype, device=t.device)
+    C, c, cc = torch.empty(t.shape + (p,), **o), torch.empty(t.shape, **o), torch.empty(t.shape[:-1], **o)
+    nat.call("quadratic_cost_l2_f64", n, p, t, w, C, c, cc)
+    return C, c, cc
+
+
+def quadratic_cost_approximation_l1(xu, t, w, alpha: float):
+    """``QuadraticCosts.quadratic_cost_approximation_l1`` (quadratic_costs.py:141-166): second-order expansion of
+    ``sum_i w_i sqrt((t_i - xu_i)^2 + alpha)`` at the trajectory ``xu (..., p)``."""
+    nat = _lib.native()
+    xu, t, w = _dev(xu), _dev(t), _dev(w)
+    if not (xu.shape == t.shape == w.shape):
+        raise ValueError(f"{tuple(xu.shape)} / {tuple(t.shape)} / {tuple(w.shape)}")
+    p = t.shape[-1]
+    n = t.numel() // p
+    o = dict(dtype=t.dtype, device=t.device)
+    C, c, cc = torch.empty(t.shape + (p,), **o), torch.empty(t.shape, **o), torch.empty(t.shape[:-1], **o)
+    nat.call("quadratic_cost_l1_f64", n, p, xu, t, w, float(alpha), C, c, cc)
+    return C, c, cc
+
+
 # =====================================================================================================
 # GMM EM (GMMPrior.update)
 # =====================================================================================================

@@ -1,7 +1,7 @@
 """Quadratic cost container (donk/costs/quadratic_costs.py:12-139).
 
-Only what the hot path consumes: ``C, c, cc``, ``compute_costs``, ``expected_costs``, ``+``/``*`` and the
-exact L2 constructor used by the synthetic benchmarks.  Symbolic / L1 cost authoring stays host-side in
+What the hot path consumes: ``C, c, cc``, ``compute_costs``, ``expected_costs``, ``+``/``*`` and the L2 / L1
+constructors, which run as device kernels.  Symbolic cost authoring stays host-side in
 the reference and is out of scope.
 """
 from __future__ import annotations
@@ -52,7 +52,20 @@ class QuadraticCosts:
 
     @staticmethod
     def quadratic_cost_approximation_l2(t, w):
-        """Exact quadratic form of ``0.5 sum_i w_i (t_i - xu_i)^2`` (quadratic_costs.py:121-139)."""
-        t, w = np.asarray(t, dtype=np.float64), np.asarray(w, dtype=np.float64)
-        n = t.shape[-1]
-        return QuadraticCosts(w[..., :, None] * np.eye(n), -w * t, np.sum(t * w * t, axis=-1) / 2)
+        """Exact quadratic form of ``0.5 sum_i w_i (t_i - xu_i)^2`` (quadratic_costs.py:121-139), built on the device
+        (``donk_quadratic_cost_l2_f64``); ``t, w (..., p)``."""
+        from donk_b200 import batched
+
+        C, c, cc = batched.quadratic_cost_approximation_l2(np.asarray(t, dtype=np.float64), np.asarray(w, dtype=np.float64))
+        return QuadraticCosts(C.cpu().numpy(), c.cpu().numpy(), cc.cpu().numpy())
+
+    @staticmethod
+    def quadratic_cost_approximation_l1(xu, t, w, alpha: float):
+        """Second-order expansion of ``sum_i w_i sqrt((t_i - xu_i)^2 + alpha)`` at ``xu`` (quadratic_costs.py:141-166),
+        built on the device (``donk_quadratic_cost_l1_f64``)."""
+        from donk_b200 import batched
+
+        f64 = lambda a: np.asarray(a, dtype=np.float64)  # noqa: E731
+        xu, t, w = np.broadcast_arrays(f64(xu), f64(t), f64(w))
+        C, c, cc = batched.quadratic_cost_approximation_l1(xu, t, w, alpha)
+        return QuadraticCosts(C.cpu().numpy(), c.cpu().numpy(), cc.cpu().numpy())

@@ -5,6 +5,7 @@
 #include "fitlr.cuh"
 #include "ilqr.cuh"
 #include "kmeans.cuh"
+#include "costs.cuh"
 
 namespace donk_abi {
 thread_local char g_err[256] = "";
@@ -84,6 +85,27 @@ template <typename R>
 __global__ void state_fit_kernel(size_t total, int N, int dX, const R* X0, size_t ss, size_t cs, R* mean, R* covar) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < total) state_fit_item<R>(N, dX, X0, ss, cs, idx, mean, covar);
+}
+
+// ---------------------------------------------------------------------------------------------
+// cost constructors / transition log-probabilities (costs.cuh)
+// ---------------------------------------------------------------------------------------------
+__global__ void cost_l2_kernel(size_t total, int p, const double* t, const double* w, double* C, double* c, double* cc) {
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
+    cost_l2_item<double>(p, t, w, C, c, cc, idx);
+}
+__global__ void cost_l1_kernel(size_t total, int p, const double* xu, const double* t, const double* w, double alpha,
+                               double* C, double* c, double* cc) {
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
+    cost_l1_item<double>(p, xu, t, w, alpha, C, c, cc, idx);
+}
+__global__ void dyn_log_prob_kernel(size_t total, int N, int T, int dX, int dU, const double* X, const double* U,
+                                    const double* F, const double* f, const double* Sinv, const double* hld,
+                                    double* out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* diff = reinterpret_cast<double*>(smem_raw) + (size_t)threadIdx.x * dX;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
+    out[idx] = dyn_log_prob_item<double>(N, T, dX, dU, X, U, F, f, Sinv, hld, idx, diff);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -226,6 +248,49 @@ int donk_state_fit_f64(int B, int N, int dX, const double* X0, size_t sample_str
   state_fit_kernel<double><<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
       total, N, dX, X0, sample_stride, cond_stride, mean, covar);
   LAUNCHED("state_fit_kernel");
+  return DONK_OK;
+}
+
+int donk_quadratic_cost_l2_f64(int n, int p, const double* t, const double* w, double* C, double* c, double* cc,
+                               void* stream) {
+  if (n < 0 || p < 1) return DONK_BAD_SHAPE;
+  const size_t total = (size_t)n * p * p;
+  if (total == 0) return DONK_OK;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cost_l2_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(total, p, t, w, C, c, cc);
+  LAUNCHED("cost_l2_kernel");
+  return DONK_OK;
+}
+
+int donk_quadratic_cost_l1_f64(int n, int p, const double* xu, const double* t, const double* w, double alpha,
+                               double* C, double* c, double* cc, void* stream) {
+  if (n < 0 || p < 1) return DONK_BAD_SHAPE;
+  const size_t total = (size_t)n * p * p;
+  if (total == 0) return DONK_OK;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cost_l1_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(total, p, xu, t, w, alpha, C, c, cc);
+  LAUNCHED("cost_l1_kernel");
+  return DONK_OK;
+}
+
+int donk_dynamics_log_prob_f64(int B, int N, int T, int dX, int dU, const double* X, const double* U, const double* F,
+                               const double* f, const double* covar_inv, const double* half_logdet, double* log_prob,
+                               void* stream) {
+  if (B < 0 || N < 0 || T < 1 || dX < 1 || dU < 1) return DONK_BAD_SHAPE;
+  const size_t total = (size_t)B * N * T;
+  if (total == 0) return DONK_OK;
+  const int threads = 64;
+  const size_t smem = (size_t)threads * dX * sizeof(double);
+  if (smem > smem_optin_cap()) return DONK_SMEM_LIMIT;
+  int rc = allow_smem(dyn_log_prob_kernel, smem);
+  if (rc != DONK_OK) return rc;
+  size_t blocks = (total + threads - 1) / threads;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  dyn_log_prob_kernel<<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(total, N, T, dX, dU, X, U, F, f,
+                                                                               covar_inv, half_logdet, log_prob);
+  LAUNCHED("dyn_log_prob_kernel");
   return DONK_OK;
 }
 

@@ -27,27 +27,18 @@ class LinearDynamics(DynamicsModel, TimeVaryingLinearGaussian):
 
     def log_prob(self, X, U):
         """Log-probabilities of transitions under this model (linear_dynamics.py:54-64): ``X (..., T+1, dX)``,
-        ``U (..., T, dU)`` -> ``(..., T)``.
-
-        Host-side diagnostic (not on the device path).  Restates ``scipy.stats.multivariate_normal.logpdf`` as the
-        reference calls it (``allow_singular=False``): eigendecomposition of every ``covar_t``, eigenvalues below
-        ``1e6 * eps * max|lambda|`` count as zero and make the call fail, as scipy does.
+        ``U (..., T, dU)`` -> ``(..., T)``, evaluated on the device (``donk_dynamics_log_prob_f64``: Cholesky factor of
+        every ``covar_t``, one thread per transition).  A ``covar_t`` that is not positive definite raises
+        ``numpy.linalg.LinAlgError``, as scipy's ``multivariate_normal.logpdf`` does for the reference.
         """
+        from donk_b200 import batched
+
         X, U = np.asarray(X, dtype=np.float64), np.asarray(U, dtype=np.float64)
-        means = self.predict(X[..., :-1, :], U, t=None)
-        diff = X[..., 1:, :] - means
-        out = np.empty(diff.shape[:-1])
-        for t in range(self.T):
-            s, u = np.linalg.eigh(self.covar[t])
-            eps = 1e6 * np.finfo(np.float64).eps * np.max(np.abs(s))
-            if np.min(s) < -eps:
-                raise ValueError("The input matrix must be symmetric positive semidefinite.")
-            if np.any(s <= eps):
-                raise np.linalg.LinAlgError("When `allow_singular is False`, the input matrix must be symmetric "
-                                            "positive definite.")
-            maha = np.sum(np.square((diff[..., t, :] @ u) / np.sqrt(s)), axis=-1)
-            out[..., t] = -0.5 * (self.dX * np.log(2 * np.pi) + np.sum(np.log(s)) + maha)
-        return out
+        lead = X.shape[:-2]
+        Xb = X.reshape((1, -1) + X.shape[-2:])
+        Ub = U.reshape((1, -1) + U.shape[-2:])
+        out = batched.dynamics_log_prob(Xb, Ub, self.F[None], self.f[None], self.covar[None])
+        return out[0].cpu().numpy().reshape(lead + (self.T,))
 
 
 def fit_lr(X: np.ndarray, U: np.ndarray, prior=None, regularization: float = 1e-6,

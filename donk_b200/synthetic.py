@@ -116,3 +116,30 @@ def gmm_pool_torch(n: int, d: int, K: int, seed: int, device):
     X += torch.as_tensor(centers, device=device)[label]
     prec0 = np.broadcast_to(np.eye(d), (K, d, d)).copy()
     return X, np.full(K, 1.0 / K), means0, prec0
+
+
+def gmm_prior(dX: int, dU: int, K: int, seed: int):
+    """A K-cluster mixture over transitions ``[x_t | u_t | x_{t+1}]`` with well-conditioned random covariances: the
+    dynamics prior of the benchmark configurations that time ``fit_lr`` under a ``GMMPrior`` (both arms of bench.py are
+    handed these very parameters).  Returns ``(weights (K,), means (K,d), covariances (K,d,d))``."""
+    d = 2 * dX + dU
+    rng = np.random.default_rng(seed)
+    w = rng.uniform(0.5, 1.5, K)
+    w /= w.sum()
+    means = 0.3 * rng.standard_normal((K, d))
+    A = rng.standard_normal((K, d, d)) / np.sqrt(d)
+    cov = A @ np.swapaxes(A, -1, -2) + 0.5 * np.eye(d)
+    return w, means, cov
+
+
+def precision_cholesky(covariances):
+    """``precisions_cholesky_`` as scikit-learn defines it: upper-triangular ``P_k`` with ``P_k P_k^T = Sigma_k^-1``
+    (the transpose of the inverse of the lower Cholesky factor of ``Sigma_k``)."""
+    from scipy.linalg import solve_triangular
+
+    cov = np.asarray(covariances, dtype=np.float64)
+    out = np.empty_like(cov)
+    eye = np.eye(cov.shape[-1])
+    for k in range(cov.shape[0]):
+        out[k] = solve_triangular(np.linalg.cholesky(cov[k]), eye, lower=True).T
+    return out

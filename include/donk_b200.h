@@ -147,6 +147,20 @@ int donk_ilqr_optimize_f64(int B, int T, int dX, int dU, const double* F, const 
                            double* kl, double* cost, double* traj_mean, double* traj_covar, int* info, int* status,
                            int* counters, void* work, size_t work_bytes, void* stream);
 
+/* Quadratic cost constructors, batched: donk/costs/quadratic_costs.py:121-139 (L2, exact) and :141-166 (L1,
+ * second-order expansion at xu).  t, w[, xu] (n,p) -> C (n,p,p), c (n,p), cc (n). */
+int donk_quadratic_cost_l2_f64(int n, int p, const double* t, const double* w, double* C, double* c, double* cc,
+                               void* stream);
+int donk_quadratic_cost_l1_f64(int n, int p, const double* xu, const double* t, const double* w, double alpha,
+                               double* C, double* c, double* cc, void* stream);
+
+/* LinearDynamics.log_prob, batched: donk/dynamics/linear_dynamics.py:54-64.
+ *   X (B,N,T+1,dX), U (B,N,T,dU), F (B,T,dX,p), f (B,T,dX), covar_inv (B,T,dX,dX), half_logdet (B,T) (both from
+ *   donk_spd_factor_f64 on covar) -> log_prob (B,N,T). */
+int donk_dynamics_log_prob_f64(int B, int N, int T, int dX, int dU, const double* X, const double* U, const double* F,
+                               const double* f, const double* covar_inv, const double* half_logdet, double* log_prob,
+                               void* stream);
+
 /* ---- dynamics fit ---------------------------------------------------------------------- */
 
 /* fit_lr batched over B conditions: donk/dynamics/linear_dynamics.py:137-189, with the GMM /

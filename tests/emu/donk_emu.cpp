@@ -20,6 +20,7 @@
 #include "../../donk_b200/csrc/kmeans.cuh"
 #include "../../donk_b200/csrc/ilqr_warp.cuh"
 #include "../../donk_b200/csrc/optimize.cuh"
+#include "../../donk_b200/csrc/costs.cuh"
 #include "../../donk_b200/csrc/ilqr_coop.cuh"
 
 namespace donk {
@@ -183,6 +184,30 @@ int donk_emu_kl_divergence_action_f64(int B, int T, int dX, int dU, const double
     }
     kl[b] = acc / T;
   }
+  return DONK_OK;
+}
+
+int donk_emu_quadratic_cost_l2_f64(int n, int p, const double* t, const double* w, double* C, double* c, double* cc, void*) {
+  if (n < 0 || p < 1) return DONK_BAD_SHAPE;
+  const size_t total = (size_t)n * p * p;
+  for (size_t it = 0; it < total; ++it) cost_l2_item<double>(p, t, w, C, c, cc, g_emu_reverse ? total - 1 - it : it);
+  return DONK_OK;
+}
+int donk_emu_quadratic_cost_l1_f64(int n, int p, const double* xu, const double* t, const double* w, double alpha,
+                                   double* C, double* c, double* cc, void*) {
+  if (n < 0 || p < 1) return DONK_BAD_SHAPE;
+  const size_t total = (size_t)n * p * p;
+  for (size_t it = 0; it < total; ++it) cost_l1_item<double>(p, xu, t, w, alpha, C, c, cc, g_emu_reverse ? total - 1 - it : it);
+  return DONK_OK;
+}
+int donk_emu_dynamics_log_prob_f64(int B, int N, int T, int dX, int dU, const double* X, const double* U, const double* F,
+                                   const double* f, const double* covar_inv, const double* half_logdet, double* log_prob,
+                                   void*) {
+  if (B < 0 || N < 0 || T < 1 || dX < 1 || dU < 1) return DONK_BAD_SHAPE;
+  std::vector<double> diff(dX);
+  const size_t total = (size_t)B * N * T;
+  for (size_t idx = 0; idx < total; ++idx)
+    log_prob[idx] = dyn_log_prob_item<double>(N, T, dX, dU, X, U, F, f, covar_inv, half_logdet, idx, diff.data());
   return DONK_OK;
 }
 
