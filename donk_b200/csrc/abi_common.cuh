@@ -57,6 +57,21 @@ inline size_t smem_optin_cap() {
   return cap;
 }
 
+// Stream-ordered scratch (cudaMallocAsync) comes from the device's default memory pool.  Its release threshold is 0 by
+// default: every synchronisation hands the freed blocks back to the driver and the next call pays for a fresh
+// allocation (~100 ms per GB).  Keep what was freed in the pool instead (set once per device).
+inline void keep_async_pool() {
+  static bool done[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done[dev] = true;
+}
+
 template <typename KernelT>
 int allow_smem(KernelT kernel, size_t bytes) {
   if (bytes > 48 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));

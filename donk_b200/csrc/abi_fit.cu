@@ -47,6 +47,7 @@ int fit_warp_launch(FitArgs<R> a, void* stream) {
   R* consts = nullptr;
   if (a.K > 0) {  // per-cluster constants of the log-probabilities: stream-ordered scratch, freed after the fit launch
     const int d = 2 * DX + DU, len = a.K * d + a.K;
+    keep_async_pool();
     if (cudaMallocAsync(reinterpret_cast<void**>(&consts), (size_t)len * sizeof(R), (cudaStream_t)stream) != cudaSuccess) {
       snprintf(g_err, sizeof(g_err), "fit_lr: cudaMallocAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
       return DONK_CUDA_ERROR;

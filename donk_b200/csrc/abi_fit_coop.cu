@@ -51,6 +51,7 @@ int fit_coop_launch(FitArgs<double>& a, void* stream) {
     if (rows_per_cond * chunk > (size_t)0x7fffffff) return DONK_BAD_SHAPE;
     const size_t wts_len = (size_t)a.B * a.T * a.K;
     const size_t need = (wts_len + (size_t)chunk * rows_per_cond * (d + a.K)) * sizeof(double);
+    keep_async_pool();
     if (cudaMallocAsync(reinterpret_cast<void**>(&scratch), need, st) != cudaSuccess) {
       snprintf(g_err, sizeof(g_err), "fit_lr: cudaMallocAsync(%zu) failed: %s", need, cudaGetErrorString(cudaGetLastError()));
       return DONK_CUDA_ERROR;

@@ -432,7 +432,7 @@ inline GmmMmaPlan gmm_mma_plan(int n, int d, int K) {
   const int nb = (d + 7) / 8;
   p.ok = nb <= 18;
   p.NB = nb <= 2 ? 2 : nb <= 5 ? 5 : nb <= 6 ? 6 : nb <= 9 ? 9 : 18;
-  p.RA = p.NB <= 9 ? 2 : 1;
+  p.RA = 2;
   p.Ge = 8;
   p.KC = 2;
   p.Gm = nb <= 9 ? 8 : 16;

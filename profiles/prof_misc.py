@@ -119,3 +119,11 @@ elif what == "config3prior":
     print(f"fit_lr + GMM prior (20,6) N=64 K={K}, B={B}: {ms:.1f} ms = {B * T / (ms * 1e-3):.0f} fits/s, info {int(info.sum())}")
     ms, _ = timed(lambda: batched.fit_lr(ro["X"], ro["U"]))
     print(f"fit_lr no prior  (20,6) N=64, B={B}: {ms:.1f} ms = {B * T / (ms * 1e-3):.0f} fits/s")
+elif what == "epass":
+    # E pass (predict_proba) alone: n rows, d features, K clusters
+    n, d, K = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+    X, w0, m0, p0 = synthetic.gmm_pool_torch(n, d, K, seed=5, device=dev)
+    gm = batched.DeviceGMM(K).set_params(w0, m0, precisions=p0)
+    ms, resp = timed(lambda: gm.predict_proba(X), 3)
+    fl = n * K * d * (d + 1)
+    print(f"E pass n={n} d={d} K={K}: {ms:.2f} ms = {fl / ms / 1e9:.2f} TFLOP/s (triangular count)")

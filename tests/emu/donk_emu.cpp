@@ -463,7 +463,7 @@ int donk_emu_gmm_em_step_mode_f64(int n_local, int d, int K, const double* X, co
       case 5: emu_gmm_e_mma<5, 2>(a, pl); break;
       case 6: emu_gmm_e_mma<6, 2>(a, pl); break;
       case 9: emu_gmm_e_mma<9, 2>(a, pl); break;
-      default: emu_gmm_e_mma<18, 1>(a, pl); break;
+      default: emu_gmm_e_mma<18, 2>(a, pl); break;
     }
   } else {
     emu_gmm_e(a);
