@@ -37,12 +37,15 @@ SIGNATURES = {
     "quadratic_cost_l1_f64": [c_int, c_int, P, P, P, c_double, P, P, P, P],
     "dynamics_log_prob_f64": [c_int] * 5 + [P] * 7 + [P],
     "fit_lr_f64": [c_int] * 5 + [P, P, c_int, P, P, P, P, c_double, c_double, c_double, P, P, P, P, P],
+    "fit_lr_f32": [c_int] * 5 + [P, P, c_int, P, P, P, P, c_float, c_float, c_float, P, P, P, P, P],
     "fit_lr_niw_f64": [c_int] * 5 + [P] * 6 + [c_double, c_double, P, P, P, P, P],
     "to_transitions_f64": [c_int] * 4 + [P, P, P, P],
     "state_fit_f64": [c_int] * 3 + [P, c_size_t, c_size_t, P, P, P],
     "gmm_em_step_f64": [c_int] * 3 + [P] * 7 + [P, c_size_t, P],
     "gmm_em_step_mode_f64": [c_int] * 3 + [P] * 7 + [P, c_size_t, c_int, P],
     "gmm_m_finalize_f64": [c_double, c_int, c_int, P, P, c_double, P, P, P, P, P, P, P],
+    "gmm_tc_prepare_f32": [c_int, c_int, P, P, P, c_size_t, P],
+    "gmm_tc_estep_f32": [c_int] * 3 + [P] * 8 + [c_size_t, P],
     "gmm_predict_proba_f64": [c_int] * 3 + [P] * 5 + [P],
     "gmm_prec_chol_from_precisions_f64": [c_int] * 2 + [P] * 3 + [P],
     "fp64_probe": [c_int, c_int, c_int, P, ctypes.POINTER(c_double), P],
@@ -53,6 +56,9 @@ _SIZE_FUNCS = {
     "gmm_workspace_bytes": [c_int, c_int, c_int],
     "kmeans_workspace_bytes": [c_int, c_int],
     "ilqr_optimize_workspace_bytes": [c_int],
+    "gmm_tc_supported": [c_int, c_int],
+    "gmm_tc_planes_bytes": [c_int, c_int],
+    "gmm_tc_workspace_bytes": [c_int, c_int, c_int],
 }
 
 

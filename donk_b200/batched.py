@@ -361,6 +361,39 @@ def fit_lr(X, U, prior: "DeviceGMM | None" = None, regularization: float = 1e-6,
     return F, f, covar, info
 
 
+def fit_lr_f32(X, U, prior: "DeviceGMM | None" = None, regularization: float = 1e-6, prior_weight: float = 1.0):
+    """:func:`fit_lr` in single precision (``donk_fit_lr_f32``): float32 tensors in and out, half the HBM traffic.
+
+    Stated tolerance against the fp64 path for well-conditioned data (N > 2(dX+dU)): ``F`` and ``f`` within 2e-3,
+    ``covar`` within 5e-3, max-norm relative (tests/test_fit_gmm_kernels.py::test_fit_lr_f32_tolerance).  The joint
+    covariance loses ~7 digits to the subtraction of the means; ill-conditioned fits (N close to dX+dU, where the
+    eigenvalue lift decides the result) belong on the fp64 path.
+    """
+    nat = _lib.native()
+    f32 = torch.float32
+    X, U = _dev(X, f32), _dev(U, f32)
+    B, N, T1, dX = X.shape
+    _, _, T, dU = U.shape
+    if T1 != T + 1 or U.shape[0] != B or U.shape[1] != N:
+        raise ValueError(f"inconsistent roll-out shapes {tuple(X.shape)} / {tuple(U.shape)}")
+    if N <= 1:
+        raise ValueError(f"Cannot fit dynamics to {N} sample(s)")
+    p = dX + dU
+    o = dict(dtype=f32, device=X.device)
+    F, f, covar = torch.empty(B, T, dX, p, **o), torch.empty(B, T, dX, **o), torch.empty(B, T, dX, dX, **o)
+    info = torch.zeros(B, T, dtype=torch.int32, device=X.device)
+    if prior is None:
+        nat.call("fit_lr_f32", B, N, T, dX, dU, X, U, 0, None, None, None, None, 0.0, 1.0, float(regularization),
+                 F, f, covar, info)
+    else:
+        if prior.d != 2 * dX + dU:
+            raise ValueError(f"prior dimension {prior.d} != {2 * dX + dU}")
+        g = [t.to(f32).contiguous() for t in (prior.weights, prior.means, prior.covariances, prior.precisions_cholesky)]
+        nat.call("fit_lr_f32", B, N, T, dX, dU, X, U, prior.K, g[0], g[1], g[2], g[3], float(prior.N),
+                 float(prior_weight), float(regularization), F, f, covar, info)
+    return F, f, covar, info
+
+
 def fit_lr_niw(X, U, mu0, Phi, N_mean, N_covar, regularization: float = 1e-6, prior_weight: float = 1.0):
     """``fit_lr`` under an explicit normal-inverse-Wishart prior per (condition, t) — the form any
     ``DynamicsPrior.eval`` result takes (linear_dynamics.py:168-175, prior.py:18-45).
@@ -446,9 +479,16 @@ class DeviceGMM:
     Defaults follow sklearn: ``tol=1e-3, reg_covar=1e-6, max_iter=100``.
     """
 
-    def __init__(self, n_clusters: int, tol: float = 1e-3, reg_covar: float = 1e-6, max_iter: int = 100):
+    def __init__(self, n_clusters: int, tol: float = 1e-3, reg_covar: float = 1e-6, max_iter: int = 100,
+                 precision: str = "fp64"):
         self.K = int(n_clusters)
         self.kernels = "auto"  # "auto" | "scalar" | "dmma": see fit()
+        # "fp64" (default: parity with scikit-learn at 1e-8) or "tf32x3": the E pass runs on the tcgen05 tensor cores at
+        # a stated fp32 tolerance (include/donk_b200.h, donk_gmm_tc_estep_f32); the M pass and all parameters stay fp64
+        if precision not in ("fp64", "tf32x3"):
+            raise ValueError(f"precision must be 'fp64' or 'tf32x3', got {precision!r}")
+        self.precision = precision
+        self._tc = None
         self.tol, self.reg_covar, self.max_iter = tol, reg_covar, max_iter
         self.d = None
         self.weights = self.means = self.covariances = self.precisions_cholesky = None
@@ -531,8 +571,14 @@ class DeviceGMM:
         n, d = X.shape
         if getattr(self, "_shift", None) is None or self._shift.shape != self.means.shape:
             self._shift = torch.empty_like(self.means)
+        mode = int(getattr(self, "_mode", 0))
+        if self._tc is not None:  # E pass on the tensor cores: responsibilities and lse totals straight into ws
+            tc = self._tc
+            nat.call("gmm_tc_estep_f32", n, d, self.K, tc["planes"], tc["center"], self.weights, self.means,
+                     self.precisions_cholesky, ws, ws[n * self.K:], tc["work"], tc["work"].numel() * 8)
+            mode = 3
         nat.call("gmm_em_step_mode_f64", n, d, self.K, X, self.weights, self.means, self.precisions_cholesky, None, stats,
-                 self._shift, ws, ws.numel() * ws.element_size(), int(getattr(self, "_mode", 0)))
+                 self._shift, ws, ws.numel() * ws.element_size(), mode)
         self._allreduce(stats, group)  # the one exchange step of the path (NCCL over NVLink)
         nat.call("gmm_m_finalize_f64", float(n_total), d, self.K, stats, self._shift, float(self.reg_covar),
                  self.weights, self.means, self.covariances, self.precisions_cholesky, self._lb, self._info)
@@ -588,6 +634,7 @@ class DeviceGMM:
         # cluster's own mean) are used whatever the pool size: results first, speed second.  The bound is evaluated
         # from the parameters going INTO every iteration (clusters move during EM), see _centring_hardness.
         self._mode = self._pick_mode(float(self._centring_hardness()))
+        self._tc = self._tc_setup(X) if self.precision == "tf32x3" else None
         lb = self.lower_bound if warm_start else -np.inf
         self.converged = False
         self.lower_bounds = []
@@ -606,12 +653,40 @@ class DeviceGMM:
                 self.converged = True
                 break
         self.lower_bound, self.n_iter, self.N = lb, n_iter, int(n_total)
+        self._tc = None  # the split copy of the pool is released with the fit
         if not self.converged and self.max_iter > 0:
             from donk_b200.dynamics.prior.prior_gmm import ConvergenceWarning
 
             warnings.warn("Best performing initialization did not converge. Try different init parameters, or "
                           "increase max_iter, tol, or check for degenerate data.", ConvergenceWarning)
         return self
+
+    def _tc_setup(self, X):
+        """Split copy of the rows for the tensor-core E pass: two TF32 planes of ``x - c`` (``c`` = the mixture mean going
+        into the fit, fixed over its iterations so that the copy is made once)."""
+        nat = _lib.native()
+        n, d = X.shape
+        if not nat.size("gmm_tc_supported", d, self.K):
+            raise DonkError(f"precision='tf32x3': d={d}, K={self.K} is outside the tensor-core E pass (d <= 80); use 'fp64'")
+        o = dict(dtype=torch.float64, device=X.device)
+        center = (self.weights[:, None] * self.means).sum(0).contiguous()
+        planes = torch.empty(nat.size("gmm_tc_planes_bytes", n, d) // 8 + 32, **o)
+        off = (-planes.data_ptr() // 8) % 32  # 256-byte aligned start
+        planes = planes[off:]
+        work = torch.empty(nat.size("gmm_tc_workspace_bytes", n, d, self.K) // 8 + 1, **o)
+        nat.call("gmm_tc_prepare_f32", n, d, X, center, planes, planes.numel() * 8)
+        return dict(center=center, planes=planes, work=work)
+
+    def predict_proba_tf32x3(self, X) -> torch.Tensor:
+        """``predict_proba`` through the tensor-core E pass (fp32 tolerance, see ``precision``)."""
+        nat = _lib.native()
+        X = _dev(X)
+        n, d = X.shape
+        tc = self._tc_setup(X)
+        out = torch.empty(n * self.K + (n + 63) // 64, dtype=X.dtype, device=X.device)
+        nat.call("gmm_tc_estep_f32", n, d, self.K, tc["planes"], tc["center"], self.weights, self.means,
+                 self.precisions_cholesky, out, out[n * self.K:], tc["work"], tc["work"].numel() * 8)
+        return out[:n * self.K].view(n, self.K)
 
     def eval_prior(self, XUX):
         """``GMMPrior.eval`` (prior_gmm.py:26-41) on the device: the NIW hyper-parameters the mixture assigns to the

@@ -69,16 +69,15 @@ int fit_warp_launch(FitArgs<R> a, void* stream) {
 
 }  // namespace
 
-extern "C" {
-
-static int fit_lr_launch(FitArgs<double>& a, void* stream) {
+template <typename R>
+static int fit_lr_launch(FitArgs<R>& a, void* stream) {
   const int B = a.B, N = a.N, T = a.T, dX = a.dX, dU = a.dU, gmm_K = a.K;
   // warp-per-fit fast path for the instantiated dimensions (with the prior: partial sums for at most 64 samples);
   // a plan that does not fit shared memory (many clusters) falls through to the generic kernel
   if ((gmm_K == 0 || N <= 64) && !a.niw_Phi && !env_int("DONK_FIT_GENERIC")) {
 #define DONK_TRY_FITW(DXV, DUV)                                          \
   if (dX == DXV && dU == DUV) {                                          \
-    const int rc_w = fit_warp_launch<double, DXV, DUV>(a, stream);       \
+    const int rc_w = fit_warp_launch<R, DXV, DUV>(a, stream);            \
     if (rc_w != DONK_SMEM_LIMIT) return rc_w;                            \
   }
     DONK_WARP_DIMS(DONK_TRY_FITW)
@@ -86,31 +85,35 @@ static int fit_lr_launch(FitArgs<double>& a, void* stream) {
   }
   // large dimensions: one fit per CTA on DMMA tiles (fitlr_coop.cuh); it flags the fits whose eigenvalue test needs the
   // eigen-solver (info == 2) and the generic kernel below redoes exactly those
-  if (!env_int("DONK_FIT_GENERIC") && a.info != nullptr) {
-    const int rc_c = fit_coop_try_launch(a, stream);
-    a.wts_in = nullptr;  // stream-ordered scratch of the cooperative launch, already released
-    if (rc_c == DONK_OK) a.redo = 1;
-    else if (rc_c >= 0 && rc_c != DONK_SMEM_LIMIT) return rc_c;
+  if constexpr (sizeof(R) == 8) {
+    if (!env_int("DONK_FIT_GENERIC") && a.info != nullptr) {
+      const int rc_c = fit_coop_try_launch(a, stream);
+      a.wts_in = nullptr;  // stream-ordered scratch of the cooperative launch, already released
+      if (rc_c == DONK_OK) a.redo = 1;
+      else if (rc_c >= 0 && rc_c != DONK_SMEM_LIMIT) return rc_c;
+    }
   }
   size_t bytes = 0;
   const int force = env_int("DONK_FIT_CHUNK");
-  a.NS = fit_plan(dX, dU, gmm_K, force > 0 ? force : N, sizeof(double), smem_optin_cap(), bytes);
+  a.NS = fit_plan(dX, dU, gmm_K, force > 0 ? force : N, sizeof(R), smem_optin_cap(), bytes);
   if (a.NS == 0) {
     snprintf(g_err, sizeof(g_err), "fit_lr: dX=%d dU=%d K=%d does not fit shared memory", dX, dU, gmm_K);
     return DONK_SMEM_LIMIT;
   }
-  { FitLayout L(dX, dU, gmm_K, N, a.NS); bytes = (size_t)L.total * sizeof(double); }
-  int rc = allow_smem(fit_lr_kernel<double>, bytes);
+  { FitLayout L(dX, dU, gmm_K, N, a.NS); bytes = (size_t)L.total * sizeof(R); }
+  int rc = allow_smem(fit_lr_kernel<R>, bytes);
   if (rc != DONK_OK) return rc;
   const int dp = round_up(2 * dX + dU, 4), nt = dp / 4;
   int threads = round_up(nt * (nt + 1) / 2, 32);
   if (threads < 128) threads = 128;
   if (threads > 512) threads = 512;
   if (env_int("DONK_FIT_THREADS") > 0) threads = env_int("DONK_FIT_THREADS");
-  fit_lr_kernel<double><<<B * T, threads, bytes, (cudaStream_t)stream>>>(a);
+  fit_lr_kernel<R><<<B * T, threads, bytes, (cudaStream_t)stream>>>(a);
   LAUNCHED("fit_lr_kernel");
   return DONK_OK;
 }
+
+extern "C" {
 
 int donk_fit_lr_f64(int B, int N, int T, int dX, int dU, const double* X, const double* U, int gmm_K,
                     const double* gmm_weights, const double* gmm_means, const double* gmm_covariances,
@@ -125,7 +128,24 @@ int donk_fit_lr_f64(int B, int N, int T, int dX, int dU, const double* X, const 
   a.n_pool = n_pool; a.prior_weight = prior_weight; a.reg = regularization;
   a.F = F; a.f = f; a.covar = covar; a.info = info;
   a.aligned16 = (((uintptr_t)X | (uintptr_t)U) & 15) == 0;
-  return fit_lr_launch(a, stream);
+  return fit_lr_launch<double>(a, stream);
+}
+
+/* single-precision storage and arithmetic (the tensor-path products still accumulate in FP64): same kernels, R = float */
+int donk_fit_lr_f32(int B, int N, int T, int dX, int dU, const float* X, const float* U, int gmm_K,
+                    const float* gmm_weights, const float* gmm_means, const float* gmm_covariances,
+                    const float* gmm_prec_chol, float n_pool, float prior_weight, float regularization,
+                    float* F, float* f, float* covar, int* info, void* stream) {
+  if (B < 0 || N <= 1 || T < 1 || dX < 1 || dU < 1 || gmm_K < 0) return DONK_BAD_SHAPE;
+  if (B == 0) return DONK_OK;
+  FitArgs<float> a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.N = N; a.T = T; a.dX = dX; a.dU = dU; a.X = X; a.U = U; a.K = gmm_K;
+  a.gw = gmm_weights; a.gmeans = gmm_means; a.gcov = gmm_covariances; a.gpc = gmm_prec_chol;
+  a.n_pool = n_pool; a.prior_weight = prior_weight; a.reg = regularization;
+  a.F = F; a.f = f; a.covar = covar; a.info = info;
+  a.aligned16 = (((uintptr_t)X | (uintptr_t)U) & 15) == 0;
+  return fit_lr_launch<float>(a, stream);
 }
 
 int donk_fit_lr_niw_f64(int B, int N, int T, int dX, int dU, const double* X, const double* U, const double* niw_mu0,
@@ -141,7 +161,7 @@ int donk_fit_lr_niw_f64(int B, int N, int T, int dX, int dU, const double* X, co
   a.prior_weight = prior_weight; a.reg = regularization;
   a.F = F; a.f = f; a.covar = covar; a.info = info;
   a.aligned16 = (((uintptr_t)X | (uintptr_t)U) & 15) == 0;
-  return fit_lr_launch(a, stream);
+  return fit_lr_launch<double>(a, stream);
 }
 
 }  // extern "C"

@@ -174,7 +174,7 @@ size_t donk_gmm_workspace_bytes(int n_local, int d, int K) { return gmm_ws_reals
 int donk_gmm_em_step_mode_f64(int n_local, int d, int K, const double* X, const double* weights, const double* means,
                               const double* prec_chol, const double* resp_in, double* stats, double* shift,
                               void* workspace, size_t workspace_bytes, int mode, void* stream) {
-  if (n_local < 0 || d < 1 || K < 1 || mode < 0 || mode > 2) return DONK_BAD_SHAPE;
+  if (n_local < 0 || d < 1 || K < 1 || mode < 0 || mode > 3) return DONK_BAD_SHAPE;
   if (workspace_bytes < donk_gmm_workspace_bytes(n_local, d, K)) return DONK_BAD_SHAPE;
   const size_t total = gmm_stats_len(d, K);
   if (n_local == 0) {
@@ -197,9 +197,12 @@ int donk_gmm_em_step_mode_f64(int n_local, int d, int K, const double* X, const 
   // own known-answer test on 660 real transitions needs that); the DMMA kernels centre on the mixture mean (shared
   // B fragments), which costs a few digits on such data and nothing measurable on pools with overlapping clusters.
   // mode 1 / 2 (or DONK_GMM_GENERIC / DONK_GMM_MMA) override the size rule.
-  const bool want_mma = mode == 2 || (mode == 0 && (n_local >= 65536 || env_int("DONK_GMM_MMA")));
+  const bool want_mma = mode == 2 || ((mode == 0 || mode == 3) && (n_local >= 65536 || env_int("DONK_GMM_MMA")));
   const bool mma = pl.ok && !env_int("DONK_GMM_GENERIC") && weights != nullptr && want_mma;
-  if (resp_in) {
+  if (mode == 3) {
+    // responsibilities and per-block log-sum-exp totals are already in the workspace (donk_gmm_tc_estep_f32)
+    if (resp_in) return DONK_BAD_SHAPE;
+  } else if (resp_in) {
     a.resp = const_cast<double*>(resp_in);
     CU(cudaMemsetAsync(a.lse_part, 0, (size_t)a.nblocks * sizeof(double), (cudaStream_t)stream));
   } else {

@@ -1,0 +1,429 @@
+// donk_b200 — C ABI, part: the E pass of GMM EM (GMMPrior.update, donk/dynamics/prior/prior_gmm.py:14-24 ->
+// sklearn GaussianMixture._e_step) at the north star's "stated fp32 tolerance" on the 5th-generation tensor cores.
+//
+// There is no FP64 tcgen05 kind: the fp64 EM kernels (gmm_mma.cuh) run on mma.sync.m8n8k4.f64 at the DFMA rate.  This
+// variant computes y = (x - c) P_k - (mu_k - c) P_k for all rows x and clusters k as ONE GEMM on tcgen05.mma kind::tf32
+// with fp32 accumulators in tensor memory, each operand split into two TF32 planes (x = x_hi + x_lo) and three products
+// (hi*hi + lo*hi + hi*lo: ~2^-21 relative, the "3xTF32" scheme); log-probabilities are reduced from the accumulators
+// straight out of TMEM.  Data flow of one CTA (persistent, one per SM, 192 threads):
+//     warp 0     one lane: TMA (cp.async.bulk.tensor.2d, 32-byte swizzle) P planes once, then the row tiles of X into a
+//                ring of shared-memory stages (full / empty mbarriers)
+//     warp 1     one lane: tcgen05.mma M=128, N = kc*dp, K=8 per instruction, 3 * dp/8 instructions per tile into one of
+//                two TMEM accumulators; tcgen05.commit releases the stage and publishes the accumulator
+//     warps 2-5  tcgen05.ld of their 32 TMEM lanes (= rows), y^2 row sums, log-probability per (row, cluster) to HBM
+// A CTA owns kc clusters (their P planes stay resident in shared memory) and walks the row tiles; the 128-row tile of X
+// is read by K/kc CTAs at about the same time (one HBM read, the rest L2 hits).  A second small kernel turns the
+// (n, K) log-probabilities into responsibilities (fp64, where the fp64 M pass expects them) and the per-block
+// log-sum-exp totals of the lower bound.  X is split into planes ONCE per fit (it does not change over the iterations).
+#include <cuda.h>
+
+#include "abi_common.cuh"
+#include "gmm.cuh"
+
+using namespace donk;
+using namespace donk_abi;
+
+namespace {
+
+constexpr int TC_M = 128;        // rows per tile = TMEM lanes
+constexpr int TC_THREADS = 192;  // TMA warp, MMA warp, four epilogue warps
+constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_TMEM_COLS = 512;
+
+struct TcParams {
+  int n, d, dp, K, kc, ncg, walkers, ntiles, stages, N;
+  const float* bias;  // (K, dp)  (mu_k - c) P_k
+  const float* cst;   // (K)      sum log diag P_k + log pi_k - d/2 log(2 pi)
+  float* logp;        // (n, K)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ float tf32_round(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// K-major operand tile of 8-float (32-byte) rows written by TMA with the 32-byte swizzle: rows 32 bytes apart,
+// groups of 8 rows 256 bytes apart (stride byte offset); the leading byte offset is unused for swizzled K-major tiles.
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version of sm_100
+  d |= (uint64_t)6 << 61;  // SWIZZLE_32B
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gmm_tc_estep_kernel(const __grid_constant__ CUtensorMap tmXhi, const __grid_constant__ CUtensorMap tmXlo,
+                    const __grid_constant__ CUtensorMap tmPhi, const __grid_constant__ CUtensorMap tmPlo,
+                    const TcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // the swizzle pattern is a function of the shared-memory address bits: operand tiles start on 256-byte boundaries
+  unsigned char* smem = smem_raw + ((256u - (smem_u32(smem_raw) & 255u)) & 255u);
+  const int KS = p.dp / 8, N = p.N;
+  const uint32_t b_plane = (uint32_t)KS * N * 32, a_plane = (uint32_t)KS * TC_M * 32;
+  unsigned char* sB = smem;                    // [plane hi|lo][k-step][N rows][32 B]
+  unsigned char* sA = sB + 2 * b_plane;        // [stage][plane hi|lo][k-step][128 rows][32 B]
+  unsigned char* tail = sA + (size_t)p.stages * 2 * a_plane;
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(tail);  // [stages]
+  unsigned long long* empty = full + TC_MAX_STAGES;                        // [stages]
+  unsigned long long* bfull = empty + TC_MAX_STAGES;                       // [1]
+  unsigned long long* tfull = bfull + 1;                                   // [2]
+  unsigned long long* tempty = tfull + 2;                                  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* sbias = reinterpret_cast<float*>(tmem_slot + 4);                  // [kc][dp]
+  float* scst = sbias + p.kc * p.dp;                                       // [kc]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cg = blockIdx.x % p.ncg, wk = blockIdx.x / p.ncg;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    mbar_init(bfull, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < p.kc * p.dp; i += TC_THREADS) sbias[i] = p.bias[(size_t)cg * p.kc * p.dp + i];
+  if (threadIdx.x < p.kc) scst[threadIdx.x] = p.cst[cg * p.kc + threadIdx.x];
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bfull, 2 * b_plane);
+      for (int kk = 0; kk < KS; ++kk) {
+        tma_load_2d(sB + (size_t)kk * N * 32, &tmPhi, 8 * kk, cg * N, bfull);
+        tma_load_2d(sB + b_plane + (size_t)kk * N * 32, &tmPlo, 8 * kk, cg * N, bfull);
+      }
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = wk; tile < p.ntiles; tile += p.walkers) {
+        mbar_wait(empty + s, ph ^ 1);
+        mbar_arrive_expect_tx(full + s, 2 * a_plane);
+        unsigned char* st = sA + (size_t)s * 2 * a_plane;
+        for (int kk = 0; kk < KS; ++kk) {
+          tma_load_2d(st + (size_t)kk * TC_M * 32, &tmXhi, 8 * kk, tile * TC_M, full + s);
+          tma_load_2d(st + a_plane + (size_t)kk * TC_M * 32, &tmXlo, 8 * kk, tile * TC_M, full + s);
+        }
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+      mbar_wait(bfull, 0);
+      int s = 0, acc = 0;
+      uint32_t ph = 0, aph = 0;
+      for (int tile = wk; tile < p.ntiles; tile += p.walkers) {
+        mbar_wait(tempty + acc, aph ^ 1);
+        mbar_wait(full + s, ph);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
+        const uint32_t a0 = smem_u32(sA + (size_t)s * 2 * a_plane), b0 = smem_u32(sB);
+        uint32_t accumulate = 0;
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {  // x_hi P_hi + x_lo P_hi + x_hi P_lo
+          const uint32_t ap = a0 + (pass == 1 ? a_plane : 0), bp = b0 + (pass == 2 ? b_plane : 0);
+          for (int kk = 0; kk < KS; ++kk) {
+            umma_tf32(d_tmem, umma_desc_sw32(ap + (uint32_t)kk * TC_M * 32), umma_desc_sw32(bp + (uint32_t)kk * N * 32),
+                      idesc, accumulate);
+            accumulate = 1;
+          }
+        }
+        tc_commit(empty + s);     // the stage may be refilled once these products have read it
+        tc_commit(tfull + acc);   // the accumulator is complete
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+        if (++acc == 2) { acc = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    const int q = warp & 3;  // a warp reads the TMEM lanes 32 (warp % 4) .. + 31
+    int acc = 0;
+    uint32_t aph = 0;
+    for (int tile = wk; tile < p.ntiles; tile += p.walkers) {
+      mbar_wait(tfull + acc, aph);
+      tc_fence_after();
+      const size_t row = (size_t)tile * TC_M + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N);
+      for (int c = 0; c < p.kc; ++c) {
+        float ss = 0.f;
+        for (int j0 = 0; j0 < p.dp; j0 += 8) {
+          float v[8];
+          tmem_ld8(taddr + (uint32_t)(c * p.dp + j0), v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float y = v[j] - sbias[c * p.dp + j0 + j];
+            ss = fmaf(y, y, ss);
+          }
+        }
+        if (row < (size_t)p.n) p.logp[row * p.K + cg * p.kc + c] = scst[c] - 0.5f * ss;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + acc);
+      if (++acc == 2) { acc = 0; aph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+// X (n, d) fp64 -> two TF32 planes of (x - c) with row pitch dp (columns d..dp-1 zero)
+__global__ void gmm_tc_split_kernel(size_t total, int d, int dp, const double* X, const double* center, float* hi, float* lo) {
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = idx / dp;
+    const int j = (int)(idx % dp);
+    float h = 0.f, l = 0.f;
+    if (j < d) {
+      const float x = (float)(X[r * d + j] - (center ? center[j] : 0.0));
+      h = tf32_round(x);
+      l = tf32_round(x - h);
+    }
+    hi[idx] = h;
+    lo[idx] = l;
+  }
+}
+
+// per-iteration operands: PT planes [(k, j)][i] = P_k[i][j] split in TF32, bias (k, j) = (mu_k - c) P_k[:, j], constants
+__global__ void gmm_tc_params_kernel(int d, int dp, int K, const double* center, const double* w, const double* means,
+                                     const double* pc, float* Phi, float* Plo, float* bias, float* cst) {
+  const size_t total = (size_t)K * dp * dp;
+  const size_t dd = (size_t)d * d;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % dp);
+    const size_t kj = idx / dp;
+    const int j = (int)(kj % dp), k = (int)(kj / dp);
+    float h = 0.f, l = 0.f;
+    if (i < d && j < d && i <= j) {
+      const float v = (float)pc[k * dd + (size_t)i * d + j];
+      h = tf32_round(v);
+      l = tf32_round(v - h);
+    }
+    Phi[idx] = h;
+    Plo[idx] = l;
+    if (i == 0) {
+      double acc = 0.0;
+      if (j < d)
+        for (int q = 0; q <= j; ++q) acc = fma(means[(size_t)k * d + q] - (center ? center[q] : 0.0), pc[k * dd + (size_t)q * d + j], acc);
+      bias[kj] = (float)acc;
+      if (j == 0) {
+        double ld = 0.0;
+        for (int q = 0; q < d; ++q) ld += log(pc[k * dd + (size_t)q * d + q]);
+        cst[k] = (float)(ld + log(w[k]) - 0.5 * d * 1.8378770664093454835606594728112);
+      }
+    }
+  }
+}
+
+// log-probabilities (n, K) fp32 -> responsibilities (n, K) fp64 and the log-sum-exp total of every GMM_TS-row block
+// (sklearn/mixture/_base.py:552-582).  256 rows per CTA, one thread per row, fixed-order sums.
+__global__ void __launch_bounds__(256) gmm_tc_softmax_kernel(int n, int K, const float* logp, double* resp, double* lse_part) {
+  __shared__ double wsum[8];
+  const size_t row = (size_t)blockIdx.x * 256 + threadIdx.x;
+  double lse = 0.0;
+  if (row < (size_t)n) {
+    const float* lp = logp + row * K;
+    double m = lp[0];
+    for (int k = 1; k < K; ++k) m = lp[k] > m ? (double)lp[k] : m;
+    double s = 0.0;
+    for (int k = 0; k < K; ++k) s += exp((double)lp[k] - m);
+    const double inv = 1.0 / s;
+    for (int k = 0; k < K; ++k) resp[row * K + k] = exp((double)lp[k] - m) * inv;
+    lse = m + log(s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lse += __shfl_xor_sync(0xffffffffu, lse, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = lse;
+  __syncthreads();
+  static_assert(GMM_TS == 64, "lse_part is kept per 64-row block");
+  if (threadIdx.x < 4) {
+    const size_t blk = (size_t)blockIdx.x * 4 + threadIdx.x;
+    if (blk * GMM_TS < (size_t)n) lse_part[blk] = wsum[2 * threadIdx.x] + wsum[2 * threadIdx.x + 1];
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor (rows, dp) with boxes of (8 floats, box_rows) and the 32-byte swizzle the UMMA descriptors expect
+int make_map(CUtensorMap* tm, const float* base, size_t rows, int dp, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled is not available"); return DONK_CUDA_ERROR; }
+  const cuuint64_t dims[2] = {(cuuint64_t)dp, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)dp * sizeof(float)};
+  const cuuint32_t box[2] = {8u, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled failed (%d)", (int)r); return DONK_CUDA_ERROR; }
+  return DONK_OK;
+}
+
+struct TcPlan {
+  int dp, kc, N, stages;
+  size_t smem;
+  bool ok;
+};
+
+TcPlan tc_plan(int d, int K) {
+  TcPlan pl{};
+  pl.dp = round_up(d, 8);
+  const size_t cap = smem_optin_cap();
+  const size_t tail = 1024 + 256 + (size_t)2 * pl.dp * sizeof(float);  // barriers, alignment slack, constants
+  for (int kc = 2; kc >= 1 && !pl.ok; --kc) {
+    if (K % kc) continue;
+    const int N = kc * pl.dp;
+    if (N % 16 || N > 256) continue;
+    const size_t b = (size_t)2 * (pl.dp / 8) * N * 32, a = (size_t)2 * (pl.dp / 8) * TC_M * 32;
+    if (b + a + tail + (size_t)kc * pl.dp * 4 > cap) continue;
+    int st = (int)((cap - b - tail - (size_t)kc * pl.dp * 4) / a);
+    if (st > TC_MAX_STAGES) st = TC_MAX_STAGES;
+    pl.kc = kc; pl.N = N; pl.stages = st;
+    pl.smem = b + (size_t)st * a + tail + (size_t)kc * pl.dp * 4;
+    pl.ok = 2 * N <= TC_TMEM_COLS;
+  }
+  return pl;
+}
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+extern "C" {
+
+/* 1 when the tensor-core E pass supports (d, K) on this device (operands must fit shared memory: d <= 80). */
+int donk_gmm_tc_supported(int d, int K) { return d >= 1 && K >= 1 && tc_plan(d, K).ok ? 1 : 0; }
+
+/* bytes of the split copy of the pool: two fp32 planes (n, round_up(d, 8)) */
+size_t donk_gmm_tc_planes_bytes(int n, int d) { return 2 * align256((size_t)n * round_up(d, 8) * sizeof(float)); }
+
+/* bytes of the per-iteration scratch: P planes, bias, constants, log-probabilities */
+size_t donk_gmm_tc_workspace_bytes(int n, int d, int K) {
+  const size_t dp = round_up(d, 8);
+  return 2 * align256((size_t)K * dp * dp * 4) + align256((size_t)K * dp * 4) + align256((size_t)K * 4) +
+         align256((size_t)n * K * 4) + 256;
+}
+
+/* X (n, d) fp64 minus center (d, may be NULL) -> planes (donk_gmm_tc_planes_bytes), once per fit. */
+int donk_gmm_tc_prepare_f32(int n, int d, const double* X, const double* center, void* planes, size_t planes_bytes,
+                            void* stream) {
+  if (n < 0 || d < 1) return DONK_BAD_SHAPE;
+  if (planes_bytes < donk_gmm_tc_planes_bytes(n, d) || ((uintptr_t)planes & 255)) return DONK_BAD_SHAPE;
+  if (n == 0) return DONK_OK;
+  const int dp = round_up(d, 8);
+  float* hi = static_cast<float*>(planes);
+  float* lo = reinterpret_cast<float*>(static_cast<char*>(planes) + align256((size_t)n * dp * sizeof(float)));
+  const size_t total = (size_t)n * dp;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  gmm_tc_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(total, d, dp, X, center, hi, lo);
+  LAUNCHED("gmm_tc_split_kernel");
+  return DONK_OK;
+}
+
+/* E pass at fp32 tolerance: planes from donk_gmm_tc_prepare_f32 (same center), current parameters (fp64) ->
+ * responsibilities (n, K) fp64 and per-64-row log-sum-exp totals, both written where the fp64 E pass puts them in the EM
+ * workspace (resp | lse_part), so that donk_gmm_em_step_mode_f64(mode = 3) continues with the M pass. */
+int donk_gmm_tc_estep_f32(int n, int d, int K, const void* planes, const double* center, const double* weights,
+                          const double* means, const double* prec_chol, double* resp, double* lse_part, void* work,
+                          size_t work_bytes, void* stream) {
+  if (n < 0 || d < 1 || K < 1) return DONK_BAD_SHAPE;
+  const TcPlan pl = tc_plan(d, K);
+  if (!pl.ok) { snprintf(g_err, sizeof(g_err), "gmm_tc: d=%d K=%d does not fit the tensor-core E pass", d, K); return DONK_SMEM_LIMIT; }
+  if (work_bytes < donk_gmm_tc_workspace_bytes(n, d, K) || ((uintptr_t)planes & 255)) return DONK_BAD_SHAPE;
+  if (n == 0) return DONK_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int dp = pl.dp;
+  char* wp = reinterpret_cast<char*>(((uintptr_t)work + 255) & ~(uintptr_t)255);
+  float* Phi = reinterpret_cast<float*>(wp); wp += align256((size_t)K * dp * dp * 4);
+  float* Plo = reinterpret_cast<float*>(wp); wp += align256((size_t)K * dp * dp * 4);
+  float* bias = reinterpret_cast<float*>(wp); wp += align256((size_t)K * dp * 4);
+  float* cst = reinterpret_cast<float*>(wp); wp += align256((size_t)K * 4);
+  float* logp = reinterpret_cast<float*>(wp);
+  const float* Xhi = static_cast<const float*>(planes);
+  const float* Xlo = reinterpret_cast<const float*>(static_cast<const char*>(planes) + align256((size_t)n * dp * sizeof(float)));
+  {
+    const size_t total = (size_t)K * dp * dp;
+    gmm_tc_params_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d, dp, K, center, weights, means, prec_chol, Phi, Plo,
+                                                                         bias, cst);
+    LAUNCHED("gmm_tc_params_kernel");
+  }
+  CUtensorMap tXh, tXl, tPh, tPl;
+  int rc = make_map(&tXh, Xhi, (size_t)n, dp, TC_M);
+  if (rc == DONK_OK) rc = make_map(&tXl, Xlo, (size_t)n, dp, TC_M);
+  if (rc == DONK_OK) rc = make_map(&tPh, Phi, (size_t)K * dp, dp, pl.N);
+  if (rc == DONK_OK) rc = make_map(&tPl, Plo, (size_t)K * dp, dp, pl.N);
+  if (rc != DONK_OK) return rc;
+  TcParams p;
+  p.n = n; p.d = d; p.dp = dp; p.K = K; p.kc = pl.kc; p.ncg = K / pl.kc; p.N = pl.N; p.stages = pl.stages;
+  p.ntiles = (n + TC_M - 1) / TC_M;
+  int walkers = 148 / p.ncg;
+  if (walkers < 1) walkers = 1;
+  if (walkers > p.ntiles) walkers = p.ntiles;
+  p.walkers = walkers;
+  p.bias = bias; p.cst = cst; p.logp = logp;
+  rc = allow_smem(gmm_tc_estep_kernel, pl.smem);
+  if (rc != DONK_OK) return rc;
+  gmm_tc_estep_kernel<<<p.ncg * walkers, TC_THREADS, pl.smem, st>>>(tXh, tXl, tPh, tPl, p);
+  LAUNCHED("gmm_tc_estep_kernel");
+  gmm_tc_softmax_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, K, logp, resp, lse_part);
+  LAUNCHED("gmm_tc_softmax_kernel");
+  return DONK_OK;
+}
+
+}  // extern "C"

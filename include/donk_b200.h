@@ -175,6 +175,15 @@ int donk_fit_lr_f64(int B, int N, int T, int dX, int dU, const double* X, const 
                     const double* gmm_prec_chol, double n_pool, double prior_weight, double regularization,
                     double* F, double* f, double* covar, int* info, void* stream);
 
+/* fit_lr in single precision (north-star "stated fp32 tolerance"): the same kernels instantiated for float storage and
+ * arithmetic (the tensor-path products accumulate in FP64).  Tolerance against the fp64 path for well-conditioned
+ * data (N > 2(dX+dU), regularisation 1e-6): F within 2e-3, f within 2e-3 of max|f|, covar within 5e-3, max-norm
+ * relative (tests/test_fit_gmm_kernels.py::test_fit_lr_f32_tolerance).  Same arguments as donk_fit_lr_f64. */
+int donk_fit_lr_f32(int B, int N, int T, int dX, int dU, const float* X, const float* U, int gmm_K,
+                    const float* gmm_weights, const float* gmm_means, const float* gmm_covariances,
+                    const float* gmm_prec_chol, float n_pool, float prior_weight, float regularization,
+                    float* F, float* f, float* covar, int* info, void* stream);
+
 /* fit_lr under an explicit normal-inverse-Wishart prior per (condition, t): what linear_dynamics.py:168-175 does
  * with ANY DynamicsPrior (donk/dynamics/prior/prior.py:62-82) after the caller has run prior.eval(xux_t):
  *   sigma_t = NIW(mu0, Phi, N_mean, N_covar).posterior(mean_t, cov_t, N / prior_weight).map_covar()  (prior.py:18-45).
@@ -216,12 +225,37 @@ int donk_gmm_em_step_f64(int n_local, int d, int K, const double* X,
                          double* stats, double* shift, void* workspace, size_t workspace_bytes, void* stream);
 /* Same, with the kernel family chosen by the caller: mode 0 = by pool size (scalar kernels below 65 536 rows), 1 = scalar
  * kernels (statistics centred on every cluster's own mean: agreement with scikit-learn at rounding level whatever the
- * spread of the clusters), 2 = DMMA kernels (centred on the mixture mean: fastest; error ~ eps (|mu_k - x_bar| / sigma)^2). */
+ * spread of the clusters), 2 = DMMA kernels (centred on the mixture mean: fastest; error ~ eps (|mu_k - x_bar| / sigma)^2),
+ * 3 = M pass only: responsibilities and per-block log-sum-exp totals were put into the workspace by
+ * donk_gmm_tc_estep_f32 (kernel family of the M pass as in mode 0). */
 int donk_gmm_em_step_mode_f64(int n_local, int d, int K, const double* X,
                               const double* weights, const double* means, const double* prec_chol,
                               const double* resp_in,
                               double* stats, double* shift, void* workspace, size_t workspace_bytes, int mode,
                               void* stream);
+
+/* ---- E pass of GMM EM at fp32 tolerance on the tcgen05 tensor cores (abi_gmm_tc.cu) ------------------------------
+ * GaussianMixture._e_step (sklearn/mixture/_base.py:552-582) behind GMMPrior.update, prior_gmm.py:14-24, for callers that
+ * accept the north star's "stated fp32 tolerance": y = (x - c)(P_k) as one GEMM on tcgen05.mma kind::tf32 (operands split
+ * into two TF32 planes, three products, fp32 accumulators in tensor memory), TMA tile loads, log-probabilities reduced
+ * out of TMEM.  Tolerance against the fp64 E pass: responsibilities within 2e-4 absolute, the mean log-likelihood within
+ * 1e-5 relative (tests/test_fit_gmm_kernels.py::test_gmm_tc_estep_tolerance).  d <= 80 (operands resident in shared
+ * memory); other shapes keep the fp64 kernels.
+ *   donk_gmm_tc_supported(d, K)          1 when the kernel handles the shape
+ *   donk_gmm_tc_planes_bytes(n, d)       bytes of the split copy of the pool (two fp32 planes, row pitch round_up(d, 8))
+ *   donk_gmm_tc_workspace_bytes(n, d, K) bytes of per-iteration scratch
+ *   donk_gmm_tc_prepare_f32              X (n,d) fp64 minus center (d, may be NULL) -> planes; once per fit
+ *   donk_gmm_tc_estep_f32                planes + current parameters -> resp (n,K) fp64 and lse_part (ceil(n/64)) fp64,
+ *                                        i.e. the first two regions of the EM workspace; continue with
+ *                                        donk_gmm_em_step_mode_f64(mode = 3), which then runs only the M pass. */
+int donk_gmm_tc_supported(int d, int K);
+size_t donk_gmm_tc_planes_bytes(int n, int d);
+size_t donk_gmm_tc_workspace_bytes(int n, int d, int K);
+int donk_gmm_tc_prepare_f32(int n, int d, const double* X, const double* center, void* planes, size_t planes_bytes,
+                            void* stream);
+int donk_gmm_tc_estep_f32(int n, int d, int K, const void* planes, const double* center, const double* weights,
+                          const double* means, const double* prec_chol, double* resp, double* lse_part, void* work,
+                          size_t work_bytes, void* stream);
 
 /* M-step finalisation from (all-reduced) statistics of n_total rows: new weights, means,
  * covariances (+ reg_covar I), precision Cholesky factors, mean log-likelihood.

@@ -381,6 +381,31 @@ int donk_emu_fit_lr_f64(int B, int N, int T, int dX, int dU, const double* X, co
   return emu_fit_lr_launch(a);
 }
 
+// single precision: the generic CTA kernel instantiated for float (the CUDA launcher also tries the warp kernels)
+int donk_emu_fit_lr_f32(int B, int N, int T, int dX, int dU, const float* X, const float* U, int gmm_K,
+                        const float* gmm_weights, const float* gmm_means, const float* gmm_covariances,
+                        const float* gmm_prec_chol, float n_pool, float prior_weight, float regularization,
+                        float* F, float* f, float* covar, int* info, void*) {
+  if (B < 0 || N <= 1 || T < 1 || dX < 1 || dU < 1 || gmm_K < 0) return DONK_BAD_SHAPE;
+  FitArgs<float> a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.N = N; a.T = T; a.dX = dX; a.dU = dU; a.X = X; a.U = U; a.K = gmm_K;
+  a.gw = gmm_weights; a.gmeans = gmm_means; a.gcov = gmm_covariances; a.gpc = gmm_prec_chol;
+  a.n_pool = n_pool; a.prior_weight = prior_weight; a.reg = regularization;
+  a.F = F; a.f = f; a.covar = covar; a.info = info; a.aligned16 = 1;
+  size_t bytes = 0;
+  a.NS = fit_plan(dX, dU, gmm_K, N, sizeof(float), kSmemCap, bytes);
+  if (a.NS == 0) return DONK_SMEM_LIMIT;
+  FitLayout L(dX, dU, gmm_K, N, a.NS);
+  std::vector<float> smem(L.total + 2);
+  Ctx ctx{0, 1};
+  for (int cta = 0; cta < B * T; ++cta) {
+    memset(smem.data(), 0xFF, smem.size() * sizeof(float));
+    fit_lr_cta<float>(ctx, a, cta, smem.data());
+  }
+  return DONK_OK;
+}
+
 int donk_emu_fit_lr_niw_f64(int B, int N, int T, int dX, int dU, const double* X, const double* U, const double* mu0,
                             const double* Phi, const double* Nm, const double* Nc, double prior_weight,
                             double regularization, double* F, double* f, double* covar, int* info, void*) {
@@ -437,10 +462,70 @@ static void emu_gmm_e_mma(GmmArgs<double>& a, const GmmMmaPlan& pl) {
 
 extern "C" {
 
+// ---- stand-in for the tensor-core E pass (abi_gmm_tc.cu is tcgen05 code with no host form): the same interface and the
+// same arithmetic in plain float (operands rounded to fp32, fp32 accumulation), so that the host logic around it can be
+// exercised on CPU.  The planes buffer holds (x - c) as float in its first plane; the second stays zero.
+int donk_emu_gmm_tc_supported(int d, int K) { return d >= 1 && d <= 80 && K >= 1 ? 1 : 0; }
+size_t donk_emu_gmm_tc_planes_bytes(int n, int d) {
+  const size_t one = ((size_t)n * round_up(d, 8) * sizeof(float) + 255) & ~(size_t)255;
+  return 2 * one;
+}
+size_t donk_emu_gmm_tc_workspace_bytes(int n, int d, int K) { return 256 + (size_t)n * K * sizeof(float) + (size_t)K * d * 8; }
+int donk_emu_gmm_tc_prepare_f32(int n, int d, const double* X, const double* center, void* planes, size_t planes_bytes, void*) {
+  if (n < 0 || d < 1 || planes_bytes < donk_emu_gmm_tc_planes_bytes(n, d)) return DONK_BAD_SHAPE;
+  const int dp = round_up(d, 8);
+  float* hi = static_cast<float*>(planes);
+  memset(planes, 0, donk_emu_gmm_tc_planes_bytes(n, d));
+  for (size_t r = 0; r < (size_t)n; ++r)
+    for (int j = 0; j < d; ++j) hi[r * dp + j] = (float)(X[r * d + j] - (center ? center[j] : 0.0));
+  return DONK_OK;
+}
+int donk_emu_gmm_tc_estep_f32(int n, int d, int K, const void* planes, const double* center, const double* weights,
+                              const double* means, const double* prec_chol, double* resp, double* lse_part, void* work,
+                              size_t work_bytes, void*) {
+  if (n < 0 || d < 1 || K < 1 || work_bytes < donk_emu_gmm_tc_workspace_bytes(n, d, K)) return DONK_BAD_SHAPE;
+  const int dp = round_up(d, 8);
+  const float* hi = static_cast<const float*>(planes);
+  const size_t dd = (size_t)d * d;
+  std::vector<float> bias((size_t)K * d), cst(K), lp(K);
+  for (int k = 0; k < K; ++k) {
+    double ld = 0.0;
+    for (int j = 0; j < d; ++j) {
+      double acc = 0.0;
+      for (int q = 0; q <= j; ++q) acc = fma(means[(size_t)k * d + q] - (center ? center[q] : 0.0), prec_chol[k * dd + (size_t)q * d + j], acc);
+      bias[(size_t)k * d + j] = (float)acc;
+      ld += log(prec_chol[k * dd + (size_t)j * d + j]);
+    }
+    cst[k] = (float)(ld + log(weights[k]) - 0.5 * d * 1.8378770664093454835606594728112);
+  }
+  const size_t nblocks = ((size_t)n + GMM_TS - 1) / GMM_TS;
+  for (size_t b = 0; b < nblocks; ++b) lse_part[b] = 0.0;
+  for (size_t r = 0; r < (size_t)n; ++r) {
+    for (int k = 0; k < K; ++k) {
+      float ss = 0.f;
+      for (int j = 0; j < d; ++j) {
+        float acc = 0.f;
+        for (int q = 0; q <= j; ++q) acc = fmaf(hi[r * dp + q], (float)prec_chol[k * dd + (size_t)q * d + j], acc);
+        const float y = acc - bias[(size_t)k * d + j];
+        ss = fmaf(y, y, ss);
+      }
+      lp[k] = cst[k] - 0.5f * ss;
+    }
+    double m = lp[0];
+    for (int k = 1; k < K; ++k) m = lp[k] > m ? (double)lp[k] : m;
+    double s = 0.0;
+    for (int k = 0; k < K; ++k) s += exp((double)lp[k] - m);
+    for (int k = 0; k < K; ++k) resp[r * K + k] = exp((double)lp[k] - m) / s;
+    lse_part[r / GMM_TS] += m + log(s);
+  }
+  (void)work;
+  return DONK_OK;
+}
+
 int donk_emu_gmm_em_step_mode_f64(int n_local, int d, int K, const double* X, const double* weights, const double* means,
                                   const double* prec_chol, const double* resp_in, double* stats, double* shift,
                                   void* workspace, size_t workspace_bytes, int mode, void*) {
-  if (n_local < 0 || d < 1 || K < 1 || mode < 0 || mode > 2) return DONK_BAD_SHAPE;
+  if (n_local < 0 || d < 1 || K < 1 || mode < 0 || mode > 3) return DONK_BAD_SHAPE;
   if (workspace_bytes < donk_emu_gmm_workspace_bytes(n_local, d, K)) return DONK_BAD_SHAPE;
   const size_t total = gmm_stats_len(d, K);
   if (n_local == 0) { memset(stats, 0, total * sizeof(double)); return DONK_OK; }
@@ -452,9 +537,11 @@ int donk_emu_gmm_em_step_mode_f64(int n_local, int d, int K, const double* X, co
   double* ws = static_cast<double*>(workspace);
   a.resp = ws; a.lse_part = ws + (size_t)n_local * K; a.part = a.lse_part + a.nblocks;
   const GmmMmaPlan pl = gmm_mma_plan(n_local, d, K);
-  const bool want_mma = mode == 2 || (mode == 0 && (n_local >= 65536 || env_int("DONK_GMM_MMA")));
+  const bool want_mma = mode == 2 || ((mode == 0 || mode == 3) && (n_local >= 65536 || env_int("DONK_GMM_MMA")));
   const bool mma = pl.ok && !env_int("DONK_GMM_GENERIC") && weights != nullptr && want_mma;  // as the CUDA launcher
-  if (resp_in) {
+  if (mode == 3) {
+    if (resp_in) return DONK_BAD_SHAPE;  // the workspace already holds resp and lse_part (donk_emu_gmm_tc_estep_f32)
+  } else if (resp_in) {
     a.resp = const_cast<double*>(resp_in);
     memset(a.lse_part, 0, (size_t)a.nblocks * sizeof(double));
   } else if (mma) {

@@ -457,3 +457,83 @@ def test_fit_lr_coop_kernel_config5_dims(backend):
     Fo, fo, co = oracle.fit_lr(c.X, c.U)
     assert int(info.sum()) == 0
     assert relerr(F[0], Fo) < 1e-8 and relerr(f[0], fo) < 1e-8 and relerr(covar[0], co) < 1e-8
+
+
+@pytest.mark.parametrize("dims,N,K", [((6, 2), 40, 0), ((20, 6), 64, 0), ((14, 7), 50, 4), ((5, 3), 30, 2)])
+def test_fit_lr_f32_tolerance(backend, dims, N, K):
+    """Single-precision fit_lr (donk_fit_lr_f32) against the fp64 oracle; STATED TOLERANCE (include/donk_b200.h):
+    F, f within 2e-3 and covar within 5e-3, max-norm relative, for N > 2 (dX + dU) samples."""
+    from donk_b200 import batched, synthetic
+    from donk_b200.batched import DeviceGMM
+    from oracle.gmm import gmm_eval_prior
+
+    dX, dU = dims
+    T, B, n_pool = 4, 2, 5000
+    conds = [synthetic.condition(61, i, T, dX, dU, N) for i in range(B)]
+    X, U = np.stack([c.X for c in conds]), np.stack([c.U for c in conds])
+    gm, prior = None, None
+    if K:
+        prm = _synthetic_prior(dX, dU, K, seed=9)
+        gm = DeviceGMM(K)
+        gm.set_params(prm.weights, prm.means, covariances=prm.covariances, precisions_cholesky=prm.precisions_cholesky)
+        gm.N = n_pool
+        prior = lambda xux: gmm_eval_prior(prm, n_pool, xux)  # noqa: E731
+    F, f, covar, info = batched.fit_lr_f32(X, U, gm)
+    assert F.dtype == torch.float32 and int(info.sum()) == 0
+    for b, c in enumerate(conds):
+        Fo, fo, co = oracle.fit_lr(c.X, c.U, prior)
+        assert relerr(F[b].double(), Fo) < 2e-3
+        assert relerr(f[b].double(), fo) < 2e-3
+        assert relerr(covar[b].double(), co) < 5e-3
+
+
+@pytest.mark.parametrize("n,d,K", [(700, 10, 4), (1500, 35, 4), (3000, 72, 16), (260, 46, 3), (129, 8, 2)])
+def test_gmm_tc_estep_tolerance(backend, n, d, K):
+    """E pass on the tcgen05 tensor cores (3xTF32, fp32 accumulators in TMEM; on CPU: the float stand-in of the emulation)
+    against the fp64 oracle.  STATED TOLERANCE (include/donk_b200.h): responsibilities within 2e-4 absolute, the mean
+    log-likelihood within 1e-5 relative.  Shapes cover a ragged last tile (n % 128 != 0), d not a multiple of 8, an odd
+    number of clusters (one cluster per CTA) and the config-4 shape d = 72, K = 16."""
+    from donk_b200 import synthetic
+    from donk_b200.batched import DeviceGMM
+    from oracle.gmm import gmm_e_step
+
+    rng = np.random.default_rng(1)
+    # overlapping clusters (responsibilities spread over several clusters) around a common offset far from the origin
+    m0 = 5.0 + 0.4 * rng.standard_normal((K, d))
+    X = 5.0 + rng.standard_normal((n, d))
+    w0 = rng.uniform(0.5, 1.5, K)
+    w0 /= w0.sum()
+    A = rng.standard_normal((K, d, d)) / np.sqrt(d)
+    prec = A @ np.swapaxes(A, 1, 2) + 0.7 * np.eye(d)  # full (non-diagonal) precisions
+    prm = params_from_precisions(w0, m0, prec)
+    gm = DeviceGMM(K, precision="tf32x3").set_params(w0, m0, precisions=prec)
+    resp = to_np(gm.predict_proba_tf32x3(X))
+    lb_o, log_resp_o = gmm_e_step(X, prm)
+    resp_o = np.exp(log_resp_o)
+    assert 0.05 < np.median(resp_o.max(1)) < 0.999  # the case is not one-hot
+    assert np.max(np.abs(resp - resp_o)) < 2e-4
+    assert np.allclose(resp.sum(1), 1.0, atol=1e-12)
+
+
+def test_gmm_tf32x3_fit_matches_fp64_fit(backend):
+    """DeviceGMM(precision='tf32x3').fit: tensor-core E pass + fp64 M pass.  Against the fp64 fit of the same start after
+    the same number of iterations: means within 1e-4 of the data scale, covariances within 1e-3 relative, the lower bound
+    within 1e-5 relative (stated fp32 tolerance)."""
+    from donk_b200 import synthetic
+    from donk_b200.batched import DeviceGMM
+
+    n, d, K = 4000, 12, 3
+    X, w0, m0, p0 = synthetic.gmm_pool(n, d, K, seed=23)
+    fits = {}
+    for prec in ("fp64", "tf32x3"):
+        gm = DeviceGMM(K, tol=0.0, max_iter=4, precision=prec).set_params(w0, m0, precisions=p0)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            gm.fit(X)
+        fits[prec] = gm
+    a, b = fits["fp64"], fits["tf32x3"]
+    assert relerr(b.means, to_np(a.means)) < 1e-4
+    assert relerr(b.covariances, to_np(a.covariances)) < 1e-3
+    assert abs(b.lower_bound - a.lower_bound) < 1e-5 * abs(a.lower_bound)
+    with pytest.raises(Exception):
+        DeviceGMM(2, precision="tf32x3").set_params(np.full(2, 0.5), np.zeros((2, 100)), precisions=np.stack([np.eye(100)] * 2)).fit(np.zeros((10, 100)))
