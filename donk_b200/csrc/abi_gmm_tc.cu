@@ -75,16 +75,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t da, uint64_t
       ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
-  uint32_t r[8];
+// 8 consecutive TMEM columns of this thread's lane; the registers are valid after tcgen05.wait::ld
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+template <int KS>  // k-steps of 8 features: dp = 8 KS (compile-time so that a cluster's columns are read from TMEM in one batch)
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gmm_tc_estep_kernel(const __grid_constant__ CUtensorMap tmXhi, const __grid_constant__ CUtensorMap tmXlo,
                     const __grid_constant__ CUtensorMap tmPhi, const __grid_constant__ CUtensorMap tmPlo,
@@ -92,7 +90,7 @@ gmm_tc_estep_kernel(const __grid_constant__ CUtensorMap tmXhi, const __grid_cons
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // the swizzle pattern is a function of the shared-memory address bits: operand tiles start on 256-byte boundaries
   unsigned char* smem = smem_raw + ((256u - (smem_u32(smem_raw) & 255u)) & 255u);
-  const int KS = p.dp / 8, N = p.N;
+  const int N = p.N;
   const uint32_t b_plane = (uint32_t)KS * N * 32, a_plane = (uint32_t)KS * TC_M * 32;
   unsigned char* sB = smem;                    // [plane hi|lo][k-step][N rows][32 B]
   unsigned char* sA = sB + 2 * b_plane;        // [stage][plane hi|lo][k-step][128 rows][32 B]
@@ -184,17 +182,24 @@ gmm_tc_estep_kernel(const __grid_constant__ CUtensorMap tmXhi, const __grid_cons
       const size_t row = (size_t)tile * TC_M + q * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N);
       for (int c = 0; c < p.kc; ++c) {
-        float ss = 0.f;
-        for (int j0 = 0; j0 < p.dp; j0 += 8) {
-          float v[8];
-          tmem_ld8(taddr + (uint32_t)(c * p.dp + j0), v);
+        // all 8 KS columns of the cluster in flight, one wait: the loads are latency-bound when waited for one by one
+        uint32_t v[KS][8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float y = v[j] - sbias[c * p.dp + j0 + j];
-            ss = fmaf(y, y, ss);
+        for (int ch = 0; ch < KS; ++ch) tmem_ld8_nowait(taddr + (uint32_t)(c * 8 * KS + 8 * ch), v[ch]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float ss0 = 0.f, ss1 = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < KS; ++ch) {
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            const float y0 = __uint_as_float(v[ch][j]) - sbias[c * 8 * KS + 8 * ch + j];
+            const float y1 = __uint_as_float(v[ch][j + 1]) - sbias[c * 8 * KS + 8 * ch + j + 1];
+            ss0 = fmaf(y0, y0, ss0);
+            ss1 = fmaf(y1, y1, ss1);
           }
         }
-        if (row < (size_t)p.n) p.logp[row * p.K + cg * p.kc + c] = scst[c] - 0.5f * ss;
+        // layout [cluster group][row][kc]: the 32 rows of a warp are one contiguous run
+        if (row < (size_t)p.n) p.logp[((size_t)cg * p.n + row) * p.kc + c] = scst[c] - 0.5f * (ss0 + ss1);
       }
       tc_fence_before();
       __syncwarp();
@@ -211,7 +216,8 @@ gmm_tc_estep_kernel(const __grid_constant__ CUtensorMap tmXhi, const __grid_cons
 }
 
 // X (n, d) fp64 -> two TF32 planes of (x - c) with row pitch dp (columns d..dp-1 zero)
-__global__ void gmm_tc_split_kernel(size_t total, int d, int dp, const double* X, const double* center, float* hi, float* lo) {
+__global__ void gmm_tc_split_kernel(size_t n, int d, int dp, const double* X, const double* center, float* hi, float* lo) {
+  const size_t total = n * dp;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const size_t r = idx / dp;
     const int j = (int)(idx % dp);
@@ -257,20 +263,24 @@ __global__ void gmm_tc_params_kernel(int d, int dp, int K, const double* center,
   }
 }
 
-// log-probabilities (n, K) fp32 -> responsibilities (n, K) fp64 and the log-sum-exp total of every GMM_TS-row block
-// (sklearn/mixture/_base.py:552-582).  256 rows per CTA, one thread per row, fixed-order sums.
-__global__ void __launch_bounds__(256) gmm_tc_softmax_kernel(int n, int K, const float* logp, double* resp, double* lse_part) {
-  __shared__ double wsum[8];
-  const size_t row = (size_t)blockIdx.x * 256 + threadIdx.x;
+// log-probabilities [K / kc][n][kc] fp32 -> responsibilities (n, K) fp64 and the log-sum-exp total of every GMM_TS-row
+// block (sklearn/mixture/_base.py:552-582).  128 rows per CTA, one thread per row, fixed-order sums; the block's
+// responsibilities are one contiguous run of the output and leave through shared memory with coalesced stores.
+__global__ void __launch_bounds__(128) gmm_tc_softmax_kernel(int n, int K, int kc, const float* logp, double* resp,
+                                                             double* lse_part, int staged) {
+  extern __shared__ double sresp[];  // [128][K] when staged
+  __shared__ double wsum[4];
+  const size_t row0 = (size_t)blockIdx.x * 128, row = row0 + threadIdx.x;
   double lse = 0.0;
   if (row < (size_t)n) {
-    const float* lp = logp + row * K;
-    double m = lp[0];
-    for (int k = 1; k < K; ++k) m = lp[k] > m ? (double)lp[k] : m;
+    auto lp = [&](int k) { return (double)logp[((size_t)(k / kc) * n + row) * kc + k % kc]; };
+    double m = lp(0);
+    for (int k = 1; k < K; ++k) { const double v = lp(k); m = v > m ? v : m; }
     double s = 0.0;
-    for (int k = 0; k < K; ++k) s += exp((double)lp[k] - m);
+    for (int k = 0; k < K; ++k) s += exp(lp(k) - m);
     const double inv = 1.0 / s;
-    for (int k = 0; k < K; ++k) resp[row * K + k] = exp((double)lp[k] - m) * inv;
+    double* out = staged ? sresp + (size_t)threadIdx.x * K : resp + row * K;
+    for (int k = 0; k < K; ++k) out[k] = exp(lp(k) - m) * inv;
     lse = m + log(s);
   }
 #pragma unroll
@@ -278,9 +288,14 @@ __global__ void __launch_bounds__(256) gmm_tc_softmax_kernel(int n, int K, const
   if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = lse;
   __syncthreads();
   static_assert(GMM_TS == 64, "lse_part is kept per 64-row block");
-  if (threadIdx.x < 4) {
-    const size_t blk = (size_t)blockIdx.x * 4 + threadIdx.x;
+  if (threadIdx.x < 2) {
+    const size_t blk = (size_t)blockIdx.x * 2 + threadIdx.x;
     if (blk * GMM_TS < (size_t)n) lse_part[blk] = wsum[2 * threadIdx.x] + wsum[2 * threadIdx.x + 1];
+  }
+  if (staged) {
+    const size_t left = (size_t)n - row0;
+    const size_t cnt = (left < 128 ? left : 128) * K;
+    for (size_t i = threadIdx.x; i < cnt; i += 128) resp[row0 * K + i] = sresp[i];
   }
 }
 
@@ -299,7 +314,9 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// 2-D fp32 tensor (rows, dp) with boxes of (8 floats, box_rows) and the 32-byte swizzle the UMMA descriptors expect
+// 2-D fp32 tensor (rows, dp) with boxes of (8 floats, box_rows) and the 32-byte swizzle the UMMA descriptors expect.
+// (Measured alternative: planes stored k-step-major [dp/8][rows][8] and ONE 3-D box per plane and tile - the tile is
+// then dp/8 contiguous 4 KB runs - was slower, 15.4 vs 13.7 ms per pass at 10 M x 72, and makes the split copy a scatter.)
 int make_map(CUtensorMap* tm, const float* base, size_t rows, int dp, int box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled is not available"); return DONK_CUDA_ERROR; }
@@ -342,6 +359,27 @@ TcPlan tc_plan(int d, int K) {
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+template <int KS>
+int tc_launch_ks(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const CUtensorMap& d, const TcParams& p,
+                 size_t smem, cudaStream_t st) {
+  int rc = allow_smem(gmm_tc_estep_kernel<KS>, smem);
+  if (rc != DONK_OK) return rc;
+  gmm_tc_estep_kernel<KS><<<p.ncg * p.walkers, TC_THREADS, smem, st>>>(a, b, c, d, p);
+  LAUNCHED("gmm_tc_estep_kernel");
+  return DONK_OK;
+}
+
+int tc_launch(int KS, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const CUtensorMap& d, const TcParams& p,
+              size_t smem, cudaStream_t st) {
+  switch (KS) {
+#define DONK_TC_CASE(V) case V: return tc_launch_ks<V>(a, b, c, d, p, smem, st);
+    DONK_TC_CASE(1) DONK_TC_CASE(2) DONK_TC_CASE(3) DONK_TC_CASE(4) DONK_TC_CASE(5) DONK_TC_CASE(6) DONK_TC_CASE(7)
+    DONK_TC_CASE(8) DONK_TC_CASE(9) DONK_TC_CASE(10)
+#undef DONK_TC_CASE
+  }
+  return DONK_SMEM_LIMIT;
+}
+
 }  // namespace
 
 extern "C" {
@@ -371,7 +409,7 @@ int donk_gmm_tc_prepare_f32(int n, int d, const double* X, const double* center,
   const size_t total = (size_t)n * dp;
   size_t blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  gmm_tc_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(total, d, dp, X, center, hi, lo);
+  gmm_tc_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((size_t)n, d, dp, X, center, hi, lo);
   LAUNCHED("gmm_tc_split_kernel");
   return DONK_OK;
 }
@@ -417,11 +455,11 @@ int donk_gmm_tc_estep_f32(int n, int d, int K, const void* planes, const double*
   if (walkers > p.ntiles) walkers = p.ntiles;
   p.walkers = walkers;
   p.bias = bias; p.cst = cst; p.logp = logp;
-  rc = allow_smem(gmm_tc_estep_kernel, pl.smem);
+  rc = tc_launch(pl.dp / 8, tXh, tXl, tPh, tPl, p, pl.smem, st);
   if (rc != DONK_OK) return rc;
-  gmm_tc_estep_kernel<<<p.ncg * walkers, TC_THREADS, pl.smem, st>>>(tXh, tXl, tPh, tPl, p);
-  LAUNCHED("gmm_tc_estep_kernel");
-  gmm_tc_softmax_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, K, logp, resp, lse_part);
+  const size_t sm_bytes = (size_t)128 * K * sizeof(double);
+  const int staged = sm_bytes <= 40 * 1024;
+  gmm_tc_softmax_kernel<<<(unsigned)((n + 127) / 128), 128, staged ? sm_bytes : 0, st>>>(n, K, pl.kc, logp, resp, lse_part, staged);
   LAUNCHED("gmm_tc_softmax_kernel");
   return DONK_OK;
 }

@@ -127,3 +127,28 @@ elif what == "epass":
     ms, resp = timed(lambda: gm.predict_proba(X), 3)
     fl = n * K * d * (d + 1)
     print(f"E pass n={n} d={d} K={K}: {ms:.2f} ms = {fl / ms / 1e9:.2f} TFLOP/s (triangular count)")
+elif what == "tc":
+    # tensor-core E pass: split copy, E pass alone, full EM iteration (tf32x3 E + fp64 M) vs the fp64 iteration
+    n, d, K = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+    X, w0, m0, p0 = synthetic.gmm_pool_torch(n, d, K, seed=5, device=dev)
+    nat = _lib.native()
+    gm = batched.DeviceGMM(K, tol=0.0, max_iter=1, precision="tf32x3").set_params(w0, m0, precisions=p0)
+    ms_prep, tc = timed(lambda: gm._tc_setup(X), 2)
+    ws = torch.empty(nat.size("gmm_workspace_bytes", n, d, K) // 8 + 1, dtype=torch.float64, device=dev)
+    def estep():
+        nat.call("gmm_tc_estep_f32", n, d, K, tc["planes"], tc["center"], gm.weights, gm.means, gm.precisions_cholesky,
+                 ws, ws[n * K:], tc["work"], tc["work"].numel() * 8)
+    ms_e, _ = timed(estep, 5)
+    fl = n * K * d * (d + 1)
+    print(f"tc E pass n={n} d={d} K={K}: split copy {ms_prep:.2f} ms (once per fit), E pass {ms_e:.2f} ms = "
+          f"{fl / ms_e / 1e9:.1f} TFLOP/s algorithmic (triangular count), {3 * 2 * n * K * round(d / 8 + 0.49) * 8 * round(d / 8 + 0.49) * 8 / ms_e / 1e9:.0f} TFLOP/s issued TF32")
+    ms64, r64 = timed(lambda: gm.predict_proba(X), 3)
+    r32 = ws[:n * K].view(n, K)
+    print(f"  fp64 E pass {ms64:.2f} ms; max |resp_tc - resp_fp64| = {float((r32 - r64).abs().max()):.2e}")
+    stats = torch.empty(nat.size("gmm_stats_size", d, K), dtype=torch.float64, device=dev)
+    for prec in ("fp64", "tf32x3"):
+        g = batched.DeviceGMM(K, tol=0.0, max_iter=1, precision=prec).set_params(w0, m0, precisions=p0)
+        g._lb = torch.zeros(1, dtype=torch.float64, device=dev); g._info = torch.zeros(K, dtype=torch.int32, device=dev)
+        g._tc = g._tc_setup(X) if prec == "tf32x3" else None
+        ms_it, _ = timed(lambda: g.em_iteration(X, float(n), ws, stats), 5)
+        print(f"  EM iteration ({prec}): {ms_it:.2f} ms, lower bound {float(g._lb):.10f}")
