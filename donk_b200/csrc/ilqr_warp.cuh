@@ -65,9 +65,20 @@ struct WarpDims {
   static constexpr int RSZ = (DX4 * PP > P4 * DXP ? DX4 * PP : P4 * DXP) + 8;
   static constexpr int KSZ = (DU4 * KLD > DX4 * KTL ? DU4 * KLD : DX4 * KTL) + 8;
   static constexpr int oM = 0, oR = oM + MSZ, oK = oR + RSZ, oKv = oK + KSZ;
-  static constexpr int oPc = oKv + 8, oLds = oPc + (DU * DU + 3) / 4 * 4, oDel = oLds + 8, oRow = oDel + 8;
+  // Forward pass: pol_covar_t (DU x DU) and k_t (DU).  The fragments of K^T (DX4 x KTL) only ever touch columns 0..7 of a
+  // row, so with KTL = 12 the columns 8..11 are free: the two small arrays live there in strips of four (PC_IN_K).  The 50
+  // reals this and the packed scalars below save are what lets a tenth (20,6) problem fit an SM at E = 1 (ILQR.optimize).
+  static constexpr int PCN = (DU * DU + 3) / 4 * 4;
+  static constexpr bool PC_IN_K = KTL >= 12 && DX4 * 4 >= PCN + DU4;
+  static constexpr int oPc = oKv + (PC_IN_K ? 0 : 8);
+  static constexpr int DUE = (DU + 1) / 2 * 2;
+  static constexpr int oLds = oPc + (PC_IN_K ? 0 : PCN), oDel = oLds + DUE;
+  static constexpr int oScal = oDel + DUE;   // scal: 0 1/eta 1 kl 2 cost 3 logdet 4 notpd
   // oRow: forward: compact copy of mu (P values, conflict-free reads in the cost phase); end: per-lane cost partials
-  static constexpr int oScal = oRow + (P4 > 32 ? P4 : 32), TEAM = oScal + 8;  // scal: 0 1/eta 1 kl 2 cost 3 logdet 4 notpd
+  static constexpr int oRow = oScal + 6, TEAM = oRow + (P4 > 32 ? P4 : 32);
+  static_assert(oRow % 2 == 0 && TEAM % 2 == 0 && oK % 2 == 0, "16-byte accesses: even offsets");
+  DONK_HD static constexpr int pc_off(int e) { return PC_IN_K ? oK + (e >> 2) * KTL + 8 + (e & 3) : oPc + e; }
+  DONK_HD static constexpr int kv_off(int i) { return PC_IN_K ? pc_off(PCN + i) : oKv + i; }
   // stage area per condition (reals): backward and forward views share the storage.  Everything the teams of a
   // condition share and that does not depend on eta is staged one step ahead with cp.async: F_t, C_kl_t (backward);
   // F_t^T, K_prev_t, Lam_prev_t, dyn_covar_t (forward).  C_t (scaled by 1/eta, and the cost weights) is the one input
@@ -478,8 +489,8 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
       for (int a2 = 0; a2 < DU; ++a2) {
         LANE_FOR(k, DX) cp_async(tp + D::oK + k * KTL + a2, a.K + pt * szK + (size_t)a2 * DX + k);
       }
-      LANE_FOR(i, DU) cp_async(tp + D::oKv + i, a.k + pt * DU + i);
-      LANE_FOR(idx, DU * DU) cp_async(tp + D::oPc + idx, a.pcov + pt * szS + idx);
+      LANE_FOR(i, DU) cp_async(tp + D::kv_off(i), a.k + pt * DU + i);
+      LANE_FOR(idx, DU * DU) cp_async(tp + D::pc_off(idx), a.pcov + pt * szS + idx);
     };
     stage_fwd(0);
     TEAMS_DO(tm) {
@@ -544,7 +555,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
                   tp[D::oM + (DX + a2) * PP + jj] = acc;
                   tp[D::oM + jj * PP + DX + a2] = acc;
                 } else if (jj == P) {
-                  const R mu_u = acc + tp[D::oKv + a2];
+                  const R mu_u = acc + tp[D::kv_off(a2)];
                   tp[D::oM + (DX + a2) * PP + P] = mu_u;
                   tp[D::oRow + DX + a2] = mu_u;
                 }
@@ -560,7 +571,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
           for (int h = 0; h < 2; ++h) {
             const int bb = j + h;
             if (a2 <= bb && bb < DU) {
-              const R val = (h ? v1 : v0) + tp[D::oPc + a2 * DU + bb];
+              const R val = (h ? v1 : v0) + tp[D::pc_off(a2 * DU + bb)];
               tp[D::oM + (DX + a2) * PP + DX + bb] = val;
               tp[D::oM + (DX + bb) * PP + DX + a2] = val;
             }
@@ -678,7 +689,7 @@ DONK_D void ilqr_warp_cta(const WCtx& w, const IlqrArgs<R>& a, int cta, int ES, 
 #pragma unroll
             for (int j = 0; j < DU; ++j) {
               const R lij = st[oPL + ln * DU + j];
-              tr = fma(lij, tp[D::oPc + j * DU + ln], tr);
+              tr = fma(lij, tp[D::pc_off(j * DU + ln)], tr);
               row = fma(lij, tp[D::oDel + j], row);
             }
             tp[D::oLds + ln] = fma(tp[D::oDel + ln], row, tr);
@@ -770,7 +781,10 @@ template <typename R, int DX, int DU>
 inline int ilqr_warp_plan(int B, int E, size_t smem_cap, int force_G, int& G, int& ES, int& grid, size_t& bytes) {
   const size_t sm_total = 228 * 1024, cta_reserved = 1024;
   int best_g = 0, best_warps = 0, best_es = 0;
-  for (int g = force_G > 0 ? force_G : 16; g >= 1; --g) {
+  // E = 1 (the Brent steps of ILQR.optimize): every warp is a different condition with its own stage area, nothing is
+  // shared, so one-warp CTAs that never meet at a CTA barrier win (config 3, 14 steps: 63.9 ms; five-warp CTAs with one
+  // more warp per SM 75.8 ms; one ten-warp CTA 101 ms)
+  for (int g = force_G > 0 ? force_G : (E == 1 ? 1 : 16); g >= 1; --g) {
     const int es = E < g ? E : g, gg = (g / es) * es;
     if (gg < 1) continue;
     const size_t by = ilqr_warp_bytes<R, DX, DU>(gg, gg / es);
