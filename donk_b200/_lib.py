@@ -46,6 +46,8 @@ SIGNATURES = {
     "gmm_m_finalize_f64": [c_double, c_int, c_int, P, P, c_double, P, P, P, P, P, P, P],
     "gmm_tc_prepare_f32": [c_int, c_int, P, P, P, c_size_t, P],
     "gmm_tc_estep_f32": [c_int] * 3 + [P] * 8 + [c_size_t, P],
+    "gmm_tc_mprepare_f32": [c_int, c_int, P, P, P, c_size_t, P],
+    "gmm_tc_mstep_f32": [c_int] * 3 + [P] * 7 + [c_size_t, P],
     "gmm_predict_proba_f64": [c_int] * 3 + [P] * 5 + [P],
     "gmm_prec_chol_from_precisions_f64": [c_int] * 2 + [P] * 3 + [P],
     "fp64_probe": [c_int, c_int, c_int, P, ctypes.POINTER(c_double), P],
@@ -59,6 +61,9 @@ _SIZE_FUNCS = {
     "gmm_tc_supported": [c_int, c_int],
     "gmm_tc_planes_bytes": [c_int, c_int],
     "gmm_tc_workspace_bytes": [c_int, c_int, c_int],
+    "gmm_tc_m_supported": [c_int, c_int],
+    "gmm_tc_mplanes_bytes": [c_int, c_int],
+    "gmm_tc_mwork_bytes": [c_int, c_int, c_int],
 }
 
 

@@ -483,11 +483,14 @@ class DeviceGMM:
                  precision: str = "fp64"):
         self.K = int(n_clusters)
         self.kernels = "auto"  # "auto" | "scalar" | "dmma": see fit()
-        # "fp64" (default: parity with scikit-learn at 1e-8) or "tf32x3": the E pass runs on the tcgen05 tensor cores at
-        # a stated fp32 tolerance (include/donk_b200.h, donk_gmm_tc_estep_f32); the M pass and all parameters stay fp64
+        # "fp64" (default: parity with scikit-learn at 1e-8) or "tf32x3": the E pass and the scatter statistics of the M
+        # pass run on the tcgen05 tensor cores at a stated fp32 tolerance (include/donk_b200.h, donk_gmm_tc_estep_f32 /
+        # donk_gmm_tc_mstep_f32); the partial sums, the all-reduce, the finalisation and all parameters stay fp64.
+        # tc_m_pass = False keeps the fp64 DMMA M pass behind the tensor-core E pass.
         if precision not in ("fp64", "tf32x3"):
             raise ValueError(f"precision must be 'fp64' or 'tf32x3', got {precision!r}")
         self.precision = precision
+        self.tc_m_pass = True
         self._tc = None
         self.tol, self.reg_covar, self.max_iter = tol, reg_covar, max_iter
         self.d = None
@@ -577,8 +580,14 @@ class DeviceGMM:
             nat.call("gmm_tc_estep_f32", n, d, self.K, tc["planes"], tc["center"], self.weights, self.means,
                      self.precisions_cholesky, ws, ws[n * self.K:], tc["work"], tc["work"].numel() * 8)
             mode = 3
-        nat.call("gmm_em_step_mode_f64", n, d, self.K, X, self.weights, self.means, self.precisions_cholesky, None, stats,
-                 self._shift, ws, ws.numel() * ws.element_size(), mode)
+        if self._tc is not None and self._tc.get("mplanes") is not None:
+            # M pass on the tensor cores too: scatter statistics about the same centre, drained into fp64 partial sums
+            tc = self._tc
+            nat.call("gmm_tc_mstep_f32", n, d, self.K, tc["mplanes"], tc["center"], ws, ws[n * self.K:], stats, self._shift,
+                     tc["mwork"], tc["mwork"].numel() * 8)
+        else:
+            nat.call("gmm_em_step_mode_f64", n, d, self.K, X, self.weights, self.means, self.precisions_cholesky, None,
+                     stats, self._shift, ws, ws.numel() * ws.element_size(), mode)
         self._allreduce(stats, group)  # the one exchange step of the path (NCCL over NVLink)
         nat.call("gmm_m_finalize_f64", float(n_total), d, self.K, stats, self._shift, float(self.reg_covar),
                  self.weights, self.means, self.covariances, self.precisions_cholesky, self._lb, self._info)
@@ -634,7 +643,7 @@ class DeviceGMM:
         # cluster's own mean) are used whatever the pool size: results first, speed second.  The bound is evaluated
         # from the parameters going INTO every iteration (clusters move during EM), see _centring_hardness.
         self._mode = self._pick_mode(float(self._centring_hardness()))
-        self._tc = self._tc_setup(X) if self.precision == "tf32x3" else None
+        self._tc = self._tc_setup(X, m_pass=True) if self.precision == "tf32x3" else None
         lb = self.lower_bound if warm_start else -np.inf
         self.converged = False
         self.lower_bounds = []
@@ -661,7 +670,7 @@ class DeviceGMM:
                           "increase max_iter, tol, or check for degenerate data.", ConvergenceWarning)
         return self
 
-    def _tc_setup(self, X):
+    def _tc_setup(self, X, m_pass: bool = False):
         """Split copy of the rows for the tensor-core E pass: two TF32 planes of ``x - c`` (``c`` = the mixture mean going
         into the fit, fixed over its iterations so that the copy is made once)."""
         nat = _lib.native()
@@ -675,7 +684,13 @@ class DeviceGMM:
         planes = planes[off:]
         work = torch.empty(nat.size("gmm_tc_workspace_bytes", n, d, self.K) // 8 + 1, **o)
         nat.call("gmm_tc_prepare_f32", n, d, X, center, planes, planes.numel() * 8)
-        return dict(center=center, planes=planes, work=work)
+        tc = dict(center=center, planes=planes, work=work, mplanes=None, mwork=None)
+        if m_pass and self.tc_m_pass and nat.size("gmm_tc_m_supported", d, self.K):
+            mplanes = torch.empty(nat.size("gmm_tc_mplanes_bytes", n, d) // 8 + 32, **o)
+            tc["mplanes"] = mplanes[(-mplanes.data_ptr() // 8) % 32:]
+            tc["mwork"] = torch.empty(nat.size("gmm_tc_mwork_bytes", n, d, self.K) // 8 + 1, **o)
+            nat.call("gmm_tc_mprepare_f32", n, d, X, center, tc["mplanes"], tc["mplanes"].numel() * 8)
+        return tc
 
     def predict_proba_tf32x3(self, X) -> torch.Tensor:
         """``predict_proba`` through the tensor-core E pass (fp32 tolerance, see ``precision``)."""

@@ -380,6 +380,382 @@ int tc_launch(int KS, const CUtensorMap& a, const CUtensorMap& b, const CUtensor
   return DONK_SMEM_LIMIT;
 }
 
+
+__device__ __forceinline__ void umma_tf32_ta(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+// 8 consecutive TMEM columns of this thread's lane
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+               "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+               "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+
+// =====================================================================================================================
+// M pass on the tensor cores: the scatter statistics  S_k = sum_n r_nk (x_n - c)(x_n - c)^T  and the first moments
+// s_k = sum_n r_nk (x_n - c)  as ONE GEMM  D[(k,i)][j] = sum_n A[(k,i)][n] B[j][n]  with the sample index as the K
+// dimension:  B = the transposed pool (features x samples, row d is all ones so that column d of D is s_k), streamed by TMA
+// from a transposed split copy made once per fit;  A[(k,i)][n] = r_nk x_ni does not exist in memory - four producer warps
+// build it tile by tile from the B tile and the responsibilities, split into TF32 planes, straight into TENSOR MEMORY
+// (tcgen05.st: thread = TMEM lane = row of the M-tile, 8 samples = 8 columns per k-step) and the products take their A
+// operand from there (tcgen05.mma [d], [a_tmem], b_desc).  The first version staged A in shared memory: 21 ms per pass at
+// 10 M x 72, K = 16, bound by the shared-memory port (A written once and read three times per tile on top of the B
+// reads: ~930 KB per 64-row tile).  Three products per k-step as in the E pass (a_hi b_hi + a_lo b_hi + a_hi b_lo).  The K*d rows of D are cut into M-tiles of 128 TMEM lanes; a CTA group
+// owns mt_per of them (accumulators N columns each) and its CTAs ("walkers") split the row tiles of the pool.  The fp32
+// accumulators are drained into fp64 partial sums every FL tiles (the tensor core accumulates with truncation: the bias
+// grows with the number of accumulation steps) by the same producer warps, double buffered in TMEM when both sets fit.
+//     warp 0     one lane: TMA  B planes (8 samples x N rows boxes) + the tile's responsibilities (1-D bulk copy)
+//     warp 1     one lane: tcgen05.mma M=128, N, K=8; commits release the A stage / B stage / publish the accumulators
+//     warps 2-5  A producer (one row of the M-tile per thread), accumulator drain
+// =====================================================================================================================
+constexpr int TM_TS = 64;            // samples per tile
+constexpr int TM_KST = TM_TS / 8;    // k-steps (UMMA instructions per plane pair) per tile
+constexpr int TM_THREADS = 192;
+constexpr int TM_MAXST = 4;
+constexpr int TM_ACOLS = 2 * TM_KST * 8;  // TMEM columns of one A stage: planes hi | lo, 8 samples per k-step
+
+struct TcMParams {
+  int n, d, K, N, mt_per, ncg, walkers, ntiles, SA, SB, FL, nacc;
+  const unsigned char* bimg;  // [ntiles][plane hi|lo][k-step][N rows][32 B, swizzled]: the B stage images
+  const float* respT;  // [ntiles][K][TM_TS]
+  double* part;        // [grid][mt_per][128][N]
+};
+
+template <int MT>  // M-tiles per CTA (compile-time: the per-tile row offsets of a thread live in registers)
+__global__ void __launch_bounds__(TM_THREADS, 1)
+gmm_tc_mstep_kernel(const TcMParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((256u - (smem_u32(smem_raw) & 255u)) & 255u);
+  const int N = p.N, K = p.K;
+  const uint32_t b_plane = (uint32_t)TM_KST * N * 32, b_stage = 2 * b_plane;
+  const uint32_t r_stage = (uint32_t)K * TM_TS * 4;
+  unsigned char* sB = smem;                                  // [SB][plane][k-step][N rows][32 B]
+  unsigned char* sR = sB + (size_t)p.SB * b_stage;           // [SB][K][TM_TS] floats
+  unsigned long long* full_b = reinterpret_cast<unsigned long long*>(sR + (size_t)p.SB * r_stage);
+  unsigned long long* empty_b = full_b + TM_MAXST;
+  unsigned long long* full_a = empty_b + TM_MAXST;
+  unsigned long long* empty_a = full_a + TM_MAXST;
+  unsigned long long* acc_full = empty_a + TM_MAXST;   // [2]
+  unsigned long long* acc_empty = acc_full + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cg = blockIdx.x % p.ncg, wk = blockIdx.x / p.ncg;
+  const int my_tiles = wk < p.ntiles ? (p.ntiles - wk + p.walkers - 1) / p.walkers : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TM_MAXST; ++s) {
+      mbar_init(full_b + s, 1); mbar_init(empty_b + s, 5);
+      mbar_init(full_a + s, 4); mbar_init(empty_a + s, 1);
+    }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int acc_cols = MT * N;
+  // TMEM columns: [nacc accumulator sets of mt_per * N] [SA stages of the A operand: plane hi | lo, 8 columns per k-step]
+  const uint32_t a_cols0 = (uint32_t)(p.nacc * acc_cols);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int tile = wk + it * p.walkers;
+        mbar_wait(empty_b + s, ph ^ 1);
+        mbar_arrive_expect_tx(full_b + s, b_stage + r_stage);
+        // the tile's B operand is stored in global memory as the image of the shared-memory stage (both planes, k-step
+        // major, 32-byte swizzle applied by the split kernel): one contiguous bulk copy instead of 16 boxes of 80 rows
+        // that lie 40 MB apart in a plain transposed copy (measured: the TMA boxes bound the kernel at 18.7 ms per pass)
+        bulk_copy_g2s(sB + (size_t)s * b_stage, p.bimg + (size_t)tile * b_stage, b_stage, full_b + s);
+        bulk_copy_g2s(sR + (size_t)s * r_stage, p.respT + (size_t)tile * K * TM_TS, r_stage, full_b + s);
+        if (++s == p.SB) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+      int sb = 0, sa = 0, acc = 0, cnt = 0;
+      uint32_t phb = 0, pha = 0, aph = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const bool fresh = cnt == 0;
+        if (fresh) mbar_wait(acc_empty + acc, aph ^ 1);  // the previous drain of this accumulator set is done
+        mbar_wait(full_b + sb, phb);
+        const uint32_t b0 = smem_u32(sB + (size_t)sb * b_stage);
+        for (int m = 0; m < MT; ++m) {
+          mbar_wait(full_a + sa, pha);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols + m * N);
+          const uint32_t a0 = tmem_base + a_cols0 + (uint32_t)sa * TM_ACOLS;
+          uint32_t accumulate = fresh ? 0u : 1u;
+#pragma unroll 1
+          for (int pass = 0; pass < 3; ++pass) {  // a_hi b_hi + a_lo b_hi + a_hi b_lo
+            const uint32_t ap = a0 + (pass == 1 ? TM_ACOLS / 2 : 0), bp = b0 + (pass == 2 ? b_plane : 0);
+            for (int kk = 0; kk < TM_KST; ++kk) {
+              umma_tf32_ta(d_tmem, ap + 8u * kk, umma_desc_sw32(bp + (uint32_t)kk * N * 32), idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+          tc_commit(empty_a + sa);
+          if (++sa == p.SA) { sa = 0; pha ^= 1; }
+        }
+        tc_commit(empty_b + sb);
+        if (++sb == p.SB) { sb = 0; phb ^= 1; }
+        if (++cnt == p.FL || it + 1 == my_tiles) {
+          tc_commit(acc_full + acc);
+          cnt = 0;
+          if (++acc == p.nacc) { acc = 0; aph ^= 1; }
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int t = q * 32 + lane;     // row of the M-tile (= TMEM lane) this thread builds and drains
+    const int KD = K * p.d;
+    int sb = 0, sa = 0, acc = 0, cnt = 0;
+    uint32_t phb = 0, pha = 0, aph = 0;
+    bool first = true;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    // row (cluster c, feature i) of every M-tile of this CTA, as byte offsets into the B stage (the feature row, with the
+    // 32-byte swizzle of that row folded in) and the responsibility stage; -1: padding row beyond K * d
+    int xoff[MT], roff[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      const int r = (cg * MT + m) * TC_M + t;
+      const int c = r / p.d, i = r % p.d;
+      xoff[m] = r < KD ? i * 32 + (((i >> 2) & 1) ? 16 : 0) : -1;
+      roff[m] = c * TM_TS * 4;
+    }
+    const float2 neg1 = make_float2(-1.f, -1.f);
+    bool valid_all = true;  // CTA-uniform: no padding rows in any M-tile of this CTA
+#pragma unroll
+    for (int m = 0; m < MT; ++m) valid_all = valid_all && (cg * MT + m + 1) * TC_M <= KD;
+    for (int it = 0; it < my_tiles; ++it) {
+      mbar_wait(full_b + sb, phb);
+      const unsigned char* bst = sB + (size_t)sb * b_stage;
+      const unsigned char* rst = sR + (size_t)sb * r_stage;
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        mbar_wait(empty_a + sa, pha ^ 1);
+        const uint32_t a_t = lane_base + a_cols0 + (uint32_t)sa * TM_ACOLS;
+        // tcgen05.st is warp-collective (.sync.aligned): every lane issues it; padding rows (beyond K * d) read row 0 and
+        // store zeros
+        const bool valid = xoff[m] >= 0;
+        const unsigned char* bh = bst + (valid ? xoff[m] : 0);
+        const unsigned char* rr = rst + (valid ? roff[m] : 0);
+        const float2 scale = valid ? make_float2(1.f, 1.f) : make_float2(0.f, 0.f);
+#pragma unroll 2
+        for (int kk = 0; kk < TM_KST; ++kk) {
+          // 8 samples of this feature (both planes; logical halves: the swizzle is in xoff) and of this cluster
+          const float4 h0 = *reinterpret_cast<const float4*>(bh), h1 = *reinterpret_cast<const float4*>(reinterpret_cast<uintptr_t>(bh) ^ 16u);
+          const float4 l0 = *reinterpret_cast<const float4*>(bh + b_plane), l1 = *reinterpret_cast<const float4*>(reinterpret_cast<uintptr_t>(bh + b_plane) ^ 16u);
+          const float4 r0 = *reinterpret_cast<const float4*>(rr), r1 = *reinterpret_cast<const float4*>(rr + 16);
+          // a = r (x_hi + x_lo) on packed fp32 pairs; a_hi = a with the 13 low mantissa bits cleared (what the tensor
+          // core keeps of a TF32 operand), a_lo = a - a_hi exactly (its own low bits are dropped by the tensor core)
+          const float2 xp[4] = {__fadd2_rn(make_float2(h0.x, h0.y), make_float2(l0.x, l0.y)), __fadd2_rn(make_float2(h0.z, h0.w), make_float2(l0.z, l0.w)),
+                                __fadd2_rn(make_float2(h1.x, h1.y), make_float2(l1.x, l1.y)), __fadd2_rn(make_float2(h1.z, h1.w), make_float2(l1.z, l1.w))};
+          float2 rp[4] = {make_float2(r0.x, r0.y), make_float2(r0.z, r0.w), make_float2(r1.x, r1.y), make_float2(r1.z, r1.w)};
+          float hi[8], lo[8];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (!valid_all) rp[e] = __fmul2_rn(rp[e], scale);  // warp-uniform branch
+            const float2 a = __fmul2_rn(rp[e], xp[e]);
+            const float2 ah = make_float2(__uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u));
+            const float2 al = __ffma2_rn(ah, neg1, a);
+            hi[2 * e] = ah.x; hi[2 * e + 1] = ah.y;
+            lo[2 * e] = al.x; lo[2 * e + 1] = al.y;
+          }
+          tmem_st8(a_t + 8u * kk, hi);
+          tmem_st8(a_t + TM_ACOLS / 2 + 8u * kk, lo);
+          bh += (size_t)N * 32;
+          rr += 32;
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();  // the stores are ordered before the arrival the MMA thread waits for
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_a + sa);
+        if (++sa == p.SA) { sa = 0; pha ^= 1; }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_b + sb);
+      if (++sb == p.SB) { sb = 0; phb ^= 1; }
+      if (++cnt == p.FL || it + 1 == my_tiles) {  // drain the accumulator set into the fp64 partial sums of this CTA
+        cnt = 0;
+        mbar_wait(acc_full + acc, aph);
+        tc_fence_after();
+        for (int m = 0; m < MT; ++m) {
+          // partial sums [cta][m][column][lane]: the 32 lanes of a warp are one contiguous 256-byte run per column
+          double* out = p.part + ((size_t)blockIdx.x * MT + m) * N * TC_M + t;
+          const uint32_t taddr = lane_base + (uint32_t)(acc * acc_cols + m * N);
+          for (int c0 = 0; c0 < N; c0 += 16) {
+            uint32_t v[2][8];
+            tmem_ld8_nowait(taddr + (uint32_t)c0, v[0]);
+            tmem_ld8_nowait(taddr + (uint32_t)c0 + 8, v[1]);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const double x = (double)__uint_as_float(v[h][j]);
+                double* o = out + (size_t)(c0 + 8 * h + j) * TC_M;
+                *o = first ? x : *o + x;
+              }
+          }
+        }
+        first = false;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty + acc);
+        if (++acc == p.nacc) { acc = 0; aph ^= 1; }
+      }
+    }
+    if (first) {  // a CTA without tiles still owns partial sums: zero them
+      for (int m = 0; m < MT; ++m) {
+        double* out = p.part + ((size_t)blockIdx.x * MT + m) * N * TC_M + t;
+        for (int j = 0; j < N; ++j) out[(size_t)j * TC_M] = 0.0;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+// X (n, d) fp64 -> per 64-row tile the image of the M kernel's B stage: [plane hi|lo][k-step][feature row j < NR][8 samples]
+// of (x - c) split into TF32 planes, row d all ones (rows beyond n: zeros), 16-byte halves of a row swapped where the
+// 32-byte swizzle of the UMMA descriptor swaps them (bit 2 of the row index)
+__global__ void __launch_bounds__(256) gmm_tc_tblock_kernel(int n, int d, int NR, const double* X, const double* center, float* img) {
+  const size_t tile = blockIdx.x;
+  const int plane_f = TM_KST * NR * 8;  // floats per plane
+  float* out = img + tile * 2 * (size_t)plane_f;
+  for (int idx = threadIdx.x; idx < plane_f; idx += 256) {
+    const int pos = idx & 7, j = (idx >> 3) % NR, kk = (idx >> 3) / NR;
+    const int half = (pos >> 2) ^ ((j >> 2) & 1);  // logical half stored at this physical position
+    const size_t r = tile * TM_TS + kk * 8 + half * 4 + (pos & 3);
+    float h = 0.f, l = 0.f;
+    if (r < (size_t)n) {
+      if (j < d) {
+        const float x = (float)(X[r * d + j] - (center ? center[j] : 0.0));
+        h = tf32_round(x);
+        l = tf32_round(x - h);
+      } else if (j == d) {
+        h = 1.f;
+      }
+    }
+    out[idx] = h;
+    out[plane_f + idx] = l;
+  }
+}
+
+// responsibilities (n, K) fp64 -> fp32 tiles [tile][K][64] (zero beyond n) and the per-tile column sums (fp64, fixed order)
+__global__ void __launch_bounds__(256) gmm_tc_respT_kernel(int n, int K, const double* resp, float* respT, double* nkpart) {
+  extern __shared__ double srt[];  // [64][K]
+  const size_t row0 = (size_t)blockIdx.x * TM_TS;
+  const size_t left = (size_t)n - row0;
+  const int rows = (int)(left < (size_t)TM_TS ? left : (size_t)TM_TS);
+  for (int idx = threadIdx.x; idx < TM_TS * K; idx += 256) srt[idx] = idx < rows * K ? resp[row0 * K + idx] : 0.0;
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < TM_TS * K; idx += 256) {
+    const int k = idx / TM_TS, s = idx % TM_TS;
+    respT[(size_t)blockIdx.x * K * TM_TS + idx] = (float)srt[s * K + k];
+  }
+  if ((int)threadIdx.x < K) {
+    double acc = 0.0;
+    for (int s = 0; s < TM_TS; ++s) acc += srt[s * K + threadIdx.x];
+    nkpart[(size_t)blockIdx.x * K + threadIdx.x] = acc;
+  }
+}
+
+// per-CTA partial sums -> packed statistics [nk | s | S | lse] (fixed order: deterministic), shift = the centre
+__global__ void __launch_bounds__(128) gmm_tc_mreduce_kernel(TcMParams p, size_t total, const double* nkpart, const double* lse_part,
+                                                             int nblocks, const double* center, double* stats, double* shift) {
+  const int d = p.d, K = p.K, N = p.N;
+  const size_t n_elem = (size_t)K * d * (1 + d);
+  if ((size_t)blockIdx.x * 128 >= n_elem) {  // the K + 1 tail blocks: nk[k] and the log-sum-exp total (cooperative sums)
+    const int which = (int)(blockIdx.x - (n_elem + 127) / 128);
+    __shared__ double red[128];
+    double acc = 0.0;
+    if (which < K) for (int t = threadIdx.x; t < p.ntiles; t += 128) acc += nkpart[(size_t)t * K + which];
+    else for (int b = threadIdx.x; b < nblocks; b += 128) acc += lse_part[b];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) stats[which < K ? (size_t)which : total - 1] = red[0];
+    return;
+  }
+  const size_t idx = (size_t)blockIdx.x * 128 + threadIdx.x;
+  if (idx >= n_elem) return;
+  int k, i, j;
+  size_t dst;
+  if (idx < (size_t)K * d) { k = (int)(idx / d); i = (int)(idx % d); j = d; dst = (size_t)K + idx; shift[idx] = center ? center[i] : 0.0; }
+  else {
+    const size_t r = idx - (size_t)K * d;
+    k = (int)(r / ((size_t)d * d)); i = (int)((r / d) % d); j = (int)(r % d);
+    dst = (size_t)K * (1 + d) + r;
+    if (i > j) { const int tswap = i; i = j; j = tswap; }  // both triangles from the upper one: exactly symmetric
+  }
+  const int row = k * d + i, mt = row / TC_M, cgi = mt / p.mt_per, m = mt % p.mt_per;
+  double acc = 0.0;
+  for (int w = 0; w < p.walkers; ++w)
+    acc += p.part[((((size_t)w * p.ncg + cgi) * p.mt_per + m) * N + j) * TC_M + row % TC_M];
+  stats[dst] = acc;
+}
+
+struct TcMPlan {
+  int N, MT, mt_per, ncg, walkers, SA, SB, nacc;
+  size_t smem;
+  bool ok;
+};
+
+TcMPlan tcm_plan(int d, int K) {
+  TcMPlan pl{};
+  pl.N = round_up(d + 1, 16);
+  if (d < 1 || K < 1 || pl.N > 256 || d > 80) return pl;  // d <= 80: the shapes the tensor-core E pass covers
+  pl.MT = (K * d + TC_M - 1) / TC_M;
+  const int cap_mt = (TC_TMEM_COLS - 2 * TM_ACOLS) / pl.N;  // accumulators next to two stages of the A operand
+  double best = 1e30;
+  for (int ncg = 1; ncg <= pl.MT && ncg <= 148; ++ncg) {
+    const int per = (pl.MT + ncg - 1) / ncg;
+    if (per > cap_mt || per > 8) continue;
+    const double cost = (double)per / (148 / ncg);
+    if (cost < best - 1e-12) { best = cost; pl.ncg = ncg; pl.mt_per = per; }
+  }
+  if (!pl.ncg) return pl;
+  pl.walkers = 148 / pl.ncg;
+  pl.nacc = 2 * pl.mt_per * pl.N + 2 * TM_ACOLS <= TC_TMEM_COLS ? 2 : 1;
+  int sa = (TC_TMEM_COLS - pl.nacc * pl.mt_per * pl.N) / TM_ACOLS;
+  pl.SA = sa > TM_MAXST ? TM_MAXST : sa;
+  const size_t cap = smem_optin_cap();
+  const size_t b_stage = (size_t)2 * TM_KST * pl.N * 32, r_stage = (size_t)K * TM_TS * 4;
+  const size_t tail = 1024 + 256;
+  if (2 * (b_stage + r_stage) + tail > cap) return pl;
+  int sb = (int)((cap - tail) / (b_stage + r_stage));
+  pl.SB = sb > TM_MAXST ? TM_MAXST : sb;
+  pl.smem = pl.SB * (b_stage + r_stage) + tail;
+  pl.ok = true;
+  return pl;
+}
+
+size_t tcm_npad(int n) { return (size_t)round_up(n > 0 ? n : 1, TM_TS); }
+
 }  // namespace
 
 extern "C" {
@@ -461,6 +837,82 @@ int donk_gmm_tc_estep_f32(int n, int d, int K, const void* planes, const double*
   const int staged = sm_bytes <= 40 * 1024;
   gmm_tc_softmax_kernel<<<(unsigned)((n + 127) / 128), 128, staged ? sm_bytes : 0, st>>>(n, K, pl.kc, logp, resp, lse_part, staged);
   LAUNCHED("gmm_tc_softmax_kernel");
+  return DONK_OK;
+}
+
+/* ---- M pass at fp32 tolerance on the tensor cores (see gmm_tc_mstep_kernel) ---- */
+int donk_gmm_tc_m_supported(int d, int K) { return tcm_plan(d, K).ok ? 1 : 0; }
+
+/* bytes of the transposed split copy of the pool: two fp32 planes (round_up(d + 1, 16), round_up(n, 64)) */
+size_t donk_gmm_tc_mplanes_bytes(int n, int d) { return align256((size_t)2 * round_up(d + 1, 16) * tcm_npad(n) * sizeof(float)); }
+
+/* bytes of the per-iteration scratch: fp32 responsibility tiles, per-tile column sums, per-CTA partial sums */
+size_t donk_gmm_tc_mwork_bytes(int n, int d, int K) {
+  const TcMPlan pl = tcm_plan(d, K);
+  const size_t ntiles = tcm_npad(n) / TM_TS;
+  const size_t grid = pl.ok ? (size_t)pl.ncg * pl.walkers : 1, per = pl.ok ? (size_t)pl.mt_per : 1;
+  return align256(ntiles * K * TM_TS * 4) + align256(ntiles * K * 8) + align256(grid * per * TC_M * round_up(d + 1, 16) * 8) + 256;
+}
+
+int donk_gmm_tc_mprepare_f32(int n, int d, const double* X, const double* center, void* mplanes, size_t mplanes_bytes,
+                             void* stream) {
+  if (n < 0 || d < 1) return DONK_BAD_SHAPE;
+  if (mplanes_bytes < donk_gmm_tc_mplanes_bytes(n, d) || ((uintptr_t)mplanes & 255)) return DONK_BAD_SHAPE;
+  if (n == 0) return DONK_OK;
+  const int NR = round_up(d + 1, 16);
+  gmm_tc_tblock_kernel<<<(unsigned)(tcm_npad(n) / TM_TS), 256, 0, (cudaStream_t)stream>>>(n, d, NR, X, center, static_cast<float*>(mplanes));
+  LAUNCHED("gmm_tc_tblock_kernel");
+  return DONK_OK;
+}
+
+/* M pass: mplanes from donk_gmm_tc_mprepare_f32 (same center), responsibilities (n, K) fp64 and per-64-row log-sum-exp
+ * totals as the E pass left them in the EM workspace -> the packed statistics (donk_gmm_stats_size) of this rank's rows,
+ * centred on `center` for every cluster (written to shift (K, d)); continue with the all-reduce and donk_gmm_m_finalize_f64. */
+int donk_gmm_tc_mstep_f32(int n, int d, int K, const void* mplanes, const double* center, const double* resp,
+                          const double* lse_part, double* stats, double* shift, void* work, size_t work_bytes, void* stream) {
+  if (n < 0 || d < 1 || K < 1) return DONK_BAD_SHAPE;
+  const TcMPlan pl = tcm_plan(d, K);
+  if (!pl.ok) { snprintf(g_err, sizeof(g_err), "gmm_tc: d=%d K=%d does not fit the tensor-core M pass", d, K); return DONK_SMEM_LIMIT; }
+  if (work_bytes < donk_gmm_tc_mwork_bytes(n, d, K) || ((uintptr_t)mplanes & 255)) return DONK_BAD_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t total = gmm_stats_len(d, K);
+  if (n == 0) {
+    CU(cudaMemsetAsync(stats, 0, total * sizeof(double), st));
+    return DONK_OK;
+  }
+  const size_t n_pad = tcm_npad(n);
+  const int ntiles = (int)(n_pad / TM_TS);
+  char* wp = reinterpret_cast<char*>(((uintptr_t)work + 255) & ~(uintptr_t)255);
+  float* respT = reinterpret_cast<float*>(wp); wp += align256((size_t)ntiles * K * TM_TS * 4);
+  double* nkpart = reinterpret_cast<double*>(wp); wp += align256((size_t)ntiles * K * 8);
+  double* part = reinterpret_cast<double*>(wp);
+  gmm_tc_respT_kernel<<<ntiles, 256, (size_t)TM_TS * K * sizeof(double), st>>>(n, K, resp, respT, nkpart);
+  LAUNCHED("gmm_tc_respT_kernel");
+  int rc = DONK_OK;
+  TcMParams p;
+  p.n = n; p.d = d; p.K = K; p.N = pl.N; p.mt_per = pl.mt_per; p.ncg = pl.ncg; p.ntiles = ntiles;
+  p.walkers = pl.walkers < ntiles ? pl.walkers : ntiles;
+  p.SA = pl.SA; p.SB = pl.SB; p.nacc = pl.nacc;
+  const int fl = env_int("DONK_GMM_TC_FLUSH");
+  p.FL = fl > 0 ? fl : 64;
+  p.respT = respT; p.part = part; p.bimg = static_cast<const unsigned char*>(mplanes);
+  switch (p.mt_per) {
+#define DONK_TCM_CASE(V)                                                                          \
+    case V:                                                                                       \
+      rc = allow_smem(gmm_tc_mstep_kernel<V>, pl.smem);                                           \
+      if (rc != DONK_OK) return rc;                                                               \
+      gmm_tc_mstep_kernel<V><<<p.ncg * p.walkers, TM_THREADS, pl.smem, st>>>(p);        \
+      break;
+    DONK_TCM_CASE(1) DONK_TCM_CASE(2) DONK_TCM_CASE(3) DONK_TCM_CASE(4) DONK_TCM_CASE(5) DONK_TCM_CASE(6) DONK_TCM_CASE(7)
+    DONK_TCM_CASE(8)
+#undef DONK_TCM_CASE
+    default: return DONK_SMEM_LIMIT;
+  }
+  LAUNCHED("gmm_tc_mstep_kernel");
+  const size_t n_elem = (size_t)K * d * (1 + d);
+  const int nblocks = (n + GMM_TS - 1) / GMM_TS;
+  gmm_tc_mreduce_kernel<<<(unsigned)((n_elem + 127) / 128 + K + 1), 128, 0, st>>>(p, total, nkpart, lse_part, nblocks, center, stats, shift);
+  LAUNCHED("gmm_tc_mreduce_kernel");
   return DONK_OK;
 }
 

@@ -257,6 +257,30 @@ int donk_gmm_tc_estep_f32(int n, int d, int K, const void* planes, const double*
                           const double* means, const double* prec_chol, double* resp, double* lse_part, void* work,
                           size_t work_bytes, void* stream);
 
+/* ---- M pass of GMM EM at fp32 tolerance on the tcgen05 tensor cores (abi_gmm_tc.cu) ------------------------------
+ * GaussianMixture._m_step (sklearn/mixture/_gaussian_mixture.py: _estimate_gaussian_parameters) behind GMMPrior.update,
+ * prior_gmm.py:14-24: the weighted scatter S_k = sum_n r_nk (x_n - c)(x_n - c)^T and first moments of all clusters as one
+ * GEMM over the sample index on tcgen05.mma kind::tf32 (3xTF32 split products, fp32 accumulators in tensor memory drained
+ * into fp64 partial sums every 64 row tiles, TMA loads of a transposed split copy of the pool, the r_nk x_n operand built in
+ * shared memory by producer warps).  Stated tolerance of a full tf32x3 fit against the fp64 fit: means within 1e-4 of the
+ * data scale, covariances within 1e-3 relative, lower bound within 1e-5 relative
+ * (tests/test_fit_gmm_kernels.py::test_gmm_tf32x3_fit_matches_fp64_fit).  Same shapes as the E pass (d <= 80).
+ *   donk_gmm_tc_m_supported(d, K)        1 when the kernel handles the shape
+ *   donk_gmm_tc_mplanes_bytes(n, d)      bytes of the transposed split copy (two fp32 planes round_up(d+1,16) x round_up(n,64))
+ *   donk_gmm_tc_mwork_bytes(n, d, K)     bytes of per-iteration scratch
+ *   donk_gmm_tc_mprepare_f32             X (n,d) fp64 minus center -> mplanes; once per fit
+ *   donk_gmm_tc_mstep_f32                mplanes + resp (n,K) fp64 + lse_part (ceil(n/64)) (as donk_gmm_tc_estep_f32 left
+ *                                        them in the EM workspace) -> stats (donk_gmm_stats_size) of this rank's rows and
+ *                                        shift (K,d) = center; continue with the all-reduce and donk_gmm_m_finalize_f64. */
+int donk_gmm_tc_m_supported(int d, int K);
+size_t donk_gmm_tc_mplanes_bytes(int n, int d);
+size_t donk_gmm_tc_mwork_bytes(int n, int d, int K);
+int donk_gmm_tc_mprepare_f32(int n, int d, const double* X, const double* center, void* mplanes, size_t mplanes_bytes,
+                             void* stream);
+int donk_gmm_tc_mstep_f32(int n, int d, int K, const void* mplanes, const double* center, const double* resp,
+                          const double* lse_part, double* stats, double* shift, void* work, size_t work_bytes,
+                          void* stream);
+
 /* M-step finalisation from (all-reduced) statistics of n_total rows: new weights, means,
  * covariances (+ reg_covar I), precision Cholesky factors, mean log-likelihood.
  * shift (K,d): the centring point written by donk_gmm_em_step_f64 (NULL: the current means); means is output

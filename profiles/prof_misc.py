@@ -146,9 +146,34 @@ elif what == "tc":
     r32 = ws[:n * K].view(n, K)
     print(f"  fp64 E pass {ms64:.2f} ms; max |resp_tc - resp_fp64| = {float((r32 - r64).abs().max()):.2e}")
     stats = torch.empty(nat.size("gmm_stats_size", d, K), dtype=torch.float64, device=dev)
-    for prec in ("fp64", "tf32x3"):
-        g = batched.DeviceGMM(K, tol=0.0, max_iter=1, precision=prec).set_params(w0, m0, precisions=p0)
+    ref = None
+    for prec in ("fp64", "tf32x3-e", "tf32x3"):
+        g = batched.DeviceGMM(K, tol=0.0, max_iter=1, precision=prec.split("-")[0]).set_params(w0, m0, precisions=p0)
+        g.tc_m_pass = not prec.endswith("-e")
         g._lb = torch.zeros(1, dtype=torch.float64, device=dev); g._info = torch.zeros(K, dtype=torch.int32, device=dev)
-        g._tc = g._tc_setup(X) if prec == "tf32x3" else None
+        g._tc = g._tc_setup(X, m_pass=True) if prec != "fp64" else None
+        g.em_iteration(X, float(n), ws, stats)
+        res = (g.means.clone(), g.covariances.clone())
+        if ref is None: ref = res
+        err = [float((a - b).abs().max() / b.abs().max()) for a, b in zip(res, ref)]
+        g.set_params(w0, m0, precisions=p0)
         ms_it, _ = timed(lambda: g.em_iteration(X, float(n), ws, stats), 5)
-        print(f"  EM iteration ({prec}): {ms_it:.2f} ms, lower bound {float(g._lb):.10f}")
+        print(f"  EM iteration ({prec}): {ms_it:.2f} ms, lower bound {float(g._lb):.10f}; after one iteration vs fp64: means {err[0]:.2e} covariances {err[1]:.2e}")
+        if prec == "tf32x3":
+            tc = g._tc
+            def mstep():
+                nat.call("gmm_tc_mstep_f32", n, d, K, tc["mplanes"], tc["center"], ws, ws[n * K:], stats, g._shift, tc["mwork"], tc["mwork"].numel() * 8)
+            ms_m, _ = timed(mstep, 5)
+            print(f"  tc M pass alone (respT + mstep + reduce): {ms_m:.2f} ms = {3 * 2 * n * K * d * round((d + 1) / 16 + 0.49) * 16 / ms_m / 1e9:.0f} TFLOP/s issued TF32")
+            import os
+            Xc = X - tc["center"]
+            R = ws[:n * K].view(n, K)
+            S64 = torch.stack([Xc.T @ (Xc * R[:, k:k + 1]) for k in range(K)])
+            nk64 = R.sum(0)
+            for fl in (4, 16, 64, 256, 1024):
+                os.environ["DONK_GMM_TC_FLUSH"] = str(fl)
+                ms_f, _ = timed(mstep, 3)
+                S32 = stats[K * (1 + d):-1].view(K, d, d)
+                err = ((S32 - S64).abs().amax(dim=(1, 2)) / S64.abs().amax(dim=(1, 2))).max()
+                print(f"    drain every {fl:4d} tiles: {ms_f:.2f} ms, max rel err of the scatter vs fp64 {float(err):.2e}, nk err {float(((stats[:K] - nk64).abs() / nk64).max()):.1e}")
+            os.environ.pop("DONK_GMM_TC_FLUSH")

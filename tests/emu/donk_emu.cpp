@@ -522,6 +522,62 @@ int donk_emu_gmm_tc_estep_f32(int n, int d, int K, const void* planes, const dou
   return DONK_OK;
 }
 
+// ---- stand-in for the tensor-core M pass: same interface; float operands, float accumulation over runs of 4096 rows
+// that are then added up in double (the kernel drains its fp32 accumulators every 64 tiles of 64 rows).  The mplanes
+// buffer holds (x - c) as float, row-major (n, d).
+int donk_emu_gmm_tc_m_supported(int d, int K) { return d >= 1 && d <= 80 && K >= 1 ? 1 : 0; }
+size_t donk_emu_gmm_tc_mplanes_bytes(int n, int d) {
+  const size_t one = ((size_t)round_up(d + 1, 16) * round_up(n > 0 ? n : 1, 64) * sizeof(float) + 255) & ~(size_t)255;
+  return 2 * one;
+}
+size_t donk_emu_gmm_tc_mwork_bytes(int n, int d, int K) { return 256 + (size_t)round_up(n > 0 ? n : 1, 64) * K * 4; }
+int donk_emu_gmm_tc_mprepare_f32(int n, int d, const double* X, const double* center, void* mplanes, size_t bytes, void*) {
+  if (n < 0 || d < 1 || bytes < donk_emu_gmm_tc_mplanes_bytes(n, d)) return DONK_BAD_SHAPE;
+  float* x = static_cast<float*>(mplanes);
+  for (size_t r = 0; r < (size_t)n; ++r)
+    for (int j = 0; j < d; ++j) x[r * d + j] = (float)(X[r * d + j] - (center ? center[j] : 0.0));
+  return DONK_OK;
+}
+int donk_emu_gmm_tc_mstep_f32(int n, int d, int K, const void* mplanes, const double* center, const double* resp,
+                              const double* lse_part, double* stats, double* shift, void* work, size_t work_bytes, void*) {
+  if (n < 0 || d < 1 || K < 1 || work_bytes < donk_emu_gmm_tc_mwork_bytes(n, d, K)) return DONK_BAD_SHAPE;
+  const size_t total = gmm_stats_len(d, K);
+  for (size_t i = 0; i < total; ++i) stats[i] = 0.0;
+  if (n == 0) return DONK_OK;
+  const float* x = static_cast<const float*>(mplanes);
+  double* nk = stats;
+  double* s1 = stats + K;
+  double* S2 = stats + (size_t)K * (1 + d);
+  std::vector<float> acc((size_t)d * (d + 1));
+  for (int k = 0; k < K; ++k) {
+    for (size_t r0 = 0; r0 < (size_t)n; r0 += 4096) {
+      std::fill(acc.begin(), acc.end(), 0.f);
+      const size_t r1 = r0 + 4096 < (size_t)n ? r0 + 4096 : (size_t)n;
+      for (size_t r = r0; r < r1; ++r) {
+        const float w = (float)resp[r * K + k];
+        nk[k] += resp[r * K + k];
+        for (int i = 0; i < d; ++i) {
+          const float a = w * x[r * d + i];
+          acc[(size_t)i * (d + 1) + d] += a;
+          for (int j = i; j < d; ++j) acc[(size_t)i * (d + 1) + j] = fmaf(a, x[r * d + j], acc[(size_t)i * (d + 1) + j]);
+        }
+      }
+      for (int i = 0; i < d; ++i) {
+        s1[(size_t)k * d + i] += acc[(size_t)i * (d + 1) + d];
+        for (int j = i; j < d; ++j) S2[((size_t)k * d + i) * d + j] += acc[(size_t)i * (d + 1) + j];
+      }
+    }
+    for (int i = 0; i < d; ++i)
+      for (int j = 0; j < i; ++j) S2[((size_t)k * d + i) * d + j] = S2[((size_t)k * d + j) * d + i];
+    for (int j = 0; j < d; ++j) shift[(size_t)k * d + j] = center ? center[j] : 0.0;
+  }
+  double lse = 0.0;
+  for (size_t b = 0; b < ((size_t)n + GMM_TS - 1) / GMM_TS; ++b) lse += lse_part[b];
+  stats[total - 1] = lse;
+  (void)work;
+  return DONK_OK;
+}
+
 int donk_emu_gmm_em_step_mode_f64(int n_local, int d, int K, const double* X, const double* weights, const double* means,
                                   const double* prec_chol, const double* resp_in, double* stats, double* shift,
                                   void* workspace, size_t workspace_bytes, int mode, void*) {

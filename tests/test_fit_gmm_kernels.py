@@ -515,25 +515,77 @@ def test_gmm_tc_estep_tolerance(backend, n, d, K):
     assert np.allclose(resp.sum(1), 1.0, atol=1e-12)
 
 
+@pytest.mark.parametrize("n,d,K,flush", [(700, 10, 4, 0), (3000, 72, 16, 0), (260, 46, 3, 0), (129, 8, 2, 0),
+                                           (40000, 24, 5, 2), (30000, 72, 16, 3)])
+def test_gmm_tc_mstep_tolerance(backend, monkeypatch, n, d, K, flush):
+    """M pass on the tcgen05 tensor cores (3xTF32 products of the scatter statistics, fp32 accumulators drained into fp64
+    partial sums; on CPU: the float stand-in of the emulation) against the same sums in numpy fp64.  STATED TOLERANCE: every
+    statistic within 2e-5 of its natural scale (nk; nk * sigma for the first moments; nk * sigma^2 for the scatter); nk
+    itself is accumulated in fp64 (1e-12).  Shapes: ragged last tile, d not a multiple of 8, K * d not a multiple of 128,
+    several M-tiles per CTA group (72, 16), several accumulator drains per CTA (flush = tiles per drain)."""
+    import torch
+
+    from donk_b200 import _lib
+
+    nat = _lib.native()
+    if flush:
+        monkeypatch.setenv("DONK_GMM_TC_FLUSH", str(flush))
+    rng = np.random.default_rng(3)
+    c = 2.0 + rng.standard_normal(d)
+    X = c + 1.5 * rng.standard_normal((n, d)) + rng.standard_normal((n, 1))  # correlated columns, unit-order scale
+    logits = 2.0 * rng.standard_normal((n, K))
+    resp = np.exp(logits - logits.max(1, keepdims=True))
+    resp /= resp.sum(1, keepdims=True)
+    lse_part = rng.standard_normal((n + 63) // 64)
+    dev = "cuda" if nat.device_type != "cpu" else "cpu"
+    o = dict(dtype=torch.float64, device=dev)
+    Xd, cd = torch.as_tensor(X, **o), torch.as_tensor(c, **o)
+    assert nat.size("gmm_tc_m_supported", d, K) == 1
+    mpl = torch.zeros(nat.size("gmm_tc_mplanes_bytes", n, d) // 8 + 32, **o)
+    mpl = mpl[(-mpl.data_ptr() // 8) % 32:]
+    work = torch.zeros(nat.size("gmm_tc_mwork_bytes", n, d, K) // 8 + 1, **o)
+    stats = torch.zeros(nat.size("gmm_stats_size", d, K), **o)
+    shift = torch.zeros(K, d, **o)
+    nat.call("gmm_tc_mprepare_f32", n, d, Xd, cd, mpl, mpl.numel() * 8)
+    nat.call("gmm_tc_mstep_f32", n, d, K, mpl, cd, torch.as_tensor(resp, **o), torch.as_tensor(lse_part, **o), stats, shift,
+             work, work.numel() * 8)
+    st = to_np(stats)
+    Xc = X - c
+    nk = resp.sum(0)
+    s1 = resp.T @ Xc
+    S2 = np.einsum("nk,ni,nj->kij", resp, Xc, Xc)
+    sig = Xc.std()
+    assert np.max(np.abs(st[:K] - nk) / nk) < 1e-12
+    assert np.max(np.abs(st[K:K * (1 + d)].reshape(K, d) - s1) / (nk[:, None] * sig)) < 2e-5
+    got = st[K * (1 + d):-1].reshape(K, d, d)
+    assert np.max(np.abs(got - S2) / (nk[:, None, None] * sig * sig)) < 2e-5
+    assert np.array_equal(got, np.swapaxes(got, 1, 2))
+    assert abs(st[-1] - lse_part.sum()) < 1e-9 * max(1.0, abs(lse_part.sum()))
+    assert np.array_equal(to_np(shift), np.broadcast_to(c, (K, d)))
+
+
 def test_gmm_tf32x3_fit_matches_fp64_fit(backend):
-    """DeviceGMM(precision='tf32x3').fit: tensor-core E pass + fp64 M pass.  Against the fp64 fit of the same start after
-    the same number of iterations: means within 1e-4 of the data scale, covariances within 1e-3 relative, the lower bound
-    within 1e-5 relative (stated fp32 tolerance)."""
+    """DeviceGMM(precision='tf32x3').fit: tensor-core E pass + tensor-core M pass (and, tc_m_pass = False, the fp64 M pass
+    behind the tensor-core E pass).  Against the fp64 fit of the same start after the same number of iterations: means
+    within 1e-4 of the data scale, covariances within 1e-3 relative, the lower bound within 1e-5 relative (stated fp32
+    tolerance)."""
     from donk_b200 import synthetic
     from donk_b200.batched import DeviceGMM
 
     n, d, K = 4000, 12, 3
     X, w0, m0, p0 = synthetic.gmm_pool(n, d, K, seed=23)
     fits = {}
-    for prec in ("fp64", "tf32x3"):
-        gm = DeviceGMM(K, tol=0.0, max_iter=4, precision=prec).set_params(w0, m0, precisions=p0)
+    for prec in ("fp64", "tf32x3", "tf32x3-e"):
+        gm = DeviceGMM(K, tol=0.0, max_iter=4, precision=prec.split("-")[0]).set_params(w0, m0, precisions=p0)
+        gm.tc_m_pass = not prec.endswith("-e")
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             gm.fit(X)
         fits[prec] = gm
-    a, b = fits["fp64"], fits["tf32x3"]
-    assert relerr(b.means, to_np(a.means)) < 1e-4
-    assert relerr(b.covariances, to_np(a.covariances)) < 1e-3
-    assert abs(b.lower_bound - a.lower_bound) < 1e-5 * abs(a.lower_bound)
+    a = fits["fp64"]
+    for b in (fits["tf32x3"], fits["tf32x3-e"]):
+        assert relerr(b.means, to_np(a.means)) < 1e-4
+        assert relerr(b.covariances, to_np(a.covariances)) < 1e-3
+        assert abs(b.lower_bound - a.lower_bound) < 1e-5 * abs(a.lower_bound)
     with pytest.raises(Exception):
         DeviceGMM(2, precision="tf32x3").set_params(np.full(2, 0.5), np.zeros((2, 100)), precisions=np.stack([np.eye(100)] * 2)).fit(np.zeros((10, 100)))
