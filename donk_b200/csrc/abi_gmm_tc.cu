@@ -26,8 +26,13 @@ using namespace donk_abi;
 namespace {
 
 constexpr int TC_M = 128;        // rows per tile = TMEM lanes
-constexpr int TC_THREADS = 192;  // TMA warp, MMA warp, four epilogue warps
-constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_THREADS = 320;  // TMA warp, MMA warp, eight epilogue warps (two per TMEM lane quarter)
+constexpr int TC_MAX_STAGES = 6;
+// A row tile of X enters shared memory in chunks of up to TC_KC k-steps (8 features each): next to the resident P planes
+// of two clusters (83 KB at d = 72) a whole 74 KB tile leaves room for ONE stage - load and products then alternate
+// (11.0 ms per pass at 10 M x 72); chunks of 3 k-steps give a ring of 5-6 stages
+constexpr int TC_KC = 3;
+__host__ __device__ constexpr int tc_kc(int KS) { return KS > TC_KC + 1 ? TC_KC : KS; }
 constexpr int TC_TMEM_COLS = 512;
 
 struct TcParams {
@@ -35,8 +40,15 @@ struct TcParams {
   const float* bias;  // (K, dp)  (mu_k - c) P_k
   const float* cst;   // (K)      sum log diag P_k + log pi_k - d/2 log(2 pi)
   float* logp;        // (n, K)
+  const unsigned char* ximg;  // [ntiles][plane hi|lo][k-step][128 rows][32 B, swizzled]: the A stage images
 };
 
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ float tf32_round(float x) {
@@ -84,24 +96,25 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t* r) {
 
 template <int KS>  // k-steps of 8 features: dp = 8 KS (compile-time so that a cluster's columns are read from TMEM in one batch)
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gmm_tc_estep_kernel(const __grid_constant__ CUtensorMap tmXhi, const __grid_constant__ CUtensorMap tmXlo,
-                    const __grid_constant__ CUtensorMap tmPhi, const __grid_constant__ CUtensorMap tmPlo,
-                    const TcParams p) {
+gmm_tc_estep_kernel(const __grid_constant__ CUtensorMap tmPhi, const __grid_constant__ CUtensorMap tmPlo, const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // the swizzle pattern is a function of the shared-memory address bits: operand tiles start on 256-byte boundaries
   unsigned char* smem = smem_raw + ((256u - (smem_u32(smem_raw) & 255u)) & 255u);
   const int N = p.N;
-  const uint32_t b_plane = (uint32_t)KS * N * 32, a_plane = (uint32_t)KS * TC_M * 32;
+  constexpr int KC = tc_kc(KS), NCH = (KS + KC - 1) / KC;  // k-steps per chunk, chunks per tile
+  constexpr uint32_t kstep_b = TC_M * 32;                      // bytes of one k-step of one plane of the tile
+  constexpr uint32_t a_stage = 2 * KC * kstep_b, a_tile = 2 * KS * kstep_b;
+  const uint32_t b_plane = (uint32_t)KS * N * 32;
   unsigned char* sB = smem;                    // [plane hi|lo][k-step][N rows][32 B]
-  unsigned char* sA = sB + 2 * b_plane;        // [stage][plane hi|lo][k-step][128 rows][32 B]
-  unsigned char* tail = sA + (size_t)p.stages * 2 * a_plane;
+  unsigned char* sA = sB + 2 * b_plane;        // [stage][plane hi|lo][k-step of the chunk][128 rows][32 B]
+  unsigned char* tail = sA + (size_t)p.stages * a_stage;
   unsigned long long* full = reinterpret_cast<unsigned long long*>(tail);  // [stages]
   unsigned long long* empty = full + TC_MAX_STAGES;                        // [stages]
   unsigned long long* bfull = empty + TC_MAX_STAGES;                       // [1]
   unsigned long long* tfull = bfull + 1;                                   // [2]
   unsigned long long* tempty = tfull + 2;                                  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* sbias = reinterpret_cast<float*>(tmem_slot + 4);                  // [kc][dp]
+  float* sbias = reinterpret_cast<float*>(tmem_slot + 6);                  // [kc][dp], NEGATED, 16-byte aligned
   float* scst = sbias + p.kc * p.dp;                                       // [kc]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cg = blockIdx.x % p.ncg, wk = blockIdx.x / p.ncg;
@@ -109,10 +122,10 @@ gmm_tc_estep_kernel(const __grid_constant__ CUtensorMap tmXhi, const __grid_cons
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
     mbar_init(bfull, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < p.kc * p.dp; i += TC_THREADS) sbias[i] = p.bias[(size_t)cg * p.kc * p.dp + i];
+  for (int i = threadIdx.x; i < p.kc * p.dp; i += TC_THREADS) sbias[i] = -p.bias[(size_t)cg * p.kc * p.dp + i];
   if (threadIdx.x < p.kc) scst[threadIdx.x] = p.cst[cg * p.kc + threadIdx.x];
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS) : "memory");
@@ -133,44 +146,54 @@ gmm_tc_estep_kernel(const __grid_constant__ CUtensorMap tmXhi, const __grid_cons
       int s = 0;
       uint32_t ph = 0;
       for (int tile = wk; tile < p.ntiles; tile += p.walkers) {
-        mbar_wait(empty + s, ph ^ 1);
-        mbar_arrive_expect_tx(full + s, 2 * a_plane);
-        unsigned char* st = sA + (size_t)s * 2 * a_plane;
-        for (int kk = 0; kk < KS; ++kk) {
-          tma_load_2d(st + (size_t)kk * TC_M * 32, &tmXhi, 8 * kk, tile * TC_M, full + s);
-          tma_load_2d(st + a_plane + (size_t)kk * TC_M * 32, &tmXlo, 8 * kk, tile * TC_M, full + s);
+        // the 128-row tile is stored in global memory as the images of its stages (chunk major; per chunk both planes,
+        // k-step major, 32-byte swizzle applied by the split kernel): one contiguous bulk copy per chunk instead of
+        // 2 KS boxes of 128 32-byte rows
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          constexpr uint32_t full_b = a_stage;
+          const uint32_t bytes = ch + 1 < NCH ? full_b : 2 * (KS - (NCH - 1) * KC) * kstep_b;
+          mbar_wait(empty + s, ph ^ 1);
+          mbar_arrive_expect_tx(full + s, bytes);
+          bulk_copy_g2s(sA + (size_t)s * a_stage, p.ximg + (size_t)tile * a_tile + (size_t)ch * a_stage, bytes, full + s);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
-        if (++s == p.stages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-      mbar_wait(bfull, 0);
-      int s = 0, acc = 0;
-      uint32_t ph = 0, aph = 0;
-      for (int tile = wk; tile < p.ntiles; tile += p.walkers) {
-        mbar_wait(tempty + acc, aph ^ 1);
+    // the whole warp walks the loop converged, one elected lane issues (addresses stay in uniform registers)
+    // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    mbar_wait(bfull, 0);
+    const uint64_t bd_hi = umma_desc_sw32(smem_u32(sB)), bd_lo = bd_hi + (uint64_t)(b_plane >> 4);
+    const uint32_t bstep = ((uint32_t)N * 32u) >> 4, astep = ((uint32_t)TC_M * 32u) >> 4;
+    int s = 0, acc = 0;
+    uint32_t ph = 0, aph = 0;
+    for (int tile = wk; tile < p.ntiles; tile += p.walkers) {
+      mbar_wait(tempty + acc, aph ^ 1);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        constexpr int k0 = 0;
+        const int len = ch + 1 < NCH ? KC : KS - (NCH - 1) * KC;  // compile-time after unrolling
         mbar_wait(full + s, ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
-        const uint32_t a0 = smem_u32(sA + (size_t)s * 2 * a_plane), b0 = smem_u32(sB);
-        uint32_t accumulate = 0;
-#pragma unroll 1
-        for (int pass = 0; pass < 3; ++pass) {  // x_hi P_hi + x_lo P_hi + x_hi P_lo
-          const uint32_t ap = a0 + (pass == 1 ? a_plane : 0), bp = b0 + (pass == 2 ? b_plane : 0);
-          for (int kk = 0; kk < KS; ++kk) {
-            umma_tf32(d_tmem, umma_desc_sw32(ap + (uint32_t)kk * TC_M * 32), umma_desc_sw32(bp + (uint32_t)kk * N * 32),
-                      idesc, accumulate);
-            accumulate = 1;
+        const uint64_t ad_hi = umma_desc_sw32(smem_u32(sA + (size_t)s * a_stage)), ad_lo = ad_hi + (uint64_t)((len * kstep_b) >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {  // x_hi P_hi + x_lo P_hi + x_hi P_lo
+            const uint64_t ad = pass == 1 ? ad_lo : ad_hi, bd = (pass == 2 ? bd_lo : bd_hi) + (uint64_t)((ch * KC) * bstep);
+#pragma unroll
+            for (int kk = k0; kk < len; ++kk)
+              umma_tf32(d_tmem, ad + (uint64_t)(kk * astep), bd + (uint64_t)(kk * bstep), idesc, (ch | pass | kk) ? 1u : 0u);
           }
+          tc_commit(empty + s);                        // the stage may be refilled once these products have read it
+          if (ch + 1 == NCH) tc_commit(tfull + acc);   // the accumulator is complete
         }
-        tc_commit(empty + s);     // the stage may be refilled once these products have read it
-        tc_commit(tfull + acc);   // the accumulator is complete
+        __syncwarp();
         if (++s == p.stages) { s = 0; ph ^= 1; }
-        if (++acc == 2) { acc = 0; aph ^= 1; }
       }
+      if (++acc == 2) { acc = 0; aph ^= 1; }
     }
   } else {
     const int q = warp & 3;  // a warp reads the TMEM lanes 32 (warp % 4) .. + 31
@@ -181,25 +204,25 @@ gmm_tc_estep_kernel(const __grid_constant__ CUtensorMap tmXhi, const __grid_cons
       tc_fence_after();
       const size_t row = (size_t)tile * TC_M + q * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N);
-      for (int c = 0; c < p.kc; ++c) {
+      for (int c = (warp - 2) >> 2; c < p.kc; c += 2) {  // the two warps of a lane quarter take alternate clusters
         // all 8 KS columns of the cluster in flight, one wait: the loads are latency-bound when waited for one by one
         uint32_t v[KS][8];
 #pragma unroll
         for (int ch = 0; ch < KS; ++ch) tmem_ld8_nowait(taddr + (uint32_t)(c * 8 * KS + 8 * ch), v[ch]);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float ss0 = 0.f, ss1 = 0.f;
+        float2 ss = make_float2(0.f, 0.f);  // packed fp32 pairs: y = acc - bias, ss += y * y
+        const float4* nb = reinterpret_cast<const float4*>(sbias + c * 8 * KS);
 #pragma unroll
         for (int ch = 0; ch < KS; ++ch) {
-#pragma unroll
-          for (int j = 0; j < 8; j += 2) {
-            const float y0 = __uint_as_float(v[ch][j]) - sbias[c * 8 * KS + 8 * ch + j];
-            const float y1 = __uint_as_float(v[ch][j + 1]) - sbias[c * 8 * KS + 8 * ch + j + 1];
-            ss0 = fmaf(y0, y0, ss0);
-            ss1 = fmaf(y1, y1, ss1);
-          }
+          const float4 b0 = nb[2 * ch], b1 = nb[2 * ch + 1];
+          const float2 y0 = __fadd2_rn(make_float2(__uint_as_float(v[ch][0]), __uint_as_float(v[ch][1])), make_float2(b0.x, b0.y));
+          const float2 y1 = __fadd2_rn(make_float2(__uint_as_float(v[ch][2]), __uint_as_float(v[ch][3])), make_float2(b0.z, b0.w));
+          const float2 y2 = __fadd2_rn(make_float2(__uint_as_float(v[ch][4]), __uint_as_float(v[ch][5])), make_float2(b1.x, b1.y));
+          const float2 y3 = __fadd2_rn(make_float2(__uint_as_float(v[ch][6]), __uint_as_float(v[ch][7])), make_float2(b1.z, b1.w));
+          ss = __ffma2_rn(y0, y0, ss); ss = __ffma2_rn(y1, y1, ss); ss = __ffma2_rn(y2, y2, ss); ss = __ffma2_rn(y3, y3, ss);
         }
         // layout [cluster group][row][kc]: the 32 rows of a warp are one contiguous run
-        if (row < (size_t)p.n) p.logp[((size_t)cg * p.n + row) * p.kc + c] = scst[c] - 0.5f * (ss0 + ss1);
+        if (row < (size_t)p.n) p.logp[((size_t)cg * p.n + row) * p.kc + c] = scst[c] - 0.5f * (ss.x + ss.y);
       }
       tc_fence_before();
       __syncwarp();
@@ -215,20 +238,31 @@ gmm_tc_estep_kernel(const __grid_constant__ CUtensorMap tmXhi, const __grid_cons
   }
 }
 
-// X (n, d) fp64 -> two TF32 planes of (x - c) with row pitch dp (columns d..dp-1 zero)
-__global__ void gmm_tc_split_kernel(size_t n, int d, int dp, const double* X, const double* center, float* hi, float* lo) {
-  const size_t total = n * dp;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const size_t r = idx / dp;
-    const int j = (int)(idx % dp);
+// X (n, d) fp64 -> per 128-row tile the image of the E kernel's A stage: [plane hi|lo][k-step][row][8 features] of (x - c)
+// split into TF32 planes (features d..dp-1 and rows beyond n: zeros), 16-byte halves of a row swapped where the 32-byte
+// swizzle of the UMMA descriptor swaps them (bit 2 of the row index)
+__global__ void __launch_bounds__(256) gmm_tc_split_kernel(size_t n, int d, int dp, const double* X, const double* center, float* img) {
+  const size_t tile = blockIdx.x;
+  const int plane_f = dp * TC_M;  // floats per plane: dp / 8 k-steps x 128 rows x 8
+  const int KS = dp / 8, KC = tc_kc(KS);
+  float* out = img + tile * 2 * (size_t)plane_f;
+  for (int idx = threadIdx.x; idx < plane_f; idx += 256) {
+    const int pos = idx & 7, row = (idx >> 3) & (TC_M - 1), kk = idx >> 10;
+    // chunk-major: [chunk][plane][k-step of the chunk][row][8]
+    const int ch = kk / KC, kin = kk % KC, len = (ch + 1) * KC <= KS ? KC : KS - ch * KC;
+    const size_t o_hi = (size_t)ch * KC * 2 * 1024 + (size_t)kin * 1024 + (size_t)(idx & 1023);
+    const size_t o_lo = o_hi + (size_t)len * 1024;
+    const int half = (pos >> 2) ^ ((row >> 2) & 1);  // logical half stored at this physical position
+    const int j = 8 * kk + 4 * half + (pos & 3);
+    const size_t r = tile * TC_M + row;
     float h = 0.f, l = 0.f;
-    if (j < d) {
+    if (r < n && j < d) {
       const float x = (float)(X[r * d + j] - (center ? center[j] : 0.0));
       h = tf32_round(x);
       l = tf32_round(x - h);
     }
-    hi[idx] = h;
-    lo[idx] = l;
+    out[o_hi] = h;
+    out[o_lo] = l;
   }
 }
 
@@ -341,13 +375,13 @@ TcPlan tc_plan(int d, int K) {
   TcPlan pl{};
   pl.dp = round_up(d, 8);
   const size_t cap = smem_optin_cap();
-  const size_t tail = 1024 + 256 + (size_t)2 * pl.dp * sizeof(float);  // barriers, alignment slack, constants
+  const size_t tail = 1024 + 256 + 16 + (size_t)2 * pl.dp * sizeof(float);  // barriers, alignment slack, constants
   for (int kc = 2; kc >= 1 && !pl.ok; --kc) {
     if (K % kc) continue;
     const int N = kc * pl.dp;
     if (N % 16 || N > 256) continue;
-    const size_t b = (size_t)2 * (pl.dp / 8) * N * 32, a = (size_t)2 * (pl.dp / 8) * TC_M * 32;
-    if (b + a + tail + (size_t)kc * pl.dp * 4 > cap) continue;
+    const size_t b = (size_t)2 * (pl.dp / 8) * N * 32, a = (size_t)2 * tc_kc(pl.dp / 8) * TC_M * 32;  // one stage = one chunk
+    if (b + 2 * a + tail + (size_t)kc * pl.dp * 4 > cap) continue;
     int st = (int)((cap - b - tail - (size_t)kc * pl.dp * 4) / a);
     if (st > TC_MAX_STAGES) st = TC_MAX_STAGES;
     pl.kc = kc; pl.N = N; pl.stages = st;
@@ -360,19 +394,17 @@ TcPlan tc_plan(int d, int K) {
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 template <int KS>
-int tc_launch_ks(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const CUtensorMap& d, const TcParams& p,
-                 size_t smem, cudaStream_t st) {
+int tc_launch_ks(const CUtensorMap& c, const CUtensorMap& d, const TcParams& p, size_t smem, cudaStream_t st) {
   int rc = allow_smem(gmm_tc_estep_kernel<KS>, smem);
   if (rc != DONK_OK) return rc;
-  gmm_tc_estep_kernel<KS><<<p.ncg * p.walkers, TC_THREADS, smem, st>>>(a, b, c, d, p);
+  gmm_tc_estep_kernel<KS><<<p.ncg * p.walkers, TC_THREADS, smem, st>>>(c, d, p);
   LAUNCHED("gmm_tc_estep_kernel");
   return DONK_OK;
 }
 
-int tc_launch(int KS, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const CUtensorMap& d, const TcParams& p,
-              size_t smem, cudaStream_t st) {
+int tc_launch(int KS, const CUtensorMap& c, const CUtensorMap& d, const TcParams& p, size_t smem, cudaStream_t st) {
   switch (KS) {
-#define DONK_TC_CASE(V) case V: return tc_launch_ks<V>(a, b, c, d, p, smem, st);
+#define DONK_TC_CASE(V) case V: return tc_launch_ks<V>(c, d, p, smem, st);
     DONK_TC_CASE(1) DONK_TC_CASE(2) DONK_TC_CASE(3) DONK_TC_CASE(4) DONK_TC_CASE(5) DONK_TC_CASE(6) DONK_TC_CASE(7)
     DONK_TC_CASE(8) DONK_TC_CASE(9) DONK_TC_CASE(10)
 #undef DONK_TC_CASE
@@ -412,11 +444,13 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
 // grows with the number of accumulation steps) by the same producer warps, double buffered in TMEM when both sets fit.
 //     warp 0     one lane: TMA  B planes (8 samples x N rows boxes) + the tile's responsibilities (1-D bulk copy)
 //     warp 1     one lane: tcgen05.mma M=128, N, K=8; commits release the A stage / B stage / publish the accumulators
-//     warps 2-5  A producer (one row of the M-tile per thread), accumulator drain
+//     warps 2-9  A producer (one row of the M-tile per thread, the two warps of a TMEM lane quarter split the k-steps),
+//                accumulator drain
 // =====================================================================================================================
-constexpr int TM_TS = 64;            // samples per tile
+constexpr int TM_TS = 64;            // samples per tile (32: 15.4 instead of 11.4 ms per pass - per-tile hand-shakes)
 constexpr int TM_KST = TM_TS / 8;    // k-steps (UMMA instructions per plane pair) per tile
-constexpr int TM_THREADS = 192;
+constexpr int TM_THREADS = 320;       // TMA warp, MMA warp, eight producer / drain warps (two per TMEM lane quarter)
+constexpr int TM_PW = 8;
 constexpr int TM_MAXST = 4;
 constexpr int TM_ACOLS = 2 * TM_KST * 8;  // TMEM columns of one A stage: planes hi | lo, 8 samples per k-step
 
@@ -447,13 +481,16 @@ gmm_tc_mstep_kernel(const TcMParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cg = blockIdx.x % p.ncg, wk = blockIdx.x / p.ncg;
   const int my_tiles = wk < p.ntiles ? (p.ntiles - wk + p.walkers - 1) / p.walkers : 0;
+  // first drain period of this CTA: the CTAs walk the same number of tiles, so drains at the same tile count would hit
+  // L2 from all SMs at once (measured 11.7 us per drain); spread over the period they overlap the other CTAs' products
+  const int cnt0 = (int)(((long long)blockIdx.x * p.FL) / gridDim.x);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TM_MAXST; ++s) {
-      mbar_init(full_b + s, 1); mbar_init(empty_b + s, 5);
-      mbar_init(full_a + s, 4); mbar_init(empty_a + s, 1);
+      mbar_init(full_b + s, 1); mbar_init(empty_b + s, TM_PW + 1);
+      mbar_init(full_a + s, TM_PW); mbar_init(empty_a + s, 1);
     }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, TM_PW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -485,46 +522,57 @@ gmm_tc_mstep_kernel(const TcMParams p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-      int sb = 0, sa = 0, acc = 0, cnt = 0;
-      uint32_t phb = 0, pha = 0, aph = 0;
-      for (int it = 0; it < my_tiles; ++it) {
-        const bool fresh = cnt == 0;
-        if (fresh) mbar_wait(acc_empty + acc, aph ^ 1);  // the previous drain of this accumulator set is done
-        mbar_wait(full_b + sb, phb);
-        const uint32_t b0 = smem_u32(sB + (size_t)sb * b_stage);
-        for (int m = 0; m < MT; ++m) {
-          mbar_wait(full_a + sa, pha);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols + m * N);
-          const uint32_t a0 = tmem_base + a_cols0 + (uint32_t)sa * TM_ACOLS;
-          uint32_t accumulate = fresh ? 0u : 1u;
-#pragma unroll 1
+    // The whole warp walks the loop converged and ONE elected lane issues: every address below is then warp-uniform and
+    // lives in uniform registers.  (With the loop under `if (lane == 0)` each tcgen05.mma cost ~19 instructions - R2UR
+    // moves inside a vote loop - ~60 cycles per 40-cycle product: the issuing thread bounded the kernel.)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    const uint32_t bstep = ((uint32_t)N * 32u) >> 4;  // descriptor address units (16 bytes) per k-step
+    int sb = 0, sa = 0, acc = 0, cnt = cnt0;
+    uint32_t phb = 0, pha = 0, aph = 0;
+    bool fresh = true;
+    for (int it = 0; it < my_tiles; ++it) {
+      if (fresh) mbar_wait(acc_empty + acc, aph ^ 1);  // the previous drain of this accumulator set is done
+      mbar_wait(full_b + sb, phb);
+      const uint64_t bd_hi = umma_desc_sw32(smem_u32(sB + (size_t)sb * b_stage));
+      const uint64_t bd_lo = bd_hi + (uint64_t)(b_plane >> 4);
+      for (int m = 0; m < MT; ++m) {
+        mbar_wait(full_a + sa, pha);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols + m * N);
+        const uint32_t a0 = tmem_base + a_cols0 + (uint32_t)sa * TM_ACOLS;
+        if (elect_one()) {
+#pragma unroll
           for (int pass = 0; pass < 3; ++pass) {  // a_hi b_hi + a_lo b_hi + a_hi b_lo
-            const uint32_t ap = a0 + (pass == 1 ? TM_ACOLS / 2 : 0), bp = b0 + (pass == 2 ? b_plane : 0);
-            for (int kk = 0; kk < TM_KST; ++kk) {
-              umma_tf32_ta(d_tmem, ap + 8u * kk, umma_desc_sw32(bp + (uint32_t)kk * N * 32), idesc, accumulate);
-              accumulate = 1;
-            }
+            const uint32_t ap = a0 + (pass == 1 ? TM_ACOLS / 2 : 0);
+            const uint64_t bd = pass == 2 ? bd_lo : bd_hi;
+#pragma unroll
+            for (int kk = 0; kk < TM_KST; ++kk)
+              umma_tf32_ta(d_tmem, ap + 8u * kk, bd + (uint64_t)(kk * bstep), idesc, (pass | kk) ? 1u : (fresh ? 0u : 1u));
           }
           tc_commit(empty_a + sa);
-          if (++sa == p.SA) { sa = 0; pha ^= 1; }
         }
+        __syncwarp();
+        if (++sa == p.SA) { sa = 0; pha ^= 1; }
+      }
+      const bool drain = ++cnt == p.FL || it + 1 == my_tiles;
+      if (elect_one()) {
         tc_commit(empty_b + sb);
-        if (++sb == p.SB) { sb = 0; phb ^= 1; }
-        if (++cnt == p.FL || it + 1 == my_tiles) {
-          tc_commit(acc_full + acc);
-          cnt = 0;
-          if (++acc == p.nacc) { acc = 0; aph ^= 1; }
-        }
+        if (drain) tc_commit(acc_full + acc);
+      }
+      __syncwarp();
+      if (++sb == p.SB) { sb = 0; phb ^= 1; }
+      fresh = drain;
+      if (drain) {
+        cnt = 0;
+        if (++acc == p.nacc) { acc = 0; aph ^= 1; }
       }
     }
   } else {
     const int q = warp & 3;          // TMEM lane quarter this warp may access
     const int t = q * 32 + lane;     // row of the M-tile (= TMEM lane) this thread builds and drains
+    const int kh = (warp - 2) >> 2;  // the two warps of a lane quarter split the k-steps (and the drained columns)
     const int KD = K * p.d;
-    int sb = 0, sa = 0, acc = 0, cnt = 0;
+    int sb = 0, sa = 0, acc = 0, cnt = cnt0;
     uint32_t phb = 0, pha = 0, aph = 0;
     bool first = true;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -553,11 +601,11 @@ gmm_tc_mstep_kernel(const TcMParams p) {
         // tcgen05.st is warp-collective (.sync.aligned): every lane issues it; padding rows (beyond K * d) read row 0 and
         // store zeros
         const bool valid = xoff[m] >= 0;
-        const unsigned char* bh = bst + (valid ? xoff[m] : 0);
-        const unsigned char* rr = rst + (valid ? roff[m] : 0);
+        const unsigned char* bh = bst + (valid ? xoff[m] : 0) + (size_t)kh * (TM_KST / 2) * N * 32;
+        const unsigned char* rr = rst + (valid ? roff[m] : 0) + kh * (TM_KST / 2) * 32;
         const float2 scale = valid ? make_float2(1.f, 1.f) : make_float2(0.f, 0.f);
 #pragma unroll 2
-        for (int kk = 0; kk < TM_KST; ++kk) {
+        for (int kk = kh * (TM_KST / 2); kk < (kh + 1) * (TM_KST / 2); ++kk) {
           // 8 samples of this feature (both planes; logical halves: the swizzle is in xoff) and of this cluster
           const float4 h0 = *reinterpret_cast<const float4*>(bh), h1 = *reinterpret_cast<const float4*>(reinterpret_cast<uintptr_t>(bh) ^ 16u);
           const float4 l0 = *reinterpret_cast<const float4*>(bh + b_plane), l1 = *reinterpret_cast<const float4*>(reinterpret_cast<uintptr_t>(bh + b_plane) ^ 16u);
@@ -599,7 +647,7 @@ gmm_tc_mstep_kernel(const TcMParams p) {
           // partial sums [cta][m][column][lane]: the 32 lanes of a warp are one contiguous 256-byte run per column
           double* out = p.part + ((size_t)blockIdx.x * MT + m) * N * TC_M + t;
           const uint32_t taddr = lane_base + (uint32_t)(acc * acc_cols + m * N);
-          for (int c0 = 0; c0 < N; c0 += 16) {
+          for (int c0 = 16 * kh; c0 < N; c0 += 32) {
             uint32_t v[2][8];
             tmem_ld8_nowait(taddr + (uint32_t)c0, v[0]);
             tmem_ld8_nowait(taddr + (uint32_t)c0 + 8, v[1]);
@@ -624,7 +672,7 @@ gmm_tc_mstep_kernel(const TcMParams p) {
     if (first) {  // a CTA without tiles still owns partial sums: zero them
       for (int m = 0; m < MT; ++m) {
         double* out = p.part + ((size_t)blockIdx.x * MT + m) * N * TC_M + t;
-        for (int j = 0; j < N; ++j) out[(size_t)j * TC_M] = 0.0;
+        for (int j = kh; j < N; j += 2) out[(size_t)j * TC_M] = 0.0;
       }
     }
   }
@@ -764,7 +812,7 @@ extern "C" {
 int donk_gmm_tc_supported(int d, int K) { return d >= 1 && K >= 1 && tc_plan(d, K).ok ? 1 : 0; }
 
 /* bytes of the split copy of the pool: two fp32 planes (n, round_up(d, 8)) */
-size_t donk_gmm_tc_planes_bytes(int n, int d) { return 2 * align256((size_t)n * round_up(d, 8) * sizeof(float)); }
+size_t donk_gmm_tc_planes_bytes(int n, int d) { return align256((size_t)2 * round_up(n > 0 ? n : 1, TC_M) * round_up(d, 8) * sizeof(float)); }
 
 /* bytes of the per-iteration scratch: P planes, bias, constants, log-probabilities */
 size_t donk_gmm_tc_workspace_bytes(int n, int d, int K) {
@@ -780,12 +828,7 @@ int donk_gmm_tc_prepare_f32(int n, int d, const double* X, const double* center,
   if (planes_bytes < donk_gmm_tc_planes_bytes(n, d) || ((uintptr_t)planes & 255)) return DONK_BAD_SHAPE;
   if (n == 0) return DONK_OK;
   const int dp = round_up(d, 8);
-  float* hi = static_cast<float*>(planes);
-  float* lo = reinterpret_cast<float*>(static_cast<char*>(planes) + align256((size_t)n * dp * sizeof(float)));
-  const size_t total = (size_t)n * dp;
-  size_t blocks = (total + 255) / 256;
-  if (blocks > 148 * 32) blocks = 148 * 32;
-  gmm_tc_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((size_t)n, d, dp, X, center, hi, lo);
+  gmm_tc_split_kernel<<<(unsigned)((n + TC_M - 1) / TC_M), 256, 0, (cudaStream_t)stream>>>((size_t)n, d, dp, X, center, static_cast<float*>(planes));
   LAUNCHED("gmm_tc_split_kernel");
   return DONK_OK;
 }
@@ -809,18 +852,14 @@ int donk_gmm_tc_estep_f32(int n, int d, int K, const void* planes, const double*
   float* bias = reinterpret_cast<float*>(wp); wp += align256((size_t)K * dp * 4);
   float* cst = reinterpret_cast<float*>(wp); wp += align256((size_t)K * 4);
   float* logp = reinterpret_cast<float*>(wp);
-  const float* Xhi = static_cast<const float*>(planes);
-  const float* Xlo = reinterpret_cast<const float*>(static_cast<const char*>(planes) + align256((size_t)n * dp * sizeof(float)));
   {
     const size_t total = (size_t)K * dp * dp;
     gmm_tc_params_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d, dp, K, center, weights, means, prec_chol, Phi, Plo,
                                                                          bias, cst);
     LAUNCHED("gmm_tc_params_kernel");
   }
-  CUtensorMap tXh, tXl, tPh, tPl;
-  int rc = make_map(&tXh, Xhi, (size_t)n, dp, TC_M);
-  if (rc == DONK_OK) rc = make_map(&tXl, Xlo, (size_t)n, dp, TC_M);
-  if (rc == DONK_OK) rc = make_map(&tPh, Phi, (size_t)K * dp, dp, pl.N);
+  CUtensorMap tPh, tPl;
+  int rc = make_map(&tPh, Phi, (size_t)K * dp, dp, pl.N);
   if (rc == DONK_OK) rc = make_map(&tPl, Plo, (size_t)K * dp, dp, pl.N);
   if (rc != DONK_OK) return rc;
   TcParams p;
@@ -830,8 +869,8 @@ int donk_gmm_tc_estep_f32(int n, int d, int K, const void* planes, const double*
   if (walkers < 1) walkers = 1;
   if (walkers > p.ntiles) walkers = p.ntiles;
   p.walkers = walkers;
-  p.bias = bias; p.cst = cst; p.logp = logp;
-  rc = tc_launch(pl.dp / 8, tXh, tXl, tPh, tPl, p, pl.smem, st);
+  p.bias = bias; p.cst = cst; p.logp = logp; p.ximg = static_cast<const unsigned char*>(planes);
+  rc = tc_launch(pl.dp / 8, tPh, tPl, p, pl.smem, st);
   if (rc != DONK_OK) return rc;
   const size_t sm_bytes = (size_t)128 * K * sizeof(double);
   const int staged = sm_bytes <= 40 * 1024;
@@ -894,7 +933,7 @@ int donk_gmm_tc_mstep_f32(int n, int d, int K, const void* mplanes, const double
   p.walkers = pl.walkers < ntiles ? pl.walkers : ntiles;
   p.SA = pl.SA; p.SB = pl.SB; p.nacc = pl.nacc;
   const int fl = env_int("DONK_GMM_TC_FLUSH");
-  p.FL = fl > 0 ? fl : 64;
+  p.FL = fl > 0 ? fl : 4096 / TM_TS;  // tiles per drain (error of the fp32 accumulation ~ 2e-7 per tile of 32 rows)
   p.respT = respT; p.part = part; p.bimg = static_cast<const unsigned char*>(mplanes);
   switch (p.mt_per) {
 #define DONK_TCM_CASE(V)                                                                          \
