@@ -15,6 +15,7 @@ its own roofline object and (N=1) the CPU figure of the same work:
   optimize         configs[2]  ILQR.optimize(kl_step=1) for 4096 conditions (one CUDA-graph launch)
   ilqr_strong      configs[2]  the headline step with 4096 conditions IN TOTAL (strong scaling)
   gmm_em           configs[3]  one EM iteration on a 10 M x 72 pool sharded over the GPUs (all-reduce inside)
+  gmm_em_tf32x3    configs[3]  the same iteration at the stated fp32 tolerance on the tcgen05 tensor cores
   gps_iteration    configs[4]  BatchedTrajOpt.iteration (fit_lr + 16-cluster prior + ILQR.optimize + step_adjust)
                                at T=500, dX=64, dU=16, N=128, 128 conditions per GPU
 
@@ -799,6 +800,54 @@ def run_ours(args):
                                             "gmm_e_mma_kernel + gmm_m_mma_kernel (mma.sync.m8n8k4.f64)")}
         em_strong = {"rows_total": n_rows * world, "n_gpus": world, "ms_per_iteration": em_ms, "scaling": "strong",
                      "collective": "all-reduce of the packed statistics (NCCL), once per iteration"}
+        # the same iteration at the stated fp32 tolerance: E pass and scatter statistics on tcgen05 (3xTF32 split products,
+        # TMEM accumulators, fp64 partial sums / all-reduce / finalisation); fp64 stays the default and the parity path
+        try:
+            if dry:
+                raise RuntimeError("host emulation has no tensor-core path")
+            ref64 = batched.DeviceGMM(K, tol=0.0, max_iter=1).set_params(w0, m0, precisions=p0)
+            ref64._lb, ref64._info = torch.zeros(1, **f64), torch.zeros(K, dtype=torch.int32, device=dev)
+            ref64.em_iteration(Xp, float(n_rows * world), ws, stats)
+            gt = batched.DeviceGMM(K, tol=0.0, max_iter=1, precision="tf32x3").set_params(w0, m0, precisions=p0)
+            gt._lb, gt._info = torch.zeros(1, **f64), torch.zeros(K, dtype=torch.int32, device=dev)
+            prep_ms = timed(lambda: setattr(gt, "_tc", gt._tc_setup(Xp, m_pass=True)), 1, 0)
+            gt.em_iteration(Xp, float(n_rows * world), ws, stats)
+            rel = lambda a, b: float(((a - b).abs().max() / b.abs().max()).item())  # noqa: E731
+            tc_err = {"means": rel(gt.means, ref64.means), "covariances": rel(gt.covariances, ref64.covariances),
+                      "weights": rel(gt.weights, ref64.weights), "lower_bound": rel(gt._lb, ref64._lb)}
+            gt.set_params(w0, m0, precisions=p0)
+            tc_ms = timed(lambda: gt.em_iteration(Xp, float(n_rows * world), ws, stats), 5, 2) / 5
+            peaks_js = json.load(open(ROOT / "MEASURED_PEAKS.json")) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+            tf32_peak = peaks_js.get("bf16_tflops", 2250.0) / 2  # TF32 dense = half the bf16 rate; burst figure (timed alone)
+            algo = em_flops_per_row(d, K) * n_rows
+            d8, d16 = -(-d // 8) * 8, -(-(d + 1) // 16) * 16
+            issued = 3 * 2 * n_rows * K * (d8 * d8 + d * d16)      # three TF32 products per fp32-accurate product, padded tiles
+            # HBM: E reads the two TF32 planes (8d B/row) and writes fp64 responsibilities; M reads its planes and them
+            tc_bytes = n_rows * (2 * 8 * d + 2 * 8 * K)
+            extra["gmm_em_tf32x3"] = {
+                "transitions_per_sec_per_iteration": n_rows * world / (tc_ms * 1e-3), "ms_per_iteration": tc_ms,
+                "speedup_vs_fp64_iteration": em_ms / tc_ms, "split_copy_ms_once_per_fit": prep_ms,
+                "max_rel_err_vs_fp64_after_one_iteration": tc_err,
+                "stated_tolerance": "means 1e-4, covariances 1e-3, lower bound 1e-5 relative to the fp64 fit, responsibilities 2e-4 "
+                                    "absolute (tests/test_fit_gmm_kernels.py); fp64 is the default and the 1e-8 parity path",
+                "config": f"DeviceGMM(precision='tf32x3'): {n_rows * world} rows total, d={d}, K={K}; E pass "
+                          f"(gmm_tc_estep_kernel) and scatter statistics (gmm_tc_mstep_kernel) on tcgen05.mma kind::tf32, "
+                          f"operands by cp.async.bulk, accumulators in TMEM",
+                # achieved = ALGORITHMIC flops (the fp64 iteration's count) per second; the tensor pipe itself executes
+                # `issued`: x3 for the split products, full instead of triangular P_k, tiles padded to the MMA shape
+                "roofline": {"bound": "tensor", "achieved": algo / (tc_ms * 1e-3) / 1e12, "peak": tf32_peak,
+                             "unit": "TFLOP/s", "frac": algo / (tc_ms * 1e-3) / 1e12 / tf32_peak, "traffic": None,
+                             "issued_tf32_tflops": issued / (tc_ms * 1e-3) / 1e12,
+                             "issued_frac": issued / (tc_ms * 1e-3) / 1e12 / tf32_peak,
+                             "kernel": "gmm_tc_estep_kernel + gmm_tc_mstep_kernel (tcgen05.mma.kind::tf32, 3 products per fp32 product)",
+                             "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 dense rate is half of bf16), burst",
+                             "issued_tf32_flops": issued, "algorithmic_flops": algo,
+                             "algorithmic_tflops": algo / (tc_ms * 1e-3) / 1e12,
+                             "hbm_gbs": tc_bytes / (tc_ms * 1e-3) / 1e9, "hbm_frac": tc_bytes / (tc_ms * 1e-3) / 1e9 / hbm_peak,
+                             "algorithmic_bytes": tc_bytes}}
+            del gt, ref64
+        except Exception as ex:
+            extra["gmm_em_tf32x3"] = {"error": repr(ex)[:300]}
         del Xp, ws, gm
         free()
         # multi-rank parity: ONE pool, rows dealt to the ranks; the all-reduced result must equal rank 0's single pass
