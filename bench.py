@@ -866,7 +866,7 @@ def run_ours(args):
                 if group_on:
                     g.em_iteration(X, float(n_par), wsx, st)
                 else:
-                    saved = batched.DeviceGMM._allreduce
+                    saved = batched.DeviceGMM.__dict__["_allreduce"]  # the staticmethod object itself, not the unwrapped function
                     batched.DeviceGMM._allreduce = staticmethod(lambda t, group: None)
                     try:
                         g.em_iteration(X, float(n_par), wsx, st)

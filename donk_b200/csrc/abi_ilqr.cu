@@ -32,8 +32,14 @@ __global__ void __launch_bounds__(512, 1) ilqr_warp_kernel_big(const IlqrArgs<R>
   WCtx w{(int)threadIdx.x, (int)blockDim.x, (int)threadIdx.x >> 5, (int)threadIdx.x & 31, (int)blockDim.x >> 5};
   ilqr_warp_cta<R, DX, DU, FULL>(w, a, (int)blockIdx.x, ES, reinterpret_cast<R*>(smem_raw));
 }
+// register budget of the warp kernel: 8-warp CTAs x 2 per SM = 128 registers per thread (occupancy experiments build
+// other shapes with -DDONK_WARP_LB_THREADS / -DDONK_WARP_LB_CTAS, profiles/build_alt.py)
+#ifndef DONK_WARP_LB_THREADS
+#define DONK_WARP_LB_THREADS 256
+#define DONK_WARP_LB_CTAS 2
+#endif
 template <typename R, int DX, int DU, bool FULL>
-__global__ void __launch_bounds__(256, 2) ilqr_warp_kernel(const IlqrArgs<R> a, int ES) {
+__global__ void __launch_bounds__(DONK_WARP_LB_THREADS, DONK_WARP_LB_CTAS) ilqr_warp_kernel(const IlqrArgs<R> a, int ES) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WCtx w{(int)threadIdx.x, (int)blockDim.x, (int)threadIdx.x >> 5, (int)threadIdx.x & 31, (int)blockDim.x >> 5};
   ilqr_warp_cta<R, DX, DU, FULL>(w, a, (int)blockIdx.x, ES, reinterpret_cast<R*>(smem_raw));
@@ -42,7 +48,7 @@ __global__ void __launch_bounds__(256, 2) ilqr_warp_kernel(const IlqrArgs<R> a, 
 template <typename R, int DX, int DU, bool FULL>
 int ilqr_warp_launch_v(const IlqrArgs<R>& a, int G, int ES, int grid, size_t bytes, void* stream) {
   int rc;
-  if (G <= 8) {
+  if (32 * G <= DONK_WARP_LB_THREADS) {
     rc = allow_smem(ilqr_warp_kernel<R, DX, DU, FULL>, bytes);
     if (rc != DONK_OK) return rc;
     ilqr_warp_kernel<R, DX, DU, FULL><<<grid, 32 * G, bytes, (cudaStream_t)stream>>>(a, ES);
