@@ -41,9 +41,9 @@ inline int cuda_fail(cudaError_t e, const char* where) {
     if (e_ != cudaSuccess) return donk_abi::cuda_fail(e_, name);          \
   } while (0)
 
-inline int env_int(const char* name) {
+inline int env_int(const char* name, int unset = 0) {
   const char* v = getenv(name);
-  return v ? atoi(v) : 0;
+  return v ? atoi(v) : unset;
 }
 
 inline size_t smem_optin_cap() {
@@ -94,5 +94,9 @@ namespace donk_abi {
 int ilqr_coop_try_launch(const donk::IlqrArgs<double>& a, void* stream);  // abi_ilqr_coop.cu; -1: no instantiation
 int fit_coop_try_launch(donk::FitArgs<double>& a, void* stream);          // abi_fit_coop.cu; -1: no instantiation
 int gmm_predict_proba_launch(int n, int d, int K, const double* X, const double* weights, const double* means,
-                             const double* prec_chol, double* resp, void* stream);  // abi_gmm.cu
+                             const double* prec_chol, double* resp, void* stream, const double* tX = nullptr,
+                             const double* tU = nullptr, int tT = 0, int tdX = 0, int tdU = 0);  // abi_gmm.cu
+// cluster weights of the GMM prior for every fit of a call (abi_fit_coop.cu): sets a.wts_in to stream-ordered scratch the
+// caller releases with cudaFreeAsync(*scratch) after the fit launch
+int fit_prior_wts_launch(donk::FitArgs<double>& a, void* stream, double** scratch);
 }

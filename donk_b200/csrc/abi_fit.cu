@@ -35,17 +35,37 @@ int fit_warp_launch(FitArgs<R> a, void* stream) {
   int G;
   size_t bytes;
   const int forced = env_int("DONK_FIT_WARPS");
-  int rc = fit_warp_plan<R, DX, DU>(smem_optin_cap() / 3 - 1024, forced, a.N, a.K, G, bytes);
-  if (rc != DONK_OK) rc = fit_warp_plan<R, DX, DU>(smem_optin_cap(), forced, a.N, a.K, G, bytes);
+  // With a prior of many clusters, calls of some size take the cluster weights of all fits from ONE E pass of the EM
+  // kernels over the B N T transitions (fit_prior_wts_launch) instead of every warp walking the K precision factors for
+  // its own N samples: at (20,6), N = 64, 4096 conditions, K = 16: 108 -> 72 ms; K = 4: 30.8 vs 33.7 ms, so few clusters
+  // and small calls keep the single-launch in-kernel form (N <= 64 only).  DONK_FIT_PRIOR_INKERNEL=1 / =0 force either.
+  bool pre_wts = false;
+  if constexpr (sizeof(R) == 8) {
+    if (a.K > 0) {
+      const int force_in = env_int("DONK_FIT_PRIOR_INKERNEL", -1);
+      pre_wts = a.N > 64 || (force_in < 0 ? (a.K >= 8 && (long long)a.B * a.N * a.T >= 32768) : force_in == 0);
+    }
+  } else {
+    if (a.K > 0 && a.N > 64) return DONK_SMEM_LIMIT;  // single precision: in-kernel prior only
+  }
+  int rc = fit_warp_plan<R, DX, DU>(smem_optin_cap() / 3 - 1024, forced, a.N, a.K, G, bytes, pre_wts);
+  if (rc != DONK_OK) rc = fit_warp_plan<R, DX, DU>(smem_optin_cap(), forced, a.N, a.K, G, bytes, pre_wts);
   if (rc != DONK_OK) return rc;
   if (G > 4) {  // the kernel is compiled for <= 128 threads
     G = 4;
-    bytes = (size_t)4 * (FitWarpDims<DX, DU>::TEAM + FitWarpDims<DX, DU>::prior_tail(a.N, a.K)) * sizeof(R);
+    bytes = (size_t)4 * (FitWarpDims<DX, DU>::TEAM + FitWarpDims<DX, DU>::prior_tail(a.N, a.K, pre_wts)) * sizeof(R);
   }
   rc = allow_smem(fit_warp_kernel<R, DX, DU>, bytes);
   if (rc != DONK_OK) return rc;
+  double* wts_scratch = nullptr;
+  if constexpr (sizeof(R) == 8) {
+    if (pre_wts) {
+      rc = fit_prior_wts_launch(a, stream, &wts_scratch);
+      if (rc != DONK_OK) return rc;
+    }
+  }
   R* consts = nullptr;
-  if (a.K > 0) {  // per-cluster constants of the log-probabilities: stream-ordered scratch, freed after the fit launch
+  if (a.K > 0 && !pre_wts) {  // per-cluster constants of the log-probabilities: stream-ordered scratch, freed after the fit launch
     const int d = 2 * DX + DU, len = a.K * d + a.K;
     keep_async_pool();
     if (cudaMallocAsync(reinterpret_cast<void**>(&consts), (size_t)len * sizeof(R), (cudaStream_t)stream) != cudaSuccess) {
@@ -63,6 +83,7 @@ int fit_warp_launch(FitArgs<R> a, void* stream) {
   const long long nfits = (long long)a.B * a.T;
   fit_warp_kernel<R, DX, DU><<<(unsigned)((nfits + G - 1) / G), 32 * G, bytes, (cudaStream_t)stream>>>(a);
   if (consts) cudaFreeAsync(consts, (cudaStream_t)stream);
+  if (wts_scratch) cudaFreeAsync(wts_scratch, (cudaStream_t)stream);
   LAUNCHED("fit_warp_kernel");
   return DONK_OK;
 }
@@ -72,9 +93,9 @@ int fit_warp_launch(FitArgs<R> a, void* stream) {
 template <typename R>
 static int fit_lr_launch(FitArgs<R>& a, void* stream) {
   const int B = a.B, N = a.N, T = a.T, dX = a.dX, dU = a.dU, gmm_K = a.K;
-  // warp-per-fit fast path for the instantiated dimensions (with the prior: partial sums for at most 64 samples);
-  // a plan that does not fit shared memory (many clusters) falls through to the generic kernel
-  if ((gmm_K == 0 || N <= 64) && !a.niw_Phi && !env_int("DONK_FIT_GENERIC")) {
+  // warp-per-fit fast path for the instantiated dimensions; a plan that does not fit shared memory (many clusters with
+  // the in-kernel prior) falls through to the generic kernel
+  if (!a.niw_Phi && !env_int("DONK_FIT_GENERIC")) {
 #define DONK_TRY_FITW(DXV, DUV)                                          \
   if (dX == DXV && dU == DUV) {                                          \
     const int rc_w = fit_warp_launch<R, DXV, DUV>(a, stream);            \

@@ -150,14 +150,18 @@ namespace donk_abi {
 
 // responsibilities of n rows (sklearn predict_proba): the tensor-path E pass for pools of at least 4096 rows (the
 // fit_lr prior at config-5 size evaluates millions of rows per call), the scalar kernel below that
+// X == nullptr: the rows are the transitions of roll-outs tX (.., T+1, dX), tU (.., T, dU) (GmmArgs: transition view)
 int gmm_predict_proba_launch(int n, int d, int K, const double* X, const double* weights, const double* means,
-                             const double* prec_chol, double* resp, void* stream) {
+                             const double* prec_chol, double* resp, void* stream, const double* tX, const double* tU,
+                             int tT, int tdX, int tdU) {
   if (n < 0 || d < 1 || K < 1) return DONK_BAD_SHAPE;
+  if (X == nullptr && (tX == nullptr || tU == nullptr || tT < 1 || d != 2 * tdX + tdU)) return DONK_BAD_SHAPE;
   if (n == 0) return DONK_OK;
   GmmArgs<double> a;
   memset(&a, 0, sizeof(a));
   a.n = n; a.d = d; a.K = K; a.X = X; a.w = weights; a.means = means; a.pc = prec_chol;
   a.resp = resp;
+  if (X == nullptr) { a.tX = tX; a.tU = tU; a.tT = tT; a.tdX = tdX; a.tdU = tdU; }
   const GmmMmaPlan pl = gmm_mma_plan(n, d, K);
   if (pl.ok && n >= 4096 && !env_int("DONK_GMM_GENERIC")) return gmm_e_mma_dispatch(a, pl, stream);
   a.nblocks = (n + GMM_TS - 1) / GMM_TS;

@@ -38,11 +38,14 @@ struct FitWarpDims {
   static constexpr int oMu = oSxx + DX * DXP + 8;  // mean (D8)
   static constexpr int oTd = oMu + D8, oTe = oTd + PA + 4, oV = oTe + PA + 4, oWw = oV + PA + 4;
   static constexpr int oScal = oWw + PA + 4, TEAM = oScal + 8;
-  // prior: runtime-sized tail behind TEAM: resp (N8 x K) | wts (K8) | mu_prior (D8)
+  // prior: runtime-sized tail behind TEAM: resp (N8 x K) | wts (K8) | mu_prior (D8); no resp when the cluster weights
+  // come precomputed (FitArgs::wts_in: one E pass of the EM kernels over all samples of the call, abi_fit_coop.cu)
   static constexpr int NSB_MAX = 8;  // sample blocks of 8 the prior path holds partial sums for (N <= 64)
   static_assert(DX % 2 == 0, "prior path: [x_t | x_{t+1}] is read as one run of 2 dX values in blocks of 4");
   static constexpr int KX4 = 2 * DX / 4, KU4 = (DU + 3) / 4, KT4 = KX4 + KU4;
-  DONK_HD static int prior_tail(int N, int K) { return K > 0 ? ((N + 7) / 8 * 8) * K + (K + 7) / 8 * 8 + D8 : 0; }
+  DONK_HD static int prior_tail(int N, int K, bool pre = false) {
+    return K > 0 ? (pre ? 0 : ((N + 7) / 8 * 8) * K) + (K + 7) / 8 * 8 + D8 : 0;
+  }
 };
 
 template <typename R, int DX, int DU>
@@ -57,7 +60,8 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
     const long long fit = (long long)cta * w.G + tm;
     if (fit >= nfits) continue;
     const int b = (int)(fit / T), t = (int)(fit % T);
-    const int team_sz = D::TEAM + D::prior_tail(N, a.K);
+    const bool pre_wts = a.wts_in != nullptr;
+    const int team_sz = D::TEAM + D::prior_tail(N, a.K, pre_wts);
     R* tp = smem + (size_t)tm * team_sz;
     R* Spp = tp + D::oSpp;  // upper triangle + diagonal: Sigma_pp; strict lower triangle: work space for factors
     R* Spx = tp + D::oSpx;  // Sigma_px, then Y = L^-1 Sigma_px, then Z = F^T
@@ -170,14 +174,17 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
     if (a.K > 0) {
       const int K = a.K, N8 = (N + 7) / 8 * 8, K8 = (K + 7) / 8 * 8;
       const size_t dd = (size_t)d * d;
-      R* resp = tp + D::TEAM;  // [N8][K]: log-probabilities, then responsibilities
-      R* wts = resp + (size_t)N8 * K;
+      R* resp = tp + D::TEAM;  // [N8][K]: log-probabilities, then responsibilities (absent with precomputed weights)
+      R* wts = resp + (pre_wts ? 0 : (size_t)N8 * K);
       R* mup = wts + K8;
       auto load_sigma = [&](int i, int j) {  // element (i <= j) of the blocked joint covariance
         if (j < P) return Spp[i * PA + j];
         if (i < P) return Spx[i * DXP + (j - P)];
         return Sxx[(i - P) * DXP + (j - P)];
       };
+      if (pre_wts) {
+        LANE_FOR(k, K) wts[k] = ldg(a.wts_in + (size_t)fit * K + k);
+      } else {
 #if !defined(DONK_EMU)
       {
         constexpr int NBD = D::NBD, KX4 = D::KX4, KT4 = D::KT4, NSB = D::NSB_MAX;
@@ -296,6 +303,7 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
         for (int n = 0; n < N; ++n) acc += resp[(size_t)n * K + k];
         wts[k] = acc / R(N);  // prior_gmm.py:33
       }
+      }  // !pre_wts
       w.team_sync();
       // Mixture moments: sum_k wts_k means_k and sum_k wts_k covariances_k.  The cluster parameters live in global
       // memory (L2); the loads of 4 clusters x 4 entries are issued together before any of them is used - a
@@ -612,9 +620,9 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
 }
 
 template <typename R, int DX, int DU>
-inline int fit_warp_plan(size_t smem_cap, int force_G, int N, int K, int& G, size_t& bytes) {
+inline int fit_warp_plan(size_t smem_cap, int force_G, int N, int K, int& G, size_t& bytes, bool pre_wts = false) {
   using D = FitWarpDims<DX, DU>;
-  const size_t per = (size_t)(D::TEAM + D::prior_tail(N, K)) * sizeof(R);
+  const size_t per = (size_t)(D::TEAM + D::prior_tail(N, K, pre_wts)) * sizeof(R);
   G = force_G > 0 ? force_G : 4;
   while (G > 1 && (size_t)G * per > smem_cap) --G;
   bytes = (size_t)G * per;

@@ -43,7 +43,23 @@ struct GmmArgs {
   int nch;                           // row ranges per cluster
   R* part;                           // (K,nch,1+d+d*d)
   R* shift_out;                      // (K,d) centring point of the statistics (written by the M pass), or null
+  // E pass only, optional: the rows are transitions read straight from roll-outs instead of a materialised pool
+  // (fit_lr's prior weights, prior_gmm.py:26-33): row (c N + n) T + t = [x_t | u_t | x_{t+1}] of tX (.., T+1, dX) and
+  // tU (.., T, dU) (donk/dynamics/utils.py:4-17); X is then null and d = 2 dX + dU
+  const R *tX, *tU;
+  int tT, tdX, tdU;
 };
+
+// element j of row `row` of the E pass input (pool row or transition view)
+template <typename R>
+DONK_D R gmm_row_item(const GmmArgs<R>& a, size_t row, int j) {
+  if (a.tX == nullptr) return ldg(a.X + row * a.d + j);
+  const size_t s = (unsigned)row / (unsigned)a.tT;  // sample (c N + n); the launcher keeps the row count below 2^31
+  const int t = (int)((unsigned)row - (unsigned)s * (unsigned)a.tT);
+  if (j < a.tdX) return ldg(a.tX + (s * (a.tT + 1) + t) * a.tdX + j);
+  if (j < a.tdX + a.tdU) return ldg(a.tU + (s * a.tT + t) * a.tdU + (j - a.tdX));
+  return ldg(a.tX + (s * (a.tT + 1) + t + 1) * a.tdX + (j - a.tdX - a.tdU));
+}
 
 // ---------------------------------------------------------------------------------------------
 // E pass: one CTA per block of GMM_TS rows (grid-stride).
@@ -83,7 +99,7 @@ DONK_D void gmm_e_cta(const Ctx& ctx, const GmmArgs<R>& a, int cta, int ncta, R*
     const size_t n0 = (size_t)blk * TS;
     TEAM_FOR(idx, TS * dp) {
       const int r = idx / dp, j = idx % dp;
-      xs[idx] = (n0 + r < (size_t)a.n && j < d) ? ldg(a.X + (n0 + r) * d + j) : R(0);
+      xs[idx] = (n0 + r < (size_t)a.n && j < d) ? gmm_row_item(a, n0 + r, j) : R(0);
     }
     ctx.sync();
     TEAM_FOR(idx, K * nrt) {

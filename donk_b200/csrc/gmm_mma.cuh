@@ -58,10 +58,50 @@ DONK_D void gmm_e_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, int ncta,
   const R cst = R(d) * R(1.8378770664093453);  // d log(2 pi)
   for (int blk = cta; blk < a.nblocks; blk += ncta) {
     const size_t n0 = (size_t)blk * TS;
+    // element idx = r d + j of the tile, consecutive threads on consecutive elements (coalesced).  The device form steps
+    // (r, j) - and for the transition view (sample, t) - incrementally: idx / d, idx % d (and row / T) per element cost
+    // ~60 instructions each, 14 % of the issue slots at d = 72, K = 16 and more with fewer clusters
+#if defined(DONK_EMU)
     CTA_FOR(idx, TS * d) {
       const int r = idx / d, j = idx % d;
-      Xt[j * ldt + r] = n0 + r < (size_t)a.n ? ldg(a.X + (n0 + r) * d + j) : R(0);
+      Xt[j * ldt + r] = n0 + r < (size_t)a.n ? gmm_row_item(a, n0 + r, j) : R(0);
     }
+#else
+    {
+      const int NT = w.nthreads, qd = NT / d, rd = NT % d;
+      int r = w.tid / d, j = w.tid % d;
+      if (a.tX == nullptr) {
+        const R* base = a.X + n0 * d;
+        const int rows = a.n - n0 < (size_t)TS ? (int)(a.n - n0) : TS;
+#pragma unroll 4
+        for (int idx = w.tid; idx < TS * d; idx += NT) {
+          Xt[j * ldt + r] = r < rows ? ldg(base + idx) : R(0);
+          r += qd; j += rd;
+          if (j >= d) { j -= d; ++r; }
+        }
+      } else {
+        const unsigned T = (unsigned)a.tT;
+        unsigned sm = (unsigned)(n0 + r) / T, t = (unsigned)(n0 + r) - sm * T;  // sample (c N + n), time step of row n0 + r
+        const int dX = a.tdX, p = a.tdX + a.tdU;
+#pragma unroll 2
+        for (int idx = w.tid; idx < TS * d; idx += NT) {
+          R v = R(0);
+          if (n0 + r < (size_t)a.n) {
+            const size_t xrow = (size_t)sm * (T + 1) + t;  // x_t and x_{t+1} are adjacent in the roll-outs
+            v = j < dX ? ldg(a.tX + xrow * dX + j)
+                       : (j < p ? ldg(a.tU + ((size_t)sm * T + t) * a.tdU + (j - dX)) : ldg(a.tX + xrow * dX + (j - a.tdU)));
+          }
+          Xt[j * ldt + r] = v;
+          int dr = qd;
+          j += rd;
+          if (j >= d) { j -= d; ++dr; }
+          r += dr;
+          t += dr;
+          while (t >= T) { t -= T; ++sm; }
+        }
+      }
+    }
+#endif
     w.cta_sync();
     for (int k = 0; k < K; ++k) {
       const R* P = a.pc + (size_t)k * dd;

@@ -67,7 +67,9 @@ def rollout_batch_torch(B: int, T: int, dX: int, dU: int, N: int, seed: int, dev
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     f64 = dict(dtype=torch.float64, device=device, generator=g)
-    Q, _ = torch.linalg.qr(torch.randn(B, dX, dX, **f64))
+    # orthogonal factors on the host: the CUDA QR of a batch of small matrices is a loop of ~8 tiny launches per matrix
+    # (33 k launches at B = 4096), which takes seconds plain and hours under a profiler
+    Q = torch.linalg.qr(torch.randn(B, dX, dX, **f64).cpu())[0].to(device)
     A = 0.97 * Q
     Bm = 0.1 * torch.randn(B, dX, dU, **f64)
     K = 0.05 * torch.randn(B, T, dU, dX, **f64)

@@ -30,9 +30,9 @@ using namespace donk;
 
 static const size_t kSmemCap = 227 * 1024;
 
-static int env_int(const char* name) {
+static int env_int(const char* name, int unset = 0) {
   const char* v = getenv(name);
-  return v ? atoi(v) : 0;
+  return v ? atoi(v) : unset;
 }
 
 template <typename R, int DX, int DU>
@@ -100,14 +100,25 @@ static int emu_ilqr_step(IlqrArgs<R> a) {
   return DONK_OK;
 }
 
+static int emu_fit_prior_wts(FitArgs<double>& a, std::vector<double>& wts);
+
 template <int DX, int DU>
 static int emu_fit_warp(FitArgs<double> a) {
   int G;
   size_t bytes;
-  int rc = fit_warp_plan<double, DX, DU>(kSmemCap, 0, a.N, a.K, G, bytes);
-  if (rc != DONK_OK) return rc;
-  std::vector<double> consts;
+  bool pre_wts = false;  // as the CUDA launcher (abi_fit.cu: fit_warp_launch)
   if (a.K > 0) {
+    const int force_in = env_int("DONK_FIT_PRIOR_INKERNEL", -1);
+    pre_wts = a.N > 64 || (force_in < 0 ? (a.K >= 8 && (long long)a.B * a.N * a.T >= 32768) : force_in == 0);
+  }
+  int rc = fit_warp_plan<double, DX, DU>(kSmemCap, 0, a.N, a.K, G, bytes, pre_wts);
+  if (rc != DONK_OK) return rc;
+  std::vector<double> consts, wts;
+  if (pre_wts) {
+    rc = emu_fit_prior_wts(a, wts);
+    if (rc != DONK_OK) return rc;
+  }
+  if (a.K > 0 && !pre_wts) {
     const int d = 2 * DX + DU, len = a.K * d + a.K;
     consts.resize(len);
     for (int i = 0; i < len; ++i) gmm_prior_consts_item<double>(d, a.K, a.gw, a.gmeans, a.gpc, consts.data(), i);
@@ -293,28 +304,42 @@ int donk_emu_brent_update_f64(int B, int phase, double xa, double xb, const doub
 extern "C" int donk_emu_gmm_predict_proba_f64(int n, int d, int K, const double* X, const double* weights, const double* means,
                                               const double* prec_chol, double* resp, void*);
 
+// as the CUDA launcher (abi_fit_coop.cu: fit_prior_wts_launch): E pass over the transition view of the roll-outs, then
+// the average over the samples of every fit
+extern "C" {
+static void emu_gmm_e(GmmArgs<double>& a);
+}
+static int emu_fit_prior_wts(FitArgs<double>& a, std::vector<double>& wts) {
+  const int d = 2 * a.dX + a.dU;
+  const size_t nrows = (size_t)a.B * a.N * a.T;
+  std::vector<double> resp(nrows * a.K);
+  wts.resize((size_t)a.B * a.T * a.K);
+  GmmArgs<double> g;
+  memset(&g, 0, sizeof(g));
+  g.n = (int)nrows; g.d = d; g.K = a.K; g.w = a.gw; g.means = a.gmeans; g.pc = a.gpc;
+  g.tX = a.X; g.tU = a.U; g.tT = a.T; g.tdX = a.dX; g.tdU = a.dU;
+  g.nblocks = (g.n + GMM_TS - 1) / GMM_TS;
+  g.resp = resp.data();
+  emu_gmm_e(g);
+  for (size_t idx = 0; idx < wts.size(); ++idx) {
+    const int k = (int)(idx % a.K);
+    const size_t bt = idx / a.K, t = bt % a.T, b = bt / a.T;
+    double acc = 0.0;
+    for (int n = 0; n < a.N; ++n) acc += resp[((b * a.N + n) * a.T + t) * a.K + k];
+    wts[idx] = acc / a.N;
+  }
+  a.wts_in = wts.data();
+  return DONK_OK;
+}
+
 template <int DX, int DU>
 static int emu_fit_coop(FitArgs<double>& a) {
   const size_t bytes = fit_coop_bytes<double, DX, DU>();
   if (bytes > kSmemCap) return DONK_SMEM_LIMIT;
-  const int d = 2 * DX + DU;
-  std::vector<double> wts, rows, resp;
-  if (a.K > 0) {  // as the CUDA launcher: gather rows, E pass, average over the samples of every fit
-    const size_t nrows = (size_t)a.B * a.N * a.T;
-    rows.resize(nrows * d);
-    resp.resize(nrows * a.K);
-    wts.resize((size_t)a.B * a.T * a.K);
-    for (size_t i = 0; i < nrows * d; ++i) rows[i] = transitions_item<double>(a.T, DX, DU, a.X, a.U, i);
-    int rc = donk_emu_gmm_predict_proba_f64((int)nrows, d, a.K, rows.data(), a.gw, a.gmeans, a.gpc, resp.data(), nullptr);
+  std::vector<double> wts;
+  if (a.K > 0) {
+    int rc = emu_fit_prior_wts(a, wts);
     if (rc != DONK_OK) return rc;
-    for (size_t idx = 0; idx < wts.size(); ++idx) {
-      const int k = (int)(idx % a.K);
-      const size_t bt = idx / a.K, t = bt % a.T, b = bt / a.T;
-      double acc = 0.0;
-      for (int n = 0; n < a.N; ++n) acc += resp[((b * a.N + n) * a.T + t) * a.K + k];
-      wts[idx] = acc / a.N;
-    }
-    a.wts_in = wts.data();
   }
   std::vector<double> smem(bytes / sizeof(double) + 4);
   int G = env_int("DONK_COOP_WARPS");
@@ -334,7 +359,7 @@ extern "C" {
 
 static int emu_fit_lr_launch(FitArgs<double>& a) {
   const int B = a.B, N = a.N, T = a.T, dX = a.dX, dU = a.dU, gmm_K = a.K;
-  if ((gmm_K == 0 || N <= 64) && !a.niw_Phi && !env_int("DONK_FIT_GENERIC")) {
+  if (!a.niw_Phi && !env_int("DONK_FIT_GENERIC")) {
     int rc = DONK_SMEM_LIMIT;
     if (dX == 20 && dU == 6) rc = emu_fit_warp<20, 6>(a);
     else if (dX == 14 && dU == 7) rc = emu_fit_warp<14, 7>(a);

@@ -211,17 +211,21 @@ def _synthetic_prior(dX, dU, K, seed):
     return GMMParams(w, means, cov, precision_cholesky(cov))
 
 
+@pytest.mark.parametrize("form", ["inkernel", "pre"])
 @pytest.mark.parametrize("dims,N,K,generic", [((14, 7), 50, 4, 0), ((20, 6), 64, 3, 0), ((6, 2), 20, 5, 0), ((6, 2), 9, 2, 0),
-                                              ((6, 2), 70, 2, 0), ((14, 7), 20, 4, 1)])
-def test_fit_lr_warp_kernel_with_prior(backend, monkeypatch, dims, N, K, generic):
-    """GMM prior inside the warp-per-fit kernel (log-probabilities on the tensor path), N up to 64 samples; more
-    samples (N=70) and DONK_FIT_GENERIC=1 take the generic CTA kernel: same results."""
+                                              ((6, 2), 70, 2, 0), ((20, 6), 130, 16, 0), ((14, 7), 20, 4, 1)])
+def test_fit_lr_warp_kernel_with_prior(backend, monkeypatch, dims, N, K, generic, form):
+    """GMM prior in the warp-per-fit kernel, both forms: "inkernel" = every warp computes the log-probabilities of its own
+    samples on the tensor path (small calls, N <= 64); "pre" = the cluster weights of all fits come from one E pass of the
+    EM kernels over the transition view of the roll-outs (large calls; the only form for N > 64).  DONK_FIT_GENERIC=1
+    takes the generic CTA kernel: same results."""
     from donk_b200 import batched, synthetic
     from donk_b200.batched import DeviceGMM
     from oracle.gmm import gmm_eval_prior
 
     if generic:
         monkeypatch.setenv("DONK_FIT_GENERIC", "1")
+    monkeypatch.setenv("DONK_FIT_PRIOR_INKERNEL", "1" if form == "inkernel" else "0")
     dX, dU = dims
     T, B, n_pool = 3, 2, 12345
     conds = [synthetic.condition(33, i, T, dX, dU, N) for i in range(B)]
