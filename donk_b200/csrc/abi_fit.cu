@@ -18,8 +18,11 @@ __global__ void __launch_bounds__(512, 1) fit_lr_kernel(const FitArgs<R> a) {
   fit_lr_cta<R>(ctx, a, (int)blockIdx.x, reinterpret_cast<R*>(smem_raw));
 }
 
+#ifndef DONK_FIT_LB_CTAS
+#define DONK_FIT_LB_CTAS 3  // 4-warp CTAs x 3 per SM: 170 registers per thread (experiments: profiles/build_alt.py)
+#endif
 template <typename R, int DX, int DU>
-__global__ void __launch_bounds__(128, 3) fit_warp_kernel(const FitArgs<R> a) {
+__global__ void __launch_bounds__(128, DONK_FIT_LB_CTAS) fit_warp_kernel(const FitArgs<R> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WCtx w{(int)threadIdx.x, (int)blockDim.x, (int)threadIdx.x >> 5, (int)threadIdx.x & 31, (int)blockDim.x >> 5};
   fit_warp_cta<R, DX, DU>(w, a, (int)blockIdx.x, reinterpret_cast<R*>(smem_raw));
@@ -48,6 +51,7 @@ int fit_warp_launch(FitArgs<R> a, void* stream) {
   } else {
     if (a.K > 0 && a.N > 64) return DONK_SMEM_LIMIT;  // single precision: in-kernel prior only
   }
+  if ((long long)a.N * (a.T + 1) * DX >= (1LL << 31)) return DONK_SMEM_LIMIT;  // 32-bit row offsets in the moments pass
   int rc = fit_warp_plan<R, DX, DU>(smem_optin_cap() / 3 - 1024, forced, a.N, a.K, G, bytes, pre_wts);
   if (rc != DONK_OK) rc = fit_warp_plan<R, DX, DU>(smem_optin_cap(), forced, a.N, a.K, G, bytes, pre_wts);
   if (rc != DONK_OK) return rc;
@@ -81,6 +85,7 @@ int fit_warp_launch(FitArgs<R> a, void* stream) {
     a.gconst = consts;
   }
   const long long nfits = (long long)a.B * a.T;
+  a.no_prefetch = env_int("DONK_FIT_NO_PREFETCH");
   fit_warp_kernel<R, DX, DU><<<(unsigned)((nfits + G - 1) / G), 32 * G, bytes, (cudaStream_t)stream>>>(a);
   if (consts) cudaFreeAsync(consts, (cudaStream_t)stream);
   if (wts_scratch) cudaFreeAsync(wts_scratch, (cudaStream_t)stream);

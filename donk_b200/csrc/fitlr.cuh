@@ -34,6 +34,7 @@ struct FitArgs {
   const R* wts_in;   // cooperative kernel with GMM prior: per-fit cluster weights mean_n predict_proba, (B,T,K)
   int aligned16;     // set by the launcher: X and U are 16-byte aligned
   int redo;          // generic kernel as second pass: only the fits another kernel flagged with info == 2
+  int no_prefetch;   // warp kernel: skip the L2 prefetch of the fit's sample rows (DONK_FIT_NO_PREFETCH=1, experiments)
   R *F, *f, *covar;  // (B,T,dX,p) (B,T,dX) (B,T,dX,dX)
   int* info;         // (B,T)
 };

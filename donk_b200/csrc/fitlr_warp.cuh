@@ -55,6 +55,7 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
   const int N = a.N, T = a.T;
   const long long nfits = (long long)a.B * T;
   const R eps = sizeof(R) == 8 ? R(2.220446049250313e-16) : R(1.1920929e-7);
+  [[maybe_unused]] const bool env_flag_no_prefetch = a.no_prefetch != 0;  // experiments: profiles/exp
 
   TEAMS_DO(tm) {
     const long long fit = (long long)cta * w.G + tm;
@@ -85,37 +86,64 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
     {
       constexpr int NBD = D::NBD, NTRI = NBD * (NBD + 1) / 2;
       const int g = w.lane >> 2, tq = w.lane & 3;
+      // all sample rows of the fit into L2 at once: the accumulation loop below keeps only two rows per lane in flight,
+      // and at DRAM latency that chain was half of the kernel (ncu: 51 % of the stall samples on its loads)
+      if (!env_flag_no_prefetch) {
+        for (int n = w.lane; n < N; n += 32) {
+          const char* xr = reinterpret_cast<const char*>(a.X + (((size_t)b * N + n) * (T + 1) + t) * DX);
+          const char* ur = reinterpret_cast<const char*>(a.U + (((size_t)b * N + n) * T + t) * DU);
+          const char* xl = reinterpret_cast<const char*>(reinterpret_cast<size_t>(xr) & ~(size_t)127);
+#pragma unroll
+          for (int o = 0; o < (int)(2 * DX * sizeof(R)) + 128; o += 128)
+            if (xl + o < xr + 2 * DX * sizeof(R)) prefetch_l2(xl + o);
+          prefetch_l2(ur);
+          if (((reinterpret_cast<size_t>(ur) + DU * sizeof(R) - 1) >> 7) != (reinterpret_cast<size_t>(ur) >> 7))
+            prefetch_l2(ur + DU * sizeof(R) - 1);
+        }
+      }
       const R invN = R(1) / R(N);
-      const R* ptr[NBD];   // address of column 8 ib + g of sample 0
-      size_t stride[NBD];  // distance between consecutive samples
+      // Register budget (3 CTAs x 4 warps per SM = 170 per thread): 84 for the accumulators, 36 for three sample rows in
+      // rotation, 12 for the column sums; addresses are a 32-bit element offset per column block from two row bases
+      // (64-bit pointers + strides per block spilled: 176 B of stack inside the loop, and a load that is spilled waits
+      // for its data), and the shift lives in shared memory (the Sxx area is free until the covariance is stored).
+      static_assert(32 * NBD <= DX * D::DXP + 8, "warp fit kernel: the shift does not fit the Sxx scratch");
+      R* shs = Sxx + w.lane;  // shs[32 ib]: shift of column 8 ib + g = the first sample
+      const R* Xb = a.X + (((size_t)b * N) * (T + 1) + t) * DX;  // sample 0: [x_t | x_{t+1}] (adjacent), then stride sx
+      const R* Ub = a.U + (((size_t)b * N) * T + t) * DU;
+      const int sx4 = 4 * (T + 1) * DX, su4 = 4 * T * DU;  // the launcher keeps N (T+1) dX below 2^31
+      // column 8 ib + g: offset in its row and which base; padding columns (>= d) read column 0 of X - their products land
+      // in rows / columns of the accumulators that are never stored
+      auto col_is_u = [&](int ib) { const int j = 8 * ib + g; return j >= DX && j < P; };
+      auto col_off = [&](int ib) { const int j = 8 * ib + g; return j < DX ? j : (j < P ? j - DX : (j < d ? j - DU : 0)); };
       bool ok[NBD];
-      R acc[NTRI][2], csum[NBD], sh[NBD], cur[NBD], nxt[NBD];
+      int off[NBD];  // element offset of row 4 s + tq, column 8 ib + g
+      R acc[NTRI][2], csum[NBD], cur[NBD], nxt[NBD];
 #pragma unroll
       for (int ib = 0; ib < NBD; ++ib) {
-        const int j = 8 * ib + g;
-        ok[ib] = j < d;
-        if (j < DX) { ptr[ib] = a.X + (((size_t)b * N) * (T + 1) + t) * DX + j; stride[ib] = (size_t)(T + 1) * DX; }
-        else if (j < P) { ptr[ib] = a.U + (((size_t)b * N) * T + t) * DU + (j - DX); stride[ib] = (size_t)T * DU; }
-        else if (j < d) { ptr[ib] = a.X + (((size_t)b * N) * (T + 1) + t + 1) * DX + (j - P); stride[ib] = (size_t)(T + 1) * DX; }
-        else { ptr[ib] = a.X; stride[ib] = 0; }
-        sh[ib] = ok[ib] ? ldg(ptr[ib]) : R(0);  // shift: the first sample
+        ok[ib] = 8 * ib + g < d;
+        const bool iu = col_is_u(ib);
+        shs[32 * ib] = ldg((iu ? Ub : Xb) + col_off(ib));
+        off[ib] = col_off(ib) + tq * ((iu ? su4 : sx4) / 4);
         csum[ib] = R(0);
       }
 #pragma unroll
       for (int q = 0; q < NTRI; ++q) { acc[q][0] = R(0); acc[q][1] = R(0); }
+      // Rows 4 s + tq of step s; the offsets advance by four samples per call.  Rows beyond N re-read sample 0 (= the
+      // shift: they contribute zeros); the choice is made on the ADDRESS - a select behind the load would make it wait for
+      // its data at once.  Three register sets in rotation by unrolling, not by copying: `nxt = nx2` moves waited for
+      // the newest load every step and left a single row in flight (ncu: 13 % of all stall samples on that move, 51 % on
+      // the loads of the loop).
       auto load = [&](int n, R* dst) {
 #pragma unroll
-        for (int ib = 0; ib < NBD; ++ib) dst[ib] = (ok[ib] && n < N) ? ldg(ptr[ib] + (size_t)n * stride[ib]) : sh[ib];
+        for (int ib = 0; ib < NBD; ++ib) {
+          const bool iu = col_is_u(ib);
+          dst[ib] = ldg((iu ? Ub : Xb) + (n < N ? off[ib] : col_off(ib)));
+          off[ib] += iu ? su4 : sx4;
+        }
       };
-      R nx2[NBD];
-      load(tq, nxt);
-      load(4 + tq, nx2);
-      for (int k4 = 0; k4 < (N + 3) / 4; ++k4) {
+      auto accumulate = [&](R* cur) {
 #pragma unroll
-        for (int ib = 0; ib < NBD; ++ib) { cur[ib] = nxt[ib]; nxt[ib] = nx2[ib]; }
-        load(4 * (k4 + 2) + tq, nx2);  // two sample rows are in flight while this one is multiplied
-#pragma unroll
-        for (int ib = 0; ib < NBD; ++ib) { cur[ib] -= sh[ib]; csum[ib] += cur[ib]; }
+        for (int ib = 0; ib < NBD; ++ib) { cur[ib] -= shs[32 * ib]; csum[ib] += cur[ib]; }
         int q = 0;
 #pragma unroll
         for (int ib = 0; ib < NBD; ++ib)
@@ -128,6 +156,22 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
             acc[q][0] = (R)d0;
             acc[q][1] = (R)d1;
           }
+      };
+      const int nsteps = (N + 3) / 4;
+      R nx2[NBD];
+      load(tq, cur);
+      load(4 + tq, nxt);
+      for (int k4 = 0; k4 < nsteps; k4 += 3) {  // two sample rows are in flight while a third is multiplied
+        load(4 * (k4 + 2) + tq, nx2);
+        accumulate(cur);
+        if (k4 + 1 < nsteps) {
+          load(4 * (k4 + 3) + tq, cur);
+          accumulate(nxt);
+        }
+        if (k4 + 2 < nsteps) {
+          load(4 * (k4 + 4) + tq, nxt);
+          accumulate(nx2);
+        }
       }
 #pragma unroll
       for (int ib = 0; ib < NBD; ++ib) {
@@ -135,8 +179,12 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
         csum[ib] = s * invN;  // every lane of the quad now holds the shifted mean of column 8 ib + g
-        if (tq == 0 && ok[ib]) mu[8 * ib + g] = sh[ib] + csum[ib];
+        if (tq == 0 && ok[ib]) mu[8 * ib + g] = shs[32 * ib] + csum[ib];
       }
+      // the shift area becomes Sxx: its padding must read as zeros again (operand fragments over-read into it)
+#pragma unroll
+      for (int ib = 0; ib < NBD; ++ib) shs[32 * ib] = R(0);
+      __syncwarp();
       // Sigma = S / N - m m^T, biased (linear_dynamics.py:165): the lane holds row 8 ib + g, columns 8 jb + 2 tq + h;
       // the shifted mean of column j lives in the quad g' = j % 8 and is fetched by shuffle
       int q = 0;
