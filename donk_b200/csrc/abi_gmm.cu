@@ -75,6 +75,11 @@ __global__ void __launch_bounds__(THREADS, OCC) gmm_m_mma_kernel(const GmmArgs<d
   gmm_m_mma_cta<double, NBW, KC>(w, a, (int)blockIdx.x, reinterpret_cast<double*>(smem_raw));
 }
 
+__global__ void gmm_pfrag_kernel(int d, int K, int NB, size_t total, const double* pc, double* pf) {
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
+    gmm_pfrag_item<double>(d, K, NB, pc, pf, idx);
+}
+
 template <int NB, int RA>
 int gmm_e_mma_launch(GmmArgs<double>& a, const GmmMmaPlan& pl, void* stream) {
   const int TS = 8 * RA * pl.Ge;
@@ -88,8 +93,24 @@ int gmm_e_mma_launch(GmmArgs<double>& a, const GmmMmaPlan& pl, void* stream) {
   if (rc != DONK_OK) return rc;
   int grid = occ2 ? 296 : 148;  // persistent CTAs walking the row tiles
   if (grid > a.nblocks) grid = a.nblocks;
+  // fragment-major copy of the precision factors (stream-ordered scratch, 368 KB at d = 72, K = 16): the B fragments
+  // of the products are then contiguous runs
+  double* pf = nullptr;
+  {
+    const size_t len = gmm_pfrag_len(NB, a.K);
+    keep_async_pool();
+    if (cudaMallocAsync(reinterpret_cast<void**>(&pf), len * sizeof(double), (cudaStream_t)stream) != cudaSuccess) {
+      snprintf(g_err, sizeof(g_err), "gmm E pass: cudaMallocAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return DONK_CUDA_ERROR;
+    }
+    gmm_pfrag_kernel<<<(unsigned)((len + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a.d, a.K, NB, len, a.pc, pf);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  a.pf = pf;
   if (occ2) gmm_e_mma_kernel_occ2<NB, RA><<<grid, 32 * pl.Ge, smem, (cudaStream_t)stream>>>(a);
   else gmm_e_mma_kernel<NB, RA><<<grid, 32 * pl.Ge, smem, (cudaStream_t)stream>>>(a);
+  a.pf = nullptr;
+  if (pf) cudaFreeAsync(pf, (cudaStream_t)stream);
   LAUNCHED("gmm_e_mma_kernel");
   return DONK_OK;
 }

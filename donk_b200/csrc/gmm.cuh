@@ -48,7 +48,27 @@ struct GmmArgs {
   // tU (.., T, dU) (donk/dynamics/utils.py:4-17); X is then null and d = 2 dX + dU
   const R *tX, *tU;
   int tT, tdX, tdU;
+  // tensor-path E pass, optional: the precision factors in fragment order (gmm_pfrag_item): the B fragment of block
+  // (fb, jb), k-step h is one contiguous 256-byte run
+  const R* pf;
 };
+
+// Fragment-major copy of the upper-triangular P_k for the tensor-path E pass: for cluster k, block row fb (features
+// 8 fb .. 8 fb + 7 = the k dimension of the product), block column jb >= fb and k-step h, lane (g = lane / 4, tq = lane % 4)
+// holds P_k[8 fb + 4 h + tq][8 jb + g] (zero outside the d x d matrix) at ((k NT + tile(fb, jb)) 2 + h) 32 + lane.
+DONK_HD int gmm_pfrag_tile(int NB, int fb, int jb) { return fb * NB - fb * (fb - 1) / 2 + (jb - fb); }
+DONK_HD size_t gmm_pfrag_len(int NB, int K) { return (size_t)K * (NB * (NB + 1) / 2) * 64; }
+template <typename R>
+DONK_HD void gmm_pfrag_item(int d, int K, int NB, const R* pc, R* pf, size_t idx) {
+  const int lane = (int)(idx % 32), h = (int)((idx / 32) % 2);
+  const size_t kt = idx / 64;
+  const int NT = NB * (NB + 1) / 2, t = (int)(kt % NT), k = (int)(kt / NT);
+  int fb = 0, rem = t;
+  while (rem >= NB - fb) { rem -= NB - fb; ++fb; }
+  const int jb = fb + rem;
+  const int f = 8 * fb + 4 * h + (lane & 3), j = 8 * jb + (lane >> 2);
+  pf[idx] = (f < d && j < d && k < K) ? pc[((size_t)k * d + f) * d + j] : R(0);
+}
 
 // element j of row `row` of the E pass input (pool row or transition view)
 template <typename R>

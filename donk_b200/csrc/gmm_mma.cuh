@@ -109,6 +109,7 @@ DONK_D void gmm_e_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, int ncta,
         const int i0 = 8 * RA * tm;
 #if !defined(DONK_EMU)
         const int g = w.lane >> 2, tq = w.lane & 3;
+        const R* pfk = a.pf + (size_t)k * (NB * (NB + 1) / 2) * 64;  // the device form always has the copy
         // Column blocks in groups of JG: the accumulators of a group (RA x JG fragments) fit the registers of a
         // two-CTA-per-SM launch without spilling; the A fragments of the rows a group needs are re-read per group.
         constexpr int JG = 3;
@@ -135,8 +136,9 @@ DONK_D void gmm_e_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, int ncta,
               for (int jj = 0; jj < JG; ++jj) {
                 const int jb = j0 + jj;
                 if (jb >= NB || jb < fb) continue;  // blocks below the diagonal are zero
-                const int j = 8 * jb + g;
-                const R bf = (f < d && j < d) ? ldg(P + (size_t)f * d + j) : R(0);
+                // B fragment from the fragment-major copy the launcher made: one contiguous 256-byte run per warp (two
+                // L1 wavefronts instead of four 64-byte rows of P_k, no predicate, no address arithmetic)
+                const R bf = ldg(pfk + ((gmm_pfrag_tile(NB, fb, jb) * 2 + h) * 32 + w.lane));
 #pragma unroll
                 for (int ra = 0; ra < RA; ++ra) {
                   double d0 = (double)c[ra][jj][0], d1 = (double)c[ra][jj][1];
