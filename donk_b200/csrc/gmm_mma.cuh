@@ -323,7 +323,13 @@ DONK_D void gmm_m_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, R* sm) {
     offA[i] = 8 * ib[i] + g; offB[i] = 8 * jb[i] + g;
     xbA[i] = xbar[offA[i]]; xbB[i] = xbar[offB[i]];
   }
-  R side[KC];  // thread tid < d: sum_n r_nc (x - x_bar)[tid]; thread tid == d: sum_n r_nc
+  // First moments and cluster sizes: column sj <= d (sj == d: the column of ones) over the rows ssub, ssub + nsub, ... of
+  // every tile, ALL threads of the CTA taking part (the first d + 1 threads alone walking all 64 rows put ~14 % more
+  // FP64 work on their three warps, and every tile barrier waited for them: 25 % of the stall samples of the kernel)
+  const int nsub = w.nthreads / (d + 1), ssub = w.tid / (d + 1), sj = w.tid % (d + 1);
+  const bool side_on = ssub < nsub;
+  const R side_xb = (side_on && sj < d) ? xbar[sj] : R(0);
+  R side[KC];  // partial sums of r_nc (x - x_bar)[sj] (sj < d) / of r_nc (sj == d)
 #pragma unroll
   for (int c = 0; c < KC; ++c) side[c] = R(0);
 #else
@@ -395,10 +401,9 @@ DONK_D void gmm_m_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, R* sm) {
         }
       }
     }
-    if (w.tid <= d) {
-      const R xb = w.tid < d ? xbar[w.tid] : R(0);
-      for (int r = 0; r < TS; ++r) {
-        const R xv = w.tid < d ? xs[r * ld + w.tid] - xb : R(1);
+    if (side_on) {
+      for (int r = ssub; r < TS; r += nsub) {
+        const R xv = sj < d ? xs[r * ld + sj] - side_xb : R(1);
 #pragma unroll
         for (int c = 0; c < KC; ++c) side[c] = fma(rk[r * KC + c], xv, side[c]);
       }
@@ -426,13 +431,23 @@ DONK_D void gmm_m_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, R* sm) {
 
   // partial of (cluster, range): [nk | s (d) | S (d,d) both halves]
 #if !defined(DONK_EMU)
+  // the row subsets of the first moments meet in the (now idle) tile buffers: [nsub][KC][d + 1], summed in fixed order
+  w.cta_sync();
+  if (side_on) {
+#pragma unroll
+    for (int c = 0; c < KC; ++c) Xs[((size_t)ssub * KC + c) * (d + 1) + sj] = side[c];
+  }
+  w.cta_sync();
 #pragma unroll
   for (int c = 0; c < KC; ++c) {
     const int k = kg * KC + c;
     if (k >= K) continue;
     R* out = a.part + ((size_t)k * a.nch + ch) * pl;
-    if (w.tid < d) out[1 + w.tid] = side[c];
-    else if (w.tid == d) out[0] = side[c];
+    if (w.tid <= d) {
+      R tot = R(0);
+      for (int sb = 0; sb < nsub; ++sb) tot += Xs[((size_t)sb * KC + c) * (d + 1) + w.tid];
+      out[w.tid < d ? 1 + w.tid : 0] = tot;
+    }
 #pragma unroll
     for (int i = 0; i < NBW; ++i) {
       if (!ok[i]) continue;
