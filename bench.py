@@ -909,9 +909,14 @@ def run_ours(args):
         def gps_once():
             holder["g5"] = algo.iteration(r5["X"], r5["U"], C5, c5v, cc5, prior=gm5)
 
-        n5 = 2 if not dry else 1
+        n5 = 3 if not dry else 1
+        if not dry:
+            gps_once()  # second warm-up: the first iteration that has a predecessor runs step_adjust for the first time
         l5 = nat.launch_count()
-        ms5 = timed(gps_once, n5, 0) / n5
+        # iterations timed one by one, median reported: an iteration is ~0.45 s, and a single allocator or clock hiccup in a
+        # two-iteration mean moved the figure by 15 % between otherwise identical runs
+        ms5_all = [timed(gps_once, 1, 0) for _ in range(n5)]
+        ms5 = float(np.median(ms5_all))
         l5 = (nat.launch_count() - l5) // n5
         n_steps5 = algo.last["n_steps"]
         fl5 = B5 * (T5 * fit_flops_per_fit(dX5, dU5, N5, K5) + n_steps5 * ilqr_flops_per_solve(T5, dX5, dU5)
@@ -923,7 +928,7 @@ def run_ours(args):
               "library_launches_per_iteration": int(l5),
               "status_counts": torch.bincount(algo.last["status"], minlength=5).tolist(),
               "kl_step_mult_range": [float(algo.kl_step_mult.min()), float(algo.kl_step_mult.max())],
-              "parts_ms": {"fit_lr_with_prior": fit5_ms},
+              "ms_per_iteration_samples": ms5_all, "parts_ms": {"fit_lr_with_prior": fit5_ms},
               "config": f"BatchedTrajOpt.iteration: {B5} conditions/GPU ({B5 * world} in total), T={T5}, dX={dX5}, dU={dU5}, "
                         f"N={N5}, {K5}-cluster GMM prior (BASELINE.json configs[4]); steady-state iteration incl. step_adjust",
               "roofline": roof(fl5, by5, ms5, f"fit_coop_kernel<{dX5},{dU5}> + gmm_e_mma_kernel + ilqr_coop_kernel<{dX5},{dU5}>")}
@@ -931,27 +936,24 @@ def run_ours(args):
         hX, hU = pin(r5["X"].cpu()), pin(r5["U"].cpu())
         hC, hc, hcc = pin(C5.cpu()), pin(c5v.cpu()), pin(cc5.cpu())
         pol_host = [pin(torch.empty_like(t, device="cpu")) for t in algo.pol]
-        dX_buf, dU_buf = torch.empty_like(r5["X"]), torch.empty_like(r5["U"])
-        dC, dc, dcc = torch.empty_like(C5), torch.empty_like(c5v), torch.empty_like(cc5)
         del r5
 
         def gps_e2e():
-            dX_buf.copy_(hX, non_blocking=True); dU_buf.copy_(hU, non_blocking=True)
-            dC.copy_(hC, non_blocking=True); dc.copy_(hc, non_blocking=True); dcc.copy_(hcc, non_blocking=True)
-            algo.iteration(dX_buf, dU_buf, dC, dc, dcc, prior=gm5)
-            for h, t in zip(pol_host, algo.pol):
-                h.copy_(t, non_blocking=True)
+            # chunked upload on a copy stream, overlapped with the state fit / fit_lr of the chunks already on the device
+            algo.iteration_from_host(hX, hU, hC, hc, hcc, prior=gm5, chunks=4, out_policy=pol_host)
             sync()
 
-        e5 = timed(gps_e2e, n5, 1 if not dry else 0) / n5
+        e5 = float(np.median([timed(gps_e2e, 1, 0) for _ in range(n5 + (0 if dry else 1))][0 if dry else 1:]))
         h2d5 = sum(t.numel() * 8 for t in (hX, hU, hC, hc, hcc))
         g5["e2e"] = {"conditions_per_sec": B5 * world / (e5 * 1e-3), "ms_per_iteration": e5, "h2d_bytes_per_iteration": h2d5,
                      "d2h_bytes_per_iteration": sum(t.numel() * 8 for t in pol_host),
-                     "h2d_gbs_per_rank_if_serial": h2d5 / max(e5 - ms5, 1e-3) / 1e6, "numa": numa,
-                     "what": "roll-outs + costs uploaded from pinned host memory once, the whole iteration on the device, "
-                             "the new policy downloaded"}
+                     "upload_exposed_ms": e5 - ms5, "chunks": 4, "numa": numa,
+                     "what": "BatchedTrajOpt.iteration_from_host: roll-outs + costs uploaded from pinned host memory in chunks "
+                             "of conditions (copy stream) while fit_lr runs on the chunks that have landed, the rest of the "
+                             "iteration on the device, the new policy downloaded"}
         extra["gps_iteration"] = g5
-        del hX, hU, hC, hc, hcc, dX_buf, dU_buf, dC, dc, dcc
+        del hX, hU, hC, hc, hcc
+        algo._host_buf = algo._host_costs = None
         holder.clear()
         free()
         # the prior update of the same GPS iteration: EM iterations over the (sharded) pool of config-5 transitions

@@ -191,6 +191,41 @@ def test_batched_gps_iteration_matches_per_condition_api(backend):
         assert abs(float(algo.kl_step_mult[b]) - single.kl_step_mult) < 1e-9
 
 
+def test_gps_iteration_from_host_equals_device_iteration(backend):
+    """BatchedTrajOpt.iteration_from_host (chunked upload overlapped with the dynamics fit, cost buffers in turn) gives
+    the iteration() results bit for bit over three iterations (the third reads the costs of the second in step_adjust)."""
+    import torch
+
+    from donk_b200 import synthetic
+    from donk_b200.batched import BatchedTrajOpt
+
+    T, dX, dU, N, B = 6, 6, 2, 10, 5
+    its = [[synthetic.condition(40 + k, i, T, dX, dU, N) for i in range(B)] for k in range(3)]
+    st = lambda xs: np.stack(xs)  # noqa: E731
+    a, b = BatchedTrajOpt(kl_step=0.7), BatchedTrajOpt(kl_step=0.7)
+    for k, it in enumerate(its):
+        X, U = st([x.X for x in it]), st([x.U for x in it])
+        C, c, cc = (st([getattr(x, n) for x in it]) * (1.0 + 0.1 * k) for n in ("C", "c", "cc"))
+        if k == 0:
+            pol = [st([getattr(x, n) for x in it]) for n in ("prev_K", "prev_k", "prev_covar")]
+            a.iteration(X, U, C, c, cc, *pol)
+            b.iteration(X, U, C, c, cc, *pol)
+            with pytest.raises(Exception):
+                BatchedTrajOpt(kl_step=0.7).iteration_from_host(X, U, C, c, cc)
+            continue
+        a.iteration(X, U, C, c, cc)
+        host = [torch.as_tensor(t) for t in (X, U, C, c, cc)]
+        if backend.device.type == "cuda":
+            host = [t.pin_memory() for t in host]
+        out = [torch.empty(t.shape, dtype=torch.float64) for t in a.pol]
+        b.iteration_from_host(*host, chunks=3, out_policy=out)
+        if backend.device.type == "cuda":
+            torch.cuda.synchronize()
+        for ta, tb, th in zip(a.pol, b.pol, out):
+            assert torch.equal(ta, tb) and np.array_equal(to_np(ta), th.numpy())
+        assert torch.equal(a.kl_step_mult, b.kl_step_mult)
+
+
 def test_device_transition_pool_matches_reference_semantics(backend):
     """batched.DeviceTransitionPool against the host TransitionPool (donk/samples/pool.py:6-56): growing pool, FIFO
     capacity with wrap-around, a batch larger than the capacity, newest-N windows."""
