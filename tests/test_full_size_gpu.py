@@ -126,6 +126,45 @@ def test_config2_fit_with_prior_batch(backend):
         assert relerr(F[b], Fo) < 1e-8 and relerr(f[b], fo) < 1e-8 and relerr(S[b], co) < 1e-8
 
 
+@pytest.mark.parametrize("dims,N,K,B,T", [((20, 6), 64, 16, 24, 100), ((14, 7), 80, 8, 16, 60), ((16, 8), 40, 8, 20, 50)])
+def test_fit_prior_weights_from_the_transition_view(backend, monkeypatch, dims, N, K, B, T):
+    """fit_lr with a many-cluster prior at sizes where the cluster weights of all fits come from ONE tensor-path E pass
+    over the transition view of the roll-outs (>= 32 768 sample rows; warp kernels with K >= 8 or N > 64, and the
+    cooperative kernel): every fit of two conditions against the oracle, and the in-kernel form of the prior (forced)
+    against the same numbers where it exists (N <= 64)."""
+    from donk_b200 import batched, synthetic
+    from oracle.gmm import GMMParams, gmm_eval_prior
+
+    dev = backend.device
+    dX, dU = dims
+    d = 2 * dX + dU
+    ro = synthetic.rollout_batch_torch(B, T, dX, dU, N, seed=13, device=dev)
+    assert B * N * T >= 32768
+    pool = batched.to_transitions(ro["X"][:4].reshape(-1, T + 1, dX), ro["U"][:4].reshape(-1, T, dU))
+    rng = np.random.default_rng(1)
+    idx = rng.choice(pool.shape[0], K, replace=False)
+    gm = batched.DeviceGMM(K, max_iter=8).set_params(np.full(K, 1 / K), pool[idx].cpu().numpy(),
+                                                    precisions=np.broadcast_to(np.eye(d), (K, d, d)).copy())
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gm.fit(pool)
+    F, f, S, info = batched.fit_lr(ro["X"], ro["U"], gm)
+    assert int(info.sum()) == 0 and torch.equal(S, S.transpose(-1, -2))
+    prm = GMMParams(gm.weights.cpu().numpy(), gm.means.cpu().numpy(), gm.covariances.cpu().numpy(),
+                    gm.precisions_cholesky.cpu().numpy())
+    for b in (0, B - 1):
+        Fo, fo, co = oracle.fit_lr(ro["X"][b].cpu().numpy(), ro["U"][b].cpu().numpy(),
+                                   lambda xux: gmm_eval_prior(prm, gm.N, xux))
+        assert relerr(F[b], Fo) < 1e-8 and relerr(f[b], fo) < 1e-8 and relerr(S[b], co) < 1e-8
+    if N <= 64 and dims != (16, 8):
+        monkeypatch.setenv("DONK_FIT_PRIOR_INKERNEL", "1")
+        F2, f2, S2, info2 = batched.fit_lr(ro["X"], ro["U"], gm)
+        assert int(info2.sum()) == 0
+        assert relerr(F2, F.cpu().numpy()) < 1e-9 and relerr(S2, S.cpu().numpy()) < 1e-9
+
+
 def test_config4_em_full_size(backend):
     """BASELINE configs[3]: EM on a 10 M-row pool, d=72, K=16."""
     from donk_b200 import _lib, batched, synthetic
