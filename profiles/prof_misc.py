@@ -27,6 +27,9 @@ def build(B, T, dX, dU, N, prior=None):
                              torch.as_tensor(cc, device=dev).expand(B, T + 1).contiguous(), x0m, x0S, prev_covar=ro["prev_covar"])
     return ro, il, ms
 
+import os as _os
+if _os.environ.get("PROF_ALT_LIB"):  # experiments: time an alternative build of the library (profiles/build_alt.py)
+    _lib.LIB_PATH = (Path(__file__).resolve().parent.parent / _os.environ["PROF_ALT_LIB"]).resolve()
 what = sys.argv[1]
 if what == "optimize":
     B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
