@@ -959,7 +959,9 @@ class DeviceKMeans:
 
     def _seed(self, X):
         """Greedy k-means++ (sklearn/cluster/_kmeans.py:_kmeans_plusplus): each new centre is the best of
-        ``2 + log K`` candidates drawn with probability proportional to the current squared distance."""
+        ``2 + log K`` candidates drawn with probability proportional to the current squared distance (inverse-CDF
+        sampling on the running sum, as scikit-learn does).  No host synchronisation: candidates, the winner and the
+        updated distances stay on the device."""
         import math
 
         n, d = X.shape
@@ -968,19 +970,17 @@ class DeviceKMeans:
         g.manual_seed(self.seed)
         trials = 2 + int(math.log(K))
         centers = torch.empty(K, d, dtype=X.dtype, device=X.device)
-        centers[0] = X[int(torch.randint(0, n, (1,), device=X.device, generator=g).item())]
+        centers[0] = X[torch.randint(0, n, (1,), device=X.device, generator=g)][0]
         _, closest, _ = self._pass(X, centers[:1], mind2=True)
         for i in range(1, K):
-            total = closest.sum()
-            if float(total) <= 0:  # fewer distinct rows than clusters
-                centers[i] = X[i % n]
-                continue
-            cand = torch.multinomial(closest / total, trials, replacement=True, generator=g)
+            cum = torch.cumsum(closest, 0)
+            u = torch.rand(trials, dtype=X.dtype, device=X.device, generator=g) * cum[-1]
+            cand = torch.searchsorted(cum, u).clamp_(max=n - 1)  # all distances zero (fewer distinct rows than centres): row 0
             _, _, D = self._pass(X, X[cand], dist=True)
-            D = torch.minimum(D, closest[:, None])
-            best = int(D.sum(0).argmin())
-            closest = D[:, best].contiguous()
-            centers[i] = X[cand[best]]
+            torch.minimum(D, closest[:, None], out=D)
+            best = D.sum(0).argmin().reshape(1)
+            closest = D.index_select(1, best)[:, 0].contiguous()
+            centers[i] = X[cand.index_select(0, best)][0]
         return centers
 
     def fit(self, X_local, group=None):

@@ -118,6 +118,13 @@ __global__ void __launch_bounds__(256, 3) kmeans_pass_kernel(int n, int d, int K
   kmeans_pass_cta<double>(ctx, n, d, K, X, centers, labels, mind2, dist, part, (int)blockIdx.x, (int)gridDim.x,
                           reinterpret_cast<double*>(smem_raw));
 }
+template <int NTW>
+__global__ void __launch_bounds__(256, 2) kmeans_pass_mma_kernel(int n, int d, int K, const double* X, const double* centers,
+                                                                 int* labels, double* mind2, double* dist, double* part) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  kmeans_pass_mma_cta<NTW>((int)threadIdx.x, n, d, K, X, centers, labels, mind2, dist, part, (int)blockIdx.x, (int)gridDim.x,
+                           reinterpret_cast<double*>(smem_raw));
+}
 __global__ void kmeans_reduce_kernel(int ncta, int len, const double* part, double* out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < len) kmeans_reduce_item<double>(ncta, len, part, out, idx);
@@ -314,15 +321,31 @@ int donk_kmeans_pass_f64(int n, int d, int K, const double* X, const double* cen
   if (n < 0 || d < 1 || K < 1) return DONK_BAD_SHAPE;
   if (sums && workspace_bytes < donk_kmeans_workspace_bytes(d, K)) return DONK_BAD_SHAPE;
   const int len = K * d + K;
-  const size_t smem = kmeans_pass_smem(d, K) * sizeof(double);
-  if (smem > smem_optin_cap() || d + 1 > 256) return DONK_SMEM_LIMIT;
-  int rc = allow_smem(kmeans_pass_kernel, smem);
-  if (rc != DONK_OK) return rc;
   int grid = KM_PASS_CTAS;
   const int nblocks = (n + KM_TS - 1) / KM_TS;
   if (grid > nblocks) grid = nblocks > 0 ? nblocks : 1;
   double* part = sums ? static_cast<double*>(workspace) : nullptr;
-  kmeans_pass_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(n, d, K, X, centers, labels, mind2, dist, part);
+  int rc;
+  const size_t smem_mma = kmeans_mma_smem(d) * sizeof(double);
+  if (kmeans_mma_ok(d, K, X) && 2 * (smem_mma + 1024) <= smem_optin_cap() && n >= 4096 && !env_int("DONK_KMEANS_SCALAR")) {
+    // tensor-path form: bulk-copied row tiles, distances and one-hot sums on DMMA, two CTAs per SM
+    if (grid > 296) grid = 296;
+    if ((d + 1 + 7) / 8 <= 8) {
+      rc = allow_smem(kmeans_pass_mma_kernel<1>, smem_mma);
+      if (rc != DONK_OK) return rc;
+      kmeans_pass_mma_kernel<1><<<grid, 256, smem_mma, (cudaStream_t)stream>>>(n, d, K, X, centers, labels, mind2, dist, part);
+    } else {
+      rc = allow_smem(kmeans_pass_mma_kernel<2>, smem_mma);
+      if (rc != DONK_OK) return rc;
+      kmeans_pass_mma_kernel<2><<<grid, 256, smem_mma, (cudaStream_t)stream>>>(n, d, K, X, centers, labels, mind2, dist, part);
+    }
+  } else {
+    const size_t smem = kmeans_pass_smem(d, K) * sizeof(double);
+    if (smem > smem_optin_cap() || d + 1 > 256) return DONK_SMEM_LIMIT;
+    rc = allow_smem(kmeans_pass_kernel, smem);
+    if (rc != DONK_OK) return rc;
+    kmeans_pass_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(n, d, K, X, centers, labels, mind2, dist, part);
+  }
   LAUNCHED("kmeans_pass_kernel");
   if (sums) {
     kmeans_reduce_kernel<<<(len + 127) / 128, 128, 0, (cudaStream_t)stream>>>(grid, len, part, sums);

@@ -197,6 +197,32 @@ def test_device_kmeans_and_prior_init(backend):
     assert abs(prior.gmm.lower_bound_ - ref.lower_bound_) < 1e-3 * abs(ref.lower_bound_)
 
 
+@pytest.mark.parametrize("n,d,K", [(4100, 72, 16), (9000, 46, 7), (5000, 144, 16), (4500, 10, 3), (6000, 35, 4), (4200, 126, 9)])
+def test_kmeans_pass_tensor_path(backend, monkeypatch, n, d, K):
+    """The tensor-path Lloyd pass (pools of >= 4096 rows, K <= 16, even d: bulk-copied tiles, distances and one-hot sums on
+    DMMA) against numpy: labels (first minimum), nearest distances, the distance matrix, per-cluster sums and counts; and
+    against the scalar pass (DONK_KMEANS_SCALAR=1) on the same input.  The last tile is ragged."""
+    from donk_b200.batched import DeviceKMeans
+
+    rng = np.random.default_rng(n + d)
+    X = rng.standard_normal((n, d)) + 3.0 * rng.integers(0, 3, size=(n, 1))
+    C = X[rng.choice(n, K, replace=False)] + 0.01
+    Xd, Cd = torch.as_tensor(X).to(backend.device), torch.as_tensor(C).to(backend.device)
+    ws = torch.empty(backend.size("kmeans_workspace_bytes", d, K) // 8 + 1, dtype=torch.float64, device=backend.device)
+    dist = ((X[:, None, :] - C[None, :, :]) ** 2).sum(-1)
+    lab = dist.argmin(1)
+    want = np.concatenate([np.stack([X[lab == k].sum(0) for k in range(K)]).ravel(), np.bincount(lab, minlength=K)])
+    for scalar in (0, 1):
+        monkeypatch.setenv("DONK_KMEANS_SCALAR", str(scalar))
+        sums = torch.full((K * d + K,), float("nan"), dtype=torch.float64, device=backend.device)
+        labels, d2, D = DeviceKMeans._pass(Xd, Cd, labels=True, mind2=True, dist=True, sums=sums, ws=ws)
+        assert np.array_equal(labels.cpu().numpy(), lab)
+        assert relerr(d2, dist.min(1)) < 1e-10 and relerr(D, dist) < 1e-10
+        assert relerr(sums, want) < 1e-12
+        l2, _, _ = DeviceKMeans._pass(Xd, Cd, labels=True)  # labels only: no sums, no distances written
+        assert np.array_equal(l2.cpu().numpy(), lab)
+
+
 def _synthetic_prior(dX, dU, K, seed):
     """A K-cluster mixture over [x_t | u_t | x_{t+1}] with well-conditioned random covariances."""
     from oracle.gmm import GMMParams, precision_cholesky
