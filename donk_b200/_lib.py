@@ -52,6 +52,7 @@ SIGNATURES = {
     "gmm_prec_chol_from_precisions_f64": [c_int] * 2 + [P] * 3 + [P],
     "fp64_probe": [c_int, c_int, c_int, P, ctypes.POINTER(c_double), P],
     "kmeans_pass_f64": [c_int] * 3 + [P] * 6 + [P, c_size_t, P],
+    "kmeanspp_round_f64": [c_int] * 3 + [P] * 5 + [P, c_size_t, P],
 }
 _SIZE_FUNCS = {
     "gmm_stats_size": [c_int, c_int],

@@ -970,16 +970,21 @@ class DeviceKMeans:
         g.manual_seed(self.seed)
         trials = 2 + int(math.log(K))
         centers = torch.empty(K, d, dtype=X.dtype, device=X.device)
+        nat = _lib.native()
         centers[0] = X[torch.randint(0, n, (1,), device=X.device, generator=g)][0]
         _, closest, _ = self._pass(X, centers[:1], mind2=True)
+        ws = torch.empty(nat.size("kmeans_workspace_bytes", d, trials) // 8 + 1, dtype=X.dtype, device=X.device)
+        dmin = torch.empty(n, trials, dtype=X.dtype, device=X.device)
+        pot = torch.empty(trials, dtype=X.dtype, device=X.device)
         for i in range(1, K):
             cum = torch.cumsum(closest, 0)
             u = torch.rand(trials, dtype=X.dtype, device=X.device, generator=g) * cum[-1]
             cand = torch.searchsorted(cum, u).clamp_(max=n - 1)  # all distances zero (fewer distinct rows than centres): row 0
-            _, _, D = self._pass(X, X[cand], dist=True)
-            torch.minimum(D, closest[:, None], out=D)
-            best = D.sum(0).argmin().reshape(1)
-            closest = D.index_select(1, best)[:, 0].contiguous()
+            # one read of the rows: distances to the candidates clamped by the current nearest distance + their column sums
+            nat.call("kmeanspp_round_f64", n, d, trials, X, X[cand].contiguous(), closest, dmin, pot, ws,
+                     ws.numel() * ws.element_size())
+            best = pot.argmin().reshape(1)
+            closest = dmin.index_select(1, best)[:, 0].contiguous()
             centers[i] = X[cand.index_select(0, best)][0]
         return centers
 

@@ -120,10 +120,31 @@ __global__ void __launch_bounds__(256, 3) kmeans_pass_kernel(int n, int d, int K
 }
 template <int NTW>
 __global__ void __launch_bounds__(256, 2) kmeans_pass_mma_kernel(int n, int d, int K, const double* X, const double* centers,
-                                                                 int* labels, double* mind2, double* dist, double* part) {
+                                                                 int* labels, double* mind2, double* dist, double* part,
+                                                                 const double* closest_in, double* pot_part) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   kmeans_pass_mma_cta<NTW>((int)threadIdx.x, n, d, K, X, centers, labels, mind2, dist, part, (int)blockIdx.x, (int)gridDim.x,
-                           reinterpret_cast<double*>(smem_raw));
+                           reinterpret_cast<double*>(smem_raw), closest_in, pot_part);
+}
+// generic k-means++ round: clamp the distance matrix by the current nearest distances; per-block sums of the columns
+__global__ void __launch_bounds__(256) kmeanspp_min_kernel(int n, int K, const double* closest, double* dmin, double* pot_part) {
+  __shared__ double red[256];
+  const int rows_per = (n + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * rows_per, r1 = min(n, r0 + rows_per);
+  for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) kmeanspp_min_item<double>(K, closest, dmin, (size_t)r);
+  __syncthreads();
+  for (int k = 0; k < K; ++k) {
+    double v = 0.0;
+    for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) v += dmin[(size_t)r * K + k];
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) pot_part[(size_t)blockIdx.x * K + k] = red[0];
+    __syncthreads();
+  }
 }
 __global__ void kmeans_reduce_kernel(int ncta, int len, const double* part, double* out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -333,11 +354,11 @@ int donk_kmeans_pass_f64(int n, int d, int K, const double* X, const double* cen
     if ((d + 1 + 7) / 8 <= 8) {
       rc = allow_smem(kmeans_pass_mma_kernel<1>, smem_mma);
       if (rc != DONK_OK) return rc;
-      kmeans_pass_mma_kernel<1><<<grid, 256, smem_mma, (cudaStream_t)stream>>>(n, d, K, X, centers, labels, mind2, dist, part);
+      kmeans_pass_mma_kernel<1><<<grid, 256, smem_mma, (cudaStream_t)stream>>>(n, d, K, X, centers, labels, mind2, dist, part, nullptr, nullptr);
     } else {
       rc = allow_smem(kmeans_pass_mma_kernel<2>, smem_mma);
       if (rc != DONK_OK) return rc;
-      kmeans_pass_mma_kernel<2><<<grid, 256, smem_mma, (cudaStream_t)stream>>>(n, d, K, X, centers, labels, mind2, dist, part);
+      kmeans_pass_mma_kernel<2><<<grid, 256, smem_mma, (cudaStream_t)stream>>>(n, d, K, X, centers, labels, mind2, dist, part, nullptr, nullptr);
     }
   } else {
     const size_t smem = kmeans_pass_smem(d, K) * sizeof(double);
@@ -351,6 +372,41 @@ int donk_kmeans_pass_f64(int n, int d, int K, const double* X, const double* cen
     kmeans_reduce_kernel<<<(len + 127) / 128, 128, 0, (cudaStream_t)stream>>>(grid, len, part, sums);
     LAUNCHED("kmeans_reduce_kernel");
   }
+  return DONK_OK;
+}
+
+
+int donk_kmeanspp_round_f64(int n, int d, int Kc, const double* X, const double* cand, const double* closest, double* dmin,
+                            double* pot, void* workspace, size_t workspace_bytes, void* stream) {
+  if (n < 1 || d < 1 || Kc < 1 || Kc > 16) return DONK_BAD_SHAPE;
+  if (workspace_bytes < donk_kmeans_workspace_bytes(d, Kc)) return DONK_BAD_SHAPE;
+  double* pot_part = static_cast<double*>(workspace);  // (CTAs, Kc): fits the Lloyd workspace
+  int grid = KM_PASS_CTAS;
+  const int nblocks = (n + KM_TS - 1) / KM_TS;
+  if (grid > nblocks) grid = nblocks;
+  int rc;
+  const size_t smem_mma = kmeans_mma_smem(d) * sizeof(double);
+  if (kmeans_mma_ok(d, Kc, X) && 2 * (smem_mma + 1024) <= smem_optin_cap() && n >= 4096 && !env_int("DONK_KMEANS_SCALAR")) {
+    if (grid > 296) grid = 296;
+    if ((d + 1 + 7) / 8 <= 8) {
+      rc = allow_smem(kmeans_pass_mma_kernel<1>, smem_mma);
+      if (rc != DONK_OK) return rc;
+      kmeans_pass_mma_kernel<1><<<grid, 256, smem_mma, (cudaStream_t)stream>>>(n, d, Kc, X, cand, nullptr, nullptr, dmin, nullptr, closest, pot_part);
+    } else {
+      rc = allow_smem(kmeans_pass_mma_kernel<2>, smem_mma);
+      if (rc != DONK_OK) return rc;
+      kmeans_pass_mma_kernel<2><<<grid, 256, smem_mma, (cudaStream_t)stream>>>(n, d, Kc, X, cand, nullptr, nullptr, dmin, nullptr, closest, pot_part);
+    }
+    LAUNCHED("kmeans_pass_kernel");
+  } else {
+    rc = donk_kmeans_pass_f64(n, d, Kc, X, cand, nullptr, nullptr, dmin, nullptr, nullptr, 0, stream);
+    if (rc != DONK_OK) return rc;
+    if (grid > 296) grid = 296;
+    kmeanspp_min_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, Kc, closest, dmin, pot_part);
+    LAUNCHED("kmeanspp_min_kernel");
+  }
+  kmeans_reduce_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(grid, Kc, pot_part, pot);
+  LAUNCHED("kmeans_reduce_kernel");
   return DONK_OK;
 }
 

@@ -140,7 +140,8 @@ DONK_HD bool kmeans_mma_ok(int d, int K, const void* X) {
 #if defined(__CUDA_ARCH__) || !defined(DONK_EMU)
 template <int NTW>  // 8-column blocks of the sums per warp (8 warps: NTW = 1 up to d = 63, 2 up to d = 127)
 DONK_D void kmeans_pass_mma_cta(int tid, int n, int d, int K, const double* X, const double* centers, int* labels,
-                                double* mind2, double* dist_out, double* part, int cta, int ncta, double* sm) {
+                                double* mind2, double* dist_out, double* part, int cta, int ncta, double* sm,
+                                const double* closest_in = nullptr, double* pot_part = nullptr) {
 #if defined(__CUDA_ARCH__)
   const int TS = KM_TS, ld = kmeans_mma_ld(d), d4 = (d + 3) / 4 * 4, KS = d4 / 4, NBD = (d + 1 + 7) / 8;
   double* xs = sm;                                 // [2][TS][ld]
@@ -180,6 +181,9 @@ DONK_D void kmeans_pass_mma_cta(int tid, int n, int d, int K, const double* X, c
   for (int t = 0; t < NTW; ++t)
 #pragma unroll
     for (int m = 0; m < 2; ++m) { S[t][m][0] = 0.0; S[t][m][1] = 0.0; }
+  // greedy k-means++ round (closest_in given): dist_out receives min(|x - c_k|^2, closest) and pot_part the per-CTA sums
+  // of those minima per candidate (the potential each candidate would leave)
+  double pot[4] = {0.0, 0.0, 0.0, 0.0};
   unsigned it = 0;
   if (cta < nblocks && tid < 64) stage(cta, 0);
   for (int blk = cta; blk < nblocks; blk += ncta, ++it) {
@@ -223,9 +227,16 @@ DONK_D void kmeans_pass_mma_cta(int tid, int n, int d, int K, const double* X, c
         if (live && mind2) { const double v = xx + bd; mind2[row] = v > 0.0 ? v : 0.0; }
       }
       if (live && dist_out) {
+        const double cl = closest_in ? __ldg(closest_in + row) : 1e300;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          if (kv[q] < K) { const double v = xx + dv[q]; dist_out[row * K + kv[q]] = v > 0.0 ? v : 0.0; }
+          if (kv[q] < K) {
+            double v = xx + dv[q];
+            v = v > 0.0 ? v : 0.0;
+            v = v < cl ? v : cl;
+            dist_out[row * K + kv[q]] = v;
+            pot[q] += v;
+          }
       }
     }
     __syncthreads();  // labels of the tile complete; every warp is done with the other buffer
@@ -247,6 +258,24 @@ DONK_D void kmeans_pass_mma_cta(int tid, int n, int d, int K, const double* X, c
       }
     }
   }
+  if (pot_part) {  // candidates k = 2 tq, 2 tq + 1, 8 + 2 tq, 9 + 2 tq: sum over the rows (g, then the warps)
+    __syncthreads();
+    double* red = xs;  // [8 warps][16]
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      double v = pot[q];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (g == 0) red[warp * 16 + (q < 2 ? 2 * tq + q : 8 + 2 * tq + (q - 2))] = v;
+    }
+    __syncthreads();
+    if (tid < K) {
+      double v = 0.0;
+      for (int wq = 0; wq < 8; ++wq) v += red[wq * 16 + tid];
+      pot_part[(size_t)cta * K + tid] = v;
+    }
+  }
   if (part) {  // per-CTA partial: [K*d sums | K counts]; the lane holds S[k = 8 m + g][j = 8 nt + 2 tq + h]
     double* out = part + (size_t)cta * ((size_t)K * d + K);
 #pragma unroll
@@ -266,6 +295,15 @@ DONK_D void kmeans_pass_mma_cta(int tid, int n, int d, int K, const double* X, c
 #endif
 }
 #endif
+
+// greedy k-means++ round, generic form (small pools, shapes outside the tensor path, emulation): item = row n of the
+// distance matrix `dmin` (n,K) filled by a pass with dist output: clamp by closest[n]; the potentials are summed by the
+// caller in row order
+template <typename R>
+DONK_HD void kmeanspp_min_item(int K, const R* closest, R* dmin, size_t row) {
+  const R cl = closest[row];
+  for (int k = 0; k < K; ++k) dmin[row * K + k] = dmin[row * K + k] < cl ? dmin[row * K + k] : cl;
+}
 
 template <typename R>
 DONK_HD void kmeans_reduce_item(int ncta, int len, const R* part, R* out, int idx) {

@@ -312,6 +312,14 @@ int donk_gmm_prec_chol_from_precisions_f64(int d, int K, const double* precision
 size_t donk_kmeans_workspace_bytes(int d, int K);
 int donk_kmeans_pass_f64(int n, int d, int K, const double* X, const double* centers, int* labels, double* mind2,
                          double* dist, double* sums, void* workspace, size_t workspace_bytes, void* stream);
+/* One round of the greedy k-means++ seeding scikit-learn's KMeans runs before Lloyd (sklearn/cluster/_kmeans.py:
+ * _kmeans_plusplus, reached from GMMPrior.update through GaussianMixture(init_params="kmeans")): for Kc <= 16 candidate
+ * centres cand (Kc,d) and the current nearest squared distances closest (n), in one read of the rows:
+ *   dmin (n,Kc) = min(|x_n - cand_c|^2, closest_n)   and   pot (Kc) = sum_n dmin[n][c]  (the potential each candidate
+ *   would leave; the winner is argmin pot and column `winner` of dmin is the next `closest`).
+ * workspace: donk_kmeans_workspace_bytes(d, Kc) bytes. */
+int donk_kmeanspp_round_f64(int n, int d, int Kc, const double* X, const double* cand, const double* closest, double* dmin,
+                            double* pot, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- diagnostics ------------------------------------------------------------------------ */
 

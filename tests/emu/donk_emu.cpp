@@ -730,4 +730,20 @@ int donk_emu_kmeans_pass_f64(int n, int d, int K, const double* X, const double*
   return DONK_OK;
 }
 
+
+int donk_emu_kmeanspp_round_f64(int n, int d, int Kc, const double* X, const double* cand, const double* closest,
+                                double* dmin, double* pot, void* workspace, size_t workspace_bytes, void*) {
+  if (n < 1 || d < 1 || Kc < 1 || Kc > 16) return DONK_BAD_SHAPE;
+  if (workspace_bytes < donk_emu_kmeans_workspace_bytes(d, Kc)) return DONK_BAD_SHAPE;
+  (void)workspace;
+  int rc = donk_emu_kmeans_pass_f64(n, d, Kc, X, cand, nullptr, nullptr, dmin, nullptr, nullptr, 0, nullptr);
+  if (rc != DONK_OK) return rc;
+  for (int k = 0; k < Kc; ++k) pot[k] = 0.0;
+  for (size_t r = 0; r < (size_t)n; ++r) {
+    kmeanspp_min_item<double>(Kc, closest, dmin, r);
+    for (int k = 0; k < Kc; ++k) pot[k] += dmin[r * Kc + k];
+  }
+  return DONK_OK;
+}
+
 }  // extern "C"

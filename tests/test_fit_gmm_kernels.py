@@ -221,6 +221,16 @@ def test_kmeans_pass_tensor_path(backend, monkeypatch, n, d, K):
         assert relerr(sums, want) < 1e-12
         l2, _, _ = DeviceKMeans._pass(Xd, Cd, labels=True)  # labels only: no sums, no distances written
         assert np.array_equal(l2.cpu().numpy(), lab)
+        # one greedy k-means++ round (donk_kmeanspp_round_f64): candidates = the first centres, current nearest distances
+        # = those to the last centre
+        Kc = min(K - 1, 4)
+        closest = dist[:, K - 1].copy()
+        dmin = torch.full((n, Kc), float("nan"), dtype=torch.float64, device=backend.device)
+        pot = torch.full((Kc,), float("nan"), dtype=torch.float64, device=backend.device)
+        backend.call("kmeanspp_round_f64", n, d, Kc, Xd, Cd[:Kc].contiguous(), torch.as_tensor(closest).to(backend.device),
+                     dmin, pot, ws, ws.numel() * 8)
+        want_min = np.minimum(dist[:, :Kc], closest[:, None])
+        assert relerr(dmin, want_min) < 1e-10 and relerr(pot, want_min.sum(0)) < 1e-12
 
 
 def _synthetic_prior(dX, dU, K, seed):
