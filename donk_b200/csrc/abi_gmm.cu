@@ -80,6 +80,11 @@ __global__ void gmm_pfrag_kernel(int d, int K, int NB, size_t total, const doubl
     gmm_pfrag_item<double>(d, K, NB, pc, pf, idx);
 }
 
+__global__ void __launch_bounds__(32 * GMM_M18_WARPS, 1) gmm_m18_kernel(const GmmArgs<double> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  gmm_m18_cta((int)threadIdx.x, a, (int)blockIdx.x, reinterpret_cast<double*>(smem_raw));
+}
+
 template <int NB, int RA>
 int gmm_e_mma_launch(GmmArgs<double>& a, const GmmMmaPlan& pl, void* stream) {
   const int TS = 8 * RA * pl.Ge;
@@ -128,6 +133,18 @@ int gmm_e_mma_dispatch(GmmArgs<double>& a, const GmmMmaPlan& pl, void* stream) {
 }
 
 int gmm_m_mma_dispatch(GmmArgs<double>& a, const GmmMmaPlan& pl, void* stream) {
+  // d = 137..144 (18 column blocks): nine warps, a pair of block rows each (gmm_m18_cta); same partials, same grid
+  if ((a.d + 7) / 8 == 18 && pl.KC == GMM_M18_KC && a.d % 2 == 0 && (reinterpret_cast<size_t>(a.X) & 15) == 0 &&
+      !env_int("DONK_GMM_M18_OFF")) {
+    const size_t smem18 = gmm_m18_smem(a.d) * sizeof(double);
+    if (smem18 <= smem_optin_cap()) {
+      int rc18 = allow_smem(gmm_m18_kernel, smem18);
+      if (rc18 != DONK_OK) return rc18;
+      gmm_m18_kernel<<<((a.K + pl.KC - 1) / pl.KC) * a.nch, 32 * GMM_M18_WARPS, smem18, (cudaStream_t)stream>>>(a);
+      LAUNCHED("gmm_m_mma_kernel");
+      return DONK_OK;
+    }
+  }
   const size_t smem = gmm_m_mma_smem(a.d, pl.KC) * sizeof(double);
   if (smem > smem_optin_cap()) return DONK_SMEM_LIMIT;
   const int grid = ((a.K + pl.KC - 1) / pl.KC) * a.nch;

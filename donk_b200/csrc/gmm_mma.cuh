@@ -477,6 +477,180 @@ DONK_D void gmm_m_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, R* sm) {
 #endif
 }
 
+// ------------------------------------------------------------------------------------------------------
+// M pass for 18 column blocks (d = 137..144: the transitions of BASELINE config 5), device only.
+// The generic shape above gives a warp 11 consecutive blocks of the upper triangle: per k-step 24 fragment loads, 22
+// centring subtractions and 22 scalings for 22 products - 2 scalar FP64 instructions per DMMA on the pipe the DMMAs
+// use (8.9 TFLOP/s at 2 M x 144, K = 16).  Here NINE warps each own a PAIR of block rows (W, 17 - W): 18 - W + W + 1 = 19
+// blocks per warp for every W, perfectly balanced, with two A fragments (scaled once per cluster: 4 multiplications)
+// and at most 18 B fragments per k-step for 38 products; the tile is centred on x_bar ONCE in shared memory after it
+// lands (one pass + one barrier per 64-row tile instead of 20 subtractions per k-step and lane).
+// ------------------------------------------------------------------------------------------------------
+#if !defined(DONK_EMU)
+enum { GMM_M18_WARPS = 9, GMM_M18_KC = 2 };
+DONK_HD size_t gmm_m18_smem(int d) {
+  const int D8 = round_up(d, 8), ld = ld_pad(D8);
+  return (size_t)2 * GMM_MTS * ld + (size_t)2 * GMM_MTS * GMM_M18_KC + D8 + 8 + 2;
+}
+
+template <int W>  // one 64-row tile for the warp that owns block rows W and 17 - W
+DONK_D void gmm_m18_tile(double (&acc)[19][GMM_M18_KC][2], const double* xs, const double* rk, int ld, int g, int tq) {
+  constexpr int NA = 18 - W, RB = 17 - W;  // blocks of row W: jb = W .. 17; blocks of row 17 - W: jb = RB .. 17
+#pragma unroll 1
+  for (int k4 = 0; k4 < GMM_MTS / 4; ++k4) {
+    const double* xrow = xs + (4 * k4 + tq) * ld + g;
+    const double r0 = rk[(4 * k4 + tq) * GMM_M18_KC], r1 = rk[(4 * k4 + tq) * GMM_M18_KC + 1];
+    const double xa = xrow[8 * W], xb = xrow[8 * RB];
+    const double a00 = xa * r0, a01 = xa * r1, a10 = xb * r0, a11 = xb * r1;
+#pragma unroll
+    for (int q = 0; q < NA; ++q) {
+      const double bv = xrow[8 * (W + q)];
+      asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(acc[q][0][0]), "+d"(acc[q][0][1]) : "d"(a00), "d"(bv));
+      asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(acc[q][1][0]), "+d"(acc[q][1][1]) : "d"(a01), "d"(bv));
+      if (W + q >= RB) {  // the same B fragment serves block (17 - W, W + q)
+        const int qb = NA + (W + q - RB);
+        asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(acc[qb][0][0]), "+d"(acc[qb][0][1]) : "d"(a10), "d"(bv));
+        asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(acc[qb][1][0]), "+d"(acc[qb][1][1]) : "d"(a11), "d"(bv));
+      }
+    }
+  }
+}
+
+template <int W>
+DONK_D void gmm_m18_store(const double (&acc)[19][GMM_M18_KC][2], double* out, int c, int d, int g, int tq) {
+  constexpr int NA = 18 - W, RB = 17 - W;
+#pragma unroll
+  for (int q = 0; q < 19; ++q) {
+    const int ib = q < NA ? W : RB, jb = q < NA ? W + q : RB + (q - NA);
+    const int gi = 8 * ib + g, gj = 8 * jb + 2 * tq;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (gi <= gj + h && gj + h < d && gi < d) {
+        out[1 + d + (size_t)gi * d + gj + h] = acc[q][c][h];
+        out[1 + d + (size_t)(gj + h) * d + gi] = acc[q][c][h];
+      }
+    }
+  }
+}
+
+DONK_D void gmm_m18_cta(int tid, const GmmArgs<double>& a, int cta, double* sm) {
+#if defined(__CUDA_ARCH__)
+  constexpr int KC = GMM_M18_KC, TS = GMM_MTS, NT = 32 * GMM_M18_WARPS;
+  const int d = a.d, K = a.K;
+  const int D8 = round_up(d, 8), ld = ld_pad(D8);
+  const int kg = cta / a.nch, ch = cta % a.nch;
+  double* Xs = sm;                                // [2][TS][ld]
+  double* rr = Xs + (size_t)2 * TS * ld;          // [2][TS][KC]
+  double* xbar = rr + (size_t)2 * TS * KC;        // [D8]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(xbar + D8 + 8);
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
+  const size_t rows_per = ((size_t)a.n + a.nch - 1) / a.nch;
+  const size_t row0 = (size_t)ch * rows_per;
+  const size_t row1 = row0 + rows_per < (size_t)a.n ? row0 + rows_per : (size_t)a.n;
+  const size_t pl = gmm_part_len(d);
+  for (int j = tid; j < D8; j += NT) {
+    double acc = 0.0;
+    if (j < d)
+      for (int k = 0; k < K; ++k) acc = fma(__ldg(a.w + k), __ldg(a.means + (size_t)k * d + j), acc);
+    xbar[j] = acc;
+  }
+  for (int idx = tid; idx < 2 * TS * ld; idx += NT) Xs[idx] = 0.0;
+  if (tid < 2) mbar_init(bars + tid, 1);
+  __syncthreads();
+  fence_proxy_async();
+  if (cta == 0 && a.shift_out)
+    for (int idx = tid; idx < K * d; idx += NT) a.shift_out[idx] = xbar[idx % d];
+
+  double acc[19][KC][2];
+#pragma unroll
+  for (int q = 0; q < 19; ++q)
+#pragma unroll
+    for (int c = 0; c < KC; ++c) { acc[q][c][0] = 0.0; acc[q][c][1] = 0.0; }
+  // first moments / cluster sizes: thread sj <= d walks the rows of every tile (5 of the 9 warps, ~3 % of their FP64 work)
+  const int sj = tid;
+  const bool side_on = sj <= d;
+  double side[KC] = {0.0, 0.0};
+
+  auto stage = [&](size_t n0, int buf) {
+    double* xs = Xs + (size_t)buf * TS * ld;
+    double* rk = rr + (size_t)buf * TS * KC;
+    const size_t left = row1 - n0;
+    const int valid = left < (size_t)TS ? (int)left : TS;
+    if (tid == 0) mbar_arrive_expect_tx(bars + buf, (unsigned)((size_t)valid * d * sizeof(double)));
+    for (int r = tid; r < TS; r += NT) {
+      if (r < valid) bulk_copy_g2s(xs + r * ld, a.X + (n0 + r) * d, (unsigned)(d * sizeof(double)), bars + buf);
+      else for (int j = 0; j < d; ++j) xs[r * ld + j] = 0.0;
+    }
+    for (int idx = tid; idx < TS * KC; idx += NT) {
+      const int r = idx / KC, c = idx % KC, k = kg * KC + c;
+      if (n0 + r < row1 && k < K) cp_async(rk + idx, a.resp + (n0 + r) * K + k);
+      else rk[idx] = 0.0;
+    }
+  };
+
+  int buf = 0;
+  unsigned tile = 0;
+  if (row0 < row1) stage(row0, 0);
+  for (size_t n0 = row0; n0 < row1; n0 += TS, ++tile) {
+    cp_async_wait_all();
+    mbar_wait(bars + buf, (tile >> 1) & 1);
+    fence_proxy_async();  // this thread's centring writes into the other buffer precede the bulk copies about to refill it
+    __syncthreads();      // the tile and its responsibilities are visible; every warp has left the other buffer
+    if (n0 + TS < row1) stage(n0 + TS, buf ^ 1);
+    double* xs = Xs + (size_t)buf * TS * ld;
+    const double* rk = rr + (size_t)buf * TS * KC;
+    {  // centre the tile on x_bar, once, in place (rows beyond the range carry r = 0)
+      const size_t left = row1 - n0;
+      const int valid = left < (size_t)TS ? (int)left : TS;
+      for (int idx = tid; idx < valid * D8; idx += NT) {
+        const int r = idx / D8, j = idx - r * D8;
+        if (j < d) xs[r * ld + j] -= xbar[j];
+      }
+    }
+    __syncthreads();
+    switch (warp) {
+      case 0: gmm_m18_tile<0>(acc, xs, rk, ld, g, tq); break;
+      case 1: gmm_m18_tile<1>(acc, xs, rk, ld, g, tq); break;
+      case 2: gmm_m18_tile<2>(acc, xs, rk, ld, g, tq); break;
+      case 3: gmm_m18_tile<3>(acc, xs, rk, ld, g, tq); break;
+      case 4: gmm_m18_tile<4>(acc, xs, rk, ld, g, tq); break;
+      case 5: gmm_m18_tile<5>(acc, xs, rk, ld, g, tq); break;
+      case 6: gmm_m18_tile<6>(acc, xs, rk, ld, g, tq); break;
+      case 7: gmm_m18_tile<7>(acc, xs, rk, ld, g, tq); break;
+      default: gmm_m18_tile<8>(acc, xs, rk, ld, g, tq); break;
+    }
+    if (side_on) {
+      for (int r = 0; r < TS; ++r) {
+        const double xv = sj < d ? xs[r * ld + sj] : 1.0;
+#pragma unroll
+        for (int c = 0; c < KC; ++c) side[c] = fma(rk[r * KC + c], xv, side[c]);
+      }
+    }
+    buf ^= 1;
+  }
+  cp_async_wait_all();
+#pragma unroll
+  for (int c = 0; c < KC; ++c) {
+    const int k = kg * KC + c;
+    if (k >= K) continue;
+    double* out = a.part + ((size_t)k * a.nch + ch) * pl;
+    if (side_on) out[sj < d ? 1 + sj : 0] = side[c];
+    switch (warp) {
+      case 0: gmm_m18_store<0>(acc, out, c, d, g, tq); break;
+      case 1: gmm_m18_store<1>(acc, out, c, d, g, tq); break;
+      case 2: gmm_m18_store<2>(acc, out, c, d, g, tq); break;
+      case 3: gmm_m18_store<3>(acc, out, c, d, g, tq); break;
+      case 4: gmm_m18_store<4>(acc, out, c, d, g, tq); break;
+      case 5: gmm_m18_store<5>(acc, out, c, d, g, tq); break;
+      case 6: gmm_m18_store<6>(acc, out, c, d, g, tq); break;
+      case 7: gmm_m18_store<7>(acc, out, c, d, g, tq); break;
+      default: gmm_m18_store<8>(acc, out, c, d, g, tq); break;
+    }
+  }
+#endif
+}
+#endif  // !DONK_EMU
+
 // ---- launch planning shared by the CUDA library and the emulation ---------------------------------------------
 struct GmmMmaPlan {
   int NB, RA, Ge;      // E pass: 8-column blocks, 8-row fragments per warp, warps per CTA

@@ -331,10 +331,12 @@ def test_em_kernel_family_follows_cluster_separation(backend):
                 assert g2._mode == mode and relerr(g2.covariances, ref.covariances) < 1e-10
 
 
-@pytest.mark.parametrize("d,K,n", [(72, 6, 1501), (56, 5, 700), (49, 4, 333), (40, 3, 500), (80, 2, 300), (120, 3, 400)])
+@pytest.mark.parametrize("d,K,n", [(72, 6, 1501), (56, 5, 700), (49, 4, 333), (40, 3, 500), (80, 2, 300), (120, 3, 400),
+                                   (144, 4, 700), (138, 3, 333)])
 def test_em_dmma_cta_shapes_match_oracle(backend, d, K, n):
     """The DMMA passes at every M-pass CTA shape: 8 warps x 6 blocks x 2 clusters (d <= 48), 16 warps x 3 blocks x 4
-    clusters (d = 49..72, K not a multiple of 4 and ragged row ranges included), 16 warps x 11 blocks (d > 72)."""
+    clusters (d = 49..72, K not a multiple of 4 and ragged row ranges included), 16 warps x 11 blocks (d > 72), and on the
+    device nine warps x a pair of block rows (d = 137..144, the config-5 transitions; odd K, ragged last column block)."""
     from donk_b200.batched import DeviceGMM
     from donk_b200 import synthetic
 
