@@ -20,6 +20,10 @@
 
 namespace donk {
 
+#ifndef DONK_E_JG_WIDE
+#define DONK_E_JG_WIDE 6
+#endif
+
 // ------------------------------------------------------------------------------------------------------
 // E pass
 // ------------------------------------------------------------------------------------------------------
@@ -112,7 +116,7 @@ DONK_D void gmm_e_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, int ncta,
         const R* pfk = a.pf + (size_t)k * (NB * (NB + 1) / 2) * 64;  // the device form always has the copy
         // Column blocks in groups of JG: the accumulators of a group (RA x JG fragments) fit the registers of a
         // two-CTA-per-SM launch without spilling; the A fragments of the rows a group needs are re-read per group.
-        constexpr int JG = 3;
+        constexpr int JG = NB >= 12 ? DONK_E_JG_WIDE : 3;  // wide kernels (d > 96) run one CTA per SM with 255 registers: wider groups, fewer A re-reads
         R ssr[RA];
 #pragma unroll
         for (int ra = 0; ra < RA; ++ra) ssr[ra] = R(0);
