@@ -485,20 +485,32 @@ DONK_D void gmm_m_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, R* sm) {
 // M pass for 18 column blocks (d = 137..144: the transitions of BASELINE config 5), device only.
 // The generic shape above gives a warp 11 consecutive blocks of the upper triangle: per k-step 24 fragment loads, 22
 // centring subtractions and 22 scalings for 22 products - 2 scalar FP64 instructions per DMMA on the pipe the DMMAs
-// use (8.9 TFLOP/s at 2 M x 144, K = 16).  Here NINE warps each own a PAIR of block rows (W, 17 - W): 18 - W + W + 1 = 19
-// blocks per warp for every W, perfectly balanced, with two A fragments (scaled once per cluster: 4 multiplications)
-// and at most 18 B fragments per k-step for 38 products; the tile is centred on x_bar ONCE in shared memory after it
-// lands (one pass + one barrier per 64-row tile instead of 20 subtractions per k-step and lane).
+// use (8.9 TFLOP/s at 2 M x 144, K = 16).  Here a warp owns a PAIR of block rows (W, 17 - W): 18 - W + W + 1 = 19
+// blocks for every W, with two A fragments (scaled once per cluster) and at most 18 B fragments per k-step; the tile is
+// centred on x_bar ONCE in shared memory after it lands (one pass + one barrier per 64-row tile instead of 20
+// subtractions per k-step and lane).  Nine pairs on nine warps put three warps on one sub-partition (44 ms per pass at
+// 2 M x 144: that sub-partition's DMMA pipe is the critical path); EIGHT warps take pairs 0..7 and share the ninth pair
+// (rows 8 and 9, whose B fragments every warp loads anyway) as 2-3 extra blocks each: 21-22 blocks per warp, two warps
+// per sub-partition, 255 registers.
 // ------------------------------------------------------------------------------------------------------
 #if !defined(DONK_EMU)
-enum { GMM_M18_WARPS = 9, GMM_M18_KC = 2 };
+enum { GMM_M18_WARPS = 8, GMM_M18_KC = 2, GMM_M18_ACC = 22 };
 DONK_HD size_t gmm_m18_smem(int d) {
   const int D8 = round_up(d, 8), ld = ld_pad(D8);
   return (size_t)2 * GMM_MTS * ld + (size_t)2 * GMM_MTS * GMM_M18_KC + D8 + 8 + 2;
 }
 
-template <int W>  // one 64-row tile for the warp that owns block rows W and 17 - W
-DONK_D void gmm_m18_tile(double (&acc)[19][GMM_M18_KC][2], const double* xs, const double* rk, int ld, int g, int tq) {
+// the ninth pair (block rows 8 and 9) dealt to the eight warps: row 8 blocks [X8, X8 + N8), row 9 blocks [X9, X9 + N9)
+template <int W> struct GmmM18Extra {
+  static constexpr int X8 = W == 0 ? 8 : W == 1 ? 11 : W == 2 ? 14 : W == 3 ? 17 : 0;
+  static constexpr int N8 = W <= 2 ? 3 : W == 3 ? 1 : 0;
+  static constexpr int X9 = W == 3 ? 9 : W == 4 ? 10 : W == 5 ? 12 : W == 6 ? 14 : W == 7 ? 16 : 0;
+  static constexpr int N9 = W == 3 ? 1 : W >= 4 ? 2 : 0;
+};
+
+template <int W>  // one 64-row tile for the warp that owns block rows W and 17 - W (+ its share of rows 8 and 9)
+DONK_D void gmm_m18_tile(double (&acc)[GMM_M18_ACC][GMM_M18_KC][2], const double* xs, const double* rk, int ld, int g, int tq) {
+  using E = GmmM18Extra<W>;
   constexpr int NA = 18 - W, RB = 17 - W;  // blocks of row W: jb = W .. 17; blocks of row 17 - W: jb = RB .. 17
 #pragma unroll 1
   for (int k4 = 0; k4 < GMM_MTS / 4; ++k4) {
@@ -506,9 +518,22 @@ DONK_D void gmm_m18_tile(double (&acc)[19][GMM_M18_KC][2], const double* xs, con
     const double r0 = rk[(4 * k4 + tq) * GMM_M18_KC], r1 = rk[(4 * k4 + tq) * GMM_M18_KC + 1];
     const double xa = xrow[8 * W], xb = xrow[8 * RB];
     const double a00 = xa * r0, a01 = xa * r1, a10 = xb * r0, a11 = xb * r1;
+    double e80 = 0.0, e81 = 0.0, e90 = 0.0, e91 = 0.0;
+    if (E::N8 > 0) { const double x8 = xrow[64]; e80 = x8 * r0; e81 = x8 * r1; }
+    if (E::N9 > 0) { const double x9 = xrow[72]; e90 = x9 * r0; e91 = x9 * r1; }
 #pragma unroll
     for (int q = 0; q < NA; ++q) {
       const double bv = xrow[8 * (W + q)];
+      if (E::N8 > 0 && W + q >= E::X8 && W + q < E::X8 + E::N8) {  // block (8, W + q)
+        const int qe = 19 + (W + q - E::X8);
+        asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(acc[qe][0][0]), "+d"(acc[qe][0][1]) : "d"(e80), "d"(bv));
+        asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(acc[qe][1][0]), "+d"(acc[qe][1][1]) : "d"(e81), "d"(bv));
+      }
+      if (E::N9 > 0 && W + q >= E::X9 && W + q < E::X9 + E::N9) {  // block (9, W + q)
+        const int qe = 19 + E::N8 + (W + q - E::X9);
+        asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(acc[qe][0][0]), "+d"(acc[qe][0][1]) : "d"(e90), "d"(bv));
+        asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(acc[qe][1][0]), "+d"(acc[qe][1][1]) : "d"(e91), "d"(bv));
+      }
       asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(acc[q][0][0]), "+d"(acc[q][0][1]) : "d"(a00), "d"(bv));
       asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(acc[q][1][0]), "+d"(acc[q][1][1]) : "d"(a01), "d"(bv));
       if (W + q >= RB) {  // the same B fragment serves block (17 - W, W + q)
@@ -521,11 +546,13 @@ DONK_D void gmm_m18_tile(double (&acc)[19][GMM_M18_KC][2], const double* xs, con
 }
 
 template <int W>
-DONK_D void gmm_m18_store(const double (&acc)[19][GMM_M18_KC][2], double* out, int c, int d, int g, int tq) {
+DONK_D void gmm_m18_store(const double (&acc)[GMM_M18_ACC][GMM_M18_KC][2], double* out, int c, int d, int g, int tq) {
+  using E = GmmM18Extra<W>;
   constexpr int NA = 18 - W, RB = 17 - W;
 #pragma unroll
-  for (int q = 0; q < 19; ++q) {
-    const int ib = q < NA ? W : RB, jb = q < NA ? W + q : RB + (q - NA);
+  for (int q = 0; q < 19 + E::N8 + E::N9; ++q) {
+    const int ib = q < NA ? W : q < 19 ? RB : q < 19 + E::N8 ? 8 : 9;
+    const int jb = q < NA ? W + q : q < 19 ? RB + (q - NA) : q < 19 + E::N8 ? E::X8 + (q - 19) : E::X9 + (q - 19 - E::N8);
     const int gi = 8 * ib + g, gj = 8 * jb + 2 * tq;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -565,12 +592,12 @@ DONK_D void gmm_m18_cta(int tid, const GmmArgs<double>& a, int cta, double* sm) 
   if (cta == 0 && a.shift_out)
     for (int idx = tid; idx < K * d; idx += NT) a.shift_out[idx] = xbar[idx % d];
 
-  double acc[19][KC][2];
+  double acc[GMM_M18_ACC][KC][2];
 #pragma unroll
-  for (int q = 0; q < 19; ++q)
+  for (int q = 0; q < GMM_M18_ACC; ++q)
 #pragma unroll
     for (int c = 0; c < KC; ++c) { acc[q][c][0] = 0.0; acc[q][c][1] = 0.0; }
-  // first moments / cluster sizes: thread sj <= d walks the rows of every tile (5 of the 9 warps, ~3 % of their FP64 work)
+  // first moments / cluster sizes: thread sj <= d walks the rows of every tile (5 of the 8 warps, ~3 % of their FP64 work)
   const int sj = tid;
   const bool side_on = sj <= d;
   double side[KC] = {0.0, 0.0};
@@ -620,8 +647,7 @@ DONK_D void gmm_m18_cta(int tid, const GmmArgs<double>& a, int cta, double* sm) 
       case 4: gmm_m18_tile<4>(acc, xs, rk, ld, g, tq); break;
       case 5: gmm_m18_tile<5>(acc, xs, rk, ld, g, tq); break;
       case 6: gmm_m18_tile<6>(acc, xs, rk, ld, g, tq); break;
-      case 7: gmm_m18_tile<7>(acc, xs, rk, ld, g, tq); break;
-      default: gmm_m18_tile<8>(acc, xs, rk, ld, g, tq); break;
+      default: gmm_m18_tile<7>(acc, xs, rk, ld, g, tq); break;
     }
     if (side_on) {
       for (int r = 0; r < TS; ++r) {
@@ -647,8 +673,7 @@ DONK_D void gmm_m18_cta(int tid, const GmmArgs<double>& a, int cta, double* sm) 
       case 4: gmm_m18_store<4>(acc, out, c, d, g, tq); break;
       case 5: gmm_m18_store<5>(acc, out, c, d, g, tq); break;
       case 6: gmm_m18_store<6>(acc, out, c, d, g, tq); break;
-      case 7: gmm_m18_store<7>(acc, out, c, d, g, tq); break;
-      default: gmm_m18_store<8>(acc, out, c, d, g, tq); break;
+      default: gmm_m18_store<7>(acc, out, c, d, g, tq); break;
     }
   }
 #endif
