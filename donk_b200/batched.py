@@ -867,7 +867,8 @@ class BatchedTrajOpt:
         which only the iLQR stage reads) while the state fit and ``fit_lr`` of chunk i run, so the upload hides behind the
         dynamics fit instead of preceding it (config 5: 8.6 GB per 128 conditions, 168 ms at 51 GB/s, against ~190 ms of
         ``fit_lr``).  The previous policy is the one of the previous iteration (a first iteration goes through
-        :meth:`iteration`).  ``out_policy``: optional pinned host tensors ``(K, k, covar)`` the new policy is copied into.
+        :meth:`iteration`).  ``out_policy``: optional pinned host tensors ``(K, k, covar)`` the new policy is copied into
+        (asynchronously on the current stream: synchronise before reading them).
         """
         if self.pol is None:
             raise DonkError("iteration_from_host continues a running optimisation: run iteration() once first")
