@@ -16,6 +16,7 @@ its own roofline object and (N=1) the CPU figure of the same work:
   ilqr_strong      configs[2]  the headline step with 4096 conditions IN TOTAL (strong scaling)
   gmm_em           configs[3]  one EM iteration on a 10 M x 72 pool sharded over the GPUs (all-reduce inside)
   gmm_em_tf32x3    configs[3]  the same iteration at the stated fp32 tolerance on the tcgen05 tensor cores
+  kmeans_pass      configs[3]  the Lloyd pass of the k-means initialisation over the same pool (HBM-bound)
   gps_iteration    configs[4]  BatchedTrajOpt.iteration (fit_lr + 16-cluster prior + ILQR.optimize + step_adjust)
                                at T=500, dX=64, dU=16, N=128, 128 conditions per GPU
 
@@ -800,6 +801,27 @@ def run_ours(args):
                                             "gmm_e_mma_kernel + gmm_m_mma_kernel (mma.sync.m8n8k4.f64)")}
         em_strong = {"rows_total": n_rows * world, "n_gpus": world, "ms_per_iteration": em_ms, "scaling": "strong",
                      "collective": "all-reduce of the packed statistics (NCCL), once per iteration"}
+        # the Lloyd pass that initialises the first GMMPrior.update over the same pool (the one HBM-bound kernel of the path)
+        try:
+            c0 = Xp[:K].contiguous()
+            kws = torch.empty(nat.size("kmeans_workspace_bytes", d, K) // 8 + 1, **f64)
+            ksums = torch.empty(K * d + K, **f64)
+            km_ms = timed(lambda: batched.DeviceKMeans._pass(Xp, c0, labels=True, sums=ksums, ws=kws), 5, 2) / 5
+            kl_ms = timed(lambda: batched.DeviceKMeans._pass(Xp, c0, labels=True), 5, 2) / 5
+            kbytes = n_rows * d * 8
+            extra["kmeans_pass"] = {
+                "ms_per_lloyd_pass": km_ms, "ms_labels_only": kl_ms, "rows_per_sec": n_rows * world / (km_ms * 1e-3),
+                "config": f"{n_rows * world} rows total ({n_rows}/GPU), d={d}, K={K}: labels + per-cluster sums in one read of the pool "
+                          f"(kmeans_pass_mma_kernel: bulk-copied tiles, distances and one-hot sums on DMMA)",
+                "roofline": {"bound": "hbm", "achieved": kbytes / (km_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": kbytes / (km_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                             "kernel": "kmeans_pass_mma_kernel", "algorithmic_bytes": kbytes,
+                             "labels_only_gbs": kbytes / (kl_ms * 1e-3) / 1e9,
+                             "labels_only_frac": kbytes / (kl_ms * 1e-3) / 1e9 / hbm_peak,
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs"}}
+            del kws, ksums, c0
+        except Exception as ex:
+            extra["kmeans_pass"] = {"error": repr(ex)[:300]}
         # the same iteration at the stated fp32 tolerance: E pass and scatter statistics on tcgen05 (3xTF32 split products,
         # TMEM accumulators, fp64 partial sums / all-reduce / finalisation); fp64 stays the default and the parity path
         try:
