@@ -302,20 +302,24 @@ __global__ void gmm_tc_params_kernel(int d, int dp, int K, const double* center,
 // responsibilities are one contiguous run of the output and leave through shared memory with coalesced stores.
 __global__ void __launch_bounds__(128) gmm_tc_softmax_kernel(int n, int K, int kc, const float* logp, double* resp,
                                                              double* lse_part, int staged) {
-  extern __shared__ double sresp[];  // [128][K] when staged
+  extern __shared__ double sresp[];  // [128][K | 1] when staged (odd row pitch: a thread per row, no bank conflicts)
+  const int KP = K | 1;
   __shared__ double wsum[4];
   const size_t row0 = (size_t)blockIdx.x * 128, row = row0 + threadIdx.x;
   double lse = 0.0;
   if (row < (size_t)n) {
-    auto lp = [&](int k) { return (double)logp[((size_t)(k / kc) * n + row) * kc + k % kc]; };
-    double m = lp(0);
-    for (int k = 1; k < K; ++k) { const double v = lp(k); m = v > m ? v : m; }
-    double s = 0.0;
-    for (int k = 0; k < K; ++k) s += exp(lp(k) - m);
-    const double inv = 1.0 / s;
-    double* out = staged ? sresp + (size_t)threadIdx.x * K : resp + row * K;
-    for (int k = 0; k < K; ++k) out[k] = exp(lp(k) - m) * inv;
-    lse = m + log(s);
+    // single precision throughout (the log-probabilities ARE fp32 and the pass is held to the fp32 tolerance): one expf
+    // per entry, kept in the output slot and normalised in place; the fp64 form (three passes of double exp per row)
+    // took 1.4 ms per 10 M rows x 16 clusters, four times its HBM time
+    auto lp = [&](int k) { return logp[((size_t)(k / kc) * n + row) * kc + k % kc]; };
+    float m = lp(0);
+    for (int k = 1; k < K; ++k) { const float v = lp(k); m = v > m ? v : m; }
+    double* out = staged ? sresp + (size_t)threadIdx.x * KP : resp + row * K;
+    float s = 0.0f;
+    for (int k = 0; k < K; ++k) { const float e = __expf(lp(k) - m); s += e; out[k] = (double)e; }
+    const double inv = 1.0 / (double)s;
+    for (int k = 0; k < K; ++k) out[k] *= inv;
+    lse = (double)m + log((double)s);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) lse += __shfl_xor_sync(0xffffffffu, lse, o);
@@ -329,7 +333,7 @@ __global__ void __launch_bounds__(128) gmm_tc_softmax_kernel(int n, int K, int k
   if (staged) {
     const size_t left = (size_t)n - row0;
     const size_t cnt = (left < 128 ? left : 128) * K;
-    for (size_t i = threadIdx.x; i < cnt; i += 128) resp[row0 * K + i] = sresp[i];
+    for (size_t i = threadIdx.x; i < cnt; i += 128) resp[row0 * K + i] = sresp[(i / K) * KP + i % K];
   }
 }
 
@@ -712,19 +716,20 @@ __global__ void __launch_bounds__(256) gmm_tc_tblock_kernel(int n, int d, int NR
 
 // responsibilities (n, K) fp64 -> fp32 tiles [tile][K][64] (zero beyond n) and the per-tile column sums (fp64, fixed order)
 __global__ void __launch_bounds__(256) gmm_tc_respT_kernel(int n, int K, const double* resp, float* respT, double* nkpart) {
-  extern __shared__ double srt[];  // [64][K]
+  extern __shared__ double srt[];  // [64][K | 1]: odd row pitch, the transposed reads below hit distinct banks
+  const int KP = K | 1;
   const size_t row0 = (size_t)blockIdx.x * TM_TS;
   const size_t left = (size_t)n - row0;
   const int rows = (int)(left < (size_t)TM_TS ? left : (size_t)TM_TS);
-  for (int idx = threadIdx.x; idx < TM_TS * K; idx += 256) srt[idx] = idx < rows * K ? resp[row0 * K + idx] : 0.0;
+  for (int idx = threadIdx.x; idx < TM_TS * K; idx += 256) srt[(idx / K) * KP + idx % K] = idx < rows * K ? resp[row0 * K + idx] : 0.0;
   __syncthreads();
   for (int idx = threadIdx.x; idx < TM_TS * K; idx += 256) {
     const int k = idx / TM_TS, s = idx % TM_TS;
-    respT[(size_t)blockIdx.x * K * TM_TS + idx] = (float)srt[s * K + k];
+    respT[(size_t)blockIdx.x * K * TM_TS + idx] = (float)srt[s * KP + k];
   }
   if ((int)threadIdx.x < K) {
     double acc = 0.0;
-    for (int s = 0; s < TM_TS; ++s) acc += srt[s * K + threadIdx.x];
+    for (int s = 0; s < TM_TS; ++s) acc += srt[s * KP + threadIdx.x];
     nkpart[(size_t)blockIdx.x * K + threadIdx.x] = acc;
   }
 }
@@ -872,7 +877,7 @@ int donk_gmm_tc_estep_f32(int n, int d, int K, const void* planes, const double*
   p.bias = bias; p.cst = cst; p.logp = logp; p.ximg = static_cast<const unsigned char*>(planes);
   rc = tc_launch(pl.dp / 8, tPh, tPl, p, pl.smem, st);
   if (rc != DONK_OK) return rc;
-  const size_t sm_bytes = (size_t)128 * K * sizeof(double);
+  const size_t sm_bytes = (size_t)128 * (K | 1) * sizeof(double);
   const int staged = sm_bytes <= 40 * 1024;
   gmm_tc_softmax_kernel<<<(unsigned)((n + 127) / 128), 128, staged ? sm_bytes : 0, st>>>(n, K, pl.kc, logp, resp, lse_part, staged);
   LAUNCHED("gmm_tc_softmax_kernel");
@@ -925,7 +930,7 @@ int donk_gmm_tc_mstep_f32(int n, int d, int K, const void* mplanes, const double
   float* respT = reinterpret_cast<float*>(wp); wp += align256((size_t)ntiles * K * TM_TS * 4);
   double* nkpart = reinterpret_cast<double*>(wp); wp += align256((size_t)ntiles * K * 8);
   double* part = reinterpret_cast<double*>(wp);
-  gmm_tc_respT_kernel<<<ntiles, 256, (size_t)TM_TS * K * sizeof(double), st>>>(n, K, resp, respT, nkpart);
+  gmm_tc_respT_kernel<<<ntiles, 256, (size_t)TM_TS * (K | 1) * sizeof(double), st>>>(n, K, resp, respT, nkpart);
   LAUNCHED("gmm_tc_respT_kernel");
   int rc = DONK_OK;
   TcMParams p;
