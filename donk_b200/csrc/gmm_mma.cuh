@@ -30,7 +30,7 @@ namespace donk {
 template <int NB, int RA>
 DONK_HD size_t gmm_e_mma_smem(int K, int G) {
   const int TS = 8 * RA * G, ldt = ld_pad(TS);
-  return (size_t)8 * NB * ldt + (size_t)K * 8 * NB + round_up(K, 4) + (size_t)TS * K + 8;
+  return (size_t)8 * NB * ldt + (size_t)K * 8 * NB + round_up(K, 4) + (size_t)TS * (K | 1) + 8;
 }
 
 template <typename R, int NB, int RA>
@@ -40,7 +40,8 @@ DONK_D void gmm_e_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, int ncta,
   R* Xt = sm;                       // [D8][ldt]   feature-major rows of the tile
   R* sP = Xt + (size_t)D8 * ldt;    // [K][D8]     -(mu_k P_k)
   R* ldet = sP + (size_t)K * D8;    // [K]         sum log diag P_k + log pi_k
-  R* logp = ldet + round_up(K, 4);  // [TS][K]
+  R* logp = ldet + round_up(K, 4);  // [TS][KP]: odd row pitch (a thread pair per row in the softmax: no bank conflicts)
+  const int KP = K | 1;
   const size_t dd = (size_t)d * d;
   CTA_FOR(idx, D8 * ldt) Xt[idx] = R(0);
   CTA_FOR(idx, K * D8) {
@@ -171,7 +172,7 @@ DONK_D void gmm_e_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, int ncta,
           R ss = ssr[ra];
           ss += __shfl_xor_sync(0xffffffffu, ss, 1);
           ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-          if (tq == 0) logp[(i0 + 8 * ra + g) * K + k] = -(cst + ss) / 2 + ldet[k];
+          if (tq == 0) logp[(i0 + 8 * ra + g) * KP + k] = -(cst + ss) / 2 + ldet[k];
         }
 #else
         for (int r = 0; r < 8 * RA; ++r) {
@@ -181,7 +182,7 @@ DONK_D void gmm_e_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, int ncta,
             for (int f = 0; f <= j; ++f) y = fma(Xt[f * ldt + i0 + r], P[(size_t)f * d + j], y);
             ss = fma(y, y, ss);
           }
-          logp[(i0 + r) * K + k] = -(cst + ss) / 2 + ldet[k];
+          logp[(i0 + r) * KP + k] = -(cst + ss) / 2 + ldet[k];
         }
 #endif
       }
@@ -195,7 +196,7 @@ DONK_D void gmm_e_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, int ncta,
       const int r = w.tid >> 1, h = w.tid & 1;
       const bool act = r < TS;  // RA = 1 tiles (d > 72) have fewer rows than thread pairs
       const bool live = act && n0 + r < (size_t)a.n;
-      R* lp = logp + (act ? r : 0) * K;
+      R* lp = logp + (act ? r : 0) * KP;
       R m = -INFINITY;
       if (act)
         for (int k = h; k < K; k += 2) m = lp[k] > m ? lp[k] : m;
@@ -215,20 +216,20 @@ DONK_D void gmm_e_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, int ncta,
       R lse = (live && h == 0) ? m + log(sum) : R(0);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) lse += __shfl_xor_sync(0xffffffffu, lse, o);
-      if (w.lane == 0) logp[TS * K + w.team] = lse;  // the 8 spare slots behind the tile
+      if (w.lane == 0) logp[TS * KP + w.team] = lse;  // the 8 spare slots behind the tile
     }
     w.cta_sync();
     if (a.lse_part) {
       CTA_FOR(one, 1) {
         R acc = R(0);
-        for (int wp = 0; wp < G; ++wp) acc += logp[TS * K + wp];
+        for (int wp = 0; wp < G; ++wp) acc += logp[TS * KP + wp];
         a.lse_part[blk] = acc;
       }
     }
 #else
     CTA_FOR(r, TS) {
-      if (n0 + r >= (size_t)a.n) { logp[r * K] = R(0); continue; }
-      R* lp = logp + r * K;
+      if (n0 + r >= (size_t)a.n) { logp[r * KP] = R(0); continue; }
+      R* lp = logp + r * KP;
       R m = lp[0];
       for (int k = 1; k < K; ++k) m = lp[k] > m ? lp[k] : m;
       R s = R(0);
@@ -241,7 +242,7 @@ DONK_D void gmm_e_mma_cta(const WCtx& w, const GmmArgs<R>& a, int cta, int ncta,
     if (a.lse_part) {
       CTA_FOR(one, 1) {
         R acc = R(0);
-        for (int r = 0; r < TS; ++r) acc += logp[r * K];
+        for (int r = 0; r < TS; ++r) acc += logp[r * KP];
         a.lse_part[blk] = acc;
       }
     }
