@@ -44,7 +44,7 @@ struct FitWarpDims {
   static_assert(DX % 2 == 0, "prior path: [x_t | x_{t+1}] is read as one run of 2 dX values in blocks of 4");
   static constexpr int KX4 = 2 * DX / 4, KU4 = (DU + 3) / 4, KT4 = KX4 + KU4;
   DONK_HD static int prior_tail(int N, int K, bool pre = false) {
-    return K > 0 ? (pre ? 0 : ((N + 7) / 8 * 8) * K) + (K + 7) / 8 * 8 + D8 : 0;
+    return K > 0 ? (pre ? 0 : ((N + 7) / 8 * 8) * (K | 1)) + (K + 7) / 8 * 8 + D8 : 0;
   }
 };
 
@@ -221,9 +221,10 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
     // ---- 1b. GMM prior -> NIW posterior MAP covariance (prior_gmm.py:26-41, prior.py:18-45) -------------------------
     if (a.K > 0) {
       const int K = a.K, N8 = (N + 7) / 8 * 8, K8 = (K + 7) / 8 * 8;
+      const int KP = K | 1;  // odd pitch of the per-sample rows: the softmax runs a lane per sample
       const size_t dd = (size_t)d * d;
       R* resp = tp + D::TEAM;  // [N8][K]: log-probabilities, then responsibilities (absent with precomputed weights)
-      R* wts = resp + (pre_wts ? 0 : (size_t)N8 * K);
+      R* wts = resp + (pre_wts ? 0 : (size_t)N8 * KP);
       R* mup = wts + K8;
       auto load_sigma = [&](int i, int j) {  // element (i <= j) of the blocked joint covariance
         if (j < P) return Spp[i * PA + j];
@@ -316,7 +317,7 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
                 s += __shfl_xor_sync(0xffffffffu, s, 8);
                 s += __shfl_xor_sync(0xffffffffu, s, 16);
                 const int n = 8 * rb + 2 * tq + h;
-                if (g == 0 && n < N) resp[(size_t)n * K + k] = lc - s / 2;
+                if (g == 0 && n < N) resp[(size_t)n * KP + k] = lc - s / 2;
               }
             }
           }
@@ -332,23 +333,23 @@ DONK_D void fit_warp_cta(const WCtx& w, const FitArgs<R>& a, int cta, R* smem) {
             for (int i = 0; i <= j; ++i) y = fma(xux_load(a, b, n, t, i), Pk[(size_t)i * d + j], y);
             ss = fma(y, y, ss);
           }
-          resp[(size_t)n * K + k] = a.gconst[(size_t)K * d + k] - ss / 2;
+          resp[(size_t)n * KP + k] = a.gconst[(size_t)K * d + k] - ss / 2;
         }
       }
 #endif
       w.team_sync();
       LANE_FOR(n, N) {  // responsibilities: softmax over the clusters (sklearn/mixture/_base.py:552-582)
-        R m = resp[(size_t)n * K];
-        for (int k = 1; k < K; ++k) m = resp[(size_t)n * K + k] > m ? resp[(size_t)n * K + k] : m;
+        R m = resp[(size_t)n * KP];
+        for (int k = 1; k < K; ++k) m = resp[(size_t)n * KP + k] > m ? resp[(size_t)n * KP + k] : m;
         R s = R(0);
-        for (int k = 0; k < K; ++k) s += exp(resp[(size_t)n * K + k] - m);
+        for (int k = 0; k < K; ++k) s += exp(resp[(size_t)n * KP + k] - m);
         const R lse = m + log(s);
-        for (int k = 0; k < K; ++k) resp[(size_t)n * K + k] = exp(resp[(size_t)n * K + k] - lse);
+        for (int k = 0; k < K; ++k) resp[(size_t)n * KP + k] = exp(resp[(size_t)n * KP + k] - lse);
       }
       w.team_sync();
       LANE_FOR(k, K) {
         R acc = R(0);
-        for (int n = 0; n < N; ++n) acc += resp[(size_t)n * K + k];
+        for (int n = 0; n < N; ++n) acc += resp[(size_t)n * KP + k];
         wts[k] = acc / R(N);  // prior_gmm.py:33
       }
       }  // !pre_wts
