@@ -46,6 +46,7 @@ SIGNATURES = {
     "gmm_m_finalize_f64": [c_double, c_int, c_int, P, P, c_double, P, P, P, P, P, P, P],
     "gmm_tc_prepare_f32": [c_int, c_int, P, P, P, c_size_t, P],
     "gmm_tc_estep_f32": [c_int] * 3 + [P] * 8 + [c_size_t, P],
+    "gmm_tc_estep_m_f32": [c_int] * 3 + [P] * 8 + [c_size_t, P, c_size_t, P],
     "gmm_tc_mprepare_f32": [c_int, c_int, P, P, P, c_size_t, P],
     "gmm_tc_mstep_f32": [c_int] * 3 + [P] * 7 + [c_size_t, P],
     "gmm_predict_proba_f64": [c_int] * 3 + [P] * 5 + [P],

@@ -575,15 +575,20 @@ class DeviceGMM:
         if getattr(self, "_shift", None) is None or self._shift.shape != self.means.shape:
             self._shift = torch.empty_like(self.means)
         mode = int(getattr(self, "_mode", 0))
-        if self._tc is not None:  # E pass on the tensor cores: responsibilities and lse totals straight into ws
-            tc = self._tc
+        tc = self._tc
+        tc_m = tc is not None and tc.get("mplanes") is not None
+        if tc is not None and not tc_m:  # E pass on the tensor cores: responsibilities and lse totals straight into ws
             nat.call("gmm_tc_estep_f32", n, d, self.K, tc["planes"], tc["center"], self.weights, self.means,
                      self.precisions_cholesky, ws, ws[n * self.K:], tc["work"], tc["work"].numel() * 8)
             mode = 3
-        if self._tc is not None and self._tc.get("mplanes") is not None:
-            # M pass on the tensor cores too: scatter statistics about the same centre, drained into fp64 partial sums
-            tc = self._tc
-            nat.call("gmm_tc_mstep_f32", n, d, self.K, tc["mplanes"], tc["center"], ws, ws[n * self.K:], stats, self._shift,
+        if tc_m:
+            # E and M pass on the tensor cores: the E pass leaves the transposed single-precision responsibilities in the M
+            # pass's scratch (no fp64 round trip, no transpose kernel); scatter statistics about the same centre, drained
+            # into fp64 partial sums
+            nat.call("gmm_tc_estep_m_f32", n, d, self.K, tc["planes"], tc["center"], self.weights, self.means,
+                     self.precisions_cholesky, ws, ws[n * self.K:], tc["work"], tc["work"].numel() * 8, tc["mwork"],
+                     tc["mwork"].numel() * 8)
+            nat.call("gmm_tc_mstep_f32", n, d, self.K, tc["mplanes"], tc["center"], None, ws[n * self.K:], stats, self._shift,
                      tc["mwork"], tc["mwork"].numel() * 8)
         else:
             nat.call("gmm_em_step_mode_f64", n, d, self.K, X, self.weights, self.means, self.precisions_cholesky, None,

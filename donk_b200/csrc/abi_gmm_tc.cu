@@ -300,8 +300,11 @@ __global__ void gmm_tc_params_kernel(int d, int dp, int K, const double* center,
 // log-probabilities [K / kc][n][kc] fp32 -> responsibilities (n, K) fp64 and the log-sum-exp total of every GMM_TS-row
 // block (sklearn/mixture/_base.py:552-582).  128 rows per CTA, one thread per row, fixed-order sums; the block's
 // responsibilities are one contiguous run of the output and leave through shared memory with coalesced stores.
+// respT / nkpart (optional, staged form only): the transposed single-precision responsibilities [tile][K][64] and their
+// per-tile column sums in the layout the tensor-core M pass reads - written from the staged rows, so that the M pass needs
+// neither the fp64 responsibilities nor its own transpose kernel (donk_gmm_tc_estep_m_f32)
 __global__ void __launch_bounds__(128) gmm_tc_softmax_kernel(int n, int K, int kc, const float* logp, double* resp,
-                                                             double* lse_part, int staged) {
+                                                             double* lse_part, int staged, float* respT, double* nkpart) {
   extern __shared__ double sresp[];  // [128][K | 1] when staged (odd row pitch: a thread per row, no bank conflicts)
   const int KP = K | 1;
   __shared__ double wsum[4];
@@ -333,7 +336,24 @@ __global__ void __launch_bounds__(128) gmm_tc_softmax_kernel(int n, int K, int k
   if (staged) {
     const size_t left = (size_t)n - row0;
     const size_t cnt = (left < 128 ? left : 128) * K;
-    for (size_t i = threadIdx.x; i < cnt; i += 128) resp[row0 * K + i] = sresp[(i / K) * KP + i % K];
+    if (resp)
+      for (size_t i = threadIdx.x; i < cnt; i += 128) resp[row0 * K + i] = sresp[(i / K) * KP + i % K];
+    if (respT) {
+      const int rows = (int)(left < 128 ? left : 128);
+      for (int idx = threadIdx.x; idx < 2 * 64 * K; idx += 128) {
+        const int t = idx / (64 * K), rem = idx - t * 64 * K, k = rem / 64, sx = rem - k * 64, rl = t * 64 + sx;
+        if ((size_t)t * 64 + row0 < (size_t)((n + 63) / 64) * 64)  // the tile exists
+          respT[((size_t)blockIdx.x * 2 + t) * K * 64 + rem] = rl < rows ? (float)sresp[rl * KP + k] : 0.0f;
+      }
+      if ((int)threadIdx.x < 2 * K) {
+        const int t = threadIdx.x / K, k = threadIdx.x - t * K;
+        if ((size_t)t * 64 + row0 < (size_t)((n + 63) / 64) * 64) {
+          double acc = 0.0;
+          for (int sx = 0; sx < 64; ++sx) { const int rl = t * 64 + sx; if (rl < rows) acc += sresp[rl * KP + k]; }
+          nkpart[((size_t)blockIdx.x * 2 + t) * K + k] = acc;
+        }
+      }
+    }
   }
 }
 
@@ -841,9 +861,18 @@ int donk_gmm_tc_prepare_f32(int n, int d, const double* X, const double* center,
 /* E pass at fp32 tolerance: planes from donk_gmm_tc_prepare_f32 (same center), current parameters (fp64) ->
  * responsibilities (n, K) fp64 and per-64-row log-sum-exp totals, both written where the fp64 E pass puts them in the EM
  * workspace (resp | lse_part), so that donk_gmm_em_step_mode_f64(mode = 3) continues with the M pass. */
-int donk_gmm_tc_estep_f32(int n, int d, int K, const void* planes, const double* center, const double* weights,
-                          const double* means, const double* prec_chol, double* resp, double* lse_part, void* work,
-                          size_t work_bytes, void* stream) {
+// layout of the M pass's per-iteration scratch (donk_gmm_tc_mwork_bytes)
+static void tcm_layout(void* work, int n, int K, float** respT, double** nkpart, double** part) {
+  const int ntiles = (int)(tcm_npad(n) / TM_TS);
+  char* wp = reinterpret_cast<char*>(((uintptr_t)work + 255) & ~(uintptr_t)255);
+  *respT = reinterpret_cast<float*>(wp); wp += align256((size_t)ntiles * K * TM_TS * 4);
+  *nkpart = reinterpret_cast<double*>(wp); wp += align256((size_t)ntiles * K * 8);
+  *part = reinterpret_cast<double*>(wp);
+}
+
+static int tc_estep_impl(int n, int d, int K, const void* planes, const double* center, const double* weights,
+                         const double* means, const double* prec_chol, double* resp, double* lse_part, void* work,
+                         size_t work_bytes, void* mwork, void* stream) {
   if (n < 0 || d < 1 || K < 1) return DONK_BAD_SHAPE;
   const TcPlan pl = tc_plan(d, K);
   if (!pl.ok) { snprintf(g_err, sizeof(g_err), "gmm_tc: d=%d K=%d does not fit the tensor-core E pass", d, K); return DONK_SMEM_LIMIT; }
@@ -879,9 +908,32 @@ int donk_gmm_tc_estep_f32(int n, int d, int K, const void* planes, const double*
   if (rc != DONK_OK) return rc;
   const size_t sm_bytes = (size_t)128 * (K | 1) * sizeof(double);
   const int staged = sm_bytes <= 40 * 1024;
-  gmm_tc_softmax_kernel<<<(unsigned)((n + 127) / 128), 128, staged ? sm_bytes : 0, st>>>(n, K, pl.kc, logp, resp, lse_part, staged);
+  float* respT = nullptr;
+  double *nkpart = nullptr, *part = nullptr;
+  if (mwork) tcm_layout(mwork, n, K, &respT, &nkpart, &part);
+  (void)part;
+  gmm_tc_softmax_kernel<<<(unsigned)((n + 127) / 128), 128, staged ? sm_bytes : 0, st>>>(
+      n, K, pl.kc, logp, resp, lse_part, staged, staged ? respT : nullptr, staged ? nkpart : nullptr);
   LAUNCHED("gmm_tc_softmax_kernel");
+  if (mwork && !staged) {  // many clusters: the rows do not fit the staging area - separate transpose
+    const int ntiles = (int)(tcm_npad(n) / TM_TS);
+    gmm_tc_respT_kernel<<<ntiles, 256, (size_t)TM_TS * (K | 1) * sizeof(double), st>>>(n, K, resp, respT, nkpart);
+    LAUNCHED("gmm_tc_respT_kernel");
+  }
   return DONK_OK;
+}
+
+int donk_gmm_tc_estep_f32(int n, int d, int K, const void* planes, const double* center, const double* weights,
+                          const double* means, const double* prec_chol, double* resp, double* lse_part, void* work,
+                          size_t work_bytes, void* stream) {
+  return tc_estep_impl(n, d, K, planes, center, weights, means, prec_chol, resp, lse_part, work, work_bytes, nullptr, stream);
+}
+
+int donk_gmm_tc_estep_m_f32(int n, int d, int K, const void* planes, const double* center, const double* weights,
+                            const double* means, const double* prec_chol, double* resp, double* lse_part, void* work,
+                            size_t work_bytes, void* mwork, size_t mwork_bytes, void* stream) {
+  if (!mwork || mwork_bytes < donk_gmm_tc_mwork_bytes(n, d, K) || !resp) return DONK_BAD_SHAPE;
+  return tc_estep_impl(n, d, K, planes, center, weights, means, prec_chol, resp, lse_part, work, work_bytes, mwork, stream);
 }
 
 /* ---- M pass at fp32 tolerance on the tensor cores (see gmm_tc_mstep_kernel) ---- */
@@ -926,12 +978,13 @@ int donk_gmm_tc_mstep_f32(int n, int d, int K, const void* mplanes, const double
   }
   const size_t n_pad = tcm_npad(n);
   const int ntiles = (int)(n_pad / TM_TS);
-  char* wp = reinterpret_cast<char*>(((uintptr_t)work + 255) & ~(uintptr_t)255);
-  float* respT = reinterpret_cast<float*>(wp); wp += align256((size_t)ntiles * K * TM_TS * 4);
-  double* nkpart = reinterpret_cast<double*>(wp); wp += align256((size_t)ntiles * K * 8);
-  double* part = reinterpret_cast<double*>(wp);
-  gmm_tc_respT_kernel<<<ntiles, 256, (size_t)TM_TS * (K | 1) * sizeof(double), st>>>(n, K, resp, respT, nkpart);
-  LAUNCHED("gmm_tc_respT_kernel");
+  float* respT;
+  double *nkpart, *part;
+  tcm_layout(work, n, K, &respT, &nkpart, &part);
+  if (resp) {  // NULL: donk_gmm_tc_estep_m_f32 left the transposed responsibilities and their column sums in `work`
+    gmm_tc_respT_kernel<<<ntiles, 256, (size_t)TM_TS * (K | 1) * sizeof(double), st>>>(n, K, resp, respT, nkpart);
+    LAUNCHED("gmm_tc_respT_kernel");
+  }
   int rc = DONK_OK;
   TcMParams p;
   p.n = n; p.d = d; p.K = K; p.N = pl.N; p.mt_per = pl.mt_per; p.ncg = pl.ncg; p.ntiles = ntiles;

@@ -280,6 +280,13 @@ int donk_gmm_tc_mprepare_f32(int n, int d, const double* X, const double* center
 int donk_gmm_tc_mstep_f32(int n, int d, int K, const void* mplanes, const double* center, const double* resp,
                           const double* lse_part, double* stats, double* shift, void* work, size_t work_bytes,
                           void* stream);
+/* E pass that hands over to the tensor-core M pass directly: as donk_gmm_tc_estep_f32, and in addition the transposed
+ * single-precision responsibilities and their per-tile column sums are written into the M pass's scratch `mwork`
+ * (donk_gmm_tc_mwork_bytes) in the layout donk_gmm_tc_mstep_f32 reads; call that with resp = NULL afterwards (it then
+ * skips its own transpose of the fp64 responsibilities).  resp (n,K) is still written (callers may read it). */
+int donk_gmm_tc_estep_m_f32(int n, int d, int K, const void* planes, const double* center, const double* weights,
+                            const double* means, const double* prec_chol, double* resp, double* lse_part, void* work,
+                            size_t work_bytes, void* mwork, size_t mwork_bytes, void* stream);
 
 /* M-step finalisation from (all-reduced) statistics of n_total rows: new weights, means,
  * covariances (+ reg_covar I), precision Cholesky factors, mean log-likelihood.

@@ -563,9 +563,22 @@ int donk_emu_gmm_tc_mprepare_f32(int n, int d, const double* X, const double* ce
     for (int j = 0; j < d; ++j) x[r * d + j] = (float)(X[r * d + j] - (center ? center[j] : 0.0));
   return DONK_OK;
 }
+// stand-in for the E pass that hands over to the M pass: the responsibilities are kept for it by address (the emulation's
+// M pass reads fp64 responsibilities; the CUDA library keeps transposed fp32 copies in `mwork` instead)
+int donk_emu_gmm_tc_estep_m_f32(int n, int d, int K, const void* planes, const double* center, const double* weights,
+                                const double* means, const double* prec_chol, double* resp, double* lse_part, void* work,
+                                size_t work_bytes, void* mwork, size_t mwork_bytes, void*) {
+  if (!mwork || !resp || mwork_bytes < donk_emu_gmm_tc_mwork_bytes(n, d, K)) return DONK_BAD_SHAPE;
+  int rc = donk_emu_gmm_tc_estep_f32(n, d, K, planes, center, weights, means, prec_chol, resp, lse_part, work, work_bytes, nullptr);
+  if (rc != DONK_OK) return rc;
+  *reinterpret_cast<const double**>((reinterpret_cast<uintptr_t>(mwork) + 15) & ~(uintptr_t)15) = resp;
+  return DONK_OK;
+}
+
 int donk_emu_gmm_tc_mstep_f32(int n, int d, int K, const void* mplanes, const double* center, const double* resp,
                               const double* lse_part, double* stats, double* shift, void* work, size_t work_bytes, void*) {
   if (n < 0 || d < 1 || K < 1 || work_bytes < donk_emu_gmm_tc_mwork_bytes(n, d, K)) return DONK_BAD_SHAPE;
+  if (!resp) resp = *reinterpret_cast<const double**>((reinterpret_cast<uintptr_t>(work) + 15) & ~(uintptr_t)15);
   const size_t total = gmm_stats_len(d, K);
   for (size_t i = 0; i < total; ++i) stats[i] = 0.0;
   if (n == 0) return DONK_OK;
