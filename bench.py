@@ -528,6 +528,12 @@ def run_ours(args):
         barrier()
         return max_over_ranks(e0.elapsed_time(e1))
 
+    def timed_median(fn, reps, warmup, inner=1):
+        """Per-call time as the median over `reps` samples of `inner` back-to-back calls each (extras: a single allocator
+        hiccup moves a short mean by 10-15 %; back-to-back calls keep multi-launch sequences pipelined)."""
+        timed(fn, 0, warmup)
+        return float(np.median([timed(fn, inner, 0) / inner for _ in range(reps)]))
+
     def free():
         if not dry:
             torch.cuda.empty_cache()
@@ -584,7 +590,7 @@ def run_ours(args):
         holder["fit"] = batched.fit_lr(ro["X"], ro["U"])
 
     nfit = max(2, args.steps // 2)
-    fit_ms = timed(fit_once, nfit, 2) / nfit
+    fit_ms = timed_median(fit_once, nfit, 2)
     F, f, dyn_covar, info = holder["fit"]
     assert int(info.sum().item()) == 0, "fit_lr: matrix not positive definite"
     extra["fit_lr"] = {"timestep_fits_per_sec": B * T * world / (fit_ms * 1e-3), "ms_per_launch": fit_ms,
@@ -754,7 +760,7 @@ def run_ours(args):
         def fit2():
             holder["f2"] = batched.fit_lr(r2["X"], r2["U"], gm2)
 
-        ms2 = timed(fit2, 3, 1) / 3
+        ms2 = timed_median(fit2, 5, 1)
         assert int(holder["f2"][3].sum().item()) == 0
         if rank == 0:  # parity of condition 0 against the oracle
             import oracle
@@ -793,7 +799,7 @@ def run_ours(args):
         stats = torch.empty(nat.size("gmm_stats_size", d, K), **f64)
         gm._lb = torch.zeros(1, **f64)
         gm._info = torch.zeros(K, dtype=torch.int32, device=dev)
-        em_ms = timed(lambda: gm.em_iteration(Xp, float(n_rows * world), ws, stats), 5, 2) / 5
+        em_ms = timed_median(lambda: gm.em_iteration(Xp, float(n_rows * world), ws, stats), 3, 2, inner=2)
         extra["gmm_em"] = {"transitions_per_sec_per_iteration": n_rows * world / (em_ms * 1e-3), "ms_per_iteration": em_ms,
                            "config": f"{n_rows * world} rows total ({n_rows}/GPU), d={d}, K={K}, one E+M iteration "
                                      f"incl. all-reduce and M finalise",
@@ -838,7 +844,7 @@ def run_ours(args):
             tc_err = {"means": rel(gt.means, ref64.means), "covariances": rel(gt.covariances, ref64.covariances),
                       "weights": rel(gt.weights, ref64.weights), "lower_bound": rel(gt._lb, ref64._lb)}
             gt.set_params(w0, m0, precisions=p0)
-            tc_ms = timed(lambda: gt.em_iteration(Xp, float(n_rows * world), ws, stats), 5, 2) / 5
+            tc_ms = timed_median(lambda: gt.em_iteration(Xp, float(n_rows * world), ws, stats), 3, 2, inner=4)
             peaks_js = json.load(open(ROOT / "MEASURED_PEAKS.json")) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
             tf32_peak = peaks_js.get("bf16_tflops", 2250.0) / 2  # TF32 dense = half the bf16 rate; burst figure (timed alone)
             algo = em_flops_per_row(d, K) * n_rows
@@ -986,7 +992,7 @@ def run_ours(args):
         stats = torch.empty(nat.size("gmm_stats_size", d5, K5), **f64)
         gmu._lb = torch.zeros(1, **f64)
         gmu._info = torch.zeros(K5, dtype=torch.int32, device=dev)
-        emu_ms = timed(lambda: gmu.em_iteration(Xp, float(n5p * world), ws, stats), 3, 1) / 3
+        emu_ms = timed_median(lambda: gmu.em_iteration(Xp, float(n5p * world), ws, stats), 3, 1, inner=2)
         extra["gps_iteration"]["prior_update"] = {
             "ms_per_em_iteration": emu_ms, "rows_total": n5p * world, "d": d5, "K": K5,
             "roofline": roof(em_flops_per_row(d5, K5) * n5p, n5p * d5 * 8, emu_ms, "gmm_e_mma_kernel + gmm_m_mma_kernel")}
