@@ -146,6 +146,30 @@ __global__ void __launch_bounds__(256) kmeanspp_min_kernel(int n, int K, const d
     __syncthreads();
   }
 }
+// tensor-path pass: two CTAs per SM when two tiles buffers fit, else one; returns -1 when the shape is outside the path
+static int kmeans_mma_launch(int n, int d, int K, const double* X, const double* centers, int* labels, double* mind2,
+                             double* dist, double* part, const double* closest, double* pot_part, int& grid, void* stream) {
+  const size_t smem_mma = kmeans_mma_smem(d) * sizeof(double);
+  if (!kmeans_mma_ok(d, K, X) || smem_mma > smem_optin_cap() || n < 4096 || env_int("DONK_KMEANS_SCALAR")) return -1;
+  const int cap = 2 * (smem_mma + 1024) <= smem_optin_cap() ? 296 : 148;
+  if (grid > cap) grid = cap;
+  const int ntw = ((d + 1 + 7) / 8 + 7) / 8;
+  int rc;
+#define DONK_KM_CASE(V)                                                                                              \
+  case V:                                                                                                            \
+    rc = allow_smem(kmeans_pass_mma_kernel<V>, smem_mma);                                                            \
+    if (rc != DONK_OK) return rc;                                                                                    \
+    kmeans_pass_mma_kernel<V><<<grid, 256, smem_mma, (cudaStream_t)stream>>>(n, d, K, X, centers, labels, mind2, dist, part, \
+                                                                            closest, pot_part);                       \
+    break;
+  switch (ntw) {
+    DONK_KM_CASE(1) DONK_KM_CASE(2) DONK_KM_CASE(3)
+    default: return -1;
+  }
+#undef DONK_KM_CASE
+  return DONK_OK;
+}
+
 __global__ void kmeans_reduce_kernel(int ncta, int len, const double* part, double* out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < len) kmeans_reduce_item<double>(ncta, len, part, out, idx);
@@ -346,21 +370,9 @@ int donk_kmeans_pass_f64(int n, int d, int K, const double* X, const double* cen
   const int nblocks = (n + KM_TS - 1) / KM_TS;
   if (grid > nblocks) grid = nblocks > 0 ? nblocks : 1;
   double* part = sums ? static_cast<double*>(workspace) : nullptr;
-  int rc;
-  const size_t smem_mma = kmeans_mma_smem(d) * sizeof(double);
-  if (kmeans_mma_ok(d, K, X) && 2 * (smem_mma + 1024) <= smem_optin_cap() && n >= 4096 && !env_int("DONK_KMEANS_SCALAR")) {
-    // tensor-path form: bulk-copied row tiles, distances and one-hot sums on DMMA, two CTAs per SM
-    if (grid > 296) grid = 296;
-    if ((d + 1 + 7) / 8 <= 8) {
-      rc = allow_smem(kmeans_pass_mma_kernel<1>, smem_mma);
-      if (rc != DONK_OK) return rc;
-      kmeans_pass_mma_kernel<1><<<grid, 256, smem_mma, (cudaStream_t)stream>>>(n, d, K, X, centers, labels, mind2, dist, part, nullptr, nullptr);
-    } else {
-      rc = allow_smem(kmeans_pass_mma_kernel<2>, smem_mma);
-      if (rc != DONK_OK) return rc;
-      kmeans_pass_mma_kernel<2><<<grid, 256, smem_mma, (cudaStream_t)stream>>>(n, d, K, X, centers, labels, mind2, dist, part, nullptr, nullptr);
-    }
-  } else {
+  int rc = kmeans_mma_launch(n, d, K, X, centers, labels, mind2, dist, part, nullptr, nullptr, grid, stream);
+  if (rc > 0) return rc;
+  if (rc < 0) {
     const size_t smem = kmeans_pass_smem(d, K) * sizeof(double);
     if (smem > smem_optin_cap() || d + 1 > 256) return DONK_SMEM_LIMIT;
     rc = allow_smem(kmeans_pass_kernel, smem);
@@ -384,19 +396,9 @@ int donk_kmeanspp_round_f64(int n, int d, int Kc, const double* X, const double*
   int grid = KM_PASS_CTAS;
   const int nblocks = (n + KM_TS - 1) / KM_TS;
   if (grid > nblocks) grid = nblocks;
-  int rc;
-  const size_t smem_mma = kmeans_mma_smem(d) * sizeof(double);
-  if (kmeans_mma_ok(d, Kc, X) && 2 * (smem_mma + 1024) <= smem_optin_cap() && n >= 4096 && !env_int("DONK_KMEANS_SCALAR")) {
-    if (grid > 296) grid = 296;
-    if ((d + 1 + 7) / 8 <= 8) {
-      rc = allow_smem(kmeans_pass_mma_kernel<1>, smem_mma);
-      if (rc != DONK_OK) return rc;
-      kmeans_pass_mma_kernel<1><<<grid, 256, smem_mma, (cudaStream_t)stream>>>(n, d, Kc, X, cand, nullptr, nullptr, dmin, nullptr, closest, pot_part);
-    } else {
-      rc = allow_smem(kmeans_pass_mma_kernel<2>, smem_mma);
-      if (rc != DONK_OK) return rc;
-      kmeans_pass_mma_kernel<2><<<grid, 256, smem_mma, (cudaStream_t)stream>>>(n, d, Kc, X, cand, nullptr, nullptr, dmin, nullptr, closest, pot_part);
-    }
+  int rc = kmeans_mma_launch(n, d, Kc, X, cand, nullptr, nullptr, dmin, nullptr, closest, pot_part, grid, stream);
+  if (rc > 0) return rc;
+  if (rc == DONK_OK) {
     LAUNCHED("kmeans_pass_kernel");
   } else {
     rc = donk_kmeans_pass_f64(n, d, Kc, X, cand, nullptr, nullptr, dmin, nullptr, nullptr, 0, stream);

@@ -134,11 +134,11 @@ DONK_HD size_t kmeans_mma_smem(int d) {
   return (size_t)2 * KM_TS * ld + (size_t)d4 * 20 + 16 + 2 * KM_TS / 2 + 4;  // tiles | centres^T (ld 20) | |c|^2 | labels | mbarriers
 }
 DONK_HD bool kmeans_mma_ok(int d, int K, const void* X) {
-  return K <= 16 && d % 2 == 0 && d >= 4 && (d + 1 + 7) / 8 <= 16 && (reinterpret_cast<size_t>(X) & 15) == 0;
+  return K <= 16 && d % 2 == 0 && d >= 4 && (d + 1 + 7) / 8 <= 24 && (reinterpret_cast<size_t>(X) & 15) == 0;
 }
 
 #if defined(__CUDA_ARCH__) || !defined(DONK_EMU)
-template <int NTW>  // 8-column blocks of the sums per warp (8 warps: NTW = 1 up to d = 63, 2 up to d = 127)
+template <int NTW>  // 8-column blocks of the sums per warp (8 warps: NTW = 1 up to d = 63, 2 up to d = 127, 3 up to d = 191)
 DONK_D void kmeans_pass_mma_cta(int tid, int n, int d, int K, const double* X, const double* centers, int* labels,
                                 double* mind2, double* dist_out, double* part, int cta, int ncta, double* sm,
                                 const double* closest_in = nullptr, double* pot_part = nullptr) {

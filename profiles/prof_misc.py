@@ -80,7 +80,7 @@ elif what == "config2":
     ms, _ = timed(lambda: batched.fit_lr(ro["X"], ro["U"]))
     print(f"fit_lr no prior  (14,7) N=50, B={B}: {ms:.1f} ms = {B * T / (ms * 1e-3):.0f} fits/s")
 elif what == "kmeans":
-    n, d, K = int(sys.argv[2]), 72, 16
+    n, d, K = int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 72, int(sys.argv[4]) if len(sys.argv) > 4 else 16
     X, _, _, _ = synthetic.gmm_pool_torch(n, d, K, seed=5, device=dev)
     km = batched.DeviceKMeans(K, random_state=0)
     c0 = X[:K].contiguous()
