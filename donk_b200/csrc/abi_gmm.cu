@@ -126,6 +126,9 @@ int gmm_e_mma_dispatch(GmmArgs<double>& a, const GmmMmaPlan& pl, void* stream) {
     case 5: return gmm_e_mma_launch<5, 2>(a, pl, stream);
     case 6: return gmm_e_mma_launch<6, 2>(a, pl, stream);
     case 9: return gmm_e_mma_launch<9, 2>(a, pl, stream);
+    // d = 73..96 and 97..120: their own block counts (the 18-block kernel did up to twice the products on zero padding)
+    case 12: return gmm_e_mma_launch<12, 2>(a, pl, stream);
+    case 15: return gmm_e_mma_launch<15, 2>(a, pl, stream);
     // d = 73..144: 16 rows per warp (one 128-row tile, one CTA per SM) - every P_k fragment read through L1 feeds two
     // products instead of one: 49.0 -> 29.4 ms per pass at 2 M x 144, K = 16 (DONK_GMM_E_RA18=1: the 8-row variant)
     default: return env_int("DONK_GMM_E_RA18") == 1 ? gmm_e_mma_launch<18, 1>(a, pl, stream) : gmm_e_mma_launch<18, 2>(a, pl, stream);

@@ -692,7 +692,7 @@ inline GmmMmaPlan gmm_mma_plan(int n, int d, int K) {
   GmmMmaPlan p{};
   const int nb = (d + 7) / 8;
   p.ok = nb <= 18;
-  p.NB = nb <= 2 ? 2 : nb <= 5 ? 5 : nb <= 6 ? 6 : nb <= 9 ? 9 : 18;
+  p.NB = nb <= 2 ? 2 : nb <= 5 ? 5 : nb <= 6 ? 6 : nb <= 9 ? 9 : nb <= 12 ? 12 : nb <= 15 ? 15 : 18;
   p.RA = 2;
   p.Ge = 8;
   p.KC = 2;

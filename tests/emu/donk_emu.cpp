@@ -644,6 +644,8 @@ int donk_emu_gmm_em_step_mode_f64(int n_local, int d, int K, const double* X, co
       case 5: emu_gmm_e_mma<5, 2>(a, pl); break;
       case 6: emu_gmm_e_mma<6, 2>(a, pl); break;
       case 9: emu_gmm_e_mma<9, 2>(a, pl); break;
+      case 12: emu_gmm_e_mma<12, 2>(a, pl); break;
+      case 15: emu_gmm_e_mma<15, 2>(a, pl); break;
       default: emu_gmm_e_mma<18, 2>(a, pl); break;
     }
   } else {
