@@ -338,3 +338,28 @@ def test_warp_kernel_reports_quu_not_positive_definite(backend):
         prob = ILQRProblem(*fits[b], c.C, c.c, c.cc, c.prev_K, c.prev_k, c.prev_covar, np.linalg.inv(c.prev_covar), *x0[b])
         ref = oracle.ilqr_step(prob, 1.0)
         assert relerr(r.K[b, 1], ref.K) < TOL and abs(float(r.kl_div[b, 1]) - ref.kl_div) < 1e-9 * max(1.0, abs(ref.kl_div))
+
+
+def test_host_pipelined_step_equals_device_step(backend):
+    """HostPipelinedILQR (chunked double-buffered upload, ragged last chunk, inputs changed in place between steps) returns
+    exactly what BatchedILQR.step returns for the same conditions."""
+    from donk_b200.batched import BatchedILQR, HostPipelinedILQR
+
+    g = load_golden("ilqr_c1")
+    B, E = 5, 3
+    rng = np.random.default_rng(3)
+    r = lambda a: np.broadcast_to(a, (B,) + a.shape).copy()  # noqa: E731
+    host = {k: torch.as_tensor(r(g[k])) for k in HostPipelinedILQR.KEYS}
+    host["f"] += torch.as_tensor(0.01 * rng.standard_normal(tuple(host["f"].shape)))   # conditions differ
+    if backend.device.type == "cuda":
+        host = {k: v.pin_memory() for k, v in host.items()}
+    eta = torch.as_tensor(np.tile(np.array([0.5, 1.0, 4.0]), (B, 1)))
+    pipe = HostPipelinedILQR(host, E, chunks=3)  # chunks of 2, 2 and 1 conditions
+    for step in range(2):
+        kl, cost, info = pipe.step(eta)
+        il = BatchedILQR(host["F"], host["f"], host["dyn_covar"], host["prev_K"], host["prev_k"], host["C"], host["c"],
+                         host["cc"], host["x0_mean"], host["x0_covar"], prev_covar=host["prev_covar"])
+        ref = il.step(eta)
+        assert int(info.sum()) == 0
+        assert np.array_equal(kl.numpy(), to_np(ref.kl_div)) and np.array_equal(cost.numpy(), to_np(ref.expected_costs))
+        host["f"] += 0.02  # a producer refills the host buffers in place: the next step must see the new inputs
